@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Golden-vector generator: runs the UNMODIFIED reference (/root/reference, CPU, fp32) and records
+inputs/outputs of the hot path as small .npz fixtures next to this script.
+
+The reference has no tests or golden vectors of its own, so parity is pinned
+by running the reference itself.  It cannot travel to the GPU box, hence the committed fixtures.
+
+Run (in the build container only):
+    PYTHONPATH=tests/golden/_shims:/root/reference python tests/golden/make_golden.py
+
+`_shims/` holds stand-ins for `urdf_parser_py` and `matplotlib`, which the reference imports but
+which are not installed here.  Nothing in this script is used by the product path.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "_shims"))
+sys.path.insert(1, "/root/reference")
+
+torch.set_num_threads(1)  # deterministic reductions
+
+with contextlib.redirect_stdout(io.StringIO()):
+    from torch_robotics.torch_kinematics_tree.models import robots as R
+    from torch_robotics.torch_kinematics_tree.geometrics.frame import Frame
+    from torch_robotics.torch_kinematics_tree.geometrics.spatial_vector import y_rot, z_rot
+    from torch_robotics.torch_kinematics_tree.geometrics.utils import SE3_distance
+    from torch_robotics.robots.robot_panda import RobotPanda
+    from torch_robotics.environments.env_spheres_3d import EnvSpheres3D
+    from torch_robotics.environments.env_base import EnvBase
+    from torch_robotics.environments.primitives import MultiSphereField, ObjectField
+    from torch_robotics.tasks.tasks import PlanningTask
+    from torch_robotics.torch_planning_objectives.fields.distance_fields import (
+        EESE3DistanceField, CollisionObjectDistanceField, CollisionWorkspaceBoundariesDistanceField)
+
+TA = dict(device="cpu", dtype=torch.float32)
+
+ROBOTS = {
+    "panda": lambda: R.DifferentiableFrankaPanda(gripper=False),
+    "panda_gripper": lambda: R.DifferentiableFrankaPanda(gripper=True),
+    "ur10": lambda: R.DifferentiableUR10(),
+    "kuka_iiwa": lambda: R.DifferentiableKUKAiiwa(),
+    "stretch": lambda: R.DifferentiableHabitatStretch(),
+    "tiago_dual_holo": lambda: R.DifferentiableTiagoDualHolo(),
+    "tiago_dual_holo_move": lambda: R.DifferentiableTiagoDualHoloMove(),
+    "shadow_hand": lambda: R.DifferentiableShadowHand(),
+    "allegro_hand": lambda: R.DifferentiableAllegroHand(),
+    "planar_2link": lambda: R.Differentiable2LinkPlanar(),
+}
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def sample_q(model, n, gen):
+    """Mix of in-limit, [0,1) (examples/forward_kinematics.py:24), out-of-limit and at-limit rows."""
+    D = model._n_dofs
+    lo = np.full(D, -np.pi, np.float32)
+    hi = np.full(D, np.pi, np.float32)
+    for c, bi in enumerate(model._controlled_joints):
+        lim = model._bodies[bi].joint_limits
+        if lim is not None:
+            lo[c], hi[c] = np.float32(lim["lower"]), np.float32(lim["upper"])
+    lo_t, hi_t = torch.from_numpy(lo), torch.from_numpy(hi)
+    k = n // 4
+    q_in = lo_t + torch.rand(k, D, generator=gen) * (hi_t - lo_t)
+    q_01 = torch.rand(k, D, generator=gen)
+    q_out = (torch.rand(k, D, generator=gen) * 2 - 1) * 3.9
+    q_at = torch.where(torch.rand(n - 3 * k, D, generator=gen) < 0.5, lo_t, hi_t)
+    return torch.cat([q_in, q_01, q_out, q_at], 0).contiguous()
+
+
+def dump_descriptor(model):
+    bodies = model._bodies
+    names = [b.name for b in bodies]
+    idx = {n: i for i, n in enumerate(names)}
+    parent = [-1] + [idx[model._model.get_name_of_parent_body(b.name)] for b in bodies[1:]]
+    lo, hi, has = [], [], []
+    for b in bodies:
+        lim = b.joint_limits
+        has.append(0 if lim is None else 1)
+        lo.append(0.0 if lim is None else lim["lower"])
+        hi.append(0.0 if lim is None else lim["upper"])
+    return dict(
+        link_names=np.array(names), parent=np.array(parent, np.int32),
+        joint_type=np.array([b.joint_type for b in bodies]),
+        fixed_rotation=torch.cat([b.fixed_rotation for b in bodies]).numpy(),
+        trans=torch.cat([b.trans for b in bodies]).numpy(),
+        joint_axis=torch.cat([b.joint_axis for b in bodies]).numpy(),
+        joint_idx=np.array([-1 if b.joint_idx is None else b.joint_idx for b in bodies], np.int32),
+        limit_lower=np.array(lo, np.float64), limit_upper=np.array(hi, np.float64),
+        has_limit_dict=np.array(has, np.int32),
+        out_link_names=np.array(model.get_link_names()),
+    )
+
+
+def golden_fk():
+    gen = torch.Generator().manual_seed(1234)
+    for name, ctor in ROBOTS.items():
+        model = quiet(ctor)
+        out = dump_descriptor(model)
+        q = sample_q(model, 32, gen).requires_grad_(True)
+        H = model.compute_forward_kinematics_all_links(q)
+        G = torch.randn(H.shape, generator=gen)
+        (H * G).sum().backward()
+        out.update(q=q.detach().numpy(), H=H.detach().numpy(), G=G.numpy(), grad_q=q.grad.numpy())
+        np.savez_compressed(os.path.join(HERE, f"fk_{name}.npz"), **out)
+        print(name, "links", len(model._bodies), "dofs", model._n_dofs, "H", tuple(H.shape))
+
+
+def ee_target():
+    # target of examples/inverse_kinematics.py:27-30
+    pos = torch.tensor([0.2, 0.4, 0.1], **TA)
+    rot = (z_rot(-torch.tensor(torch.pi / 2)) @ y_rot(-torch.tensor(torch.pi))).to(**TA)
+    return Frame(rot=rot, trans=pos, device="cpu").get_transform_matrix()   # [1,4,4]
+
+
+def obstacle_argmin(env, pos):
+    """Index of the nearest sphere per collision point, from the reference's own primitive tensors."""
+    out = []
+    for obj in env.get_df_obj_list():
+        assert len(obj.fields) == 1
+        f = obj.fields[0]
+        from torch_robotics.torch_kinematics_tree.geometrics.quaternion import q_to_rotation_matrix
+        from torch_robotics.torch_kinematics_tree.geometrics.utils import rotate_point
+        rot = q_to_rotation_matrix(obj.ori).squeeze().transpose(-2, -1)
+        x = rotate_point(pos - obj.pos, rot)
+        sdfs = torch.norm(x.unsqueeze(-2) - f.centers.unsqueeze(0), dim=-1) - f.radii
+        out.append(torch.min(sdfs, dim=-1)[1])
+    return torch.stack(out, dim=-2)   # [..., n_obj, S]
+
+
+def planning_case(tag, robot, env, task, q, H_target, ee_kwargs, ws=True):
+    """Record every term of the objective and its gradient for q [b,h,7]."""
+    out = {}
+    b, h, _ = q.shape
+    terms = {}
+
+    def run(which):
+        qq = q.clone().requires_grad_(True)
+        pos = robot.fk_map_collision(qq)
+        if which == "self":
+            c = task.df_collision_self.compute_cost(qq, pos, field_type="sdf")
+        elif which == "obj":
+            c = task.df_collision_objects.compute_cost(qq, pos, field_type="sdf")
+        elif which == "ws":
+            c = task.df_collision_ws_boundaries.compute_cost(qq, pos, field_type="sdf")
+        elif which == "ee":
+            Hs = robot.diff_panda.compute_forward_kinematics_all_links(qq.reshape(-1, 7))
+            ee = EESE3DistanceField(H_target, **ee_kwargs)
+            c = ee.compute_costs_impl(qq, Hs).reshape(b, h)
+        elif which == "collision":
+            c = task.compute_collision_cost(qq)
+        c.sum().backward()
+        return c.detach().numpy(), qq.grad.numpy(), pos.detach().numpy()
+
+    for which in ("self", "obj", "ws", "ee", "collision"):
+        c, g, pos = run(which)
+        out[f"cost_{which}"] = c
+        out[f"grad_{which}"] = g
+    out["link_pos"] = pos
+    out["q"] = q.numpy()
+    out["H_target"] = H_target.numpy().reshape(4, 4)
+    # occupancy masks: per field, default margins and margin=0 (tasks.py:251)
+    with torch.no_grad():
+        pos_t = robot.fk_map_collision(q)
+        for mtag, kw in (("default", {}), ("zero", {"margin": 0.0})):
+            out[f"occ_self_{mtag}"] = task.df_collision_self.compute_cost(q, pos_t, field_type="occupancy", **kw).numpy()
+            out[f"occ_obj_{mtag}"] = task.df_collision_objects.compute_cost(q, pos_t, field_type="occupancy", **kw).numpy()
+            out[f"occ_ws_{mtag}"] = task.df_collision_ws_boundaries.compute_cost(q, pos_t, field_type="occupancy", **kw).numpy()
+            out[f"occ_all_{mtag}"] = task.compute_collision(q, **kw).numpy()
+        pts = pos_t[..., robot.link_idxs_for_object_collision_checking, :]
+        out["obj_argmin"] = obstacle_argmin(env, pts).numpy().astype(np.int32)
+    # environment description, so tests do not need the reference classes
+    objs = env.get_df_obj_list()
+    out["n_obj"] = np.int32(len(objs))
+    for oi, obj in enumerate(objs):
+        out[f"obj{oi}_centers"] = obj.fields[0].centers.numpy()
+        out[f"obj{oi}_radii"] = obj.fields[0].radii.numpy()
+        out[f"obj{oi}_pos"] = obj.pos.numpy()
+        out[f"obj{oi}_ori_wxyz"] = obj.ori.numpy()
+    out["ws_min"] = task.ws_min.numpy()
+    out["ws_max"] = task.ws_max.numpy()
+    out["pt_link"] = np.array(robot.link_idxs_for_object_collision_checking, np.int32)
+    out["pt_radius"] = robot.link_margins_for_object_collision_checking_tensor.numpy()
+    out["obstacle_cutoff_margin"] = np.float64(task.df_collision_objects.cutoff_margin)
+    out["self_link_idxs"] = np.array(robot.link_idxs_for_self_collision_checking, np.int32)
+    out["self_pairs_local"] = np.array(robot.df_collision_self.idxs_links_distance_matrix, np.int32)
+    out["self_margin"] = robot.df_collision_self.cutoff_margin.numpy()
+    out["ee_w_pos"] = np.float64(ee_kwargs.get("w_pos", 1.0))
+    out["ee_w_rot"] = np.float64(ee_kwargs.get("w_rot", 1.0))
+    out["ee_square"] = np.int32(ee_kwargs.get("square", True))
+    np.savez_compressed(os.path.join(HERE, f"planning_{tag}.npz"), **out)
+    print("planning", tag, "cost_collision[0,:3]", out["cost_collision"][0, :3])
+
+
+def golden_planning():
+    gen = torch.Generator().manual_seed(4321)
+    robot = quiet(RobotPanda, tensor_args=TA)
+    H_target = ee_target()
+
+    def sample(b, h):
+        lo, hi = robot.q_min, robot.q_max
+        q = lo + torch.rand(b, h, 7, generator=gen) * (hi - lo)
+        q[0, 0] = torch.rand(7, generator=gen) * 7.8 - 3.9     # out-of-limit row
+        return q.contiguous()
+
+    # (1) config 3 of BASELINE.json: EnvSpheres3D, default PlanningTask
+    env = quiet(EnvSpheres3D, tensor_args=TA)
+    task = quiet(PlanningTask, env=env, robot=robot, tensor_args=TA)
+    planning_case("panda_spheres3d", robot, env, task, sample(8, 16), H_target, dict(w_pos=1.0, w_rot=1.0, square=True))
+
+    # (2) two objects, one with a non-identity pose, non-uniform radii, un-squared EE weights
+    c1 = torch.tensor([[0.4, 0.1, 0.5], [-0.2, 0.4, 0.6], [0.1, -0.5, 0.3]])
+    r1 = torch.tensor([0.12, 0.2, 0.07])
+    c2 = torch.tensor([[0.0, 0.0, 0.0], [0.25, 0.0, 0.1], [0.0, 0.3, -0.1], [-0.3, -0.2, 0.2]])
+    r2 = torch.tensor([0.1, 0.15, 0.05, 0.2])
+    o1 = ObjectField([MultiSphereField(c1, r1, tensor_args=TA)], "o1")
+    quat = torch.tensor([0.8, 0.2, -0.4, 0.4], **TA)
+    quat = quat / quat.norm()
+    o2 = ObjectField([MultiSphereField(c2, r2, tensor_args=TA)], "o2",
+                     pos=torch.tensor([0.3, -0.1, 0.5], **TA), ori=quat)
+    env2 = EnvBase(name="two_objects", limits=torch.tensor([[-0.6, -0.7, -0.1], [0.7, 0.6, 1.0]], **TA),
+                   obj_fixed_list=[o1, o2], tensor_args=TA)
+    task2 = quiet(PlanningTask, env=env2, robot=robot, obstacle_cutoff_margin=0.03, tensor_args=TA)
+    planning_case("panda_two_objects", robot, env2, task2, sample(4, 8), H_target, dict(w_pos=2.0, w_rot=0.5, square=False))
+
+
+def golden_stretch_objective():
+    """Config 5: Stretch has no collision model in the reference; compose the generic field classes
+    exactly as SURVEY.md section 8(d) item 5 specifies."""
+    gen = torch.Generator().manual_seed(99)
+    model = quiet(R.DifferentiableHabitatStretch)
+    names = model.get_link_names()
+    pt_links = list(model._controlled_joints) + [names.index("link_straight_gripper")]
+    radius = torch.full((len(pt_links),), 0.05, **TA)
+    env = quiet(EnvSpheres3D, tensor_args=TA)
+
+    class _Stub:   # the fields only read robot.grasped_object (distance_fields.py:137)
+        grasped_object = None
+    f_obj = CollisionObjectDistanceField(_Stub(), df_obj_list_fn=env.get_df_obj_list,
+                                         link_idxs_for_collision_checking=pt_links,
+                                         link_margins_for_object_collision_checking_tensor=radius,
+                                         cutoff_margin=0.01, tensor_args=TA)
+    f_ws = CollisionWorkspaceBoundariesDistanceField(_Stub(), link_idxs_for_collision_checking=pt_links,
+                                                     link_margins_for_object_collision_checking_tensor=radius,
+                                                     cutoff_margin=0.01, ws_bounds_min=env.limits[0],
+                                                     ws_bounds_max=env.limits[1], tensor_args=TA)
+    H_target = ee_target()
+    ee_idx = names.index("link_straight_gripper")
+    q = sample_q(model, 32, gen)
+    out = dict(q=q.numpy(), pt_link=np.array(pt_links, np.int32), pt_radius=radius.numpy(), ee_link=np.int32(ee_idx),
+               H_target=H_target.numpy().reshape(4, 4), centers=env.obj_fixed_list[0].fields[0].centers.numpy(),
+               radii=env.obj_fixed_list[0].fields[0].radii.numpy(), ws_min=env.limits[0].numpy(), ws_max=env.limits[1].numpy())
+    for which in ("obj", "ws", "ee", "total"):
+        qq = q.clone().requires_grad_(True)
+        Hs = model.compute_forward_kinematics_all_links(qq)
+        pos = Hs[..., :3, 3]
+        c_obj = f_obj.compute_cost(qq, pos, field_type="sdf").reshape(-1)
+        c_ws = f_ws.compute_cost(qq, pos, field_type="sdf").reshape(-1)
+        c_ee = torch.square(SE3_distance(Hs[:, ee_idx], H_target, w_pos=1.0, w_rot=1.0))
+        c = dict(obj=c_obj, ws=c_ws, ee=c_ee, total=c_obj + c_ws + c_ee)[which]
+        c.sum().backward()
+        out[f"cost_{which}"] = c.detach().numpy()
+        out[f"grad_{which}"] = qq.grad.numpy()
+    with torch.no_grad():
+        pos = model.compute_forward_kinematics_all_links(q)[..., :3, 3]
+        out["occ_obj"] = f_obj.compute_cost(q, pos, field_type="occupancy").reshape(-1).numpy()
+        out["occ_ws"] = f_ws.compute_cost(q, pos, field_type="occupancy").reshape(-1).numpy()
+    np.savez_compressed(os.path.join(HERE, "objective_stretch.npz"), **out)
+    print("stretch objective total[:3]", out["cost_total"][:3])
+
+
+def golden_ik():
+    gen = torch.Generator().manual_seed(7)
+    model = quiet(R.DifferentiableFrankaPanda, gripper=False)
+    H_target = ee_target()
+    lower, upper, _, _ = model.get_joint_limit_array()
+    eps = torch.pi / 64
+    lo = torch.tensor(lower + eps, **TA)
+    hi = torch.tensor(upper - eps, **TA)
+    S = 24
+    q0 = (lo + torch.rand(S, 7, generator=gen) * (hi - lo)).contiguous()
+    q_probe = q0.clone()
+    q_probe[:4] += 0.3    # some rows outside the shrunk limits
+    qq = q_probe.clone().requires_grad_(True)
+    err = model.loss_fn_ik_per_q(qq, H_target, "ee_link", w_se3=1.0, w_joint_limits=300.0, lower=lo, upper=hi,
+                                 w_q_rest=1.0, q_rest=None)
+    err.sum().backward()
+    idx_valid = model.ik_termination(q_probe, H_target, "ee_link", lo, hi, se3_eps=0.5)
+    out = dict(q_probe=q_probe.numpy(), loss=err.detach().numpy(), loss_grad=qq.grad.numpy(),
+               idx_valid_eps0p5=idx_valid.numpy().astype(np.int64), lower=lo.numpy(), upper=hi.numpy(),
+               H_target=H_target.numpy().reshape(4, 4), q0=q0.numpy())
+    for iters in (1, 5, 40):
+        q_ik, idx = quiet(model.inverse_kinematics, H_target, link_name="ee_link", batch_size=S, max_iters=iters,
+                          lr=2e-1, se3_eps=5e-2, q0=q0.clone(), q0_noise=0.0, eps_joint_lim=eps, print_freq=-1)
+        out[f"q_ik_{iters}"] = q_ik.detach().numpy()
+        out[f"idx_valid_{iters}"] = idx.numpy().astype(np.int64)
+    np.savez_compressed(os.path.join(HERE, "ik_panda.npz"), **out)
+    print("ik: valid after 40 iters:", out["idx_valid_40"])
+
+
+if __name__ == "__main__":
+    golden_fk()
+    golden_planning()
+    golden_stretch_objective()
+    golden_ik()

@@ -1,0 +1,381 @@
+"""Host-side model compiler: URDF text -> flat kinematic-tree descriptor arrays.
+
+This is the once-per-model step that the reference spreads over
+`URDFRobotModel.get_body_parameters` (torch_kinematics_tree/models/utils.py:199-313),
+`DifferentiableRigidBody.__init__` (models/rigid_body.py:74-123) and
+`DifferentiableTree.__init__` (models/robot_tree.py:77-126).  The output is what the CUDA
+kernels consume through `trk_model_create` (include/trk_b200.h): one row per link, in URDF
+`<link>` order ("body order"), plus a parents-first processing order.
+
+Reference semantics that are reproduced on purpose (SURVEY.md section 8a "quirks"):
+  * body 0 (= first <link>) is the root: zero offset, fixed (models/utils.py:204-211);
+  * q column i drives the i-th non-fixed body in <link> order (robot_tree.py:111-115);
+  * R_fixed = (Rz(yaw) @ Ry(pitch)) @ Rx(roll) evaluated with fp32 torch ops (rigid_body.py:93),
+    so e.g. cos(fp32(-1.57079632679)) = -4.37e-8 is kept, not rounded to 0;
+  * revolute axis: |a_x|==1 -> x, elif |a_y|==1 -> y, else z with sign(a_z)
+    (rigid_body.py:163-168) - an oblique axis turns about z, a zero axis does not turn at all;
+  * prismatic translation uses the raw axis vector, not rotated by the joint rpy
+    (rigid_body.py:176-181);
+  * FK clamps q to [lower, upper] unless the joint is 'continuous' or has no <limit>
+    (rigid_body.py:157-160); continuous joints with a <limit> store +-pi (models/utils.py:240-242).
+"""
+from __future__ import annotations
+
+import math
+import xml.etree.ElementTree as ET
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+KIND_FIXED, KIND_REVOLUTE, KIND_PRISMATIC = 0, 1, 2
+MAX_LINKS = 64   # must match TRK_MAX_LINKS in include/trk_b200.h
+MAX_DOFS = 32    # must match TRK_MAX_DOFS
+
+
+def _floats(text: Optional[str]) -> List[float]:
+    if text is None:
+        return [0.0, 0.0, 0.0]
+    return [float(v) for v in text.split()]
+
+
+def _axis_rot(k: int, angle: torch.Tensor) -> torch.Tensor:
+    """fp32 [1,3,3] axis rotation built the way spatial_vector.py:8-47 does (zeros + cos/sin)."""
+    c, s = torch.cos(angle), torch.sin(angle)
+    R = torch.zeros((1, 3, 3), dtype=torch.float32)
+    if k == 0:
+        R[:, 0, 0] = 1.0
+        R[:, 1, 1] = c
+        R[:, 1, 2] = -s
+        R[:, 2, 1] = s
+        R[:, 2, 2] = c
+    elif k == 1:
+        R[:, 0, 0] = c
+        R[:, 0, 2] = s
+        R[:, 1, 1] = 1.0
+        R[:, 2, 0] = -s
+        R[:, 2, 2] = c
+    else:
+        R[:, 0, 0] = c
+        R[:, 0, 1] = -s
+        R[:, 1, 0] = s
+        R[:, 1, 1] = c
+        R[:, 2, 2] = 1.0
+    return R
+
+
+def fixed_rotation_from_rpy(rpy) -> np.ndarray:
+    """(Rz(yaw) @ Ry(pitch)) @ Rx(roll) in fp32 torch CPU arithmetic (rigid_body.py:88-93)."""
+    r = torch.tensor(rpy, dtype=torch.float32)
+    R = (_axis_rot(2, r[2]) @ _axis_rot(1, r[1])) @ _axis_rot(0, r[0])
+    return R[0].numpy().copy()
+
+
+@dataclass
+class TreeDescriptor:
+    name: str
+    link_names: List[str]
+    joint_names: List[str]
+    joint_types: List[str]
+    parent: np.ndarray      # int32 [L], -1 for the root
+    kind: np.ndarray        # int32 [L]  KIND_*
+    axis_k: np.ndarray      # int32 [L]  0/1/2 rotation axis of revolute joints
+    axis_s: np.ndarray      # float32 [L] sign applied to q (-1, 0, +1)
+    axis: np.ndarray        # float32 [L,3] raw <axis xyz>
+    q_index: np.ndarray     # int32 [L]  column of q, -1 for fixed bodies
+    R_fixed: np.ndarray     # float32 [L,3,3]
+    trans: np.ndarray       # float32 [L,3]
+    lo: np.ndarray          # float32 [L]  clamp bounds used by FK
+    hi: np.ndarray          # float32 [L]
+    has_lim: np.ndarray     # int32 [L]  1 when FK clamps this joint
+    topo: np.ndarray        # int32 [L]  processing order, parents before children
+    depth: np.ndarray       # int32 [L]
+    limits: List[Optional[Dict[str, float]]]   # per body, as models/utils.py:234-243 stores them
+    controlled: List[int] = field(default_factory=list)   # body index per q column
+    base_R: np.ndarray = field(default_factory=lambda: np.eye(3, dtype=np.float32))
+    base_t: np.ndarray = field(default_factory=lambda: np.zeros(3, dtype=np.float32))
+
+    @property
+    def n_links(self) -> int:
+        return len(self.link_names)
+
+    @property
+    def n_dofs(self) -> int:
+        return len(self.controlled)
+
+    def name_to_idx(self) -> Dict[str, int]:
+        # later duplicates win, like the dict assignment at robot_tree.py:119
+        return {n: i for i, n in enumerate(self.link_names)}
+
+    def signature(self) -> bytes:
+        """Byte string identifying the kinematics (used to pick a compiled-in specialisation)."""
+        parts = [self.parent, self.kind, self.axis_k, self.axis_s, self.axis, self.q_index,
+                 self.R_fixed, self.trans, self.lo, self.hi, self.has_lim]
+        return b"".join(np.ascontiguousarray(p).tobytes() for p in parts)
+
+
+def compile_urdf(path: str, name: str = "") -> TreeDescriptor:
+    root = ET.parse(str(path)).getroot()
+    link_names = [el.get("name") for el in root if el.tag == "link"]
+    joints = [el for el in root if el.tag == "joint"]
+    L = len(link_names)
+    if L == 0:
+        raise ValueError(f"{path}: no <link> elements")
+    if L > MAX_LINKS:
+        raise ValueError(f"{path}: {L} links exceeds the compiled maximum of {MAX_LINKS}")
+
+    def joint_of(child_name):   # first joint whose child is this link (models/utils.py:188-192)
+        for j in joints:
+            if j.find("child").get("link") == child_name:
+                return j
+        return None
+
+    name_to_idx = {n: i for i, n in enumerate(link_names)}
+    parent = np.full(L, -1, np.int32)
+    kind = np.zeros(L, np.int32)
+    axis_k = np.full(L, 2, np.int32)
+    axis_s = np.zeros(L, np.float32)
+    axis = np.zeros((L, 3), np.float32)
+    q_index = np.full(L, -1, np.int32)
+    R_fixed = np.tile(np.eye(3, dtype=np.float32), (L, 1, 1))
+    trans = np.zeros((L, 3), np.float32)
+    lo = np.zeros(L, np.float32)
+    hi = np.zeros(L, np.float32)
+    has_lim = np.zeros(L, np.int32)
+    limits: List[Optional[Dict[str, float]]] = [None] * L
+    joint_names = ["base_joint"] * L
+    joint_types = ["fixed"] * L
+    controlled: List[int] = []
+
+    if joint_of(link_names[0]) is not None:
+        raise ValueError(f"{path}: the first <link> ({link_names[0]}) must be the tree root "
+                         "(the reference roots the recursion there, robot_tree.py:293)")
+
+    for i in range(1, L):
+        j = joint_of(link_names[i])
+        if j is None:
+            raise ValueError(f"{path}: link {link_names[i]} has no parent joint (multiple roots)")
+        jt = j.get("type")
+        joint_names[i] = j.get("name")
+        joint_types[i] = jt
+        parent[i] = name_to_idx[j.find("parent").get("link")]
+        org = j.find("origin")
+        xyz = _floats(org.get("xyz")) if org is not None else [0.0, 0.0, 0.0]
+        rpy = _floats(org.get("rpy")) if org is not None else [0.0, 0.0, 0.0]
+        trans[i] = np.asarray(xyz, np.float32)
+        R_fixed[i] = fixed_rotation_from_rpy(rpy)
+        ax = j.find("axis")
+        if ax is not None:
+            axis[i] = np.asarray(_floats(ax.get("xyz")), np.float32)
+        if jt == "fixed":
+            continue
+        if jt not in ("revolute", "continuous", "prismatic"):
+            raise NotImplementedError(f"{path}: joint type '{jt}' (rigid_body.py:183 raises too)")
+        q_index[i] = len(controlled)
+        controlled.append(i)
+        if len(controlled) > MAX_DOFS:
+            raise ValueError(f"{path}: more than {MAX_DOFS} degrees of freedom")
+        kind[i] = KIND_PRISMATIC if jt == "prismatic" else KIND_REVOLUTE
+        a = axis[i]
+        if abs(a[0]) == 1:
+            axis_k[i], axis_s[i] = 0, np.sign(a[0])
+        elif abs(a[1]) == 1:
+            axis_k[i], axis_s[i] = 1, np.sign(a[1])
+        else:
+            axis_k[i], axis_s[i] = 2, np.sign(a[2])
+        lim = j.find("limit")
+        if lim is not None:
+            d = {"effort": float(lim.get("effort", 0.0)), "lower": float(lim.get("lower", 0.0)),
+                 "upper": float(lim.get("upper", 0.0)), "velocity": float(lim.get("velocity", 0.0))}
+            if jt == "continuous":
+                d["lower"], d["upper"] = -math.pi, math.pi
+            limits[i] = d
+            if jt != "continuous":
+                has_lim[i] = 1
+                lo[i], hi[i] = np.float32(d["lower"]), np.float32(d["upper"])
+
+    # parents-first processing order (stable: body order among ready links) and depth
+    depth = np.full(L, -1, np.int32)
+    depth[0] = 0
+    topo = [0]
+    placed = {0}
+    while len(topo) < L:
+        progressed = False
+        for i in range(1, L):
+            if i not in placed and int(parent[i]) in placed:
+                placed.add(i)
+                topo.append(i)
+                depth[i] = depth[parent[i]] + 1
+                progressed = True
+        if not progressed:
+            missing = [link_names[i] for i in range(L) if i not in placed]
+            raise ValueError(f"{path}: links not reachable from the root: {missing}")
+
+    return TreeDescriptor(
+        name=name or root.get("name", ""), link_names=link_names, joint_names=joint_names,
+        joint_types=joint_types, parent=parent, kind=kind, axis_k=axis_k, axis_s=axis_s, axis=axis,
+        q_index=q_index, R_fixed=R_fixed, trans=trans, lo=lo, hi=hi, has_lim=has_lim,
+        topo=np.asarray(topo, np.int32), depth=depth, limits=limits, controlled=controlled)
+
+
+# ----------------------------------------------------------------------------------------------
+# Planning-objective descriptor (collision points, obstacle spheres, self pairs, ws bounds, EE)
+# ----------------------------------------------------------------------------------------------
+MAX_POINTS = 64     # TRK_MAX_POINTS
+MAX_SPHERES = 256   # TRK_MAX_SPHERES
+MAX_OBJECTS = 16    # TRK_MAX_OBJECTS
+MAX_PAIRS = 128     # TRK_MAX_PAIRS
+
+
+@dataclass
+class CostDescriptor:
+    """Flat description of the objective evaluated on the FK result.
+
+    Mirrors what PlanningTask wires together (tasks/tasks.py:44-86) from RobotPanda's collision
+    model (robots/robot_panda.py:47-127, robots/robot_base.py:57-141) and the environment's
+    object list (environments/env_base.py:75-88):
+
+      self term  : sum_p ( margin_p - |x_i - x_j| )                distance_fields.py:194-208,113-124
+      object term: sum_s max_o ( (r_s + cutoff) - min_k(|x_s - c_k| - r_k) )   :307-316, primitives.py:108-112
+      ws term    : sum_s max_6 ( (r_s + cutoff) - halfspace distance )          :326-332
+      ee term    : (w_rot (1 - (tr(R R_t^T) - 1)/2) + w_pos |p - p_t|)^(2 if square)   :347-356, utils.py:130-154
+
+    All margins are fp32 values computed with the same fp32 additions the reference performs.
+    """
+    # collision points (object + ws terms): one point at the origin of `pt_link[s]`
+    pt_link: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    pt_margin_obj: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))   # r_s + cutoff (object term)
+    pt_margin_ws: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))    # r_s + cutoff (ws term)
+    # obstacle objects: object o owns spheres [obj_start[o], obj_start[o+1])
+    obj_start: np.ndarray = field(default_factory=lambda: np.zeros(1, np.int32))
+    obj_R: np.ndarray = field(default_factory=lambda: np.zeros((0, 3, 3), np.float32))   # object rotation (world <- object)
+    obj_pos: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.float32))
+    obj_identity: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    sph_center: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.float32))
+    sph_radius: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))
+    # workspace box
+    ws_enabled: int = 0
+    ws_min: np.ndarray = field(default_factory=lambda: np.zeros(3, np.float32))
+    ws_max: np.ndarray = field(default_factory=lambda: np.zeros(3, np.float32))
+    # self-collision pairs (body indices) and their margins
+    pair_i: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    pair_j: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    pair_margin: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))
+    # end-effector SE(3) term
+    ee_enabled: int = 0
+    ee_link: int = 0
+    ee_w_pos: float = 1.0
+    ee_w_rot: float = 1.0
+    ee_square: int = 1
+    ee_target: np.ndarray = field(default_factory=lambda: np.eye(4, dtype=np.float32))
+    # relu on (margin - sdf) per term: self, object, ws  (distance_fields.py:117)
+    clamp_self: int = 0
+    clamp_obj: int = 0
+    clamp_ws: int = 0
+    # weights of the four terms in the total: self, object, ws, ee
+    weights: np.ndarray = field(default_factory=lambda: np.ones(4, np.float32))
+
+    @property
+    def n_points(self) -> int:
+        return int(self.pt_link.shape[0])
+
+    @property
+    def n_objects(self) -> int:
+        return int(self.obj_start.shape[0]) - 1
+
+    @property
+    def n_spheres(self) -> int:
+        return int(self.sph_radius.shape[0])
+
+    @property
+    def n_pairs(self) -> int:
+        return int(self.pair_i.shape[0])
+
+    def validate(self, n_links: int) -> None:
+        if self.n_points > MAX_POINTS or self.n_spheres > MAX_SPHERES or self.n_objects > MAX_OBJECTS \
+                or self.n_pairs > MAX_PAIRS:
+            raise ValueError("cost descriptor exceeds compiled table sizes")
+        for arr in (self.pt_link, self.pair_i, self.pair_j):
+            if arr.size and (arr.min() < 0 or arr.max() >= n_links):
+                raise ValueError("cost descriptor references a link outside the model")
+        if self.ee_enabled and not (0 <= self.ee_link < n_links):
+            raise ValueError("ee_link outside the model")
+
+
+# ----------------------------------------------------------------------------------------------
+# builders
+# ----------------------------------------------------------------------------------------------
+def quat_wxyz_to_matrix(q) -> np.ndarray:
+    """fp32 rotation matrix of a (not necessarily unit) wxyz quaternion, same arithmetic as
+    geometrics/quaternion.py:102-120."""
+    q = torch.as_tensor(np.asarray(q, np.float32)).reshape(4)
+    w, x, y, z = torch.unbind(q, -1)
+    dc = 2.0 / (q ** 2).sum(-1)
+    o = torch.stack((1 - dc * (y * y + z * z), dc * (x * y - z * w), dc * (x * z + y * w),
+                     dc * (x * y + z * w), 1 - dc * (x * x + z * z), dc * (y * z - x * w),
+                     dc * (x * z - y * w), dc * (y * z + x * w), 1 - dc * (x * x + y * y)), dim=-1)
+    return o.reshape(3, 3).numpy().copy()
+
+
+def _f32(x) -> np.ndarray:
+    if torch.is_tensor(x):
+        x = x.detach().cpu().numpy()
+    return np.ascontiguousarray(np.asarray(x, np.float32))
+
+
+def build_cost_descriptor(
+        pt_link=(), pt_radius=(), cutoff_obj=0.0, cutoff_ws=None,
+        objects=(), ws_min=None, ws_max=None,
+        self_pairs=(), self_margin=(),
+        ee_link=None, ee_target=None, ee_w_pos=1.0, ee_w_rot=1.0, ee_square=True,
+        clamp_self=False, clamp_obj=False, clamp_ws=False, weights=(1.0, 1.0, 1.0, 1.0)) -> CostDescriptor:
+    """Assemble a CostDescriptor.
+
+    pt_link/pt_radius: collision points (body index, sphere radius) - RobotBase's
+        link_idxs_for_object_collision_checking / link_margins_..._tensor (robot_base.py:57-85).
+    cutoff_*: the fields' cutoff_margin; the per-point margin is the fp32 sum radius + cutoff
+        (distance_fields.py:113).
+    objects: iterable of (centers [K,3], radii [K], pos [3] | None, ori_wxyz [4] | None) - one entry
+        per ObjectField; several primitive sphere fields of one object are simply concatenated
+        (min over fields of min over spheres, primitives.py:402-405).
+    self_pairs: (body_i, body_j) pairs, self_margin their margins (robot_base.py:105-141).
+    """
+    c = CostDescriptor()
+    c.pt_link = np.ascontiguousarray(np.asarray(pt_link, np.int32).reshape(-1))
+    rad = torch.as_tensor(_f32(pt_radius).reshape(-1))
+    cutoff_ws = cutoff_obj if cutoff_ws is None else cutoff_ws
+    c.pt_margin_obj = (rad + cutoff_obj).numpy().astype(np.float32) if rad.numel() else np.zeros(0, np.float32)
+    c.pt_margin_ws = (rad + cutoff_ws).numpy().astype(np.float32) if rad.numel() else np.zeros(0, np.float32)
+    starts, Rs, poss, idents, cs, rs = [0], [], [], [], [], []
+    for obj in objects:
+        centers, radii = _f32(obj[0]).reshape(-1, 3), _f32(obj[1]).reshape(-1)
+        pos = None if len(obj) < 3 or obj[2] is None else _f32(obj[2]).reshape(3)
+        ori = None if len(obj) < 4 or obj[3] is None else _f32(obj[3]).reshape(4)
+        ident = (pos is None or not np.any(pos)) and (ori is None or (ori[0] == 1 and not np.any(ori[1:])))
+        Rs.append(np.eye(3, dtype=np.float32) if ori is None else quat_wxyz_to_matrix(ori))
+        poss.append(np.zeros(3, np.float32) if pos is None else pos)
+        idents.append(1 if ident else 0)
+        cs.append(centers)
+        rs.append(radii)
+        starts.append(starts[-1] + len(radii))
+    c.obj_start = np.asarray(starts, np.int32)
+    c.obj_R = np.stack(Rs).astype(np.float32) if Rs else np.zeros((0, 3, 3), np.float32)
+    c.obj_pos = np.stack(poss).astype(np.float32) if poss else np.zeros((0, 3), np.float32)
+    c.obj_identity = np.asarray(idents, np.int32)
+    c.sph_center = np.concatenate(cs).astype(np.float32) if cs else np.zeros((0, 3), np.float32)
+    c.sph_radius = np.concatenate(rs).astype(np.float32) if rs else np.zeros(0, np.float32)
+    if ws_min is not None:
+        c.ws_enabled, c.ws_min, c.ws_max = 1, _f32(ws_min).reshape(3), _f32(ws_max).reshape(3)
+    pairs = np.asarray(self_pairs, np.int32).reshape(-1, 2)
+    c.pair_i, c.pair_j = np.ascontiguousarray(pairs[:, 0]), np.ascontiguousarray(pairs[:, 1])
+    m = _f32(self_margin).reshape(-1)
+    c.pair_margin = np.broadcast_to(m, (len(pairs),)).astype(np.float32).copy() if len(pairs) else np.zeros(0, np.float32)
+    if ee_link is not None:
+        c.ee_enabled, c.ee_link = 1, int(ee_link)
+        c.ee_w_pos, c.ee_w_rot, c.ee_square = float(ee_w_pos), float(ee_w_rot), int(bool(ee_square))
+        if ee_target is not None:
+            c.ee_target = _f32(ee_target).reshape(4, 4)
+    c.clamp_self, c.clamp_obj, c.clamp_ws = int(clamp_self), int(clamp_obj), int(clamp_ws)
+    c.weights = _f32(weights).reshape(4)
+    return c
