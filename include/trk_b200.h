@@ -1,0 +1,188 @@
+/*
+ * trk_b200.h - C ABI of the B200-native FK + planning-objective hot path.
+ *
+ * The reference (anindex/torch_robotics) is pure Python on PyTorch and has no FFI of its own;
+ * its boundary for this path is a set of Python methods.  Every entry point below names the
+ * reference method it stands behind (paths relative to /root/reference/torch_robotics).  The
+ * Python drop-in layer (torch_robotics_b200/) binds these symbols with ctypes and wraps them in
+ * torch.autograd.Function; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types cross the boundary;
+ *   - every data pointer is a DEVICE pointer to contiguous fp32/int32/uint8 memory owned by the
+ *     caller, unless the parameter is documented as host memory;
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*): no allocation, no
+ *     synchronisation, no host read-back on the data path;
+ *   - return value: 0 = OK, <0 = invalid argument (TRK_E_*), >0 = cudaError_t;
+ *     trk_last_error() returns a thread-local message for the last non-zero status;
+ *   - handles are immutable after creation (except the documented setters) and may be shared
+ *     between host threads; one handle per (model, device).
+ */
+#ifndef TRK_B200_H
+#define TRK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRK_ABI_VERSION 1
+
+#define TRK_MAX_LINKS   64
+#define TRK_MAX_DOFS    32
+#define TRK_MAX_POINTS  64
+#define TRK_MAX_SPHERES 256
+#define TRK_MAX_OBJECTS 16
+#define TRK_MAX_PAIRS   128
+
+#define TRK_OK              0
+#define TRK_E_NULL         -1   /* required pointer is null */
+#define TRK_E_RANGE        -2   /* count / index out of range */
+#define TRK_E_ALIGN        -3   /* pointer not aligned as required */
+#define TRK_E_UNSUPPORTED  -4   /* valid request the library does not implement */
+
+#define TRK_KIND_FIXED      0
+#define TRK_KIND_REVOLUTE   1   /* also 'continuous' (has_lim = 0) */
+#define TRK_KIND_PRISMATIC  2
+
+/* occupancy bits written by trk_objective / trk_cost_stage */
+#define TRK_OCC_SELF   1u
+#define TRK_OCC_OBJECT 2u
+#define TRK_OCC_WS     4u
+
+typedef struct trk_model trk_model;   /* opaque: kinematic tree resident on one GPU */
+typedef struct trk_cost  trk_cost;    /* opaque: planning-objective tables resident on one GPU */
+
+/*
+ * Kinematic tree, one entry per body in URDF <link> order (HOST arrays, copied at creation).
+ * Produced by torch_robotics_b200/descriptor.py:compile_urdf, which restates
+ *   torch_kinematics_tree/models/utils.py:199-313   (URDFRobotModel.get_body_parameters)
+ *   torch_kinematics_tree/models/rigid_body.py:74-123 (DifferentiableRigidBody.__init__)
+ *   torch_kinematics_tree/models/robot_tree.py:77-126 (DifferentiableTree.__init__).
+ */
+typedef struct trk_model_desc {
+    int32_t        n_links;   /* L <= TRK_MAX_LINKS */
+    int32_t        n_dofs;    /* D <= TRK_MAX_DOFS  */
+    const int32_t* parent;    /* [L] body index of the parent, -1 for the root (body 0) */
+    const int32_t* kind;      /* [L] TRK_KIND_* */
+    const int32_t* axis_k;    /* [L] revolute: rotation axis 0=x 1=y 2=z (rigid_body.py:163-168) */
+    const float*   axis_s;    /* [L] revolute: sign multiplying q (-1, 0, +1) */
+    const float*   axis;      /* [L*3] raw <axis xyz>; prismatic offset = axis * q (rigid_body.py:176) */
+    const int32_t* q_index;   /* [L] column of q driving this body, -1 if fixed */
+    const float*   R_fixed;   /* [L*9] row-major joint-origin rotation (rigid_body.py:93) */
+    const float*   trans;     /* [L*3] joint-origin translation */
+    const float*   lo;        /* [L] clamp bounds, fp32(lower/upper) (rigid_body.py:157-160) */
+    const float*   hi;
+    const int32_t* has_lim;   /* [L] 1 when FK clamps q to [lo, hi] */
+    const int32_t* topo;      /* [L] processing order: every parent precedes its children */
+    const float*   base_pose; /* [12] row-major [R | t] world pose of the root, NULL = identity
+                                 (DifferentiableTree.update_base_pose, robot_tree.py:133) */
+} trk_model_desc;
+
+/*
+ * Planning objective evaluated on the FK result (HOST arrays, copied at creation).
+ * Restates what PlanningTask wires together, tasks/tasks.py:44-86, from
+ *   robots/robot_base.py:57-141 + robots/robot_panda.py:47-127      (collision model)
+ *   torch_planning_objectives/fields/distance_fields.py:107-130,180-215,269-356 (cost fields)
+ *   environments/primitives.py:90-112,348-405                       (sphere SDF, object pose)
+ */
+typedef struct trk_cost_desc {
+    int32_t        n_points;       /* S collision points, each at the origin of body pt_link[s] */
+    const int32_t* pt_link;        /* [S] */
+    const float*   pt_margin_obj;  /* [S] fp32(radius + cutoff) for the object term (distance_fields.py:113) */
+    const float*   pt_margin_ws;   /* [S] fp32(radius + cutoff) for the workspace term */
+    int32_t        n_objects;      /* ObjectFields; object o owns spheres [obj_start[o], obj_start[o+1]) */
+    const int32_t* obj_start;      /* [n_objects + 1] */
+    const int32_t* obj_identity;   /* [n_objects] 1 = identity pose: points are used untransformed */
+    const float*   obj_R;          /* [n_objects*9] world<-object rotation (primitives.py:397) */
+    const float*   obj_pos;        /* [n_objects*3] */
+    int32_t        n_spheres;      /* K */
+    const float*   sph_center;     /* [K*3] in the object frame */
+    const float*   sph_radius;     /* [K] */
+    int32_t        ws_enabled;
+    float          ws_min[3];      /* distance_fields.py:326-332 */
+    float          ws_max[3];
+    int32_t        n_pairs;        /* P self-collision pairs (body indices), robot_base.py:105-116 */
+    const int32_t* pair_i;
+    const int32_t* pair_j;
+    const float*   pair_margin;    /* [P] */
+    int32_t        ee_enabled;
+    int32_t        ee_link;        /* body whose pose enters SE3_distance (distance_fields.py:347-350) */
+    float          ee_w_pos, ee_w_rot;
+    int32_t        ee_square;
+    float          ee_target[16];  /* row-major 4x4 shared target (EESE3DistanceField.target_H) */
+    int32_t        clamp_self, clamp_obj, clamp_ws;   /* relu(margin - sdf), distance_fields.py:117 */
+    float          weights[4];     /* total = w0*self + w1*object + w2*ws + w3*ee */
+} trk_cost_desc;
+
+int         trk_abi_version(void);
+const char* trk_last_error(void);
+
+/* Replaces DifferentiableTree.__init__ (robot_tree.py:77-126) for the device side. */
+int  trk_model_create(const trk_model_desc* desc, int device, trk_model** out);
+void trk_model_destroy(trk_model* model);
+/* Name of the kernel family serving this model: "generic" or a compiled-in robot such as "panda". */
+const char* trk_model_kernel_family(const trk_model* model);
+
+/*
+ * DifferentiableTree.compute_forward_kinematics_all_links (robot_tree.py:267-301).
+ *   q        [n, D]  device fp32, row-major
+ *   link_sel [n_sel] HOST int32 body indices in output order, each body at most once; NULL = all bodies
+ *   H_out    [n, n_sel, 4, 4] device fp32, 16-byte aligned
+ */
+int trk_fk_forward(const trk_model* model, const float* q, int64_t n,
+                   const int32_t* link_sel, int32_t n_sel, float* H_out, void* stream);
+
+/*
+ * Reverse mode of the above (the reference uses autograd over rigid_body.py:146-211).
+ * Recomputes FK from q; G [n, n_sel, 4, 4] is the upstream gradient (bottom rows ignored);
+ * grad_q [n, D] is overwritten.
+ */
+int trk_fk_backward(const trk_model* model, const float* q, int64_t n,
+                    const int32_t* link_sel, int32_t n_sel, const float* G, float* grad_q, void* stream);
+
+/* Device tables for PlanningTask's fields (tasks.py:44-86) + EESE3DistanceField (distance_fields.py:335). */
+int  trk_cost_create(const trk_model* model, const trk_cost_desc* desc, trk_cost** out);
+void trk_cost_destroy(trk_cost* cost);
+/* EESE3DistanceField.update_target (distance_fields.py:344): H_target16 is HOST memory, row-major 4x4. */
+int  trk_cost_set_ee_target(trk_cost* cost, const float* H_target16, void* stream);
+/* Replace the four term weights (HOST memory). */
+int  trk_cost_set_weights(trk_cost* cost, const float* weights4, void* stream);
+
+/*
+ * Fused FK + objective + reverse mode:
+ *   PlanningTask._compute_collision_or_cost (tasks.py:139-232) + EESE3DistanceField.compute_costs_impl
+ *   (distance_fields.py:352-356) + cost.sum().backward().
+ *   q             [n, D]
+ *   ee_target_cfg [n, 4, 4] per-configuration EE targets, or NULL to use the shared target
+ *   margin_override  occupancy threshold replacing every per-point/pair margin (the `margin=` kwarg,
+ *                    tasks.py:251); pass NaN for the default margins
+ *   cost_total [n]        weighted sum of the terms                      (nullable)
+ *   cost_terms [n, 4]     self, object, ws, ee                           (nullable)
+ *   grad_q     [n, D]     d cost_total / d q                             (nullable: forward only)
+ *   occupancy  [n] uint8  TRK_OCC_* bits (compute_collision, tasks.py:131) (nullable)
+ *   argmin     [n, n_objects, S] int32 nearest sphere per object and point, index within the object (nullable)
+ */
+int trk_objective(const trk_model* model, const trk_cost* cost, const float* q, int64_t n,
+                  const float* ee_target_cfg, float margin_override,
+                  float* cost_total, float* cost_terms, float* grad_q,
+                  uint8_t* occupancy, int32_t* argmin, void* stream);
+
+/*
+ * Cost stage alone, on caller-supplied link positions - the DistanceField.compute_cost entry
+ * (distance_fields.py:26-55) which receives FK output as a tensor.
+ *   link_pos [n, L, 3]  world positions of all bodies (RobotBase.fk_map_collision, robot_base.py:171)
+ *   ee_pose  [n, 4, 4]  pose of the EE body (nullable unless the EE term is enabled)
+ *   grad_pos [n, L, 3]  d cost_total / d link_pos  (nullable)
+ *   grad_ee  [n, 4, 4]  d (w3 * ee term) / d ee_pose (nullable)
+ */
+int trk_cost_stage(const trk_model* model, const trk_cost* cost, const float* link_pos, const float* ee_pose,
+                   int64_t n, const float* ee_target_cfg, float margin_override,
+                   float* cost_total, float* cost_terms, float* grad_pos, float* grad_ee,
+                   uint8_t* occupancy, int32_t* argmin, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRK_B200_H */

@@ -1,0 +1,182 @@
+"""CUDA kernels (through the C ABI) against the oracle and the golden vectors.  Needs a GPU."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROBOT_NAMES, get_desc, load_golden, planning_cost_from_golden, rel_err, stretch_cost_from_golden
+from oracle import restatement as orc
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL, GRAD_TOL = 1e-5, 1e-4
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def models():
+    from torch_robotics_b200._lib import DeviceModel
+    return {r: DeviceModel(get_desc(r), DEV) for r in ROBOT_NAMES}
+
+
+def t(a):
+    return torch.as_tensor(np.ascontiguousarray(a), device=DEV)
+
+
+@pytest.mark.parametrize("robot", ROBOT_NAMES)
+def test_fk_forward_backward_vs_golden(models, robot):
+    g, d, m = load_golden(f"fk_{robot}"), get_desc(robot), models[robot]
+    sel = [d.link_names.index(n) for n in g["out_link_names"]]
+    sel_arg = None if sel == list(range(d.n_links)) else sel
+    H = m.fk_forward(t(g["q"]), sel_arg).cpu().numpy()
+    assert H.shape == g["H"].shape
+    assert rel_err(H, g["H"]) < POSE_TOL
+    assert np.array_equal(H[..., 3, :], np.broadcast_to(np.array([0, 0, 0, 1], np.float32), H[..., 3, :].shape))
+    grad = m.fk_backward(t(g["q"]), t(g["G"]), sel_arg).cpu().numpy()
+    assert rel_err(grad, g["grad_q"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("robot", ["panda", "stretch", "shadow_hand", "tiago_dual_holo_move"])
+@pytest.mark.parametrize("n", [1, 31, 33, 1000, 20011])
+def test_fk_vs_oracle_ragged_sizes(models, robot, n):
+    d, m = get_desc(robot), models[robot]
+    rng = np.random.default_rng(n)
+    q = (rng.uniform(-3.5, 3.5, (n, d.n_dofs))).astype(np.float32)
+    Rw, pw = orc.fk_forward(d, q, np.float32)
+    H = m.fk_forward(t(q)).cpu().numpy()
+    assert rel_err(H, orc.homogeneous(Rw, pw)) < POSE_TOL
+    # a permuted sub-selection of links
+    sel = [int(v) for v in rng.permutation(d.n_links)[: max(1, d.n_links // 2)]]
+    Hs = m.fk_forward(t(q), sel).cpu().numpy()
+    assert np.array_equal(Hs, H[:, sel])
+    G = rng.standard_normal(Hs.shape).astype(np.float32)
+    grad = m.fk_backward(t(q), t(G), sel).cpu().numpy()
+    assert rel_err(grad, orc.fk_backward(d, q, G, sel, np.float32)) < GRAD_TOL
+
+
+def test_fk_empty_batch(models):
+    m = models["panda"]
+    H = m.fk_forward(torch.empty((0, 7), device=DEV))
+    assert H.shape == (0, 11, 4, 4)
+
+
+def test_autograd_function_matches_raw(models):
+    from torch_robotics_b200 import ops
+    g, m = load_golden("fk_panda"), models["panda"]
+    q = t(g["q"]).requires_grad_(True)
+    H = ops.fk(m, q)
+    (H * t(g["G"])).sum().backward()
+    assert rel_err(q.grad.cpu().numpy(), g["grad_q"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("case", ["panda_spheres3d", "panda_two_objects"])
+def test_objective_vs_golden(models, case):
+    from torch_robotics_b200._lib import DeviceCost
+    g, m = load_golden(f"planning_{case}"), models["panda"]
+    cost = planning_cost_from_golden(g)
+    dc = DeviceCost(m, cost)
+    q = t(g["q"].reshape(-1, 7))
+    r = dc.objective(q, want_grad=True, want_terms=True, want_occupancy=True, want_argmin=True)
+    terms = r["terms"].cpu().numpy()
+    for k, name in enumerate(["self", "obj", "ws", "ee"]):
+        assert rel_err(terms[:, k], g[f"cost_{name}"].reshape(-1)) < POSE_TOL, name
+        w = np.zeros(4, np.float32)
+        w[k] = 1
+        dc.set_weights(w)
+        rk = dc.objective(q)
+        assert rel_err(rk["grad_q"].cpu().numpy(), g[f"grad_{name}"].reshape(-1, 7)) < GRAD_TOL, name
+        assert rel_err(rk["total"].cpu().numpy(), g[f"cost_{name}"].reshape(-1)) < POSE_TOL
+    dc.set_weights([1, 1, 1, 0])
+    rc = dc.objective(q, want_occupancy=True)
+    assert rel_err(rc["total"].cpu().numpy(), g["cost_collision"].reshape(-1)) < POSE_TOL
+    assert rel_err(rc["grad_q"].cpu().numpy(), g["grad_collision"].reshape(-1, 7)) < GRAD_TOL
+    # end-to-end occupancy: equal to the reference (no entry of these fixtures sits within a few ulp
+    # of a threshold)
+    occ = rc["occupancy"].cpu().numpy()
+    assert np.array_equal(occ != 0, g["occ_all_default"].reshape(-1))
+    occ0 = dc.objective(q, want_grad=False, want_occupancy=True, margin_override=0.0)["occupancy"].cpu().numpy()
+    assert np.array_equal((occ0 & 1) != 0, g["occ_self_zero"].reshape(-1))
+    assert np.array_equal((occ0 & 2) != 0, g["occ_obj_zero"].reshape(-1))
+    assert np.array_equal((occ0 & 4) != 0, g["occ_ws_zero"].reshape(-1))
+
+
+@pytest.mark.parametrize("case", ["panda_spheres3d", "panda_two_objects"])
+def test_cost_stage_bit_exact_on_reference_positions(models, case):
+    """Stage-wise exactness: fed the reference's link positions, masks, arg-min
+    and the decision-chain costs are bit-identical with the oracle, and the masks with the reference."""
+    from torch_robotics_b200._lib import DeviceCost
+    g, m = load_golden(f"planning_{case}"), models["panda"]
+    cost = planning_cost_from_golden(g, with_ee=False)
+    dc = DeviceCost(m, cost)
+    pw = np.ascontiguousarray(g["link_pos"].reshape(-1, 11, 3))
+    x = pw[:, cost.pt_link]
+    for tag, mo in (("default", None), ("zero", 0.0)):
+        r = dc.cost_stage(t(pw), want_grad=False, want_occupancy=True, want_argmin=True, margin_override=mo)
+        occ = r["occupancy"].cpu().numpy()
+        assert np.array_equal((occ & 1) != 0, g[f"occ_self_{tag}"].reshape(-1))
+        assert np.array_equal((occ & 2) != 0, g[f"occ_obj_{tag}"].reshape(-1))
+        assert np.array_equal((occ & 4) != 0, g[f"occ_ws_{tag}"].reshape(-1))
+    ro = orc.object_term(cost, x, np.float32)
+    assert np.array_equal(r["argmin"].cpu().numpy(), ro["argmin"])
+    terms = r["terms"].cpu().numpy()
+    assert np.array_equal(terms[:, 0], orc.self_term(cost, pw, np.float32)["cost"])
+    assert np.array_equal(terms[:, 1], ro["cost"])
+    assert np.array_equal(terms[:, 2], orc.ws_term(cost, x, np.float32)["cost"])
+
+
+def test_cost_stage_autograd_chain_matches_fused(models):
+    """FK (autograd.Function) -> cost stage (autograd.Function) gives the same gradient as the fused kernel."""
+    from torch_robotics_b200 import ops
+    from torch_robotics_b200._lib import DeviceCost
+    g, m = load_golden("planning_panda_spheres3d"), models["panda"]
+    dc = DeviceCost(m, planning_cost_from_golden(g))
+    q = t(g["q"].reshape(-1, 7)).requires_grad_(True)
+    H = ops.fk(m, q)
+    c = ops.cost_stage(dc, H[:, :, :3, 3], H[:, 10])
+    c.sum().backward()
+    fused = dc.objective(q.detach())
+    assert rel_err(c.detach().cpu().numpy(), fused["total"].cpu().numpy()) < POSE_TOL
+    assert rel_err(q.grad.cpu().numpy(), fused["grad_q"].cpu().numpy()) < GRAD_TOL
+    q2 = t(g["q"].reshape(-1, 7)).requires_grad_(True)
+    (ops.objective(dc, q2) * 2.0).sum().backward()
+    assert rel_err(q2.grad.cpu().numpy(), 2.0 * fused["grad_q"].cpu().numpy()) < 1e-6
+
+
+def test_objective_vs_oracle_large_with_near_tie_report(models):
+    """Fused kernel vs oracle at 100k configs: costs/gradients within tolerance; masks and arg-min
+    equal except a handful of entries that sit on a decision boundary (count printed)."""
+    from torch_robotics_b200._lib import DeviceCost
+    g, d, m = load_golden("planning_panda_spheres3d"), get_desc("panda"), models["panda"]
+    cost = planning_cost_from_golden(g)
+    dc = DeviceCost(m, cost)
+    rng = np.random.default_rng(5)
+    lo, hi = d.lo[d.controlled], d.hi[d.controlled]
+    q = (lo + rng.random((100_000, 7)) * (hi - lo)).astype(np.float32)
+    r = dc.objective(t(q), want_grad=True, want_terms=True, want_occupancy=True, want_argmin=True)
+    o = orc.objective(d, cost, q, dtype=np.float32)
+    assert rel_err(r["terms"].cpu().numpy(), o["terms"]) < POSE_TOL
+    assert rel_err(r["total"].cpu().numpy(), o["total"]) < POSE_TOL
+    assert rel_err(r["grad_q"].cpu().numpy(), o["grad_q"]) < GRAD_TOL
+    am, occ = r["argmin"].cpu().numpy(), r["occupancy"].cpu().numpy()
+    bad_am = np.argwhere(am != o["argmin"])
+    bad_occ = np.argwhere(occ != o["occ"])
+    print(f"argmin mismatches: {len(bad_am)} of {am.size}; occupancy mismatches: {len(bad_occ)} of {occ.size}")
+    assert len(bad_am) <= 20 and len(bad_occ) <= 20
+
+
+def test_stretch_objective(models):
+    from torch_robotics_b200._lib import DeviceCost
+    g, m = load_golden("objective_stretch"), models["stretch"]
+    dc = DeviceCost(m, stretch_cost_from_golden(g))
+    r = dc.objective(t(g["q"]), want_terms=True)
+    assert rel_err(r["total"].cpu().numpy(), g["cost_total"]) < POSE_TOL
+    assert rel_err(r["grad_q"].cpu().numpy(), g["grad_total"]) < GRAD_TOL
+
+
+def test_rejects_cpu_tensors_and_wrong_dtype(models):
+    m = models["panda"]
+    with pytest.raises(RuntimeError):
+        m.fk_forward(torch.zeros(4, 7))
+    with pytest.raises(RuntimeError):
+        m.fk_forward(torch.zeros(4, 7, device=DEV, dtype=torch.float64))
+    with pytest.raises(RuntimeError):
+        m.fk_forward(torch.zeros(4, 6, device=DEV))

@@ -1,0 +1,293 @@
+"""ctypes binding of the C ABI in include/trk_b200.h (csrc/libtrk_b200.so).
+
+There is deliberately no fallback: if the CUDA library is missing or a tensor is not a contiguous
+fp32 CUDA tensor the call raises.  Build the library with `python -c "import __graft_entry__ as g;
+g.build()"` (or `make -C torch_robotics_b200/csrc`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import threading
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libtrk_b200.so")
+
+c_float_p = C.POINTER(C.c_float)
+c_int32_p = C.POINTER(C.c_int32)
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("n_links", C.c_int32), ("n_dofs", C.c_int32),
+                ("parent", c_int32_p), ("kind", c_int32_p), ("axis_k", c_int32_p), ("axis_s", c_float_p),
+                ("axis", c_float_p), ("q_index", c_int32_p), ("R_fixed", c_float_p), ("trans", c_float_p),
+                ("lo", c_float_p), ("hi", c_float_p), ("has_lim", c_int32_p), ("topo", c_int32_p),
+                ("base_pose", c_float_p)]
+
+
+class CostDesc(C.Structure):
+    _fields_ = [("n_points", C.c_int32), ("pt_link", c_int32_p), ("pt_margin_obj", c_float_p), ("pt_margin_ws", c_float_p),
+                ("n_objects", C.c_int32), ("obj_start", c_int32_p), ("obj_identity", c_int32_p), ("obj_R", c_float_p),
+                ("obj_pos", c_float_p), ("n_spheres", C.c_int32), ("sph_center", c_float_p), ("sph_radius", c_float_p),
+                ("ws_enabled", C.c_int32), ("ws_min", C.c_float * 3), ("ws_max", C.c_float * 3),
+                ("n_pairs", C.c_int32), ("pair_i", c_int32_p), ("pair_j", c_int32_p), ("pair_margin", c_float_p),
+                ("ee_enabled", C.c_int32), ("ee_link", C.c_int32), ("ee_w_pos", C.c_float), ("ee_w_rot", C.c_float),
+                ("ee_square", C.c_int32), ("ee_target", C.c_float * 16),
+                ("clamp_self", C.c_int32), ("clamp_obj", C.c_int32), ("clamp_ws", C.c_int32), ("weights", C.c_float * 4)]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+
+EXPORTS = [
+    "trk_abi_version", "trk_last_error", "trk_model_create", "trk_model_destroy", "trk_model_kernel_family",
+    "trk_fk_forward", "trk_fk_backward", "trk_cost_create", "trk_cost_destroy", "trk_cost_set_ee_target",
+    "trk_cost_set_weights", "trk_objective", "trk_cost_stage",
+]
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: the sm_100a CUDA library has not been built. "
+                "Run `python -c \"import __graft_entry__ as g; g.build()\"` in the repository root. "
+                "There is no CPU or PyTorch fallback for this path.")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+        L.trk_abi_version.restype = C.c_int
+        L.trk_last_error.restype = C.c_char_p
+        L.trk_model_create.argtypes = [C.POINTER(ModelDesc), C.c_int, C.POINTER(vp)]
+        L.trk_model_destroy.argtypes = [vp]
+        L.trk_model_destroy.restype = None
+        L.trk_model_kernel_family.argtypes = [vp]
+        L.trk_model_kernel_family.restype = C.c_char_p
+        L.trk_fk_forward.argtypes = [vp, vp, i64, c_int32_p, i32, vp, vp]
+        L.trk_fk_backward.argtypes = [vp, vp, i64, c_int32_p, i32, vp, vp, vp]
+        L.trk_cost_create.argtypes = [vp, C.POINTER(CostDesc), C.POINTER(vp)]
+        L.trk_cost_destroy.argtypes = [vp]
+        L.trk_cost_destroy.restype = None
+        L.trk_cost_set_ee_target.argtypes = [vp, c_float_p, vp]
+        L.trk_cost_set_weights.argtypes = [vp, c_float_p, vp]
+        L.trk_objective.argtypes = [vp, vp, vp, i64, vp, f32, vp, vp, vp, vp, vp, vp]
+        L.trk_cost_stage.argtypes = [vp, vp, vp, vp, i64, vp, f32, vp, vp, vp, vp, vp, vp, vp]
+        for name in EXPORTS:
+            fn = getattr(L, name)
+            if fn.restype is C.c_int and name not in ("trk_abi_version",):
+                pass
+        if L.trk_abi_version() != 1:
+            raise ImportError("libtrk_b200.so ABI version mismatch")
+        _lib = L
+        return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().trk_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (status {rc}): {msg}")
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(c_float_p)
+
+
+def _ip(a: np.ndarray):
+    return a.ctypes.data_as(c_int32_p)
+
+
+def _c32(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype))
+
+
+def require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not torch.is_tensor(t):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} lives on {t.device}: the B200-native path only accepts CUDA tensors "
+                           "(there is no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class DeviceModel:
+    """Device-resident kinematic tree (trk_model) for one (descriptor, device)."""
+
+    def __init__(self, desc, device):
+        self.desc = desc
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError(f"cannot create a device model on '{device}': CUDA only")
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        torch.cuda.init()
+        self._keep = dict(
+            parent=_c32(desc.parent, np.int32), kind=_c32(desc.kind, np.int32), axis_k=_c32(desc.axis_k, np.int32),
+            axis_s=_c32(desc.axis_s, np.float32), axis=_c32(desc.axis, np.float32), q_index=_c32(desc.q_index, np.int32),
+            R_fixed=_c32(desc.R_fixed, np.float32), trans=_c32(desc.trans, np.float32), lo=_c32(desc.lo, np.float32),
+            hi=_c32(desc.hi, np.float32), has_lim=_c32(desc.has_lim, np.int32), topo=_c32(desc.topo, np.int32),
+            base=_c32(np.concatenate([np.asarray(desc.base_R, np.float32).reshape(9), np.asarray(desc.base_t, np.float32).reshape(3)]), np.float32))
+        k = self._keep
+        md = ModelDesc(desc.n_links, desc.n_dofs, _ip(k["parent"]), _ip(k["kind"]), _ip(k["axis_k"]), _fp(k["axis_s"]),
+                       _fp(k["axis"]), _ip(k["q_index"]), _fp(k["R_fixed"]), _fp(k["trans"]), _fp(k["lo"]), _fp(k["hi"]),
+                       _ip(k["has_lim"]), _ip(k["topo"]), _fp(k["base"]))
+        h = C.c_void_p()
+        check(lib().trk_model_create(C.byref(md), idx, C.byref(h)), "trk_model_create")
+        self.handle = h
+        self.n_links, self.n_dofs = desc.n_links, desc.n_dofs
+
+    @property
+    def kernel_family(self) -> str:
+        return lib().trk_model_kernel_family(self.handle).decode()
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h and _lib is not None:
+            try:
+                _lib.trk_model_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    # -- raw calls (no autograd) ---------------------------------------------------------------
+    def _sel(self, link_sel: Optional[Sequence[int]]):
+        if link_sel is None:
+            return None, self.n_links, None
+        arr = np.ascontiguousarray(np.asarray(link_sel, np.int32))
+        return _ip(arr), int(arr.shape[0]), arr
+
+    def fk_forward(self, q: torch.Tensor, link_sel=None) -> torch.Tensor:
+        q = require_cuda_f32(q, "q")
+        if q.ndim != 2 or q.shape[1] != self.n_dofs:
+            raise RuntimeError(f"q must be [N, {self.n_dofs}], got {tuple(q.shape)}")
+        if q.device != self.device:
+            raise RuntimeError(f"q is on {q.device} but the model lives on {self.device}")
+        p, n_sel, keep = self._sel(link_sel)
+        H = torch.empty((q.shape[0], n_sel, 4, 4), dtype=torch.float32, device=q.device)
+        check(lib().trk_fk_forward(self.handle, q.data_ptr(), q.shape[0], p, n_sel, H.data_ptr(), stream_ptr(q.device)),
+              "trk_fk_forward")
+        return H
+
+    def fk_backward(self, q: torch.Tensor, G: torch.Tensor, link_sel=None) -> torch.Tensor:
+        q = require_cuda_f32(q, "q")
+        G = require_cuda_f32(G, "grad_H")
+        p, n_sel, keep = self._sel(link_sel)
+        if tuple(G.shape) != (q.shape[0], n_sel, 4, 4):
+            raise RuntimeError(f"grad_H must be [{q.shape[0]}, {n_sel}, 4, 4], got {tuple(G.shape)}")
+        grad = torch.empty_like(q)
+        check(lib().trk_fk_backward(self.handle, q.data_ptr(), q.shape[0], p, n_sel, G.data_ptr(), grad.data_ptr(),
+                                    stream_ptr(q.device)), "trk_fk_backward")
+        return grad
+
+
+class DeviceCost:
+    """Device-resident planning-objective tables (trk_cost) bound to a DeviceModel."""
+
+    def __init__(self, model: DeviceModel, cost):
+        cost.validate(model.n_links)
+        self.model, self.cost = model, cost
+        k = self._keep = dict(
+            pt_link=_c32(cost.pt_link, np.int32), mobj=_c32(cost.pt_margin_obj, np.float32), mws=_c32(cost.pt_margin_ws, np.float32),
+            obj_start=_c32(cost.obj_start, np.int32), obj_ident=_c32(cost.obj_identity, np.int32),
+            obj_R=_c32(cost.obj_R, np.float32), obj_pos=_c32(cost.obj_pos, np.float32),
+            sph_c=_c32(cost.sph_center, np.float32), sph_r=_c32(cost.sph_radius, np.float32),
+            pi=_c32(cost.pair_i, np.int32), pj=_c32(cost.pair_j, np.int32), pm=_c32(cost.pair_margin, np.float32))
+        cd = CostDesc()
+        cd.n_points, cd.pt_link, cd.pt_margin_obj, cd.pt_margin_ws = cost.n_points, _ip(k["pt_link"]), _fp(k["mobj"]), _fp(k["mws"])
+        cd.n_objects, cd.obj_start, cd.obj_identity = cost.n_objects, _ip(k["obj_start"]), _ip(k["obj_ident"])
+        cd.obj_R, cd.obj_pos = _fp(k["obj_R"]), _fp(k["obj_pos"])
+        cd.n_spheres, cd.sph_center, cd.sph_radius = cost.n_spheres, _fp(k["sph_c"]), _fp(k["sph_r"])
+        cd.ws_enabled = int(cost.ws_enabled)
+        cd.ws_min = (C.c_float * 3)(*[float(v) for v in cost.ws_min])
+        cd.ws_max = (C.c_float * 3)(*[float(v) for v in cost.ws_max])
+        cd.n_pairs, cd.pair_i, cd.pair_j, cd.pair_margin = cost.n_pairs, _ip(k["pi"]), _ip(k["pj"]), _fp(k["pm"])
+        cd.ee_enabled, cd.ee_link = int(cost.ee_enabled), int(cost.ee_link)
+        cd.ee_w_pos, cd.ee_w_rot, cd.ee_square = float(cost.ee_w_pos), float(cost.ee_w_rot), int(cost.ee_square)
+        cd.ee_target = (C.c_float * 16)(*[float(v) for v in np.asarray(cost.ee_target, np.float32).reshape(16)])
+        cd.clamp_self, cd.clamp_obj, cd.clamp_ws = int(cost.clamp_self), int(cost.clamp_obj), int(cost.clamp_ws)
+        cd.weights = (C.c_float * 4)(*[float(v) for v in cost.weights])
+        h = C.c_void_p()
+        check(lib().trk_cost_create(model.handle, C.byref(cd), C.byref(h)), "trk_cost_create")
+        self.handle = h
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h and _lib is not None:
+            try:
+                _lib.trk_cost_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    def set_ee_target(self, H) -> None:
+        H = np.ascontiguousarray(np.asarray(H.detach().cpu().numpy() if torch.is_tensor(H) else H, np.float32).reshape(16))
+        check(lib().trk_cost_set_ee_target(self.handle, _fp(H), stream_ptr(self.model.device)), "trk_cost_set_ee_target")
+        self.cost.ee_target = H.reshape(4, 4).copy()
+
+    def set_weights(self, w) -> None:
+        w = np.ascontiguousarray(np.asarray(w, np.float32).reshape(4))
+        check(lib().trk_cost_set_weights(self.handle, _fp(w), stream_ptr(self.model.device)), "trk_cost_set_weights")
+        self.cost.weights = w.copy()
+
+    def objective(self, q: torch.Tensor, want_grad=True, want_terms=True, want_occupancy=False, want_argmin=False,
+                  ee_target_cfg: Optional[torch.Tensor] = None, margin_override: Optional[float] = None):
+        """Raw fused call.  Returns dict(total, terms, grad_q, occupancy, argmin) (None where not requested)."""
+        m = self.model
+        q = require_cuda_f32(q, "q")
+        if q.ndim != 2 or q.shape[1] != m.n_dofs:
+            raise RuntimeError(f"q must be [N, {m.n_dofs}], got {tuple(q.shape)}")
+        if q.device != m.device:
+            raise RuntimeError(f"q is on {q.device} but the model lives on {m.device}")
+        n = q.shape[0]
+        dev = q.device
+        total = torch.empty(n, dtype=torch.float32, device=dev)
+        terms = torch.empty((n, 4), dtype=torch.float32, device=dev) if want_terms else None
+        grad = torch.empty_like(q) if want_grad else None
+        occ = torch.empty(n, dtype=torch.uint8, device=dev) if want_occupancy else None
+        amin = torch.empty((n, self.cost.n_objects, self.cost.n_points), dtype=torch.int32, device=dev) if want_argmin else None
+        tgt = None
+        if ee_target_cfg is not None:
+            tgt = require_cuda_f32(ee_target_cfg, "ee_target_cfg")
+            if tuple(tgt.shape) != (n, 4, 4):
+                raise RuntimeError(f"ee_target_cfg must be [{n}, 4, 4]")
+        mo = float("nan") if margin_override is None else float(margin_override)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        check(lib().trk_objective(m.handle, self.handle, q.data_ptr(), n, ptr(tgt), mo, ptr(total), ptr(terms), ptr(grad),
+                                  ptr(occ), ptr(amin), stream_ptr(dev)), "trk_objective")
+        return dict(total=total, terms=terms, grad_q=grad, occupancy=occ, argmin=amin)
+
+    def cost_stage(self, link_pos: torch.Tensor, ee_pose: Optional[torch.Tensor] = None, want_grad=True,
+                   want_occupancy=False, want_argmin=False, ee_target_cfg=None, margin_override: Optional[float] = None):
+        m = self.model
+        link_pos = require_cuda_f32(link_pos, "link_pos")
+        if link_pos.ndim != 3 or link_pos.shape[1:] != (m.n_links, 3):
+            raise RuntimeError(f"link_pos must be [N, {m.n_links}, 3], got {tuple(link_pos.shape)}")
+        n, dev = link_pos.shape[0], link_pos.device
+        if ee_pose is not None:
+            ee_pose = require_cuda_f32(ee_pose, "ee_pose")
+        total = torch.empty(n, dtype=torch.float32, device=dev)
+        terms = torch.empty((n, 4), dtype=torch.float32, device=dev)
+        gpos = torch.empty_like(link_pos) if want_grad else None
+        gee = torch.zeros((n, 4, 4), dtype=torch.float32, device=dev) if (want_grad and ee_pose is not None) else None
+        occ = torch.empty(n, dtype=torch.uint8, device=dev) if want_occupancy else None
+        amin = torch.empty((n, self.cost.n_objects, self.cost.n_points), dtype=torch.int32, device=dev) if want_argmin else None
+        tgt = None if ee_target_cfg is None else require_cuda_f32(ee_target_cfg, "ee_target_cfg")
+        mo = float("nan") if margin_override is None else float(margin_override)
+        ptr = lambda t: None if t is None else t.data_ptr()
+        check(lib().trk_cost_stage(m.handle, self.handle, link_pos.data_ptr(), ptr(ee_pose), n, ptr(tgt), mo, ptr(total),
+                                   ptr(terms), ptr(gpos), ptr(gee), ptr(occ), ptr(amin), stream_ptr(dev)), "trk_cost_stage")
+        return dict(total=total, terms=terms, grad_pos=gpos, grad_ee=gee, occupancy=occ, argmin=amin)

@@ -1,0 +1,698 @@
+// trk_b200.cu - runtime-tree ("generic") kernel family and the C ABI (include/trk_b200.h).
+//
+// One thread evaluates one configuration.  The kinematic tree and the cost tables are staged once
+// per block in shared memory and read as warp-uniform broadcasts; per-thread link poses live in a
+// thread-local array indexed by body (the tree is runtime data here - compiled-in robots use the
+// register-resident family in trk_static.cuh).  Dense FK output / upstream-gradient tiles are
+// transposed through a per-warp shared-memory stage so that every global access is a 16-byte
+// vector covering whole 64-byte link matrices (8 configurations per instruction).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "trk_device.cuh"
+#include "trk_static.cuh"
+
+using namespace trk;
+
+// ------------------------------------------------------------------------------------------
+// per-warp 32 x 64-byte transpose stage (XOR swizzle, conflict-free both ways)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int stage_idx(int cfg_in_warp, int row) { return cfg_in_warp * 4 + (row ^ ((cfg_in_warp >> 1) & 3)); }
+
+// each lane holds one 4x4 matrix (rows m0..m3); the warp writes 32 matrices of slot `s`
+__device__ __forceinline__ void warp_store_link(float4* stage, int lane, const float4& m0, const float4& m1, const float4& m2,
+                                                long long warp_cfg0, long long n, int n_sel, int s, float* __restrict__ H) {
+    stage[stage_idx(lane, 0)] = m0;
+    stage[stage_idx(lane, 1)] = m1;
+    stage[stage_idx(lane, 2)] = m2;
+    stage[stage_idx(lane, 3)] = make_float4(0.f, 0.f, 0.f, 1.f);
+    __syncwarp();
+    const int r = lane & 3;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int c = (lane >> 2) + 8 * it;
+        const long long g = warp_cfg0 + c;
+        const float4 v = stage[stage_idx(c, r)];
+        if (g < n) __stcs(reinterpret_cast<float4*>(H) + ((g * n_sel + s) * 4 + r), v);
+    }
+    __syncwarp();
+}
+
+// the warp reads 32 matrices of slot `s`; each lane receives rows 0..2 of its own matrix
+__device__ __forceinline__ void warp_load_link(float4* stage, int lane, long long warp_cfg0, long long n, int n_sel, int s,
+                                               const float* __restrict__ G, float4& m0, float4& m1, float4& m2) {
+    const int r = lane & 3;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int c = (lane >> 2) + 8 * it;
+        const long long g = warp_cfg0 + c;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g < n) v = __ldcs(reinterpret_cast<const float4*>(G) + ((g * n_sel + s) * 4 + r));
+        stage[stage_idx(c, r)] = v;
+    }
+    __syncwarp();
+    m0 = stage[stage_idx(lane, 0)];
+    m1 = stage[stage_idx(lane, 1)];
+    m2 = stage[stage_idx(lane, 2)];
+    __syncwarp();
+}
+
+constexpr int kBlock = 128;
+constexpr int kWarps = kBlock / 32;
+
+// ------------------------------------------------------------------------------------------
+// generic kernels
+// ------------------------------------------------------------------------------------------
+template <int MAXL>
+__global__ void __launch_bounds__(kBlock) k_fk_forward_generic(const float* __restrict__ tree_words, int tree_nwords,
+                                                               const float* __restrict__ q, long long n, SlotMap slots,
+                                                               int n_sel, float* __restrict__ H) {
+    extern __shared__ __align__(16) float smem[];
+    float* tw = smem;
+    float4* stage = reinterpret_cast<float4*>(smem + tree_nwords) + (threadIdx.x >> 5) * 128;
+    block_copy_words(tw, tree_words, tree_nwords);
+    __syncthreads();
+    const TreeHeader* hdr = reinterpret_cast<const TreeHeader*>(tw);
+    const LinkRec* recs = reinterpret_cast<const LinkRec*>(tw + 16);
+    const int lane = threadIdx.x & 31, D = hdr->D, L = hdr->L;
+    for (long long base = (long long)blockIdx.x * kBlock; base < n; base += (long long)gridDim.x * kBlock) {
+        const long long cfg = base + threadIdx.x;
+        const long long warp_cfg0 = base + (threadIdx.x & ~31);
+        if (warp_cfg0 >= n) continue;   // warp-uniform
+        float W[MAXL][12];
+        unsigned long long pass;
+        fk_generic<MAXL>(hdr, recs, q + (cfg < n ? cfg : n - 1) * D, W, pass);
+        for (int i = 0; i < L; ++i) {
+            const int b = recs[i].body;
+            const int s = slots.slot[b];
+            if (s < 0) continue;
+            const float* w = W[b];
+            warp_store_link(stage, lane, make_float4(w[0], w[1], w[2], w[9]), make_float4(w[3], w[4], w[5], w[10]),
+                            make_float4(w[6], w[7], w[8], w[11]), warp_cfg0, n, n_sel, s, H);
+        }
+    }
+}
+
+template <int MAXL>
+__global__ void __launch_bounds__(kBlock) k_fk_backward_generic(const float* __restrict__ tree_words, int tree_nwords,
+                                                                const float* __restrict__ q, long long n, SlotMap slots,
+                                                                int n_sel, const float* __restrict__ G,
+                                                                float* __restrict__ grad_q) {
+    extern __shared__ __align__(16) float smem[];
+    float* tw = smem;
+    float4* stage = reinterpret_cast<float4*>(smem + tree_nwords) + (threadIdx.x >> 5) * 128;
+    block_copy_words(tw, tree_words, tree_nwords);
+    __syncthreads();
+    const TreeHeader* hdr = reinterpret_cast<const TreeHeader*>(tw);
+    const LinkRec* recs = reinterpret_cast<const LinkRec*>(tw + 16);
+    const int lane = threadIdx.x & 31, D = hdr->D, L = hdr->L;
+    for (long long base = (long long)blockIdx.x * kBlock; base < n; base += (long long)gridDim.x * kBlock) {
+        const long long cfg = base + threadIdx.x;
+        const long long warp_cfg0 = base + (threadIdx.x & ~31);
+        if (warp_cfg0 >= n) continue;
+        float W[MAXL][12], F[MAXL][3], T[MAXL][3];
+        unsigned long long pass;
+        fk_generic<MAXL>(hdr, recs, q + (cfg < n ? cfg : n - 1) * D, W, pass);
+        for (int i = 0; i < L; ++i) {
+            const int b = recs[i].body;
+            const int s = slots.slot[b];
+            if (s < 0) {
+                F[b][0] = F[b][1] = F[b][2] = 0.f;
+                T[b][0] = T[b][1] = T[b][2] = 0.f;
+                continue;
+            }
+            float4 m0, m1, m2;
+            warp_load_link(stage, lane, warp_cfg0, n, n_sel, s, G, m0, m1, m2);
+            const float gR[9] = {m0.x, m0.y, m0.z, m1.x, m1.y, m1.z, m2.x, m2.y, m2.z};
+            const float gx = m0.w, gy = m1.w, gz = m2.w;
+            const float* w = W[b];
+            float ax, ay, az;
+            axial_gR_Rt(gR, w, ax, ay, az);
+            F[b][0] = gx; F[b][1] = gy; F[b][2] = gz;
+            T[b][0] = w[10] * gz - w[11] * gy + ax;
+            T[b][1] = w[11] * gx - w[9] * gz + ay;
+            T[b][2] = w[9] * gy - w[10] * gx + az;
+        }
+        if (cfg < n) tree_backward_generic<MAXL>(hdr, recs, W, F, T, pass, grad_q + cfg * D);
+    }
+}
+
+template <int MAXL, bool WANT_GRAD>
+__global__ void __launch_bounds__(kBlock) k_objective_generic(const float* __restrict__ tree_words, int tree_nwords,
+                                                              const float* __restrict__ cost_words, int cost_nwords,
+                                                              const float* __restrict__ q, long long n,
+                                                              const float* __restrict__ ee_target_cfg, float margin_override,
+                                                              int use_override, float* __restrict__ cost_total,
+                                                              float* __restrict__ cost_terms, float* __restrict__ grad_q,
+                                                              uint8_t* __restrict__ occupancy, int* __restrict__ argmin) {
+    extern __shared__ __align__(16) float smem[];
+    float* tw = smem;
+    float* cw = smem + tree_nwords;
+    block_copy_words(tw, tree_words, tree_nwords);
+    block_copy_words(cw, cost_words, cost_nwords);
+    __syncthreads();
+    const TreeHeader* hdr = reinterpret_cast<const TreeHeader*>(tw);
+    const LinkRec* recs = reinterpret_cast<const LinkRec*>(tw + 16);
+    const CostView cv(cw);
+    const CostHeader* h = cv.h;
+    const int D = hdr->D, L = hdr->L;
+    for (long long cfg = (long long)blockIdx.x * kBlock + threadIdx.x; cfg < n; cfg += (long long)gridDim.x * kBlock) {
+        float W[MAXL][12], F[MAXL][3];
+        unsigned long long pass;
+        fk_generic<MAXL>(hdr, recs, q + cfg * D, W, pass);
+        if (WANT_GRAD)
+            for (int b = 0; b < L; ++b) F[b][0] = F[b][1] = F[b][2] = 0.f;
+        float terms[4] = {0.f, 0.f, 0.f, 0.f};
+        unsigned occ;
+        collision_terms<WANT_GRAD>(
+            cv, [&](int b, float& x, float& y, float& z) { x = W[b][9]; y = W[b][10]; z = W[b][11]; },
+            [&](int b, float gx, float gy, float gz) { F[b][0] += gx; F[b][1] += gy; F[b][2] += gz; }, margin_override,
+            use_override != 0, terms, occ, argmin ? argmin + cfg * (long long)(h->nObj * h->S) : nullptr);
+        float gR[9], gp[3];
+        if (h->ee_enabled) {
+            float Rt[9], pt[3];
+            if (ee_target_cfg) {
+                const float* Ht = ee_target_cfg + cfg * 16;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    Rt[i * 3 + 0] = __ldg(Ht + i * 4 + 0); Rt[i * 3 + 1] = __ldg(Ht + i * 4 + 1);
+                    Rt[i * 3 + 2] = __ldg(Ht + i * 4 + 2); pt[i] = __ldg(Ht + i * 4 + 3);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Rt[i] = h->ee_R[i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) pt[i] = h->ee_t[i];
+            }
+            const float* w = W[h->ee_link];
+            terms[3] = ee_term<WANT_GRAD>(h, w, w + 9, Rt, pt, gR, gp);
+        }
+        if (cost_total) cost_total[cfg] = weighted_total(h, terms);
+        if (cost_terms) reinterpret_cast<float4*>(cost_terms)[cfg] = make_float4(terms[0], terms[1], terms[2], terms[3]);
+        if (occupancy) occupancy[cfg] = (uint8_t)occ;
+        if (WANT_GRAD) {
+            float T[MAXL][3];
+            for (int b = 0; b < L; ++b) {
+                const float* w = W[b];
+                const float fx = F[b][0], fy = F[b][1], fz = F[b][2];
+                T[b][0] = w[10] * fz - w[11] * fy;
+                T[b][1] = w[11] * fx - w[9] * fz;
+                T[b][2] = w[9] * fy - w[10] * fx;
+            }
+            if (h->ee_enabled) {
+                const int e = h->ee_link;
+                const float* w = W[e];
+                float ax, ay, az;
+                axial_gR_Rt(gR, w, ax, ay, az);
+                F[e][0] += gp[0]; F[e][1] += gp[1]; F[e][2] += gp[2];
+                T[e][0] += w[10] * gp[2] - w[11] * gp[1] + ax;
+                T[e][1] += w[11] * gp[0] - w[9] * gp[2] + ay;
+                T[e][2] += w[9] * gp[1] - w[10] * gp[0] + az;
+            }
+            tree_backward_generic<MAXL>(hdr, recs, W, F, T, pass, grad_q + cfg * D);
+        }
+    }
+}
+
+// cost stage on caller-supplied positions (DistanceField.compute_cost, distance_fields.py:26-55)
+template <int MAXL, bool WANT_GRAD>
+__global__ void __launch_bounds__(kBlock) k_cost_stage(const float* __restrict__ cost_words, int cost_nwords, int L,
+                                                       const float* __restrict__ link_pos, const float* __restrict__ ee_pose,
+                                                       long long n, const float* __restrict__ ee_target_cfg,
+                                                       float margin_override, int use_override,
+                                                       float* __restrict__ cost_total, float* __restrict__ cost_terms,
+                                                       float* __restrict__ grad_pos, float* __restrict__ grad_ee,
+                                                       uint8_t* __restrict__ occupancy, int* __restrict__ argmin) {
+    extern __shared__ __align__(16) float smem[];
+    float* cw = smem;
+    block_copy_words(cw, cost_words, cost_nwords);
+    __syncthreads();
+    const CostView cv(cw);
+    const CostHeader* h = cv.h;
+    for (long long cfg = (long long)blockIdx.x * kBlock + threadIdx.x; cfg < n; cfg += (long long)gridDim.x * kBlock) {
+        const float* P = link_pos + cfg * (long long)L * 3;
+        float F[MAXL][3];
+        if (WANT_GRAD)
+            for (int b = 0; b < L; ++b) F[b][0] = F[b][1] = F[b][2] = 0.f;
+        float terms[4] = {0.f, 0.f, 0.f, 0.f};
+        unsigned occ;
+        collision_terms<WANT_GRAD>(
+            cv, [&](int b, float& x, float& y, float& z) { x = __ldg(P + b * 3); y = __ldg(P + b * 3 + 1); z = __ldg(P + b * 3 + 2); },
+            [&](int b, float gx, float gy, float gz) { F[b][0] += gx; F[b][1] += gy; F[b][2] += gz; }, margin_override,
+            use_override != 0, terms, occ, argmin ? argmin + cfg * (long long)(h->nObj * h->S) : nullptr);
+        if (h->ee_enabled && ee_pose) {
+            float R[9], p[3], Rt[9], pt[3], gR[9], gp[3];
+            const float* He = ee_pose + cfg * 16;
+            const float* Ht = ee_target_cfg ? ee_target_cfg + cfg * 16 : nullptr;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    R[i * 3 + j] = __ldg(He + i * 4 + j);
+                    Rt[i * 3 + j] = Ht ? __ldg(Ht + i * 4 + j) : h->ee_R[i * 3 + j];
+                }
+                p[i] = __ldg(He + i * 4 + 3);
+                pt[i] = Ht ? __ldg(Ht + i * 4 + 3) : h->ee_t[i];
+            }
+            terms[3] = ee_term<WANT_GRAD>(h, R, p, Rt, pt, gR, gp);
+            if (WANT_GRAD && grad_ee) {
+                float* Ge = grad_ee + cfg * 16;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    Ge[i * 4 + 0] = gR[i * 3 + 0]; Ge[i * 4 + 1] = gR[i * 3 + 1]; Ge[i * 4 + 2] = gR[i * 3 + 2];
+                    Ge[i * 4 + 3] = gp[i];
+                }
+                Ge[12] = Ge[13] = Ge[14] = Ge[15] = 0.f;
+            }
+        }
+        if (cost_total) cost_total[cfg] = weighted_total(h, terms);
+        if (cost_terms) reinterpret_cast<float4*>(cost_terms)[cfg] = make_float4(terms[0], terms[1], terms[2], terms[3]);
+        if (occupancy) occupancy[cfg] = (uint8_t)occ;
+        if (WANT_GRAD && grad_pos) {
+            float* Gp = grad_pos + cfg * (long long)L * 3;
+            for (int b = 0; b < L; ++b) { Gp[b * 3] = F[b][0]; Gp[b * 3 + 1] = F[b][1]; Gp[b * 3 + 2] = F[b][2]; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: handles, validation, launches
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+
+struct trk_model {
+    int device;
+    int L, D;
+    int maxl_bucket;            // 16 / 32 / 64
+    int n_sms;
+    float* d_words;             // device tree buffer
+    int nwords;
+    int family;                 // trk::StaticFamily id, 0 = generic
+    int32_t parent[TRK_MAX_LINKS];
+};
+
+struct trk_cost {
+    int device;
+    int L;
+    int S, nObj, K, P;
+    int ee_enabled;
+    float* d_words;
+    int nwords;
+    std::vector<float> h_words;  // host mirror, for the setters
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+static int grid_for(const trk_model* m, long long n, int blocks_per_sm) {
+    long long need = (n + kBlock - 1) / kBlock;
+    long long cap = (long long)m->n_sms * blocks_per_sm;
+    return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+static int build_slots(const trk_model* m, const int32_t* link_sel, int32_t n_sel, SlotMap& sm, int& n_out) {
+    for (int i = 0; i < TRK_MAX_LINKS; ++i) sm.slot[i] = -1;
+    if (!link_sel) {
+        for (int i = 0; i < m->L; ++i) sm.slot[i] = (int8_t)i;
+        n_out = m->L;
+        return TRK_OK;
+    }
+    if (n_sel <= 0 || n_sel > m->L) return fail(TRK_E_RANGE, "n_sel=%d outside [1, %d]", n_sel, m->L);
+    for (int s = 0; s < n_sel; ++s) {
+        const int b = link_sel[s];
+        if (b < 0 || b >= m->L) return fail(TRK_E_RANGE, "link_sel[%d]=%d outside the model", s, b);
+        if (sm.slot[b] >= 0) return fail(TRK_E_UNSUPPORTED, "link_sel lists body %d twice", b);
+        sm.slot[b] = (int8_t)s;
+    }
+    n_out = n_sel;
+    return TRK_OK;
+}
+
+#define TRK_CHECK_PTR(p, name) \
+    if (!(p)) return fail(TRK_E_NULL, "%s is null", name)
+#define TRK_CHECK_ALIGN16(p, name) \
+    if ((reinterpret_cast<uintptr_t>(p) & 15u) != 0) return fail(TRK_E_ALIGN, "%s must be 16-byte aligned", name)
+
+template <typename K>
+static cudaError_t allow_smem(K kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+extern "C" {
+
+int trk_abi_version(void) { return TRK_ABI_VERSION; }
+const char* trk_last_error(void) { return g_err; }
+
+int trk_model_create(const trk_model_desc* d, int device, trk_model** out) {
+    TRK_CHECK_PTR(d, "desc");
+    TRK_CHECK_PTR(out, "out");
+    *out = nullptr;
+    if (d->n_links < 1 || d->n_links > TRK_MAX_LINKS) return fail(TRK_E_RANGE, "n_links=%d outside [1, %d]", d->n_links, TRK_MAX_LINKS);
+    if (d->n_dofs < 0 || d->n_dofs > TRK_MAX_DOFS) return fail(TRK_E_RANGE, "n_dofs=%d outside [0, %d]", d->n_dofs, TRK_MAX_DOFS);
+    TRK_CHECK_PTR(d->parent, "parent"); TRK_CHECK_PTR(d->kind, "kind"); TRK_CHECK_PTR(d->axis_k, "axis_k");
+    TRK_CHECK_PTR(d->axis_s, "axis_s"); TRK_CHECK_PTR(d->axis, "axis"); TRK_CHECK_PTR(d->q_index, "q_index");
+    TRK_CHECK_PTR(d->R_fixed, "R_fixed"); TRK_CHECK_PTR(d->trans, "trans"); TRK_CHECK_PTR(d->lo, "lo");
+    TRK_CHECK_PTR(d->hi, "hi"); TRK_CHECK_PTR(d->has_lim, "has_lim"); TRK_CHECK_PTR(d->topo, "topo");
+    const int L = d->n_links, D = d->n_dofs;
+    // validate topology: topo is a permutation, parents first, exactly one root, q columns used once
+    bool seen[TRK_MAX_LINKS] = {false};
+    bool qseen[TRK_MAX_DOFS] = {false};
+    int roots = 0;
+    for (int i = 0; i < L; ++i) {
+        const int b = d->topo[i];
+        if (b < 0 || b >= L || seen[b]) return fail(TRK_E_RANGE, "topo is not a permutation of the bodies");
+        const int p = d->parent[b];
+        if (p < 0) {
+            ++roots;
+        } else if (p >= L || !seen[p]) {
+            return fail(TRK_E_RANGE, "topo lists body %d before its parent %d", b, p);
+        }
+        seen[b] = true;
+        const int k = d->kind[b];
+        if (k < 0 || k > 2) return fail(TRK_E_RANGE, "kind[%d]=%d", b, k);
+        const int qi = d->q_index[b];
+        if (k == TRK_KIND_FIXED) {
+            if (qi >= 0) return fail(TRK_E_RANGE, "fixed body %d has a q column", b);
+        } else {
+            if (p < 0) return fail(TRK_E_RANGE, "the root cannot be actuated");
+            if (qi < 0 || qi >= D || qseen[qi]) return fail(TRK_E_RANGE, "q_index[%d]=%d invalid or duplicated", b, qi);
+            qseen[qi] = true;
+            if (d->axis_k[b] < 0 || d->axis_k[b] > 2) return fail(TRK_E_RANGE, "axis_k[%d]", b);
+        }
+    }
+    if (roots != 1) return fail(TRK_E_RANGE, "expected exactly one root, found %d", roots);
+    for (int c = 0; c < D; ++c)
+        if (!qseen[c]) return fail(TRK_E_RANGE, "q column %d drives no body", c);
+
+    const int nwords = 16 + 24 * L;
+    std::vector<float> words(nwords, 0.f);
+    TreeHeader* hdr = reinterpret_cast<TreeHeader*>(words.data());
+    hdr->L = L; hdr->D = D; hdr->pad0 = hdr->pad1 = 0;
+    const float ident[12] = {1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0};
+    memcpy(hdr->base, d->base_pose ? d->base_pose : ident, sizeof(ident));
+    LinkRec* recs = reinterpret_cast<LinkRec*>(words.data() + 16);
+    for (int i = 0; i < L; ++i) {
+        const int b = d->topo[i];
+        LinkRec& r = recs[i];
+        memcpy(r.Rf, d->R_fixed + 9 * b, 9 * sizeof(float));
+        memcpy(r.t, d->trans + 3 * b, 3 * sizeof(float));
+        memcpy(r.ax, d->axis + 3 * b, 3 * sizeof(float));
+        r.s = d->axis_s[b];
+        r.lo = d->lo[b]; r.hi = d->hi[b];
+        r.flags = d->kind[b] | (d->axis_k[b] << F_AXIS_SHIFT) | (d->has_lim[b] ? F_HAS_LIM : 0);
+        r.parent = d->parent[b];
+        r.body = b;
+        r.qidx = d->q_index[b];
+        r.pad0 = r.pad1 = 0;
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    trk_model* m = new (std::nothrow) trk_model();
+    if (!m) return fail(TRK_E_RANGE, "out of host memory");
+    m->device = device; m->L = L; m->D = D; m->nwords = nwords;
+    m->maxl_bucket = L <= 16 ? 16 : (L <= 32 ? 32 : 64);
+    memcpy(m->parent, d->parent, L * sizeof(int32_t));
+    cudaError_t e = cudaDeviceGetAttribute(&m->n_sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) { delete m; return cuda_fail(e, "cudaDeviceGetAttribute"); }
+    e = cudaMalloc(&m->d_words, nwords * sizeof(float));
+    if (e != cudaSuccess) { delete m; return cuda_fail(e, "cudaMalloc(tree)"); }
+    e = cudaMemcpy(m->d_words, words.data(), nwords * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(m->d_words); delete m; return cuda_fail(e, "cudaMemcpy(tree)"); }
+    m->family = trk::match_static_family(words.data(), nwords);
+    *out = m;
+    return TRK_OK;
+}
+
+void trk_model_destroy(trk_model* m) {
+    if (!m) return;
+    DeviceGuard guard(m->device);
+    cudaFree(m->d_words);
+    delete m;
+}
+
+const char* trk_model_kernel_family(const trk_model* m) { return m ? trk::static_family_name(m->family) : "null"; }
+
+int trk_fk_forward(const trk_model* m, const float* q, int64_t n, const int32_t* link_sel, int32_t n_sel, float* H,
+                   void* stream) {
+    TRK_CHECK_PTR(m, "model");
+    if (n < 0) return fail(TRK_E_RANGE, "n=%lld", (long long)n);
+    if (n == 0) return TRK_OK;
+    TRK_CHECK_PTR(q, "q"); TRK_CHECK_PTR(H, "H_out");
+    TRK_CHECK_ALIGN16(H, "H_out");
+    SlotMap sm; int n_out;
+    int rc = build_slots(m, link_sel, n_sel, sm, n_out);
+    if (rc) return rc;
+    DeviceGuard guard(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->family) {
+        cudaError_t e = trk::launch_static_fk_forward(m->family, m->n_sms, q, n, sm, n_out, H, st);
+        return e == cudaSuccess ? TRK_OK : cuda_fail(e, "fk_forward(static)");
+    }
+    const size_t smem = (size_t)m->nwords * 4 + kWarps * 2048;
+    const int grid = grid_for(m, n, 16);
+    switch (m->maxl_bucket) {
+        case 16: k_fk_forward_generic<16><<<grid, kBlock, smem, st>>>(m->d_words, m->nwords, q, n, sm, n_out, H); break;
+        case 32: k_fk_forward_generic<32><<<grid, kBlock, smem, st>>>(m->d_words, m->nwords, q, n, sm, n_out, H); break;
+        default: k_fk_forward_generic<64><<<grid, kBlock, smem, st>>>(m->d_words, m->nwords, q, n, sm, n_out, H); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? TRK_OK : cuda_fail(e, "fk_forward launch");
+}
+
+int trk_fk_backward(const trk_model* m, const float* q, int64_t n, const int32_t* link_sel, int32_t n_sel, const float* G,
+                    float* grad_q, void* stream) {
+    TRK_CHECK_PTR(m, "model");
+    if (n < 0) return fail(TRK_E_RANGE, "n=%lld", (long long)n);
+    if (n == 0) return TRK_OK;
+    TRK_CHECK_PTR(q, "q"); TRK_CHECK_PTR(G, "G"); TRK_CHECK_PTR(grad_q, "grad_q");
+    TRK_CHECK_ALIGN16(G, "G");
+    SlotMap sm; int n_out;
+    int rc = build_slots(m, link_sel, n_sel, sm, n_out);
+    if (rc) return rc;
+    DeviceGuard guard(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->family) {
+        cudaError_t e = trk::launch_static_fk_backward(m->family, m->n_sms, q, n, sm, n_out, G, grad_q, st);
+        return e == cudaSuccess ? TRK_OK : cuda_fail(e, "fk_backward(static)");
+    }
+    const size_t smem = (size_t)m->nwords * 4 + kWarps * 2048;
+    const int grid = grid_for(m, n, 16);
+    switch (m->maxl_bucket) {
+        case 16: k_fk_backward_generic<16><<<grid, kBlock, smem, st>>>(m->d_words, m->nwords, q, n, sm, n_out, G, grad_q); break;
+        case 32: k_fk_backward_generic<32><<<grid, kBlock, smem, st>>>(m->d_words, m->nwords, q, n, sm, n_out, G, grad_q); break;
+        default: k_fk_backward_generic<64><<<grid, kBlock, smem, st>>>(m->d_words, m->nwords, q, n, sm, n_out, G, grad_q); break;
+    }
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? TRK_OK : cuda_fail(e, "fk_backward launch");
+}
+
+static int align4(int x) { return (x + 3) & ~3; }
+
+int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) {
+    TRK_CHECK_PTR(m, "model"); TRK_CHECK_PTR(d, "desc"); TRK_CHECK_PTR(out, "out");
+    *out = nullptr;
+    const int S = d->n_points, nObj = d->n_objects, K = d->n_spheres, P = d->n_pairs;
+    if (S < 0 || S > TRK_MAX_POINTS) return fail(TRK_E_RANGE, "n_points=%d", S);
+    if (nObj < 0 || nObj > TRK_MAX_OBJECTS) return fail(TRK_E_RANGE, "n_objects=%d", nObj);
+    if (K < 0 || K > TRK_MAX_SPHERES) return fail(TRK_E_RANGE, "n_spheres=%d", K);
+    if (P < 0 || P > TRK_MAX_PAIRS) return fail(TRK_E_RANGE, "n_pairs=%d", P);
+    if (S) { TRK_CHECK_PTR(d->pt_link, "pt_link"); TRK_CHECK_PTR(d->pt_margin_obj, "pt_margin_obj"); TRK_CHECK_PTR(d->pt_margin_ws, "pt_margin_ws"); }
+    if (nObj) { TRK_CHECK_PTR(d->obj_start, "obj_start"); TRK_CHECK_PTR(d->obj_identity, "obj_identity"); TRK_CHECK_PTR(d->obj_R, "obj_R"); TRK_CHECK_PTR(d->obj_pos, "obj_pos"); }
+    if (K) { TRK_CHECK_PTR(d->sph_center, "sph_center"); TRK_CHECK_PTR(d->sph_radius, "sph_radius"); }
+    if (P) { TRK_CHECK_PTR(d->pair_i, "pair_i"); TRK_CHECK_PTR(d->pair_j, "pair_j"); TRK_CHECK_PTR(d->pair_margin, "pair_margin"); }
+    for (int s = 0; s < S; ++s)
+        if (d->pt_link[s] < 0 || d->pt_link[s] >= m->L) return fail(TRK_E_RANGE, "pt_link[%d]=%d", s, d->pt_link[s]);
+    for (int p = 0; p < P; ++p)
+        if (d->pair_i[p] < 0 || d->pair_i[p] >= m->L || d->pair_j[p] < 0 || d->pair_j[p] >= m->L)
+            return fail(TRK_E_RANGE, "self pair %d references a body outside the model", p);
+    if (nObj) {
+        if (d->obj_start[0] != 0 || d->obj_start[nObj] != K) return fail(TRK_E_RANGE, "obj_start must span [0, n_spheres]");
+        for (int o = 0; o < nObj; ++o)
+            if (d->obj_start[o + 1] < d->obj_start[o]) return fail(TRK_E_RANGE, "obj_start must be non-decreasing");
+    }
+    if (d->ee_enabled && (d->ee_link < 0 || d->ee_link >= m->L)) return fail(TRK_E_RANGE, "ee_link=%d", d->ee_link);
+
+    int off = 64;
+    auto take = [&](int nw) { int o = off; off = align4(off + nw); return o; };
+    const int o_pt_link = take(S), o_mobj = take(S), o_mws = take(S), o_ostart = take(nObj + 1), o_oid = take(nObj),
+              o_oR = take(nObj * 9), o_opos = take(nObj * 3), o_sph = take(K * 4), o_pi = take(P), o_pj = take(P), o_pm = take(P);
+    const int nwords = off;
+    trk_cost* c = new (std::nothrow) trk_cost();
+    if (!c) return fail(TRK_E_RANGE, "out of host memory");
+    c->h_words.assign(nwords, 0.f);
+    float* w = c->h_words.data();
+    int* iw = reinterpret_cast<int*>(w);
+    CostHeader* h = reinterpret_cast<CostHeader*>(w);
+    h->S = S; h->nObj = nObj; h->K = K; h->P = P;
+    h->ws_enabled = d->ws_enabled ? 1 : 0; h->ee_enabled = d->ee_enabled ? 1 : 0; h->ee_link = d->ee_link; h->ee_square = d->ee_square ? 1 : 0;
+    h->clamp_self = d->clamp_self ? 1 : 0; h->clamp_obj = d->clamp_obj ? 1 : 0; h->clamp_ws = d->clamp_ws ? 1 : 0; h->total_words = nwords;
+    for (int i = 0; i < 4; ++i) h->w[i] = d->weights[i];
+    h->ee_w_pos = d->ee_w_pos; h->ee_w_rot = d->ee_w_rot;
+    for (int i = 0; i < 3; ++i) { h->ws_min[i] = d->ws_min[i]; h->ws_max[i] = d->ws_max[i]; }
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) h->ee_R[i * 3 + j] = d->ee_target[i * 4 + j];
+        h->ee_t[i] = d->ee_target[i * 4 + 3];
+    }
+    h->off_pt_link = o_pt_link; h->off_pt_mobj = o_mobj; h->off_pt_mws = o_mws; h->off_obj_start = o_ostart;
+    h->off_obj_ident = o_oid; h->off_obj_R = o_oR; h->off_obj_pos = o_opos; h->off_sph = o_sph;
+    h->off_pair_i = o_pi; h->off_pair_j = o_pj; h->off_pair_m = o_pm;
+    for (int s = 0; s < S; ++s) { iw[o_pt_link + s] = d->pt_link[s]; w[o_mobj + s] = d->pt_margin_obj[s]; w[o_mws + s] = d->pt_margin_ws[s]; }
+    if (nObj) {
+        for (int o = 0; o <= nObj; ++o) iw[o_ostart + o] = d->obj_start[o];
+        for (int o = 0; o < nObj; ++o) iw[o_oid + o] = d->obj_identity[o] ? 1 : 0;
+        memcpy(w + o_oR, d->obj_R, nObj * 9 * sizeof(float));
+        memcpy(w + o_opos, d->obj_pos, nObj * 3 * sizeof(float));
+    } else {
+        iw[o_ostart] = 0;
+    }
+    for (int k = 0; k < K; ++k) {
+        w[o_sph + 4 * k + 0] = d->sph_center[3 * k + 0]; w[o_sph + 4 * k + 1] = d->sph_center[3 * k + 1];
+        w[o_sph + 4 * k + 2] = d->sph_center[3 * k + 2]; w[o_sph + 4 * k + 3] = d->sph_radius[k];
+    }
+    for (int p = 0; p < P; ++p) { iw[o_pi + p] = d->pair_i[p]; iw[o_pj + p] = d->pair_j[p]; w[o_pm + p] = d->pair_margin[p]; }
+    c->device = m->device; c->L = m->L; c->S = S; c->nObj = nObj; c->K = K; c->P = P; c->ee_enabled = h->ee_enabled; c->nwords = nwords;
+    DeviceGuard guard(m->device);
+    cudaError_t e = cudaMalloc(&c->d_words, nwords * sizeof(float));
+    if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaMalloc(cost)"); }
+    e = cudaMemcpy(c->d_words, w, nwords * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(c->d_words); delete c; return cuda_fail(e, "cudaMemcpy(cost)"); }
+    *out = c;
+    return TRK_OK;
+}
+
+void trk_cost_destroy(trk_cost* c) {
+    if (!c) return;
+    DeviceGuard guard(c->device);
+    cudaFree(c->d_words);
+    delete c;
+}
+
+static int cost_upload_header(trk_cost* c, void* stream) {
+    DeviceGuard guard(c->device);
+    // the header is 256 bytes; cudaMemcpyAsync from pageable memory stages the bytes before returning
+    cudaError_t e = cudaMemcpyAsync(c->d_words, c->h_words.data(), sizeof(CostHeader), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    return e == cudaSuccess ? TRK_OK : cuda_fail(e, "cudaMemcpyAsync(cost header)");
+}
+
+int trk_cost_set_ee_target(trk_cost* c, const float* H, void* stream) {
+    TRK_CHECK_PTR(c, "cost"); TRK_CHECK_PTR(H, "H_target16");
+    CostHeader* h = reinterpret_cast<CostHeader*>(c->h_words.data());
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) h->ee_R[i * 3 + j] = H[i * 4 + j];
+        h->ee_t[i] = H[i * 4 + 3];
+    }
+    return cost_upload_header(c, stream);
+}
+
+int trk_cost_set_weights(trk_cost* c, const float* w4, void* stream) {
+    TRK_CHECK_PTR(c, "cost"); TRK_CHECK_PTR(w4, "weights4");
+    CostHeader* h = reinterpret_cast<CostHeader*>(c->h_words.data());
+    for (int i = 0; i < 4; ++i) h->w[i] = w4[i];
+    return cost_upload_header(c, stream);
+}
+
+int trk_objective(const trk_model* m, const trk_cost* c, const float* q, int64_t n, const float* ee_target_cfg,
+                  float margin_override, float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy,
+                  int32_t* argmin, void* stream) {
+    TRK_CHECK_PTR(m, "model"); TRK_CHECK_PTR(c, "cost");
+    if (c->device != m->device || c->L != m->L) return fail(TRK_E_RANGE, "cost tables were built for a different model");
+    if (n < 0) return fail(TRK_E_RANGE, "n=%lld", (long long)n);
+    if (n == 0) return TRK_OK;
+    TRK_CHECK_PTR(q, "q");
+    if (cost_terms) TRK_CHECK_ALIGN16(cost_terms, "cost_terms");
+    const int use_override = std::isnan(margin_override) ? 0 : 1;
+    DeviceGuard guard(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->family && trk::static_objective_supported(m->family)) {
+        cudaError_t e = trk::launch_static_objective(m->family, m->n_sms, c->d_words, c->nwords, q, n, ee_target_cfg,
+                                                     margin_override, use_override, cost_total, cost_terms, grad_q,
+                                                     occupancy, argmin, st);
+        return e == cudaSuccess ? TRK_OK : cuda_fail(e, "objective(static)");
+    }
+    const size_t smem = (size_t)(m->nwords + c->nwords) * 4;
+    const int grid = grid_for(m, n, 16);
+#define LAUNCH_OBJ(MAXL)                                                                                                \
+    do {                                                                                                                \
+        if (grad_q)                                                                                                     \
+            k_objective_generic<MAXL, true><<<grid, kBlock, smem, st>>>(m->d_words, m->nwords, c->d_words, c->nwords, q, n, \
+                ee_target_cfg, margin_override, use_override, cost_total, cost_terms, grad_q, occupancy, argmin);       \
+        else                                                                                                            \
+            k_objective_generic<MAXL, false><<<grid, kBlock, smem, st>>>(m->d_words, m->nwords, c->d_words, c->nwords, q, n, \
+                ee_target_cfg, margin_override, use_override, cost_total, cost_terms, grad_q, occupancy, argmin);       \
+    } while (0)
+    switch (m->maxl_bucket) {
+        case 16: LAUNCH_OBJ(16); break;
+        case 32: LAUNCH_OBJ(32); break;
+        default: LAUNCH_OBJ(64); break;
+    }
+#undef LAUNCH_OBJ
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? TRK_OK : cuda_fail(e, "objective launch");
+}
+
+int trk_cost_stage(const trk_model* m, const trk_cost* c, const float* link_pos, const float* ee_pose, int64_t n,
+                   const float* ee_target_cfg, float margin_override, float* cost_total, float* cost_terms,
+                   float* grad_pos, float* grad_ee, uint8_t* occupancy, int32_t* argmin, void* stream) {
+    TRK_CHECK_PTR(m, "model"); TRK_CHECK_PTR(c, "cost");
+    if (c->device != m->device || c->L != m->L) return fail(TRK_E_RANGE, "cost tables were built for a different model");
+    if (n < 0) return fail(TRK_E_RANGE, "n=%lld", (long long)n);
+    if (n == 0) return TRK_OK;
+    TRK_CHECK_PTR(link_pos, "link_pos");
+    if (c->ee_enabled && !ee_pose) return fail(TRK_E_NULL, "ee_pose is required when the EE term is enabled");
+    if (cost_terms) TRK_CHECK_ALIGN16(cost_terms, "cost_terms");
+    const int use_override = std::isnan(margin_override) ? 0 : 1;
+    DeviceGuard guard(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)c->nwords * 4;
+    const int grid = grid_for(m, n, 16);
+    const bool want_grad = grad_pos || grad_ee;
+#define LAUNCH_STAGE(MAXL)                                                                                              \
+    do {                                                                                                                \
+        if (want_grad)                                                                                                  \
+            k_cost_stage<MAXL, true><<<grid, kBlock, smem, st>>>(c->d_words, c->nwords, m->L, link_pos, ee_pose, n,     \
+                ee_target_cfg, margin_override, use_override, cost_total, cost_terms, grad_pos, grad_ee, occupancy, argmin); \
+        else                                                                                                            \
+            k_cost_stage<MAXL, false><<<grid, kBlock, smem, st>>>(c->d_words, c->nwords, m->L, link_pos, ee_pose, n,    \
+                ee_target_cfg, margin_override, use_override, cost_total, cost_terms, grad_pos, grad_ee, occupancy, argmin); \
+    } while (0)
+    switch (m->maxl_bucket) {
+        case 16: LAUNCH_STAGE(16); break;
+        case 32: LAUNCH_STAGE(32); break;
+        default: LAUNCH_STAGE(64); break;
+    }
+#undef LAUNCH_STAGE
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? TRK_OK : cuda_fail(e, "cost_stage launch");
+}
+
+}  // extern "C"
