@@ -1,0 +1,167 @@
+"""The reference-facing Python API (same class / method names as anindex/torch_robotics) on the GPU,
+against golden vectors recorded from the reference itself."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TA = dict(device=DEV, dtype=torch.float32)
+
+
+def t(a):
+    return torch.as_tensor(np.ascontiguousarray(a), device=DEV)
+
+
+def test_differentiable_tree_api():
+    from torch_robotics_b200.torch_kinematics_tree.models.robots import (
+        DifferentiableFrankaPanda, DifferentiableHabitatStretch, DifferentiableTiagoDualHoloMove)
+    g = load_golden("fk_panda")
+    panda = DifferentiableFrankaPanda(gripper=False, device=DEV)
+    q = t(g["q"]).requires_grad_(True)
+    H = panda.compute_forward_kinematics_all_links(q)
+    assert H.shape == (32, 11, 4, 4) and H.dtype == torch.float32 and H.is_cuda
+    assert rel_err(H.detach().cpu().numpy(), g["H"]) < 1e-5
+    (H * t(g["G"])).sum().backward()
+    assert rel_err(q.grad.cpu().numpy(), g["grad_q"]) < 1e-4
+    ee = panda.compute_forward_kinematics_all_links(q.detach(), link_list=["ee_link"])
+    assert ee.shape == (32, 1, 4, 4) and torch.equal(ee[:, 0], H.detach()[:, 10])
+    d = panda.compute_forward_kinematics_all_links(q.detach()[0], return_dict=True)
+    assert set(d) == set(panda.get_link_names())
+    assert torch.equal(d["panda_hand"].get_transform_matrix()[0], H.detach()[0, 9])
+    assert torch.equal(d["panda_hand"].translation[0], H.detach()[0, 9, :3, 3])
+    # duplicates and arbitrary order in link_list
+    sel = panda.compute_forward_kinematics_all_links(q.detach(), link_list=["ee_link", "panda_link3", "ee_link"])
+    assert torch.equal(sel[:, 0], H.detach()[:, 10]) and torch.equal(sel[:, 1], H.detach()[:, 3]) and torch.equal(sel[:, 2], sel[:, 0])
+    assert panda._n_dofs == 7 and len(panda.get_joint_limits()) == 7
+    lo, hi, vlo, vhi = panda.get_joint_limit_array()
+    assert lo[3] == -3.0718 and hi[3] == -0.0698
+    tiago = DifferentiableTiagoDualHoloMove(device=DEV)
+    gt = load_golden("fk_tiago_dual_holo_move")
+    Ht = tiago.compute_forward_kinematics_all_links(t(gt["q"]))
+    assert Ht.shape == (32, 19, 4, 4) and rel_err(Ht.cpu().numpy(), gt["H"]) < 1e-5
+    gs = load_golden("fk_stretch")
+    Hs = DifferentiableHabitatStretch(device=DEV).compute_forward_kinematics_all_links(t(gs["q"]))
+    assert rel_err(Hs.cpu().numpy(), gs["H"]) < 1e-5
+    with pytest.raises(RuntimeError):
+        panda.compute_forward_kinematics_all_links(torch.zeros(2, 7))     # CPU tensor: no fallback
+
+
+def test_base_pose():
+    from torch_robotics_b200.torch_kinematics_tree.models.robots import DifferentiableFrankaPanda
+    g = load_golden("fk_panda")
+    panda = DifferentiableFrankaPanda(device=DEV)
+    H0 = panda.compute_forward_kinematics_all_links(t(g["q"]))
+    panda.update_base_pose(torch.tensor([0.5, -0.25, 0.125, 0.0, 0.0, 0.0, 1.0]))   # 180 deg about z
+    H1 = panda.compute_forward_kinematics_all_links(t(g["q"]))
+    B = torch.eye(4, device=DEV)
+    B[0, 0] = B[1, 1] = -1.0
+    B[:3, 3] = torch.tensor([0.5, -0.25, 0.125])
+    assert torch.allclose(H1, B @ H0, atol=1e-6)
+
+
+@pytest.fixture(scope="module")
+def planning():
+    from torch_robotics_b200.environments.env_spheres_3d import EnvSpheres3D
+    from torch_robotics_b200.robots.robot_panda import RobotPanda
+    from torch_robotics_b200.tasks.tasks import PlanningTask
+    robot = RobotPanda(tensor_args=TA)
+    env = EnvSpheres3D(tensor_args=TA)
+    return robot, env, PlanningTask(env=env, robot=robot, tensor_args=TA)
+
+
+def test_planning_task_cost_and_collision(planning):
+    robot, env, task = planning
+    g = load_golden("planning_panda_spheres3d")
+    q = t(g["q"]).requires_grad_(True)                 # [8,16,7]
+    cost = task.compute_collision_cost(q)
+    assert cost.shape == (8, 16) and cost.dtype == torch.float32
+    assert rel_err(cost.detach().cpu().numpy(), g["cost_collision"]) < 1e-5
+    cost.sum().backward()
+    assert rel_err(q.grad.cpu().numpy(), g["grad_collision"]) < 1e-4
+    coll = task.compute_collision(q.detach())
+    assert coll.dtype == torch.bool and np.array_equal(coll.cpu().numpy(), g["occ_all_default"])
+    assert np.array_equal(task.compute_collision(q.detach(), margin=0.0).cpu().numpy(), g["occ_all_zero"])
+    # 2-D and 1-D inputs follow the reference's shape rules (tasks.py:145-155)
+    assert task.compute_collision_cost(q.detach()[0]).shape == (16, 1)
+    assert task.compute_collision_cost(q.detach()[0, 0]).shape == (1,)
+
+
+def test_individual_fields_match_reference(planning):
+    robot, env, task = planning
+    g = load_golden("planning_panda_spheres3d")
+    names = ["self", "obj", "ws"]
+    for field, name in zip(task.get_collision_fields(), names):
+        q = t(g["q"]).requires_grad_(True)
+        pos = robot.fk_map_collision(q)
+        assert pos.shape == (8, 16, 11, 3)
+        c = field.compute_cost(q, pos, field_type="sdf")
+        assert rel_err(c.detach().cpu().numpy(), g[f"cost_{name}"]) < 1e-5, name
+        c.sum().backward()
+        assert rel_err(q.grad.cpu().numpy(), g[f"grad_{name}"]) < 1e-4, name
+        for tag, kw in (("default", {}), ("zero", {"margin": 0.0})):
+            occ = field.compute_cost(q.detach(), pos.detach(), field_type="occupancy", **kw)
+            assert np.array_equal(occ.cpu().numpy(), g[f"occ_{name}_{tag}"]), (name, tag)
+    assert rel_err(robot.fk_map_collision(t(g["q"])).cpu().numpy(), g["link_pos"]) < 1e-5
+
+
+def test_objective_with_ee_field(planning):
+    from torch_robotics_b200.torch_planning_objectives.fields.distance_fields import EESE3DistanceField
+    robot, env, task = planning
+    g = load_golden("planning_panda_spheres3d")
+    ee = EESE3DistanceField(t(g["H_target"]), w_pos=1.0, w_rot=1.0, square=True)
+    q = t(g["q"]).requires_grad_(True)
+    c = task.compute_objective(q, ee)
+    assert rel_err(c.detach().cpu().numpy(), g["cost_collision"] + g["cost_ee"]) < 1e-5
+    c.sum().backward()
+    assert rel_err(q.grad.cpu().numpy(), g["grad_collision"] + g["grad_ee"]) < 1e-4
+    # the eager EE field on FK output agrees too (distance_fields.py:352-356)
+    q2 = t(g["q"]).reshape(-1, 7).requires_grad_(True)
+    H = robot.diff_panda.compute_forward_kinematics_all_links(q2)
+    c2 = ee.compute_costs_impl(q2, H)
+    assert rel_err(c2.detach().cpu().numpy(), g["cost_ee"].reshape(-1)) < 1e-5
+    c2.sum().backward()
+    assert rel_err(q2.grad.cpu().numpy(), g["grad_ee"].reshape(-1, 7)) < 1e-4
+    # moving the target re-uses the device tables
+    H2 = t(g["H_target"]).clone()
+    H2[:3, 3] += 0.1
+    ee.update_target(H2)
+    c3 = task.compute_objective(q.detach(), ee)
+    assert not torch.allclose(c3, c.detach())
+
+
+def test_inverse_kinematics_matches_reference_iterates():
+    from torch_robotics_b200.torch_kinematics_tree.models.robots import DifferentiableFrankaPanda
+    g = load_golden("ik_panda")
+    panda = DifferentiableFrankaPanda(gripper=False, device=DEV)
+    Ht = t(g["H_target"])
+    lo, hi = t(g["lower"]), t(g["upper"])
+    qp = t(g["q_probe"]).requires_grad_(True)
+    loss = panda.loss_fn_ik_per_q(qp, Ht, "ee_link", w_se3=1.0, w_joint_limits=300.0, lower=lo, upper=hi)
+    assert rel_err(loss.detach().cpu().numpy(), g["loss"]) < 1e-5
+    loss.sum().backward()
+    assert rel_err(qp.grad.cpu().numpy(), g["loss_grad"]) < 1e-4
+    idx = panda.ik_termination(qp.detach(), Ht, "ee_link", lo, hi, se3_eps=0.5)
+    assert idx.dtype == torch.int64 and np.array_equal(idx.cpu().numpy(), g["idx_valid_eps0p5"])
+    for iters in (1, 5, 40):
+        q_ik, idx = panda.inverse_kinematics(Ht, link_name="ee_link", batch_size=24, max_iters=iters, lr=2e-1, se3_eps=5e-2,
+                                             q0=t(g["q0"]).clone(), q0_noise=0.0, eps_joint_lim=torch.pi / 64, print_freq=-1)
+        assert rel_err(q_ik.detach().cpu().numpy(), g[f"q_ik_{iters}"]) < (1e-4 if iters < 40 else 5e-3)
+        if iters < 40:
+            assert np.array_equal(idx.cpu().numpy(), g[f"idx_valid_{iters}"])
+
+
+def test_host_pipeline_matches_device_call(planning):
+    from torch_robotics_b200.host_pipeline import HostObjectivePipeline
+    robot, env, task = planning
+    dc = task._fused_cost(torch.device(DEV))
+    n = 10_001
+    q_host = (torch.rand(n, 7) * 2 - 1).pin_memory()
+    pipe = HostObjectivePipeline(dc, n, n_chunks=4)
+    cost_host = torch.empty(n).pin_memory()
+    grad_host = torch.empty(n, 7).pin_memory()
+    pipe.run(q_host, cost_host, grad_host)
+    r = dc.objective(q_host.to(DEV))
+    assert torch.equal(cost_host, r["total"].cpu()) and torch.equal(grad_host, r["grad_q"].cpu())

@@ -244,8 +244,10 @@ class DeviceCost:
         self.cost.weights = w.copy()
 
     def objective(self, q: torch.Tensor, want_grad=True, want_terms=True, want_occupancy=False, want_argmin=False,
-                  ee_target_cfg: Optional[torch.Tensor] = None, margin_override: Optional[float] = None):
-        """Raw fused call.  Returns dict(total, terms, grad_q, occupancy, argmin) (None where not requested)."""
+                  ee_target_cfg: Optional[torch.Tensor] = None, margin_override: Optional[float] = None,
+                  out_total: Optional[torch.Tensor] = None, out_grad: Optional[torch.Tensor] = None):
+        """Raw fused call.  Returns dict(total, terms, grad_q, occupancy, argmin) (None where not requested).
+        out_total [n] / out_grad [n, D]: optional preallocated contiguous fp32 CUDA outputs."""
         m = self.model
         q = require_cuda_f32(q, "q")
         if q.ndim != 2 or q.shape[1] != m.n_dofs:
@@ -254,9 +256,13 @@ class DeviceCost:
             raise RuntimeError(f"q is on {q.device} but the model lives on {m.device}")
         n = q.shape[0]
         dev = q.device
-        total = torch.empty(n, dtype=torch.float32, device=dev)
+        total = torch.empty(n, dtype=torch.float32, device=dev) if out_total is None else out_total
         terms = torch.empty((n, 4), dtype=torch.float32, device=dev) if want_terms else None
-        grad = torch.empty_like(q) if want_grad else None
+        grad = (torch.empty_like(q) if out_grad is None else out_grad) if want_grad else None
+        for name, buf, shape in (("out_total", out_total, (n,)), ("out_grad", out_grad, (n, m.n_dofs))):
+            if buf is not None and (tuple(buf.shape) != shape or buf.dtype != torch.float32 or buf.device != dev
+                                    or not buf.is_contiguous()):
+                raise RuntimeError(f"{name} must be a contiguous float32 tensor of shape {shape} on {dev}")
         occ = torch.empty(n, dtype=torch.uint8, device=dev) if want_occupancy else None
         amin = torch.empty((n, self.cost.n_objects, self.cost.n_points), dtype=torch.int32, device=dev) if want_argmin else None
         tgt = None

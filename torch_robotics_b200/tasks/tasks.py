@@ -1,0 +1,140 @@
+"""PlanningTask: composes FK and the collision fields into a per-waypoint cost / collision flag
+(reference: tasks/tasks.py:22-232).
+
+`compute_collision_cost` and `compute_collision` keep their signatures; underneath, ONE fused kernel
+launch evaluates FK of all links, the self / object / workspace terms and - for the cost - the analytic
+gradient w.r.t. q (trk_objective), instead of FK + three field passes + autograd.  The individual
+fields remain available through `get_collision_fields()` and give identical numbers.
+`compute_objective` additionally folds an EESE3DistanceField into the same launch (BASELINE config 3).
+"""
+from __future__ import annotations
+
+from abc import ABC
+
+import torch
+
+from .. import ops
+from .._lib import DeviceCost
+from ..descriptor import build_cost_descriptor
+from ..torch_planning_objectives.fields.distance_fields import (
+    CollisionObjectDistanceField, CollisionWorkspaceBoundariesDistanceField, _tree_of)
+
+
+class Task(ABC):
+    def __init__(self, env=None, robot=None, tensor_args=None, **kwargs):
+        self.env = env
+        self.robot = robot
+        self.tensor_args = tensor_args
+
+
+class PlanningTask(Task):
+    def __init__(self, ws_limits=None, use_occupancy_map=False, cell_size=0.01, obstacle_cutoff_margin=0.01, **kwargs):
+        super().__init__(**kwargs)
+        if use_occupancy_map:
+            raise NotImplementedError("occupancy maps are outside the hot path (the reference raises too, tasks.py:160)")
+        self.ws_limits = self.env.limits if ws_limits is None else ws_limits
+        self.ws_min, self.ws_max = self.ws_limits[0], self.ws_limits[1]
+        self.use_occupancy_map = False
+        self.obstacle_cutoff_margin = obstacle_cutoff_margin
+        r = self.robot
+        common = dict(link_idxs_for_collision_checking=r.link_idxs_for_object_collision_checking,
+                      num_interpolated_points=r.num_interpolated_points_for_object_collision_checking,
+                      link_margins_for_object_collision_checking_tensor=r.link_margins_for_object_collision_checking_tensor,
+                      cutoff_margin=obstacle_cutoff_margin, tensor_args=self.tensor_args)
+        self.df_collision_self = r.df_collision_self
+        self.df_collision_objects = CollisionObjectDistanceField(r, df_obj_list_fn=self.env.get_df_obj_list, **common)
+        self.df_collision_ws_boundaries = CollisionWorkspaceBoundariesDistanceField(
+            r, ws_bounds_min=self.ws_min, ws_bounds_max=self.ws_max, **common)
+        if self.env.obj_extra_list is not None:
+            from functools import partial
+            self.df_collision_extra_objects = CollisionObjectDistanceField(
+                r, df_obj_list_fn=partial(self.env.get_df_obj_list, return_extra_objects_only=True), **common)
+            self._collision_fields_extra_objects = [self.df_collision_extra_objects]
+        else:
+            self._collision_fields_extra_objects = []
+        self._collision_fields = [self.df_collision_self, self.df_collision_objects, self.df_collision_ws_boundaries]
+        self._fused = {}
+
+    def get_collision_fields(self):
+        return self._collision_fields
+
+    def get_collision_fields_extra_objects(self):
+        return self._collision_fields_extra_objects
+
+    def distance_q(self, q1, q2):
+        return self.robot.distance_q(q1, q2)
+
+    # ---------------------------------------------------------------------------------- fused tables
+    def cost_descriptor(self, ee_field=None, ee_link_name=None):
+        """CostDescriptor equivalent to the three collision fields (+ optional EE field)."""
+        r = self.robot
+        tree = _tree_of(r)
+        f_self, f_obj = self.df_collision_self, self.df_collision_objects
+        pairs, self_margin = [], []
+        if f_self is not None:
+            links = list(f_self.link_idxs_for_collision_checking)
+            pairs = [(links[a], links[b]) for a, b in f_self.idxs_links_distance_matrix]
+            self_margin = (torch.as_tensor(f_self.cutoff_margin, dtype=torch.float32).reshape(-1).cpu() + 0.0).numpy()
+        ee = {}
+        if ee_field is not None:
+            name = ee_link_name or getattr(r, "link_name_ee", None) or tree.get_link_names()[-1]
+            ee = dict(ee_link=tree._name_to_idx_map[name], ee_target=torch.as_tensor(ee_field.target_H).reshape(4, 4),
+                      ee_w_pos=ee_field.w_pos, ee_w_rot=ee_field.w_rot, ee_square=ee_field.square)
+        return build_cost_descriptor(
+            pt_link=r.link_idxs_for_object_collision_checking,
+            pt_radius=r.link_margins_for_object_collision_checking_tensor.detach().float().cpu(),
+            cutoff_obj=self.obstacle_cutoff_margin, objects=[o.as_sphere_table() for o in f_obj._objects()],
+            ws_min=self.ws_min, ws_max=self.ws_max, self_pairs=pairs, self_margin=self_margin,
+            clamp_self=bool(f_self.clamp_sdf) if f_self is not None else False,
+            clamp_obj=f_obj.clamp_sdf, clamp_ws=self.df_collision_ws_boundaries.clamp_sdf, **ee)
+
+    def _fused_cost(self, device, ee_field=None, ee_link_name=None) -> DeviceCost:
+        key = (torch.device(device).index, self.df_collision_objects._signature(), id(ee_field), ee_link_name)
+        dc = self._fused.get(key)
+        if dc is None:
+            if len(self._fused) > 8:
+                self._fused.clear()
+            dc = DeviceCost(_tree_of(self.robot).device_model(device), self.cost_descriptor(ee_field, ee_link_name))
+            self._fused[key] = dc
+        if ee_field is not None:
+            tgt = torch.as_tensor(ee_field.target_H).reshape(4, 4).detach().float().cpu().numpy()
+            if (tgt != dc.cost.ee_target).any():
+                dc.set_ee_target(tgt)
+        return dc
+
+    @staticmethod
+    def _as_bhd(q):
+        if q.ndim == 1:
+            return q.reshape(1, 1, -1), (1,)
+        if q.ndim == 2:
+            return q.unsqueeze(1), (q.shape[0], 1)
+        if q.ndim == 3:
+            return q, (q.shape[0], q.shape[1])
+        raise NotImplementedError
+
+    # ---------------------------------------------------------------------------------- public API
+    def compute_collision(self, x, **kwargs):
+        return self._compute_collision_or_cost(self.robot.get_position(x), field_type="occupancy", **kwargs)
+
+    def compute_collision_cost(self, x, **kwargs):
+        return self._compute_collision_or_cost(self.robot.get_position(x), field_type="sdf", **kwargs)
+
+    def _compute_collision_or_cost(self, q, field_type="occupancy", **kwargs):
+        """q [..., q_dim] with up to (batch, horizon) leading dims -> [batch, horizon] cost (fp32) or
+        collision flag (bool).  Reference: tasks.py:139-232."""
+        q3, out_shape = self._as_bhd(q)
+        flat = q3.reshape(-1, q3.shape[-1])
+        dc = self._fused_cost(flat.device)
+        if field_type == "sdf":
+            return ops.objective(dc, flat).reshape(out_shape)
+        if field_type == "occupancy":
+            r = dc.objective(flat.detach(), want_grad=False, want_terms=False, want_occupancy=True,
+                             margin_override=kwargs.get("margin", None))
+            return (r["occupancy"] != 0).reshape(out_shape)
+        raise NotImplementedError(field_type)
+
+    def compute_objective(self, x, ee_field, ee_link_name=None):
+        """Collision cost + EESE3DistanceField cost of the EE link in one fused launch -> [batch, horizon]."""
+        q3, out_shape = self._as_bhd(self.robot.get_position(x))
+        flat = q3.reshape(-1, q3.shape[-1])
+        return ops.objective(self._fused_cost(flat.device, ee_field, ee_link_name), flat).reshape(out_shape)

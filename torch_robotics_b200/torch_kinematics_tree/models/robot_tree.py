@@ -1,0 +1,193 @@
+"""DifferentiableTree: the reference's kinematic-tree class (models/robot_tree.py:75-492) with the
+stateless FK path routed to the sm_100a kernels.
+
+Kept: constructor signature, `compute_forward_kinematics_all_links`, `inverse_kinematics`,
+`loss_fn_ik_per_q`, `ik_termination`, the accessors (`get_link_names`, `get_joint_limits`,
+`get_joint_limit_array`, `print_link_names`, `update_base_pose`) and the attributes callers read
+(`_n_dofs`, `_controlled_joints`, `_name_to_idx_map`, `_bodies`, `link_list`).
+Not provided (out of the hot path): the stateful velocity
+propagation (`update_kinematic_state`) and the Jacobian helpers built on it.
+
+q must be a float32 CUDA tensor: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from ... import ops
+from ..._lib import DeviceModel
+from ...descriptor import TreeDescriptor, compile_urdf, quat_wxyz_to_matrix
+from ...torch_utils.torch_utils import to_torch, torch_intersect_1d
+from ..geometrics.frame import Frame
+from ..geometrics.utils import SE3_distance
+
+
+def convert_link_dict_to_tensor(link_dict, link_list):
+    return torch.stack([link_dict[name].get_transform_matrix() for name in link_list], dim=1)
+
+
+class BodyView:
+    """Read-only stand-in for the reference's DifferentiableRigidBody (models/rigid_body.py:66-123):
+    the constants of one link and its parent joint."""
+
+    def __init__(self, desc: TreeDescriptor, i: int):
+        self.name = desc.link_names[i]
+        self.joint_id = i
+        self.joint_name = desc.joint_names[i]
+        self.joint_type = desc.joint_types[i]
+        self.joint_idx = None if desc.q_index[i] < 0 else int(desc.q_index[i])
+        self.joint_limits = desc.limits[i]
+        self.joint_axis = torch.from_numpy(desc.axis[i:i + 1].copy())
+        self.trans = torch.from_numpy(desc.trans[i:i + 1].copy())
+        self.fixed_rotation = torch.from_numpy(desc.R_fixed[i:i + 1].copy())
+        self.is_root = i == 0
+        self.parent_idx = int(desc.parent[i])
+
+    def get_joint_limits(self):
+        return self.joint_limits
+
+
+class DifferentiableTree(torch.nn.Module):
+
+    def __init__(self, model_path: str, name="", link_list=None, device="cpu"):
+        super().__init__()
+        self.name = name
+        self.link_list = link_list
+        self._device = device
+        self.model_type = str(model_path).split(".")[-1]
+        if self.model_type != "urdf":
+            raise NotImplementedError(f"{self.model_type} is not supported (the reference's MJCF loader is "
+                                      "self-declared broken, models/utils.py:43)")
+        self._desc = compile_urdf(model_path, name)
+        self._bodies = [BodyView(self._desc, i) for i in range(self._desc.n_links)]
+        self._n_dofs = self._desc.n_dofs
+        self._controlled_joints = list(self._desc.controlled)
+        self._name_to_idx_map = self._desc.name_to_idx()
+        self._device_models: Dict[int, DeviceModel] = {}
+
+    # ------------------------------------------------------------------------------------ device side
+    def device_model(self, device) -> DeviceModel:
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError(f"forward kinematics was requested on '{device}': this implementation runs on "
+                               "CUDA (sm_100a) only and has no CPU fallback")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if idx not in self._device_models:
+            self._device_models[idx] = DeviceModel(self._desc, torch.device("cuda", idx))
+        return self._device_models[idx]
+
+    def update_base_pose(self, pose_vec):
+        """pose_vec: x, y, z, qw, qx, qy, qz (reference: robot_tree.py:133, frame.py:42-51)."""
+        p = np.asarray(pose_vec.detach().cpu().numpy() if torch.is_tensor(pose_vec) else pose_vec, np.float32).reshape(-1)
+        self._desc.base_t = p[:3].copy()
+        self._desc.base_R = quat_wxyz_to_matrix(p[3:7])
+        self._device_models.clear()
+
+    def reset(self):
+        pass
+
+    # ------------------------------------------------------------------------------------ FK
+    def compute_forward_kinematics_all_links(self, q: torch.Tensor, return_dict=False, link_list=None):
+        """Stateless FK.  q [B, n_dofs] (or [n_dofs]) -> [B, len(link_list), 4, 4], or a dict
+        name -> Frame when return_dict=True (reference: robot_tree.py:267-301)."""
+        if q.ndim == 1:
+            q = q.unsqueeze(0)
+        if link_list is None:
+            link_list = self.link_list
+        if link_list is None:
+            link_list = self.get_link_names()
+        idx = [self._name_to_idx_map[n] for n in link_list]
+        uniq = sorted(set(idx), key=idx.index)
+        all_in_order = uniq == list(range(self._desc.n_links))
+        H = ops.fk(self.device_model(q.device), q, None if all_in_order else uniq)
+        if len(uniq) != len(idx):
+            H = H[:, [uniq.index(i) for i in idx]]
+        if not return_dict:
+            return H
+        return {n: Frame(rot=H[:, k, :3, :3], trans=H[:, k, :3, 3], device=q.device) for k, n in enumerate(link_list)}
+
+    def compute_forward_kinematics(self, q, qd=None, link_name=None, state_less=True):
+        if not state_less:
+            raise NotImplementedError("only the stateless FK path is provided")
+        return self.compute_forward_kinematics_all_links(q, link_list=[link_name])
+
+    # ------------------------------------------------------------------------------------ IK
+    def inverse_kinematics(self, H_target, link_name="ee_link", batch_size=1, max_iters=1000, lr=1e-2, se3_eps=1e-1,
+                           q0=None, q0_noise=torch.pi / 8, eps_joint_lim=torch.pi / 100, print_freq=50, debug=False):
+        """Batched Adam IK with the reference's loop structure (robot_tree.py:303-384): every seed is
+        updated every iteration; stops early when every seed satisfies the termination test."""
+        device = H_target.device if torch.is_tensor(H_target) and H_target.is_cuda else torch.device(self._device)
+        if H_target.ndim == 2:
+            H_target = H_target.unsqueeze(0)
+        lower, upper, _, _ = self.get_joint_limit_array()
+        lower = to_torch(lower + eps_joint_lim, device=device)
+        upper = to_torch(upper - eps_joint_lim, device=device)
+        if q0 is None:
+            q0 = lower + torch.rand(batch_size, self._n_dofs, device=device) * (upper - lower)
+        else:
+            q0 = q0 + torch.randn(batch_size, self._n_dofs, device=device) * q0_noise
+            q0 = torch.clamp(q0, lower, upper)
+            assert q0.shape == (batch_size, self._n_dofs)
+        q = q0.clone().requires_grad_(True)
+        optimizer = torch.optim.Adam([q], lr=lr)
+        idx_valid = torch.empty(0, dtype=torch.int64, device=device)
+        err_per_q = None
+        for i in range(max_iters):
+            optimizer.zero_grad()
+            idx_valid = self.ik_termination(q, H_target, link_name, lower, upper, se3_eps=se3_eps, debug=debug)
+            if idx_valid.nelement() == batch_size:
+                if print_freq != -1:
+                    print(f"\nIK converged for all joint configurations in {i} iterations")
+                break
+            err_per_q = self.loss_fn_ik_per_q(q, H_target, link_name, w_se3=1.0, w_joint_limits=300.0,
+                                              lower=lower, upper=upper, w_q_rest=1.0, q_rest=None, debug=debug)
+            if (i == 0 or (i % print_freq) == 0) and print_freq != -1:
+                print(f"\n---> Iter {i}/{max_iters}")
+                print(f"Error mean, std: {err_per_q.mean():.3f}, {err_per_q.std():.3f}")
+                print(f"idx_valid: {len(idx_valid)}/{batch_size}")
+            err_per_q.sum().backward()
+            optimizer.step()
+        else:
+            if print_freq != -1 and err_per_q is not None:
+                print("\nIK did not converge for all joint configurations!")
+                print(f"idx_valid: {len(idx_valid)}/{batch_size}")
+        return q, idx_valid
+
+    def loss_fn_ik_per_q(self, q, H_target, link_name, w_se3=1.0, w_joint_limits=1.0, lower=None, upper=None,
+                         w_q_rest=1.0, q_rest=None, debug=False):
+        H = self.compute_forward_kinematics_all_links(q, link_list=[link_name]).squeeze(1)
+        err_se3 = SE3_distance(H, H_target, w_pos=1.0, w_rot=1.0)
+        below = (q < lower).to(q.dtype)
+        above = (q > upper).to(q.dtype)
+        err_limits = ((lower - q).pow(2) * below).sum(-1) + ((upper - q).pow(2) * above).sum(-1)
+        err_rest = 0.0 if q_rest is None else torch.linalg.norm(q - q_rest, dim=-1)
+        return w_se3 * err_se3 + w_joint_limits * err_limits + w_q_rest * err_rest
+
+    def ik_termination(self, q, H_target, link_name, lower, upper, se3_eps=1e-1, debug=False):
+        in_limits = torch.atleast_1d(torch.argwhere(torch.all((q >= lower) & (q <= upper), dim=-1)).squeeze())
+        with torch.no_grad():
+            H = self.compute_forward_kinematics_all_links(q.detach(), link_list=[link_name]).squeeze(1)
+            err_se3 = SE3_distance(H, H_target, w_pos=1.0, w_rot=1.0)
+        close = torch.atleast_1d(torch.argwhere(err_se3 < se3_eps).squeeze())
+        return torch_intersect_1d(in_limits, close)
+
+    # ------------------------------------------------------------------------------------ accessors
+    def get_joint_limits(self) -> List[Optional[Dict[str, float]]]:
+        return [self._bodies[i].get_joint_limits() for i in self._controlled_joints]
+
+    def get_joint_limit_array(self) -> Tuple[np.ndarray, ...]:
+        lims = self.get_joint_limits()
+        lo = np.array([d["lower"] for d in lims])
+        hi = np.array([d["upper"] for d in lims])
+        vel = np.array([d["velocity"] for d in lims])
+        return lo, hi, -vel, vel
+
+    def get_link_names(self) -> List[str]:
+        return list(self._desc.link_names)
+
+    def print_link_names(self) -> None:
+        for n in self.get_link_names():
+            print(n)
