@@ -20,48 +20,7 @@
 
 using namespace trk;
 
-// ------------------------------------------------------------------------------------------
-// per-warp 32 x 64-byte transpose stage (XOR swizzle, conflict-free both ways)
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int stage_idx(int cfg_in_warp, int row) { return cfg_in_warp * 4 + (row ^ ((cfg_in_warp >> 1) & 3)); }
-
-// each lane holds one 4x4 matrix (rows m0..m3); the warp writes 32 matrices of slot `s`
-__device__ __forceinline__ void warp_store_link(float4* stage, int lane, const float4& m0, const float4& m1, const float4& m2,
-                                                long long warp_cfg0, long long n, int n_sel, int s, float* __restrict__ H) {
-    stage[stage_idx(lane, 0)] = m0;
-    stage[stage_idx(lane, 1)] = m1;
-    stage[stage_idx(lane, 2)] = m2;
-    stage[stage_idx(lane, 3)] = make_float4(0.f, 0.f, 0.f, 1.f);
-    __syncwarp();
-    const int r = lane & 3;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int c = (lane >> 2) + 8 * it;
-        const long long g = warp_cfg0 + c;
-        const float4 v = stage[stage_idx(c, r)];
-        if (g < n) __stcs(reinterpret_cast<float4*>(H) + ((g * n_sel + s) * 4 + r), v);
-    }
-    __syncwarp();
-}
-
-// the warp reads 32 matrices of slot `s`; each lane receives rows 0..2 of its own matrix
-__device__ __forceinline__ void warp_load_link(float4* stage, int lane, long long warp_cfg0, long long n, int n_sel, int s,
-                                               const float* __restrict__ G, float4& m0, float4& m1, float4& m2) {
-    const int r = lane & 3;
-#pragma unroll
-    for (int it = 0; it < 4; ++it) {
-        const int c = (lane >> 2) + 8 * it;
-        const long long g = warp_cfg0 + c;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g < n) v = __ldcs(reinterpret_cast<const float4*>(G) + ((g * n_sel + s) * 4 + r));
-        stage[stage_idx(c, r)] = v;
-    }
-    __syncwarp();
-    m0 = stage[stage_idx(lane, 0)];
-    m1 = stage[stage_idx(lane, 1)];
-    m2 = stage[stage_idx(lane, 2)];
-    __syncwarp();
-}
+// (the per-warp transpose stage lives in trk_static.cuh and is shared by both families)
 
 constexpr int kBlock = 128;
 constexpr int kWarps = kBlock / 32;

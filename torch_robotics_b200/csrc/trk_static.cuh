@@ -1,16 +1,515 @@
-// Register-resident kernel family for compiled-in robots (filled in below the generic family).
+// Register-resident kernel family for compiled-in robots.
+//
+// For a robot whose kinematic tables are known at compile time (robots_generated.cuh) the whole tree
+// walk is unrolled: parents, joint kinds, axes, fixed rotations and offsets are immediates, exact zeros
+// and ones in them are dropped structurally, and every link pose lives in registers - no table loads,
+// no thread-local arrays.  The planning-objective tables (collision points, obstacle spheres, self
+// pairs, workspace box, EE target) stay runtime data in shared memory; since they index bodies at run
+// time, link positions and the per-body position gradients are kept in a per-thread column of shared
+// memory ([slot][thread] layout: conflict-free, warp-coalesced).
+//
+// trk_model_create() selects a family by comparing the model's table image with each robot's
+// `words` image; anything else is served by the runtime-tree family in trk_b200.cu.
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstring>
+#include <type_traits>
+#include <utility>
+
+#include "robots_generated.cuh"
 #include "trk_device.cuh"
 
 namespace trk {
 
-inline int match_static_family(const float* /*tree_words*/, int /*nwords*/) { return 0; }
-inline const char* static_family_name(int family) { return family == 0 ? "generic" : "?"; }
-inline bool static_objective_supported(int /*family*/) { return false; }
-inline cudaError_t launch_static_fk_forward(int, int, const float*, long long, const SlotMap&, int, float*, cudaStream_t) { return cudaErrorNotSupported; }
-inline cudaError_t launch_static_fk_backward(int, int, const float*, long long, const SlotMap&, int, const float*, float*, cudaStream_t) { return cudaErrorNotSupported; }
-inline cudaError_t launch_static_objective(int, int, const float*, int, const float*, long long, const float*, float, int, float*, float*, float*, uint8_t*, int*, cudaStream_t) { return cudaErrorNotSupported; }
+// ------------------------------------------------------------------------------------------
+// compile-time loops
+// ------------------------------------------------------------------------------------------
+template <int V>
+struct IC {
+    static constexpr int value = V;
+    __host__ __device__ constexpr operator int() const { return V; }
+};
+template <int... Is, class F>
+__device__ __forceinline__ void sfor_impl(std::integer_sequence<int, Is...>, F&& f) {
+    (f(IC<Is>{}), ...);
+}
+template <int N, class F>
+__device__ __forceinline__ void sfor(F&& f) {
+    sfor_impl(std::make_integer_sequence<int, N>{}, static_cast<F&&>(f));
+}
+
+// acc (+)= w * c where c is an immediate: zero terms vanish, +-1 become add/sub (exact for finite values)
+__device__ __forceinline__ void cterm(float& acc, bool& started, float w, float c) {
+    if (c == 0.f) return;
+    if (!started) {
+        started = true;
+        acc = (c == 1.f) ? w : ((c == -1.f) ? -w : w * c);
+        return;
+    }
+    acc = (c == 1.f) ? acc + w : ((c == -1.f) ? acc - w : fmaf(w, c, acc));
+}
+
+template <class R>
+struct STree {
+    static constexpr int L = R::L, D = R::D;
+
+    // child pose from parent pose: rigid_body.py:162-192 + geometrics/utils.py:11-17, link I of the tables
+    template <int I>
+    static __device__ __forceinline__ void compose(const float (&Wp)[12], float theta, float (&Wc)[12]) {
+        constexpr int kind = R::kind[I];
+        float A[9];
+        sfor<3>([&](auto ic) {
+            sfor<3>([&](auto jc) {
+                constexpr int i = decltype(ic)::value, j = decltype(jc)::value;
+                constexpr float c0 = R::Rf[I][0 + j], c1 = R::Rf[I][3 + j], c2 = R::Rf[I][6 + j];
+                float acc = 0.f;
+                bool st = false;
+                cterm(acc, st, Wp[i * 3 + 0], c0);
+                cterm(acc, st, Wp[i * 3 + 1], c1);
+                cterm(acc, st, Wp[i * 3 + 2], c2);
+                A[i * 3 + j] = acc;
+            });
+        });
+        // translation: p = Wp.R * t + Wp.p  (prismatic: t + axis * theta, raw axis - rigid_body.py:176)
+        sfor<3>([&](auto ic) {
+            constexpr int i = ic;
+            float acc = Wp[9 + i];
+            bool st = true;
+            sfor<3>([&](auto kc) {
+                constexpr int k = kc;
+                constexpr float tk = R::t[I][k], ak = R::ax[I][k];
+                if constexpr (kind == TRK_KIND_PRISMATIC && ak != 0.f) {
+                    acc = fmaf(Wp[i * 3 + k], fmaf(ak, theta, tk), acc);
+                } else {
+                    cterm(acc, st, Wp[i * 3 + k], tk);
+                }
+            });
+            Wc[9 + i] = acc;
+        });
+        if constexpr (kind == TRK_KIND_REVOLUTE && R::axis_s[I] != 0.f) {
+            float sn, cs;
+            sincosf(theta, &sn, &cs);
+            if constexpr (R::axis_s[I] < 0.f) sn = -sn;
+            constexpr int k = R::axis_k[I], ci = (k + 1) % 3, cj = (k + 2) % 3;
+            sfor<3>([&](auto ic) {
+                constexpr int i = ic;
+                const float a = A[i * 3 + ci], b = A[i * 3 + cj];
+                Wc[i * 3 + ci] = fmaf(cs, a, sn * b);
+                Wc[i * 3 + cj] = fmaf(cs, b, -(sn * a));
+                Wc[i * 3 + k] = A[i * 3 + k];
+            });
+        } else {
+            sfor<9>([&](auto ic) { Wc[ic] = A[ic]; });
+        }
+    }
+
+    // qf(col) -> joint value.  pass: bit per q column, set where torch.clamp's backward passes gradient.
+    // visit(IC<i>, W[parent], W[body]) is called right after the pose of the i-th link (parents-first
+    // order) is known, so callers can consume a pose while only its parent chain is live.
+    template <class QF, class VF>
+    static __device__ __forceinline__ void forward(QF qf, float (&W)[L][12], unsigned& pass, VF visit) {
+        pass = 0u;
+        sfor<L>([&](auto ic) {
+            constexpr int i = ic, b = R::body[i], p = R::parent[i];
+            if constexpr (p < 0) {
+                sfor<12>([&](auto kc) { W[b][kc] = (kc == 0 || kc == 4 || kc == 8) ? 1.f : 0.f; });
+            } else {
+                float theta = 0.f;
+                constexpr int qi = R::qidx[i];
+                if constexpr (qi >= 0) {
+                    const float qv = qf(qi);
+                    if constexpr (R::has_lim[i] != 0) {
+                        constexpr float lo = R::lo[i], hi = R::hi[i];
+                        if (qv >= lo && qv <= hi) pass |= (1u << qi);
+                        const float c = fminf(fmaxf(qv, lo), hi);
+                        theta = (qv != qv) ? qv : c;
+                    } else {
+                        pass |= (1u << qi);
+                        theta = qv;
+                    }
+                }
+                compose<i>(W[p], theta, W[b]);
+            }
+            visit(IC<i>{}, W[p < 0 ? b : p], W[b]);
+        });
+    }
+
+    // world-frame joint axis of link i: revolute s * R_w[:, k]; prismatic R_w[parent] * a
+    template <int I>
+    static __device__ __forceinline__ void joint_axis(const float (&Wp)[12], const float (&Wb)[12], float (&ja)[3]) {
+        if constexpr (R::kind[I] == TRK_KIND_REVOLUTE) {
+            constexpr int k = R::axis_k[I];
+            constexpr float sgn = R::axis_s[I];
+            ja[0] = sgn * Wb[0 + k]; ja[1] = sgn * Wb[3 + k]; ja[2] = sgn * Wb[6 + k];
+        } else {
+            constexpr float a0 = R::ax[I][0], a1 = R::ax[I][1], a2 = R::ax[I][2];
+            sfor<3>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                float a = 0.f;
+                bool st = false;
+                cterm(a, st, Wp[r * 3 + 0], a0);
+                cterm(a, st, Wp[r * 3 + 1], a1);
+                cterm(a, st, Wp[r * 3 + 2], a2);
+                ja[r] = a;
+            });
+        }
+    }
+
+    // Leaf->root wrench accumulation (F force, T torque about the world origin) and projection on the
+    // joint axes.  JA[col] = world joint axis (joint_axis above); ownf(IC<b>, f[3], t[3], p[3]) yields body
+    // b's own wrench and world position when the sweep reaches it (so only the open subtree sums are
+    // live); gf(col, g) receives d cost / d q[col].
+    template <class OF, class GF>
+    static __device__ __forceinline__ void backward(const float (&JA)[D > 0 ? D : 1][3], OF ownf, unsigned pass, GF gf) {
+        float F[L][3], T[L][3];
+        sfor<L>([&](auto bc) { F[bc][0] = F[bc][1] = F[bc][2] = 0.f; T[bc][0] = T[bc][1] = T[bc][2] = 0.f; });
+        sfor<L>([&](auto ic) {
+            constexpr int i = L - 1 - decltype(ic)::value, b = R::body[i], p = R::parent[i];
+            if constexpr (p >= 0) {
+                float f[3], t[3], pos[3];
+                ownf(IC<b>{}, f, t, pos);
+                sfor<3>([&](auto rc) { F[b][rc] += f[rc]; T[b][rc] += t[rc]; });
+                constexpr int qi = R::qidx[i];
+                if constexpr (qi >= 0) {
+                    float g;
+                    if constexpr (R::kind[i] == TRK_KIND_REVOLUTE) {
+                        const float mx = T[b][0] - (pos[1] * F[b][2] - pos[2] * F[b][1]);
+                        const float my = T[b][1] - (pos[2] * F[b][0] - pos[0] * F[b][2]);
+                        const float mz = T[b][2] - (pos[0] * F[b][1] - pos[1] * F[b][0]);
+                        g = JA[qi][0] * mx + JA[qi][1] * my + JA[qi][2] * mz;
+                    } else {
+                        g = JA[qi][0] * F[b][0] + JA[qi][1] * F[b][1] + JA[qi][2] * F[b][2];
+                    }
+                    gf(qi, ((pass >> qi) & 1u) ? g : 0.f);
+                }
+                sfor<3>([&](auto rc) { F[p][rc] += F[b][rc]; T[p][rc] += T[b][rc]; });
+            }
+        });
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// per-warp 32 x 64-byte transpose stage (XOR swizzle, conflict-free both ways)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int stage_idx(int cfg_in_warp, int row) { return cfg_in_warp * 4 + (row ^ ((cfg_in_warp >> 1) & 3)); }
+
+// each lane holds rows 0..2 of one 4x4 link matrix; the warp writes 32 matrices into output slot s
+__device__ __forceinline__ void warp_store_link(float4* stage, int lane, const float4& m0, const float4& m1, const float4& m2,
+                                                long long warp_cfg0, long long n, int n_sel, int s, float* __restrict__ H) {
+    stage[stage_idx(lane, 0)] = m0;
+    stage[stage_idx(lane, 1)] = m1;
+    stage[stage_idx(lane, 2)] = m2;
+    stage[stage_idx(lane, 3)] = make_float4(0.f, 0.f, 0.f, 1.f);
+    __syncwarp();
+    const int r = lane & 3;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int c = (lane >> 2) + 8 * it;
+        const long long g = warp_cfg0 + c;
+        const float4 v = stage[stage_idx(c, r)];
+        if (g < n) __stcs(reinterpret_cast<float4*>(H) + ((g * n_sel + s) * 4 + r), v);
+    }
+    __syncwarp();
+}
+
+// the warp reads 32 matrices of slot s; each lane receives rows 0..2 of its own matrix
+__device__ __forceinline__ void warp_load_link(float4* stage, int lane, long long warp_cfg0, long long n, int n_sel, int s,
+                                               const float* __restrict__ G, float4& m0, float4& m1, float4& m2) {
+    const int r = lane & 3;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int c = (lane >> 2) + 8 * it;
+        const long long g = warp_cfg0 + c;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g < n) v = __ldcs(reinterpret_cast<const float4*>(G) + ((g * n_sel + s) * 4 + r));
+        stage[stage_idx(c, r)] = v;
+    }
+    __syncwarp();
+    m0 = stage[stage_idx(lane, 0)];
+    m1 = stage[stage_idx(lane, 1)];
+    m2 = stage[stage_idx(lane, 2)];
+    __syncwarp();
+}
+
+constexpr int kSBlock = 128;
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+template <class R>
+__global__ void __launch_bounds__(kSBlock) k_fk_forward_static(const float* __restrict__ q, long long n, SlotMap slots, int n_sel,
+                                                               float* __restrict__ H) {
+    __shared__ __align__(16) float4 stage_all[(kSBlock / 32) * 128];
+    float4* stage = stage_all + (threadIdx.x >> 5) * 128;
+    const int lane = threadIdx.x & 31;
+    constexpr int L = R::L, D = R::D;
+    for (long long base = (long long)blockIdx.x * kSBlock; base < n; base += (long long)gridDim.x * kSBlock) {
+        const long long cfg = base + threadIdx.x;
+        const long long warp_cfg0 = base + (threadIdx.x & ~31);
+        if (warp_cfg0 >= n) continue;
+        const float* qrow = q + (cfg < n ? cfg : n - 1) * D;
+        float W[L][12];
+        unsigned pass;
+        STree<R>::forward([&](int c) { return __ldg(qrow + c); }, W, pass, [&](auto ic, const float (&)[12], const float (&w)[12]) {
+            constexpr int b = R::body[decltype(ic)::value];
+            const int s = slots.slot[b];
+            if (s >= 0)
+                warp_store_link(stage, lane, make_float4(w[0], w[1], w[2], w[9]), make_float4(w[3], w[4], w[5], w[10]),
+                                make_float4(w[6], w[7], w[8], w[11]), warp_cfg0, n, n_sel, s, H);
+        });
+    }
+}
+
+template <class R>
+__global__ void __launch_bounds__(kSBlock) k_fk_backward_static(const float* __restrict__ q, long long n, SlotMap slots, int n_sel,
+                                                                const float* __restrict__ G, float* __restrict__ grad_q) {
+    __shared__ __align__(16) float4 stage_all[(kSBlock / 32) * 128];
+    float4* stage = stage_all + (threadIdx.x >> 5) * 128;
+    const int lane = threadIdx.x & 31;
+    constexpr int L = R::L, D = R::D;
+    for (long long base = (long long)blockIdx.x * kSBlock; base < n; base += (long long)gridDim.x * kSBlock) {
+        const long long cfg = base + threadIdx.x;
+        const long long warp_cfg0 = base + (threadIdx.x & ~31);
+        if (warp_cfg0 >= n) continue;
+        const float* qrow = q + (cfg < n ? cfg : n - 1) * D;
+        float W[L][12], F[L][3], T[L][3], P[L][3], JA[D > 0 ? D : 1][3];
+        unsigned pass;
+        STree<R>::forward([&](int c) { return __ldg(qrow + c); }, W, pass, [&](auto ic, const float (&wp)[12], const float (&w)[12]) {
+            constexpr int i = decltype(ic)::value, b = R::body[i];
+            const int s = slots.slot[b];
+            P[b][0] = w[9]; P[b][1] = w[10]; P[b][2] = w[11];
+            constexpr int qi = R::qidx[i];
+            if constexpr (qi >= 0) STree<R>::template joint_axis<i>(wp, w, JA[qi]);
+            F[b][0] = F[b][1] = F[b][2] = 0.f;
+            T[b][0] = T[b][1] = T[b][2] = 0.f;
+            if (s >= 0) {
+                float4 m0, m1, m2;
+                warp_load_link(stage, lane, warp_cfg0, n, n_sel, s, G, m0, m1, m2);
+                const float gR[9] = {m0.x, m0.y, m0.z, m1.x, m1.y, m1.z, m2.x, m2.y, m2.z};
+                float ax, ay, az;
+                axial_gR_Rt(gR, w, ax, ay, az);
+                F[b][0] = m0.w; F[b][1] = m1.w; F[b][2] = m2.w;
+                T[b][0] = w[10] * m2.w - w[11] * m1.w + ax;
+                T[b][1] = w[11] * m0.w - w[9] * m2.w + ay;
+                T[b][2] = w[9] * m1.w - w[10] * m0.w + az;
+            }
+        });
+        float* grow = grad_q + cfg * D;
+        const bool valid = cfg < n;
+        STree<R>::backward(JA, [&](auto bc, float (&f)[3], float (&t)[3], float (&pos)[3]) {
+                               constexpr int b = decltype(bc)::value;
+                               sfor<3>([&](auto rc) { f[rc] = F[b][rc]; t[rc] = T[b][rc]; pos[rc] = P[b][rc]; });
+                           }, pass, [&](int c, float g) { if (valid) grow[c] = g; });
+    }
+}
+
+template <class R, bool WANT_GRAD>
+__global__ void __launch_bounds__(kSBlock) k_objective_static(const float* __restrict__ cost_words, int cost_nwords,
+                                                              const float* __restrict__ q, long long n,
+                                                              const float* __restrict__ ee_target_cfg, float margin_override,
+                                                              int use_override, float* __restrict__ cost_total,
+                                                              float* __restrict__ cost_terms, float* __restrict__ grad_q,
+                                                              uint8_t* __restrict__ occupancy, int* __restrict__ argmin) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int L = R::L, D = R::D;
+    float* cw = smem;
+    float* spos = smem + cost_nwords;                 // [3L][kSBlock]
+    float* sgrd = spos + 3 * L * kSBlock;             // [3L][kSBlock]
+    block_copy_words(cw, cost_words, cost_nwords);
+    __syncthreads();
+    const CostView cv(cw);
+    const CostHeader* h = cv.h;
+    const int tid = threadIdx.x;
+    for (long long cfg = (long long)blockIdx.x * kSBlock + tid; cfg < n; cfg += (long long)gridDim.x * kSBlock) {
+        const float* qrow = q + cfg * D;
+        float terms[4] = {0.f, 0.f, 0.f, 0.f};
+        float Rt[9], pt[3];
+        const int e = h->ee_enabled ? h->ee_link : -1;
+        if (e >= 0) {
+            if (ee_target_cfg) {
+                const float* Ht = ee_target_cfg + cfg * 16;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    Rt[i * 3 + 0] = __ldg(Ht + i * 4 + 0); Rt[i * 3 + 1] = __ldg(Ht + i * 4 + 1);
+                    Rt[i * 3 + 2] = __ldg(Ht + i * 4 + 2); pt[i] = __ldg(Ht + i * 4 + 3);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Rt[i] = h->ee_R[i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) pt[i] = h->ee_t[i];
+            }
+        }
+        float W[L][12], JA[D > 0 ? D : 1][3];
+        float eF[3] = {0.f, 0.f, 0.f}, eT[3] = {0.f, 0.f, 0.f};   // EE wrench (evaluated where its body index is static)
+        unsigned pass;
+        STree<R>::forward([&](int c) { return __ldg(qrow + c); }, W, pass, [&](auto ic, const float (&wp)[12], const float (&w)[12]) {
+            constexpr int i = decltype(ic)::value, b = R::body[i];
+            spos[(b * 3 + 0) * kSBlock + tid] = w[9];
+            spos[(b * 3 + 1) * kSBlock + tid] = w[10];
+            spos[(b * 3 + 2) * kSBlock + tid] = w[11];
+            if (WANT_GRAD) {
+                sgrd[(b * 3 + 0) * kSBlock + tid] = 0.f;
+                sgrd[(b * 3 + 1) * kSBlock + tid] = 0.f;
+                sgrd[(b * 3 + 2) * kSBlock + tid] = 0.f;
+                constexpr int qi = R::qidx[i];
+            if constexpr (qi >= 0) STree<R>::template joint_axis<i>(wp, w, JA[qi]);
+            }
+            if (b == e) {
+                float gR[9], gp[3];
+                terms[3] = ee_term<WANT_GRAD>(h, w, &w[9], Rt, pt, gR, gp);
+                if (WANT_GRAD) {
+                    float ax, ay, az;
+                    axial_gR_Rt(gR, w, ax, ay, az);
+                    eF[0] = gp[0]; eF[1] = gp[1]; eF[2] = gp[2];
+                    eT[0] = w[10] * gp[2] - w[11] * gp[1] + ax;
+                    eT[1] = w[11] * gp[0] - w[9] * gp[2] + ay;
+                    eT[2] = w[9] * gp[1] - w[10] * gp[0] + az;
+                }
+            }
+        });
+        unsigned occ;
+        collision_terms<WANT_GRAD>(
+            cv,
+            [&](int b, float& x, float& y, float& z) {
+                x = spos[(b * 3 + 0) * kSBlock + tid]; y = spos[(b * 3 + 1) * kSBlock + tid]; z = spos[(b * 3 + 2) * kSBlock + tid];
+            },
+            [&](int b, float gx, float gy, float gz) {
+                sgrd[(b * 3 + 0) * kSBlock + tid] += gx; sgrd[(b * 3 + 1) * kSBlock + tid] += gy; sgrd[(b * 3 + 2) * kSBlock + tid] += gz;
+            },
+            margin_override, use_override != 0, terms, occ, argmin ? argmin + cfg * (long long)(h->nObj * h->S) : nullptr);
+        if (cost_total) cost_total[cfg] = weighted_total(h, terms);
+        if (cost_terms) reinterpret_cast<float4*>(cost_terms)[cfg] = make_float4(terms[0], terms[1], terms[2], terms[3]);
+        if (occupancy) occupancy[cfg] = (uint8_t)occ;
+        if (WANT_GRAD) {
+            float* grow = grad_q + cfg * D;
+            STree<R>::backward(JA, [&](auto bc, float (&f)[3], float (&t)[3], float (&pos)[3]) {
+                constexpr int b = decltype(bc)::value;
+                sfor<3>([&](auto rc) {
+                    pos[rc] = spos[(b * 3 + rc) * kSBlock + tid];
+                    f[rc] = sgrd[(b * 3 + rc) * kSBlock + tid];
+                });
+                t[0] = pos[1] * f[2] - pos[2] * f[1];
+                t[1] = pos[2] * f[0] - pos[0] * f[2];
+                t[2] = pos[0] * f[1] - pos[1] * f[0];
+                if (b == e) sfor<3>([&](auto rc) { f[rc] += eF[rc]; t[rc] += eT[rc]; });
+            }, pass, [&](int c, float g) { grow[c] = g; });
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: family table and launchers
+// ------------------------------------------------------------------------------------------
+template <class R>
+inline bool words_match(const float* words, int nwords) {
+    return nwords == R::n_words && std::memcmp(words, R::words, sizeof(unsigned) * R::n_words) == 0;
+}
+
+inline int match_static_family(const float* tree_words, int nwords) {
+    int id = 0;
+#define X(Rb) \
+    ++id;     \
+    if (words_match<Rb>(tree_words, nwords)) return id;
+    TRK_FOR_EACH_STATIC_ROBOT(X)
+#undef X
+    return 0;
+}
+
+inline const char* static_family_name(int family) {
+    if (family == 0) return "generic";
+    int id = 0;
+#define X(Rb) \
+    ++id;     \
+    if (family == id) return Rb::name;
+    TRK_FOR_EACH_STATIC_ROBOT(X)
+#undef X
+    return "?";
+}
+
+inline bool static_objective_supported(int family) { return family != 0; }
+
+template <typename K>
+inline int persistent_grid(K kernel, int n_sms, size_t smem, long long n) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kSBlock, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const long long need = (n + kSBlock - 1) / kSBlock;
+    const long long cap = (long long)n_sms * per_sm;
+    return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+template <class R>
+inline cudaError_t launch_fk_forward_t(int n_sms, const float* q, long long n, const SlotMap& sm, int n_sel, float* H,
+                                       cudaStream_t st) {
+    auto k = k_fk_forward_static<R>;
+    k<<<persistent_grid(k, n_sms, 0, n), kSBlock, 0, st>>>(q, n, sm, n_sel, H);
+    return cudaGetLastError();
+}
+
+template <class R>
+inline cudaError_t launch_fk_backward_t(int n_sms, const float* q, long long n, const SlotMap& sm, int n_sel, const float* G,
+                                        float* grad_q, cudaStream_t st) {
+    auto k = k_fk_backward_static<R>;
+    k<<<persistent_grid(k, n_sms, 0, n), kSBlock, 0, st>>>(q, n, sm, n_sel, G, grad_q);
+    return cudaGetLastError();
+}
+
+template <class R>
+inline cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwords, const float* q, long long n,
+                                      const float* ee_target_cfg, float margin_override, int use_override, float* cost_total,
+                                      float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin, cudaStream_t st) {
+    const size_t smem = ((size_t)cost_nwords + (size_t)6 * R::L * kSBlock) * sizeof(float);
+    cudaError_t e;
+    if (grad_q) {
+        auto k = k_objective_static<R, true>;
+        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<persistent_grid(k, n_sms, smem, n), kSBlock, smem, st>>>(cost_words, cost_nwords, q, n, ee_target_cfg, margin_override,
+                                                                     use_override, cost_total, cost_terms, grad_q, occupancy, argmin);
+    } else {
+        auto k = k_objective_static<R, false>;
+        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        k<<<persistent_grid(k, n_sms, smem, n), kSBlock, smem, st>>>(cost_words, cost_nwords, q, n, ee_target_cfg, margin_override,
+                                                                     use_override, cost_total, cost_terms, grad_q, occupancy, argmin);
+    }
+    return cudaGetLastError();
+}
+
+inline cudaError_t launch_static_fk_forward(int family, int n_sms, const float* q, long long n, const SlotMap& sm, int n_sel,
+                                            float* H, cudaStream_t st) {
+    int id = 0;
+#define X(Rb) \
+    ++id;     \
+    if (family == id) return launch_fk_forward_t<Rb>(n_sms, q, n, sm, n_sel, H, st);
+    TRK_FOR_EACH_STATIC_ROBOT(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+inline cudaError_t launch_static_fk_backward(int family, int n_sms, const float* q, long long n, const SlotMap& sm, int n_sel,
+                                             const float* G, float* grad_q, cudaStream_t st) {
+    int id = 0;
+#define X(Rb) \
+    ++id;     \
+    if (family == id) return launch_fk_backward_t<Rb>(n_sms, q, n, sm, n_sel, G, grad_q, st);
+    TRK_FOR_EACH_STATIC_ROBOT(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+inline cudaError_t launch_static_objective(int family, int n_sms, const float* cost_words, int cost_nwords, const float* q,
+                                           long long n, const float* ee_target_cfg, float margin_override, int use_override,
+                                           float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin,
+                                           cudaStream_t st) {
+    int id = 0;
+#define X(Rb) \
+    ++id;     \
+    if (family == id)  \
+        return launch_objective_t<Rb>(n_sms, cost_words, cost_nwords, q, n, ee_target_cfg, margin_override, use_override, \
+                                      cost_total, cost_terms, grad_q, occupancy, argmin, st);
+    TRK_FOR_EACH_STATIC_ROBOT(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
 
 }  // namespace trk
