@@ -182,6 +182,13 @@ int trk_cost_stage(const trk_model* model, const trk_cost* cost, const float* li
                    float* cost_total, float* cost_terms, float* grad_pos, float* grad_ee,
                    uint8_t* occupancy, int32_t* argmin, void* stream);
 
+/*
+ * Self-test of the branch-free correctly-rounded square root used for every distance that feeds a
+ * comparison (trk_device.cuh: sqrt_rn_core): y_core[i] from that routine, y_ref[i] from sqrt.rn.f32.
+ * The two must be bit-identical for x == 0 and 2^-100 <= x < 2^126.  All pointers are device memory.
+ */
+int trk_selftest_sqrt(const float* x, int64_t n, float* y_core, float* y_ref, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

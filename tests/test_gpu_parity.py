@@ -180,3 +180,60 @@ def test_rejects_cpu_tensors_and_wrong_dtype(models):
         m.fk_forward(torch.zeros(4, 7, device=DEV, dtype=torch.float64))
     with pytest.raises(RuntimeError):
         m.fk_forward(torch.zeros(4, 6, device=DEV))
+
+
+def test_decision_sqrt_is_correctly_rounded():
+    """sqrt_rn_core (branch-free) == sqrt.rn.f32 bit for bit on 0, on 2^-100..2^126 and on the range
+    squared distances actually take."""
+    from torch_robotics_b200 import _lib
+    g = torch.Generator(device=DEV).manual_seed(0)
+    n = 1 << 24
+    expo = torch.randint(-100, 126, (n,), device=DEV, generator=g).float()
+    mant = 1.0 + torch.rand(n, device=DEV, generator=g)
+    wide = torch.ldexp(mant, expo.to(torch.int32))
+    near = torch.rand(n, device=DEV, generator=g) * 16.0            # squared distances of a few metres
+    tiny = torch.rand(n, device=DEV, generator=g) * 1e-6
+    special = torch.tensor([0.0, 2.0 ** -100, 1.0, 4.0, 2.0, 3.0, 2.0 ** 125], device=DEV)
+    x = torch.cat([wide, near, tiny, special]).contiguous()
+    a, b = torch.empty_like(x), torch.empty_like(x)
+    _lib.check(_lib.lib().trk_selftest_sqrt(x.data_ptr(), x.numel(), a.data_ptr(), b.data_ptr(), _lib.stream_ptr(x.device)),
+               "trk_selftest_sqrt")
+    assert torch.equal(a, b)
+    assert torch.equal(b, torch.sqrt(x))
+
+
+def test_posed_nonuniform_objects_bit_exact_vs_oracle(models):
+    """Objects with unequal radii / a pose take the MUFU-key scan; value, arg-min and masks must still
+    equal the all-exact oracle on identical positions, including deliberately tied spheres."""
+    from torch_robotics_b200._lib import DeviceCost
+    from torch_robotics_b200.descriptor import build_cost_descriptor
+    m = models["panda"]
+    rng = np.random.default_rng(11)
+    c_a = rng.uniform(-0.8, 0.8, (37, 3)).astype(np.float32)
+    r_a = rng.uniform(0.02, 0.3, 37).astype(np.float32)
+    c_b = rng.uniform(-0.8, 0.8, (16, 3)).astype(np.float32)
+    c_b[5] = c_b[2]                                   # exact duplicate sphere: first index must win
+    r_b = np.full(16, 0.1, np.float32)
+    c_c = np.array([[0.1, 0.2, 0.3]], np.float32)     # single-sphere object
+    cost = build_cost_descriptor(
+        pt_link=[2, 3, 5, 7, 9], pt_radius=[0.125, 0.125, 0.13, 0.1, 0.08], cutoff_obj=0.01,
+        objects=[(c_a, r_a, None, None), (c_b, r_b, [0.1, -0.2, 0.3], [0.9, 0.1, -0.3, 0.2]), (c_c, [0.25], None, None)],
+        ws_min=[-1, -1, -1], ws_max=[1, 1, 1], weights=(0, 1, 1, 0))
+    dc = DeviceCost(m, cost)
+    n = 200_000
+    pw = rng.uniform(-1.0, 1.0, (n, 11, 3)).astype(np.float32)
+    pw[:1000, 2] = c_a[3]                             # points exactly on sphere centres
+    pw[1000:2000, 3] = c_c[0]
+    r = dc.cost_stage(t(pw), want_grad=True, want_occupancy=True, want_argmin=True)
+    x = pw[:, cost.pt_link]
+    ro = orc.object_term(cost, x, np.float32)
+    rw = orc.ws_term(cost, x, np.float32)
+    assert np.array_equal(r["argmin"].cpu().numpy(), ro["argmin"])
+    terms = r["terms"].cpu().numpy()
+    assert np.array_equal(terms[:, 1], ro["cost"])
+    assert np.array_equal(terms[:, 2], rw["cost"])
+    occ = r["occupancy"].cpu().numpy()
+    assert np.array_equal((occ & 2) != 0, ro["occ"]) and np.array_equal((occ & 4) != 0, rw["occ"])
+    gp = np.zeros_like(pw)
+    np.add.at(gp, (slice(None), cost.pt_link), ro["gx"] + rw["gx"])
+    assert rel_err(r["grad_pos"].cpu().numpy(), gp) < 1e-5

@@ -47,7 +47,7 @@ _lib_lock = threading.Lock()
 EXPORTS = [
     "trk_abi_version", "trk_last_error", "trk_model_create", "trk_model_destroy", "trk_model_kernel_family",
     "trk_fk_forward", "trk_fk_backward", "trk_cost_create", "trk_cost_destroy", "trk_cost_set_ee_target",
-    "trk_cost_set_weights", "trk_objective", "trk_cost_stage",
+    "trk_cost_set_weights", "trk_objective", "trk_cost_stage", "trk_selftest_sqrt",
 ]
 
 
@@ -81,6 +81,7 @@ def lib() -> C.CDLL:
         L.trk_cost_set_weights.argtypes = [vp, c_float_p, vp]
         L.trk_objective.argtypes = [vp, vp, vp, i64, vp, f32, vp, vp, vp, vp, vp, vp]
         L.trk_cost_stage.argtypes = [vp, vp, vp, vp, i64, vp, f32, vp, vp, vp, vp, vp, vp, vp]
+        L.trk_selftest_sqrt.argtypes = [vp, i64, vp, vp, vp]
         for name in EXPORTS:
             fn = getattr(L, name)
             if fn.restype is C.c_int and name not in ("trk_abi_version",):

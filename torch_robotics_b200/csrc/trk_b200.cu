@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kBlock) k_objective_generic(const float* __res
             for (int b = 0; b < L; ++b) F[b][0] = F[b][1] = F[b][2] = 0.f;
         float terms[4] = {0.f, 0.f, 0.f, 0.f};
         unsigned occ;
-        collision_terms<WANT_GRAD>(
+        collision_terms<WANT_GRAD, true>(
             cv, [&](int b, float& x, float& y, float& z) { x = W[b][9]; y = W[b][10]; z = W[b][11]; },
             [&](int b, float gx, float gy, float gz) { F[b][0] += gx; F[b][1] += gy; F[b][2] += gz; }, margin_override,
             use_override != 0, terms, occ, argmin ? argmin + cfg * (long long)(h->nObj * h->S) : nullptr);
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(kBlock) k_cost_stage(const float* __restrict__
             for (int b = 0; b < L; ++b) F[b][0] = F[b][1] = F[b][2] = 0.f;
         float terms[4] = {0.f, 0.f, 0.f, 0.f};
         unsigned occ;
-        collision_terms<WANT_GRAD>(
+        collision_terms<WANT_GRAD, true>(
             cv, [&](int b, float& x, float& y, float& z) { x = __ldg(P + b * 3); y = __ldg(P + b * 3 + 1); z = __ldg(P + b * 3 + 2); },
             [&](int b, float gx, float gy, float gz) { F[b][0] += gx; F[b][1] += gy; F[b][2] += gz; }, margin_override,
             use_override != 0, terms, occ, argmin ? argmin + cfg * (long long)(h->nObj * h->S) : nullptr);
@@ -237,6 +237,15 @@ __global__ void __launch_bounds__(kBlock) k_cost_stage(const float* __restrict__
             float* Gp = grad_pos + cfg * (long long)L * 3;
             for (int b = 0; b < L; ++b) { Gp[b * 3] = F[b][0]; Gp[b * 3 + 1] = F[b][1]; Gp[b * 3 + 2] = F[b][2]; }
         }
+    }
+}
+
+// self-test: the branch-free square root used on the decision path against sqrt.rn.f32
+__global__ void k_selftest_sqrt(const float* __restrict__ x, long long n, float* __restrict__ y_core, float* __restrict__ y_ref) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float rs;
+        y_core[i] = sqrt_rn_core(x[i], rs);
+        y_ref[i] = __fsqrt_rn(x[i]);
     }
 }
 
@@ -497,14 +506,14 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
     if (nObj) {
         if (d->obj_start[0] != 0 || d->obj_start[nObj] != K) return fail(TRK_E_RANGE, "obj_start must span [0, n_spheres]");
         for (int o = 0; o < nObj; ++o)
-            if (d->obj_start[o + 1] < d->obj_start[o]) return fail(TRK_E_RANGE, "obj_start must be non-decreasing");
+            if (d->obj_start[o + 1] <= d->obj_start[o]) return fail(TRK_E_RANGE, "every object needs at least one sphere");
     }
     if (d->ee_enabled && (d->ee_link < 0 || d->ee_link >= m->L)) return fail(TRK_E_RANGE, "ee_link=%d", d->ee_link);
 
     int off = 64;
     auto take = [&](int nw) { int o = off; off = align4(off + nw); return o; };
     const int o_pt_link = take(S), o_mobj = take(S), o_mws = take(S), o_ostart = take(nObj + 1), o_oid = take(nObj),
-              o_oR = take(nObj * 9), o_opos = take(nObj * 3), o_sph = take(K * 4), o_pi = take(P), o_pj = take(P), o_pm = take(P);
+              o_oR = take(nObj * 9), o_opos = take(nObj * 3), o_sph = take(K * 4), o_pi = take(P), o_pj = take(P), o_pm = take(P), o_ormax = take(nObj);
     const int nwords = off;
     trk_cost* c = new (std::nothrow) trk_cost();
     if (!c) return fail(TRK_E_RANGE, "out of host memory");
@@ -524,11 +533,24 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
     }
     h->off_pt_link = o_pt_link; h->off_pt_mobj = o_mobj; h->off_pt_mws = o_mws; h->off_obj_start = o_ostart;
     h->off_obj_ident = o_oid; h->off_obj_R = o_oR; h->off_obj_pos = o_opos; h->off_sph = o_sph;
-    h->off_pair_i = o_pi; h->off_pair_j = o_pj; h->off_pair_m = o_pm;
+    h->off_pair_i = o_pi; h->off_pair_j = o_pj; h->off_pair_m = o_pm; h->off_obj_rmax = o_ormax;
     for (int s = 0; s < S; ++s) { iw[o_pt_link + s] = d->pt_link[s]; w[o_mobj + s] = d->pt_margin_obj[s]; w[o_mws + s] = d->pt_margin_ws[s]; }
     if (nObj) {
         for (int o = 0; o <= nObj; ++o) iw[o_ostart + o] = d->obj_start[o];
-        for (int o = 0; o < nObj; ++o) iw[o_oid + o] = d->obj_identity[o] ? 1 : 0;
+        for (int o = 0; o < nObj; ++o) {
+            // per-object scan parameters: equal radii -> squared-distance keys; bits = index width packed in the key
+            const int k0 = d->obj_start[o], k1 = d->obj_start[o + 1];
+            bool uniform = true;
+            float rmax = 0.f;
+            for (int k = k0; k < k1; ++k) {
+                if (d->sph_radius[k] != d->sph_radius[k0]) uniform = false;
+                rmax = fmaxf(rmax, fabsf(d->sph_radius[k]));
+            }
+            int bits = 1;
+            while ((1 << bits) < (k1 - k0)) ++bits;
+            iw[o_oid + o] = (d->obj_identity[o] ? OBJ_IDENTITY : 0) | (uniform ? OBJ_UNIFORM_RADIUS : 0) | (bits << OBJ_BITS_SHIFT);
+            w[o_ormax + o] = rmax;
+        }
         memcpy(w + o_oR, d->obj_R, nObj * 9 * sizeof(float));
         memcpy(w + o_opos, d->obj_pos, nObj * 3 * sizeof(float));
     } else {
@@ -593,7 +615,9 @@ int trk_objective(const trk_model* m, const trk_cost* c, const float* q, int64_t
     DeviceGuard guard(m->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (m->family && trk::static_objective_supported(m->family)) {
-        cudaError_t e = trk::launch_static_objective(m->family, m->n_sms, c->d_words, c->nwords, q, n, ee_target_cfg,
+        const CostHeader* hh = reinterpret_cast<const CostHeader*>(c->h_words.data());
+        const int clamp_any = hh->clamp_self | hh->clamp_obj | hh->clamp_ws;
+        cudaError_t e = trk::launch_static_objective(m->family, m->n_sms, c->d_words, c->nwords, clamp_any, q, n, ee_target_cfg,
                                                      margin_override, use_override, cost_total, cost_terms, grad_q,
                                                      occupancy, argmin, st);
         return e == cudaSuccess ? TRK_OK : cuda_fail(e, "objective(static)");
@@ -617,6 +641,14 @@ int trk_objective(const trk_model* m, const trk_cost* c, const float* q, int64_t
 #undef LAUNCH_OBJ
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? TRK_OK : cuda_fail(e, "objective launch");
+}
+
+int trk_selftest_sqrt(const float* x, int64_t n, float* y_core, float* y_ref, void* stream) {
+    if (n <= 0) return TRK_OK;
+    TRK_CHECK_PTR(x, "x"); TRK_CHECK_PTR(y_core, "y_core"); TRK_CHECK_PTR(y_ref, "y_ref");
+    k_selftest_sqrt<<<1184, 256, 0, (cudaStream_t)stream>>>(x, n, y_core, y_ref);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? TRK_OK : cuda_fail(e, "selftest_sqrt launch");
 }
 
 int trk_cost_stage(const trk_model* m, const trk_cost* c, const float* link_pos, const float* ee_pose, int64_t n,

@@ -20,6 +20,11 @@
 #include "robots_generated.cuh"
 #include "trk_device.cuh"
 
+#ifdef TRK_ONLY_PANDA   // development builds: instantiate the compiled-in family for one robot only
+#undef TRK_FOR_EACH_STATIC_ROBOT
+#define TRK_FOR_EACH_STATIC_ROBOT(X) X(robots::Panda)
+#endif
+
 namespace trk {
 
 // ------------------------------------------------------------------------------------------
@@ -304,7 +309,7 @@ __global__ void __launch_bounds__(kSBlock) k_fk_backward_static(const float* __r
     }
 }
 
-template <class R, bool WANT_GRAD>
+template <class R, bool WANT_GRAD, bool CLAMP>
 __global__ void __launch_bounds__(kSBlock) k_objective_static(const float* __restrict__ cost_words, int cost_nwords,
                                                               const float* __restrict__ q, long long n,
                                                               const float* __restrict__ ee_target_cfg, float margin_override,
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(kSBlock) k_objective_static(const float* __res
             }
         });
         unsigned occ;
-        collision_terms<WANT_GRAD>(
+        collision_terms<WANT_GRAD, CLAMP>(
             cv,
             [&](int b, float& x, float& y, float& z) {
                 x = spos[(b * 3 + 0) * kSBlock + tid]; y = spos[(b * 3 + 1) * kSBlock + tid]; z = spos[(b * 3 + 2) * kSBlock + tid];
@@ -455,24 +460,31 @@ inline cudaError_t launch_fk_backward_t(int n_sms, const float* q, long long n, 
     return cudaGetLastError();
 }
 
-template <class R>
-inline cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwords, const float* q, long long n,
+template <class R, bool WANT_GRAD, bool CLAMP>
+inline cudaError_t launch_objective_k(int n_sms, const float* cost_words, int cost_nwords, const float* q, long long n,
                                       const float* ee_target_cfg, float margin_override, int use_override, float* cost_total,
                                       float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin, cudaStream_t st) {
     const size_t smem = ((size_t)cost_nwords + (size_t)6 * R::L * kSBlock) * sizeof(float);
-    cudaError_t e;
-    if (grad_q) {
-        auto k = k_objective_static<R, true>;
-        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<persistent_grid(k, n_sms, smem, n), kSBlock, smem, st>>>(cost_words, cost_nwords, q, n, ee_target_cfg, margin_override,
-                                                                     use_override, cost_total, cost_terms, grad_q, occupancy, argmin);
-    } else {
-        auto k = k_objective_static<R, false>;
-        if (smem > 48 * 1024 && (e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        k<<<persistent_grid(k, n_sms, smem, n), kSBlock, smem, st>>>(cost_words, cost_nwords, q, n, ee_target_cfg, margin_override,
-                                                                     use_override, cost_total, cost_terms, grad_q, occupancy, argmin);
+    auto k = k_objective_static<R, WANT_GRAD, CLAMP>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
     }
+    k<<<persistent_grid(k, n_sms, smem, n), kSBlock, smem, st>>>(cost_words, cost_nwords, q, n, ee_target_cfg, margin_override,
+                                                                 use_override, cost_total, cost_terms, grad_q, occupancy, argmin);
     return cudaGetLastError();
+}
+
+template <class R>
+inline cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwords, int clamp_any, const float* q,
+                                      long long n, const float* ee_target_cfg, float margin_override, int use_override,
+                                      float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin,
+                                      cudaStream_t st) {
+#define TRK_OBJ_ARGS n_sms, cost_words, cost_nwords, q, n, ee_target_cfg, margin_override, use_override, cost_total, cost_terms, \
+                     grad_q, occupancy, argmin, st
+    if (grad_q) return clamp_any ? launch_objective_k<R, true, true>(TRK_OBJ_ARGS) : launch_objective_k<R, true, false>(TRK_OBJ_ARGS);
+    return clamp_any ? launch_objective_k<R, false, true>(TRK_OBJ_ARGS) : launch_objective_k<R, false, false>(TRK_OBJ_ARGS);
+#undef TRK_OBJ_ARGS
 }
 
 inline cudaError_t launch_static_fk_forward(int family, int n_sms, const float* q, long long n, const SlotMap& sm, int n_sel,
@@ -497,15 +509,15 @@ inline cudaError_t launch_static_fk_backward(int family, int n_sms, const float*
     return cudaErrorInvalidValue;
 }
 
-inline cudaError_t launch_static_objective(int family, int n_sms, const float* cost_words, int cost_nwords, const float* q,
-                                           long long n, const float* ee_target_cfg, float margin_override, int use_override,
+inline cudaError_t launch_static_objective(int family, int n_sms, const float* cost_words, int cost_nwords, int clamp_any,
+                                           const float* q, long long n, const float* ee_target_cfg, float margin_override, int use_override,
                                            float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin,
                                            cudaStream_t st) {
     int id = 0;
 #define X(Rb) \
     ++id;     \
     if (family == id)  \
-        return launch_objective_t<Rb>(n_sms, cost_words, cost_nwords, q, n, ee_target_cfg, margin_override, use_override, \
+        return launch_objective_t<Rb>(n_sms, cost_words, cost_nwords, clamp_any, q, n, ee_target_cfg, margin_override, use_override, \
                                       cost_total, cost_terms, grad_q, occupancy, argmin, st);
     TRK_FOR_EACH_STATIC_ROBOT(X)
 #undef X
