@@ -513,7 +513,7 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
     int off = 64;
     auto take = [&](int nw) { int o = off; off = align4(off + nw); return o; };
     const int o_pt_link = take(S), o_mobj = take(S), o_mws = take(S), o_ostart = take(nObj + 1), o_oid = take(nObj),
-              o_oR = take(nObj * 9), o_opos = take(nObj * 3), o_sph = take(K * 4), o_pi = take(P), o_pj = take(P), o_pm = take(P), o_ormax = take(nObj);
+              o_oR = take(nObj * 9), o_opos = take(nObj * 3), o_sph = take(K * 4), o_pi = take(P), o_pj = take(P), o_pm = take(P), o_ormax = take(nObj), o_oc2 = take(nObj), o_sphq = take(K * 4);
     const int nwords = off;
     trk_cost* c = new (std::nothrow) trk_cost();
     if (!c) return fail(TRK_E_RANGE, "out of host memory");
@@ -533,7 +533,7 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
     }
     h->off_pt_link = o_pt_link; h->off_pt_mobj = o_mobj; h->off_pt_mws = o_mws; h->off_obj_start = o_ostart;
     h->off_obj_ident = o_oid; h->off_obj_R = o_oR; h->off_obj_pos = o_opos; h->off_sph = o_sph;
-    h->off_pair_i = o_pi; h->off_pair_j = o_pj; h->off_pair_m = o_pm; h->off_obj_rmax = o_ormax;
+    h->off_pair_i = o_pi; h->off_pair_j = o_pj; h->off_pair_m = o_pm; h->off_obj_rmax = o_ormax; h->off_obj_c2max = o_oc2; h->off_sphq = o_sphq;
     for (int s = 0; s < S; ++s) { iw[o_pt_link + s] = d->pt_link[s]; w[o_mobj + s] = d->pt_margin_obj[s]; w[o_mws + s] = d->pt_margin_ws[s]; }
     if (nObj) {
         for (int o = 0; o <= nObj; ++o) iw[o_ostart + o] = d->obj_start[o];
@@ -541,11 +541,17 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
             // per-object scan parameters: equal radii -> squared-distance keys; bits = index width packed in the key
             const int k0 = d->obj_start[o], k1 = d->obj_start[o + 1];
             bool uniform = true;
-            float rmax = 0.f;
+            float rmax = 0.f, c2max = 0.f;
             for (int k = k0; k < k1; ++k) {
                 if (d->sph_radius[k] != d->sph_radius[k0]) uniform = false;
                 rmax = fmaxf(rmax, fabsf(d->sph_radius[k]));
+                const float* cc = d->sph_center + 3 * k;
+                const float c2 = cc[0] * cc[0] + cc[1] * cc[1] + cc[2] * cc[2];
+                c2max = fmaxf(c2max, c2);
+                w[o_sphq + 4 * k + 0] = -2.f * cc[0]; w[o_sphq + 4 * k + 1] = -2.f * cc[1];
+                w[o_sphq + 4 * k + 2] = -2.f * cc[2]; w[o_sphq + 4 * k + 3] = c2;
             }
+            w[o_oc2 + o] = c2max;
             int bits = 1;
             while ((1 << bits) < (k1 - k0)) ++bits;
             iw[o_oid + o] = (d->obj_identity[o] ? OBJ_IDENTITY : 0) | (uniform ? OBJ_UNIFORM_RADIUS : 0) | (bits << OBJ_BITS_SHIFT);

@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kSBlock) k_fk_backward_static(const float* __r
 }
 
 template <class R, bool WANT_GRAD, bool CLAMP>
-__global__ void __launch_bounds__(kSBlock) k_objective_static(const float* __restrict__ cost_words, int cost_nwords,
+__global__ void __launch_bounds__(kSBlock, R::L <= 16 ? 5 : 1) k_objective_static(const float* __restrict__ cost_words, int cost_nwords,
                                                               const float* __restrict__ q, long long n,
                                                               const float* __restrict__ ee_target_cfg, float margin_override,
                                                               int use_override, float* __restrict__ cost_total,
