@@ -235,6 +235,45 @@ def main():
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
 
+    # ---- secondary kernels of the path (BASELINE config 2): FK forward and FK fwd+bwd at 1,048,576 configs, HBM-bound
+    extra = {}
+    if rank == 0:
+        n2 = 1 << 20
+        q2 = q[:n2].contiguous()
+        Hbuf = model.fk_forward(q2)
+        Gbuf = torch.randn_like(Hbuf)
+        L = desc.n_links
+
+        def timed(fn, reps=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record(); torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            return float(np.median(ts))
+        lib, check, sp = None, None, None
+        from torch_robotics_b200 import _lib as L_
+        gq = torch.empty_like(q2)
+
+        def fwd():
+            L_.check(L_.lib().trk_fk_forward(model.handle, q2.data_ptr(), n2, None, L, Hbuf.data_ptr(), L_.stream_ptr(dev)), "fk_forward")
+
+        def bwd():
+            L_.check(L_.lib().trk_fk_backward(model.handle, q2.data_ptr(), n2, None, L, Gbuf.data_ptr(), gq.data_ptr(), L_.stream_ptr(dev)), "fk_backward")
+        ms_f, ms_b = timed(fwd), timed(bwd)
+        by_f, by_b = n2 * (desc.n_dofs * 4 + L * 64), n2 * (2 * desc.n_dofs * 4 + L * 64)
+        hbm = measured_peaks()["hbm_gbs"]
+        extra = {"fk_forward_1M": {"ms": ms_f, "configs_per_s": n2 / ms_f * 1e3, "GBps": by_f / ms_f / 1e6, "hbm_frac": by_f / ms_f / 1e6 / hbm,
+                                   "bytes_per_config": by_f / n2},
+                 "fk_backward_1M": {"ms": ms_b, "configs_per_s": n2 / ms_b * 1e3, "GBps": by_b / ms_b / 1e6, "hbm_frac": by_b / ms_b / 1e6 / hbm,
+                                    "bytes_per_config": by_b / n2},
+                 "fk_fwd_bwd_1M_configs_per_s": n2 / (ms_f + ms_b) * 1e3,
+                 "note": "1,048,576 configs: H (738 MB) exceeds L2; CUDA events per launch, median of 10"}
+        del Hbuf, Gbuf
+
     times = torch.tensor([span_ms, total_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -273,6 +312,7 @@ def main():
                     "d2h_bytes_per_step": n * (desc.n_dofs + 1) * 4, "ms_per_step": e2e_s * 1e3,
                     "api": "HostObjectivePipeline.run(pinned q) -> pinned cost, grad_q (chunked, copy/compute overlap)"},
             "gpu_launches": args.steps,
+            "extra_kernels": extra,
             "clocks": sampler.result(),
             "wall_s_timed_region": t_wall,
         }

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libtrk_b200.so")
+LIB_PATH = os.environ.get("TRK_B200_LIB") or os.path.join(_HERE, "csrc", "libtrk_b200.so")   # env override: development builds
 
 c_float_p = C.POINTER(C.c_float)
 c_int32_p = C.POINTER(C.c_int32)

@@ -237,7 +237,13 @@ __device__ __forceinline__ void warp_load_link(float4* stage, int lane, long lon
     __syncwarp();
 }
 
-constexpr int kSBlock = 128;
+#ifndef TRK_SBLOCK
+#define TRK_SBLOCK 128
+#endif
+#ifndef TRK_OBJ_MINBLOCKS
+#define TRK_OBJ_MINBLOCKS 5
+#endif
+constexpr int kSBlock = TRK_SBLOCK;
 
 // ------------------------------------------------------------------------------------------
 // kernels
@@ -310,7 +316,7 @@ __global__ void __launch_bounds__(kSBlock) k_fk_backward_static(const float* __r
 }
 
 template <class R, bool WANT_GRAD, bool CLAMP>
-__global__ void __launch_bounds__(kSBlock, R::L <= 16 ? 5 : 1) k_objective_static(const float* __restrict__ cost_words, int cost_nwords,
+__global__ void __launch_bounds__(kSBlock, R::L <= 16 ? TRK_OBJ_MINBLOCKS : 1) k_objective_static(const float* __restrict__ cost_words, int cost_nwords,
                                                               const float* __restrict__ q, long long n,
                                                               const float* __restrict__ ee_target_cfg, float margin_override,
                                                               int use_override, float* __restrict__ cost_total,

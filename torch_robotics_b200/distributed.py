@@ -1,0 +1,94 @@
+"""Multi-GPU plumbing for the hot path: one process per GPU, torch.distributed (NCCL over NVLink /
+NVSwitch on the B200 box, gloo in CPU tests).
+
+The path shards without a data-path exchange: every configuration / waypoint / IK seed is independent
+and the model and cost tables (< 4 KB) are replicated.  Rows are partitioned into contiguous blocks
+with whole trajectories kept on one rank, so a [b, h] cost never crosses ranks.  The only collectives
+are the ones the callers of the path need:
+  * all_reduce(SUM) of the scalar / per-term total cost;
+  * all_gather of each rank's k best IK solutions followed by a local top-k;
+  * all_reduce(MIN) of an "every seed valid" flag (emulates robot_tree.py:356 without a host sync
+    per iteration when called every few dozen iterations).
+Payloads are bytes to KB: latency-bound, so they are issued once per batch, never per kernel.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_bounds(n_rows: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) block of `n_rows` units (trajectories, seeds, configurations) for `rank`;
+    the first n_rows % world_size ranks get one extra row."""
+    base, extra = divmod(int(n_rows), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard_trajectories(x: torch.Tensor, rank: int | None = None, world_size: int | None = None) -> torch.Tensor:
+    """Slice of a [b, h, d] (or [n, d]) batch owned by this rank; whole trajectories stay together."""
+    r, w = world()
+    rank = r if rank is None else rank
+    world_size = w if world_size is None else world_size
+    lo, hi = shard_bounds(x.shape[0], rank, world_size)
+    return x[lo:hi]
+
+
+def total_cost(local_cost: torch.Tensor) -> torch.Tensor:
+    """Sum of the cost over every rank's shard (fp64 accumulation of the per-rank fp32 sums)."""
+    s = local_cost.double().sum().reshape(1)
+    if world()[1] > 1:
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    return s[0]
+
+
+def total_cost_terms(local_terms: torch.Tensor) -> torch.Tensor:
+    """Per-term totals [4] (self, object, ws, ee) over all ranks."""
+    s = local_terms.double().reshape(-1, local_terms.shape[-1]).sum(0)
+    if world()[1] > 1:
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    return s
+
+
+def all_valid(local_all_valid: bool, device) -> bool:
+    flag = torch.tensor([1 if local_all_valid else 0], dtype=torch.int32, device=device)
+    if world()[1] > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item())
+
+
+def gather_best_solutions(q_local: torch.Tensor, err_local: torch.Tensor, valid_local: torch.Tensor, k: int):
+    """Global k best IK solutions.
+
+    q_local [S, D], err_local [S] (SE(3) error), valid_local [S] bool on this rank.  Each rank selects its
+    k best valid seeds (invalid ones are ranked last), the [k, D+2] blocks are all-gathered and every rank
+    takes the global top-k.  Returns (q [k, D], err [k], valid [k] bool), identical on all ranks and equal
+    to a single-process top-k over the concatenated seeds (ties broken by global seed order)."""
+    rank, w = world()
+    S, D = q_local.shape
+    kk = min(k, S)
+    key = torch.where(valid_local, err_local, torch.full_like(err_local, float("inf")))
+    order = torch.argsort(key, stable=True)[:kk]
+    block = torch.full((k, D + 2), float("inf"), dtype=q_local.dtype, device=q_local.device)
+    block[:kk, :D] = q_local[order]
+    block[:kk, D] = err_local[order]
+    block[:kk, D + 1] = valid_local[order].to(q_local.dtype)
+    block[kk:, D + 1] = 0
+    if w > 1:
+        blocks = [torch.empty_like(block) for _ in range(w)]
+        dist.all_gather(blocks, block)
+        allb = torch.cat(blocks, 0)
+    else:
+        allb = block
+    gkey = torch.where(allb[:, D + 1] > 0, allb[:, D], torch.full_like(allb[:, D], float("inf")))
+    top = torch.argsort(gkey, stable=True)[:k]
+    sel = allb[top]
+    return sel[:, :D], sel[:, D], sel[:, D + 1] > 0
