@@ -105,6 +105,28 @@ def emit_robot(name, d):
     return cname, "\n".join(out)
 
 
+def emit_panda_collision():
+    """Compile-time collision model of RobotPanda (robots/robot_panda.py:47-127 in the reference; constants in
+    torch_robotics_b200/robots/robot_panda.py): collision-point bodies and self-collision body pairs."""
+    from torch_robotics_b200.robots.robot_panda import OBJECT_COLLISION_SPHERES, SELF_COLLISION_PAIRS, GRASPED_OBJECT_SELF_LINKS
+    d = compile_urdf(os.path.join(DATA, dict(ROBOTS)["panda"]), "panda")
+    idx = d.name_to_idx()
+    pts = [idx[n] for n in OBJECT_COLLISION_SPHERES]
+    links = set(GRASPED_OBJECT_SELF_LINKS)
+    for k, v in SELF_COLLISION_PAIRS.items():
+        links.add(k)
+        links.update(v)
+    links = sorted(links)
+    pairs = [(idx[a], idx[b]) for a in links for b in SELF_COLLISION_PAIRS.get(a, [])]
+    out = ["struct PandaCollision {   // RobotPanda: 5 object-collision points, 10 self-collision pairs",
+           f"    static constexpr int S = {len(pts)}, P = {len(pairs)};",
+           f"    static constexpr int pt_link[S] = {{{', '.join(map(str, pts))}}};",
+           f"    static constexpr int pair_i[P] = {{{', '.join(str(a) for a, _ in pairs)}}};",
+           f"    static constexpr int pair_j[P] = {{{', '.join(str(b) for _, b in pairs)}}};",
+           "};"]
+    return "\n".join(out)
+
+
 def main():
     parts = ["// GENERATED by tools/gen_static_robots.py - do not edit.",
              "// constexpr kinematic tables of the shipped robots (parents-first order).",
@@ -115,6 +137,7 @@ def main():
         cname, text = emit_robot(name, d)
         names.append(cname)
         parts += [text, ""]
+    parts += [emit_panda_collision(), ""]
     parts += ["}  // namespace robots", "",
               "#define TRK_FOR_EACH_STATIC_ROBOT(X) " + " ".join(f"X(robots::{n})" for n in names), "",
               "}  // namespace trk", ""]

@@ -283,6 +283,7 @@ struct trk_cost {
     int L;
     int S, nObj, K, P;
     int ee_enabled;
+    int cm_match;               // cost table equals the compile-time collision model of the model's family
     float* d_words;
     int nwords;
     std::vector<float> h_words;  // host mirror, for the setters
@@ -567,6 +568,7 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
         w[o_sph + 4 * k + 2] = d->sph_center[3 * k + 2]; w[o_sph + 4 * k + 3] = d->sph_radius[k];
     }
     for (int p = 0; p < P; ++p) { iw[o_pi + p] = d->pair_i[p]; iw[o_pj + p] = d->pair_j[p]; w[o_pm + p] = d->pair_margin[p]; }
+    c->cm_match = trk::static_cm_match(m->family, w);
     c->device = m->device; c->L = m->L; c->S = S; c->nObj = nObj; c->K = K; c->P = P; c->ee_enabled = h->ee_enabled; c->nwords = nwords;
     DeviceGuard guard(m->device);
     cudaError_t e = cudaMalloc(&c->d_words, nwords * sizeof(float));
@@ -623,7 +625,7 @@ int trk_objective(const trk_model* m, const trk_cost* c, const float* q, int64_t
     if (m->family && trk::static_objective_supported(m->family)) {
         const CostHeader* hh = reinterpret_cast<const CostHeader*>(c->h_words.data());
         const int clamp_any = hh->clamp_self | hh->clamp_obj | hh->clamp_ws;
-        cudaError_t e = trk::launch_static_objective(m->family, m->n_sms, c->d_words, c->nwords, clamp_any, q, n, ee_target_cfg,
+        cudaError_t e = trk::launch_static_objective(m->family, m->n_sms, c->d_words, c->nwords, clamp_any, c->cm_match, q, n, ee_target_cfg,
                                                      margin_override, use_override, cost_total, cost_terms, grad_q,
                                                      occupancy, argmin, st);
         return e == cudaSuccess ? TRK_OK : cuda_fail(e, "objective(static)");

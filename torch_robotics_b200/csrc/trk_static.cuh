@@ -94,7 +94,7 @@ struct STree {
         });
         if constexpr (kind == TRK_KIND_REVOLUTE && R::axis_s[I] != 0.f) {
             float sn, cs;
-            sincosf(theta, &sn, &cs);
+            trk_sincos(theta, sn, cs);
             if constexpr (R::axis_s[I] < 0.f) sn = -sn;
             constexpr int k = R::axis_k[I], ci = (k + 1) % 3, cj = (k + 2) % 3;
             sfor<3>([&](auto ic) {
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(kSBlock, R::L <= 16 ? TRK_OBJ_MINBLOCKS : 1) k
             }
         }
         float W[L][12], JA[D > 0 ? D : 1][3];
-        float eF[3] = {0.f, 0.f, 0.f}, eT[3] = {0.f, 0.f, 0.f};   // EE wrench (evaluated where its body index is static)
+        float eF[3] = {0.f, 0.f, 0.f}, eT[3] = {0.f, 0.f, 0.f}, Wee[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         unsigned pass;
         STree<R>::forward([&](int c) { return __ldg(qrow + c); }, W, pass, [&](auto ic, const float (&wp)[12], const float (&w)[12]) {
             constexpr int i = decltype(ic)::value, b = R::body[i];
@@ -367,19 +367,20 @@ __global__ void __launch_bounds__(kSBlock, R::L <= 16 ? TRK_OBJ_MINBLOCKS : 1) k
                 constexpr int qi = R::qidx[i];
             if constexpr (qi >= 0) STree<R>::template joint_axis<i>(wp, w, JA[qi]);
             }
-            if (b == e) {
-                float gR[9], gp[3];
-                terms[3] = ee_term<WANT_GRAD>(h, w, &w[9], Rt, pt, gR, gp);
-                if (WANT_GRAD) {
-                    float ax, ay, az;
-                    axial_gR_Rt(gR, w, ax, ay, az);
-                    eF[0] = gp[0]; eF[1] = gp[1]; eF[2] = gp[2];
-                    eT[0] = w[10] * gp[2] - w[11] * gp[1] + ax;
-                    eT[1] = w[11] * gp[0] - w[9] * gp[2] + ay;
-                    eT[2] = w[9] * gp[1] - w[10] * gp[0] + az;
-                }
-            }
+            if (b == e) sfor<12>([&](auto kc) { Wee[kc] = w[kc]; });   // the EE body is chosen at run time: keep a copy
         });
+        if (e >= 0) {
+            float gR[9], gp[3];
+            terms[3] = ee_term<WANT_GRAD>(h, Wee, &Wee[9], Rt, pt, gR, gp);
+            if (WANT_GRAD) {
+                float ax, ay, az;
+                axial_gR_Rt(gR, Wee, ax, ay, az);
+                eF[0] = gp[0]; eF[1] = gp[1]; eF[2] = gp[2];
+                eT[0] = Wee[10] * gp[2] - Wee[11] * gp[1] + ax;
+                eT[1] = Wee[11] * gp[0] - Wee[9] * gp[2] + ay;
+                eT[2] = Wee[9] * gp[1] - Wee[10] * gp[0] + az;
+            }
+        }
         unsigned occ;
         collision_terms<WANT_GRAD, CLAMP>(
             cv,
@@ -408,6 +409,164 @@ __global__ void __launch_bounds__(kSBlock, R::L <= 16 ? TRK_OBJ_MINBLOCKS : 1) k
             }, pass, [&](int c, float g) { grow[c] = g; });
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused objective with a compile-time collision model CM (which bodies carry collision points, which
+// body pairs are checked): positions and position gradients stay in registers, no per-thread
+// shared-memory columns, no table-driven body indexing.  Margins, obstacle spheres, workspace box, EE
+// target and weights remain runtime data.  Used when the cost tables handed to trk_cost_create list
+// exactly CM's points and pairs (RobotPanda's model); any other table takes k_objective_static.
+// ------------------------------------------------------------------------------------------
+template <class CM, int L>
+struct CMInfo {
+    __host__ __device__ static constexpr bool touched(int b) {
+        for (int s = 0; s < CM::S; ++s) if (CM::pt_link[s] == b) return true;
+        for (int p = 0; p < CM::P; ++p) if (CM::pair_i[p] == b || CM::pair_j[p] == b) return true;
+        return false;
+    }
+};
+
+template <class R, class CM, bool WANT_GRAD, bool CLAMP>
+__global__ void __launch_bounds__(kSBlock, 4) k_objective_cm(const float* __restrict__ cost_words, int cost_nwords,
+                                                             const float* __restrict__ q, long long n,
+                                                             const float* __restrict__ ee_target_cfg, float margin_override,
+                                                             int use_override, float* __restrict__ cost_total,
+                                                             float* __restrict__ cost_terms, float* __restrict__ grad_q,
+                                                             uint8_t* __restrict__ occupancy, int* __restrict__ argmin) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int L = R::L, D = R::D;
+    float* cw = smem;
+    float* spt = smem + cost_nwords;                  // [3 * CM::S][kSBlock] collision-point positions / gradients
+    block_copy_words(cw, cost_words, cost_nwords);
+    __syncthreads();
+    const CostView cv(cw);
+    const CostHeader* h = cv.h;
+    const int tid = threadIdx.x;
+    for (long long cfg = (long long)blockIdx.x * kSBlock + tid; cfg < n; cfg += (long long)gridDim.x * kSBlock) {
+        const float* qrow = q + cfg * D;
+        float terms[4] = {0.f, 0.f, 0.f, 0.f};
+        float Rt[9], pt[3];
+        const int e = h->ee_enabled ? h->ee_link : -1;
+        if (e >= 0) {
+            if (ee_target_cfg) {
+                const float* Ht = ee_target_cfg + cfg * 16;
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    Rt[i * 3 + 0] = __ldg(Ht + i * 4 + 0); Rt[i * 3 + 1] = __ldg(Ht + i * 4 + 1);
+                    Rt[i * 3 + 2] = __ldg(Ht + i * 4 + 2); pt[i] = __ldg(Ht + i * 4 + 3);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Rt[i] = h->ee_R[i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) pt[i] = h->ee_t[i];
+            }
+        }
+        float W[L][12], P[L][3], G[L][3], JA[D > 0 ? D : 1][3];
+        float eF[3] = {0.f, 0.f, 0.f}, eT[3] = {0.f, 0.f, 0.f}, Wee[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        unsigned pass;
+        STree<R>::forward([&](int c) { return __ldg(qrow + c); }, W, pass, [&](auto ic, const float (&wp)[12], const float (&w)[12]) {
+            constexpr int i = decltype(ic)::value, b = R::body[i];
+            P[b][0] = w[9]; P[b][1] = w[10]; P[b][2] = w[11];
+            G[b][0] = G[b][1] = G[b][2] = 0.f;
+            if (WANT_GRAD) {
+                constexpr int qi = R::qidx[i];
+                if constexpr (qi >= 0) STree<R>::template joint_axis<i>(wp, w, JA[qi]);
+            }
+            if (b == e) sfor<12>([&](auto kc) { Wee[kc] = w[kc]; });   // the EE body is chosen at run time: keep a copy
+        });
+        if (e >= 0) {
+            float gR[9], gp[3];
+            terms[3] = ee_term<WANT_GRAD>(h, Wee, &Wee[9], Rt, pt, gR, gp);
+            if (WANT_GRAD) {
+                float ax, ay, az;
+                axial_gR_Rt(gR, Wee, ax, ay, az);
+                eF[0] = gp[0]; eF[1] = gp[1]; eF[2] = gp[2];
+                eT[0] = Wee[10] * gp[2] - Wee[11] * gp[1] + ax;
+                eT[1] = Wee[11] * gp[0] - Wee[9] * gp[2] + ay;
+                eT[2] = Wee[9] * gp[1] - Wee[10] * gp[0] + az;
+            }
+        }
+        unsigned occ = 0u;
+        float c_self = 0.f, c_obj = 0.f, c_ws = 0.f;
+        sfor<CM::P>([&](auto pc) {
+            constexpr int p = decltype(pc)::value, bi = CM::pair_i[p], bj = CM::pair_j[p];
+            const float m = cv.pair_m[p];
+            float ux, uy, uz;
+            c_self = __fadd_rn(c_self, pair_term<WANT_GRAD, CLAMP>(h, P[bi][0], P[bi][1], P[bi][2], P[bj][0], P[bj][1], P[bj][2], m,
+                                                                    use_override ? margin_override : m, occ, ux, uy, uz));
+            if (WANT_GRAD) {
+                G[bi][0] -= ux; G[bi][1] -= uy; G[bi][2] -= uz;
+                G[bj][0] += ux; G[bj][1] += uy; G[bj][2] += uz;
+            }
+        });
+        int* amrow = argmin ? argmin + cfg * (long long)(h->nObj * h->S) : nullptr;
+        // collision points: positions parked in a [3S][thread] shared column so that the (large) point code
+        // exists once and runs as a loop; gradients come back the same way
+        sfor<CM::S>([&](auto sc) {
+            constexpr int s = decltype(sc)::value, b = CM::pt_link[s];
+            sfor<3>([&](auto rc) { spt[(s * 3 + rc) * kSBlock + tid] = P[b][rc]; });
+        });
+#pragma unroll 1
+        for (int s = 0; s < CM::S; ++s) {
+            const float x = spt[(s * 3 + 0) * kSBlock + tid], y = spt[(s * 3 + 1) * kSBlock + tid], z = spt[(s * 3 + 2) * kSBlock + tid];
+            float gx = 0.f, gy = 0.f, gz = 0.f;
+            if (h->nObj > 0) {
+                const float m = cv.pt_mobj[s];
+                c_obj = __fadd_rn(c_obj, object_point_term<WANT_GRAD, CLAMP>(cv, x, y, z, m, use_override ? margin_override : m, occ,
+                                                                             amrow, s, gx, gy, gz));
+            }
+            if (h->ws_enabled) {
+                const float m = cv.pt_mws[s];
+                c_ws = __fadd_rn(c_ws, ws_point_term<WANT_GRAD, CLAMP>(h, x, y, z, m, use_override ? margin_override : m, occ, gx, gy, gz));
+            }
+            if (WANT_GRAD) {
+                spt[(s * 3 + 0) * kSBlock + tid] = gx; spt[(s * 3 + 1) * kSBlock + tid] = gy; spt[(s * 3 + 2) * kSBlock + tid] = gz;
+            }
+        }
+        if (WANT_GRAD)
+            sfor<CM::S>([&](auto sc) {
+                constexpr int s = decltype(sc)::value, b = CM::pt_link[s];
+                sfor<3>([&](auto rc) { G[b][rc] += spt[(s * 3 + rc) * kSBlock + tid]; });
+            });
+        terms[0] = c_self; terms[1] = c_obj; terms[2] = c_ws;
+        if (cost_total) cost_total[cfg] = weighted_total(h, terms);
+        if (cost_terms) reinterpret_cast<float4*>(cost_terms)[cfg] = make_float4(terms[0], terms[1], terms[2], terms[3]);
+        if (occupancy) occupancy[cfg] = (uint8_t)occ;
+        if (WANT_GRAD) {
+            float* grow = grad_q + cfg * D;
+            STree<R>::backward(JA, [&](auto bc, float (&f)[3], float (&t)[3], float (&pos)[3]) {
+                constexpr int b = decltype(bc)::value;
+                sfor<3>([&](auto rc) { pos[rc] = P[b][rc]; });
+                if constexpr (CMInfo<CM, L>::touched(b)) {
+                    sfor<3>([&](auto rc) { f[rc] = G[b][rc]; });
+                    t[0] = pos[1] * f[2] - pos[2] * f[1];
+                    t[1] = pos[2] * f[0] - pos[0] * f[2];
+                    t[2] = pos[0] * f[1] - pos[1] * f[0];
+                } else {
+                    sfor<3>([&](auto rc) { f[rc] = 0.f; t[rc] = 0.f; });
+                }
+                if (b == e) sfor<3>([&](auto rc) { f[rc] += eF[rc]; t[rc] += eT[rc]; });
+            }, pass, [&](int c, float g) { grow[c] = g; });
+        }
+    }
+}
+
+// which compile-time collision model (if any) belongs to a compiled-in robot
+template <class R> struct CollisionModelOf { using type = void; };
+template <> struct CollisionModelOf<robots::Panda> { using type = robots::PandaCollision; };
+
+// does a runtime cost table list exactly CM's points and pairs?
+template <class CM>
+inline bool cost_matches_cm(const float* cost_words) {
+    const CostHeader* h = reinterpret_cast<const CostHeader*>(cost_words);
+    const int* iw = reinterpret_cast<const int*>(cost_words);
+    if (h->S != CM::S || h->P != CM::P) return false;
+    for (int s = 0; s < CM::S; ++s) if (iw[h->off_pt_link + s] != CM::pt_link[s]) return false;
+    for (int p = 0; p < CM::P; ++p)
+        if (iw[h->off_pair_i + p] != CM::pair_i[p] || iw[h->off_pair_j + p] != CM::pair_j[p]) return false;
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -481,13 +640,31 @@ inline cudaError_t launch_objective_k(int n_sms, const float* cost_words, int co
     return cudaGetLastError();
 }
 
+template <class R, class CM, bool WANT_GRAD, bool CLAMP>
+inline cudaError_t launch_objective_cm_k(int n_sms, const float* cost_words, int cost_nwords, const float* q, long long n,
+                                         const float* ee_target_cfg, float margin_override, int use_override, float* cost_total,
+                                         float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin, cudaStream_t st) {
+    const size_t smem = ((size_t)cost_nwords + (size_t)3 * CM::S * kSBlock) * sizeof(float);
+    auto k = k_objective_cm<R, CM, WANT_GRAD, CLAMP>;
+    k<<<persistent_grid(k, n_sms, smem, n), kSBlock, smem, st>>>(cost_words, cost_nwords, q, n, ee_target_cfg, margin_override,
+                                                                 use_override, cost_total, cost_terms, grad_q, occupancy, argmin);
+    return cudaGetLastError();
+}
+
 template <class R>
-inline cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwords, int clamp_any, const float* q,
+inline cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwords, int clamp_any, int cm_match, const float* q,
                                       long long n, const float* ee_target_cfg, float margin_override, int use_override,
                                       float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin,
                                       cudaStream_t st) {
 #define TRK_OBJ_ARGS n_sms, cost_words, cost_nwords, q, n, ee_target_cfg, margin_override, use_override, cost_total, cost_terms, \
                      grad_q, occupancy, argmin, st
+    using CM = typename CollisionModelOf<R>::type;
+    if constexpr (!std::is_void<CM>::value) {
+        if (cm_match) {
+            if (grad_q) return clamp_any ? launch_objective_cm_k<R, CM, true, true>(TRK_OBJ_ARGS) : launch_objective_cm_k<R, CM, true, false>(TRK_OBJ_ARGS);
+            return clamp_any ? launch_objective_cm_k<R, CM, false, true>(TRK_OBJ_ARGS) : launch_objective_cm_k<R, CM, false, false>(TRK_OBJ_ARGS);
+        }
+    }
     if (grad_q) return clamp_any ? launch_objective_k<R, true, true>(TRK_OBJ_ARGS) : launch_objective_k<R, true, false>(TRK_OBJ_ARGS);
     return clamp_any ? launch_objective_k<R, false, true>(TRK_OBJ_ARGS) : launch_objective_k<R, false, false>(TRK_OBJ_ARGS);
 #undef TRK_OBJ_ARGS
@@ -515,7 +692,22 @@ inline cudaError_t launch_static_fk_backward(int family, int n_sms, const float*
     return cudaErrorInvalidValue;
 }
 
-inline cudaError_t launch_static_objective(int family, int n_sms, const float* cost_words, int cost_nwords, int clamp_any,
+// 1 when `family` has a compile-time collision model and the (host copy of the) cost table matches it
+inline int static_cm_match(int family, const float* host_cost_words) {
+    int id = 0;
+#define X(Rb)                                                                          \
+    ++id;                                                                              \
+    if (family == id) {                                                                \
+        using CM = typename CollisionModelOf<Rb>::type;                                \
+        if constexpr (!std::is_void<CM>::value) return cost_matches_cm<CM>(host_cost_words) ? 1 : 0; \
+        return 0;                                                                      \
+    }
+    TRK_FOR_EACH_STATIC_ROBOT(X)
+#undef X
+    return 0;
+}
+
+inline cudaError_t launch_static_objective(int family, int n_sms, const float* cost_words, int cost_nwords, int clamp_any, int cm_match,
                                            const float* q, long long n, const float* ee_target_cfg, float margin_override, int use_override,
                                            float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin,
                                            cudaStream_t st) {
@@ -523,7 +715,7 @@ inline cudaError_t launch_static_objective(int family, int n_sms, const float* c
 #define X(Rb) \
     ++id;     \
     if (family == id)  \
-        return launch_objective_t<Rb>(n_sms, cost_words, cost_nwords, clamp_any, q, n, ee_target_cfg, margin_override, use_override, \
+        return launch_objective_t<Rb>(n_sms, cost_words, cost_nwords, clamp_any, cm_match, q, n, ee_target_cfg, margin_override, use_override, \
                                       cost_total, cost_terms, grad_q, occupancy, argmin, st);
     TRK_FOR_EACH_STATIC_ROBOT(X)
 #undef X
