@@ -183,6 +183,40 @@ int trk_cost_stage(const trk_model* model, const trk_cost* cost, const float* li
                    uint8_t* occupancy, int32_t* argmin, void* stream);
 
 /*
+ * Fused batched Adam inverse kinematics: DifferentiableTree.inverse_kinematics (robot_tree.py:303-384) with
+ * loss_fn_ik_per_q (:386-417) and ik_termination (:419-442) evaluated inside one kernel; q and the Adam
+ * moments stay in registers for all iterations.  Iteration `it` (0-based) first tests termination on the
+ * current q, then - if it < n_updates - applies one torch.optim.Adam step (default betas/eps semantics).
+ * Calling with n_iters = n_updates = max_iters reproduces the reference loop that never breaks early; the
+ * per-iteration count of valid seeds lets the host detect the iteration at which every seed was valid
+ * (robot_tree.py:356) and re-run with n_iters = it + 1, n_updates = it.
+ *   step_size [n_iters]  device fp32: lr / (1 - beta1^(it+1))
+ *   bc2_sqrt  [n_iters]  device fp32: sqrt(1 - beta2^(it+1))
+ *   target_seed [n, 4, 4] device fp32 per-seed targets, or NULL to use params->H_target
+ *   q_io      [n, D]     device fp32: seeds in, solutions out
+ *   err_out   [n]        SE3_distance at the last termination test            (nullable)
+ *   valid_out [n] uint8  result of the last termination test                  (nullable)
+ *   valid_count [n_iters] device int32: seeds passing the test at each iteration (zeroed by the call)
+ *   loss_sum / loss_sqsum [n_iters] device fp32 sums of the loss and its square (nullable, zeroed by the call)
+ * Returns TRK_E_UNSUPPORTED for models served by the runtime-tree family (callers then run the
+ * iteration loop over trk_fk_forward / trk_fk_backward, still on the GPU).
+ */
+typedef struct trk_ik_params {
+    int32_t      ee_link;          /* body whose pose is driven to the target */
+    int32_t      n_iters;          /* termination tests performed */
+    int32_t      n_updates;        /* Adam steps performed (<= n_iters) */
+    float        lr, beta1, beta2, eps;
+    float        w_se3, w_joint_limits, se3_eps;
+    const float* lower;            /* HOST [D] limits used by the loss / termination test */
+    const float* upper;            /* HOST [D] */
+    const float* H_target;         /* HOST 16 floats (row-major 4x4), may be NULL when target_seed is given */
+} trk_ik_params;
+
+int trk_ik_adam(const trk_model* model, const trk_ik_params* params, const float* step_size, const float* bc2_sqrt,
+                const float* target_seed, int64_t n, float* q_io, float* err_out, uint8_t* valid_out,
+                int32_t* valid_count, float* loss_sum, float* loss_sqsum, void* stream);
+
+/*
  * Self-test of the branch-free correctly-rounded square root used for every distance that feeds a
  * comparison (trk_device.cuh: sqrt_rn_core): y_core[i] from that routine, y_ref[i] from sqrt.rn.f32.
  * The two must be bit-identical for x == 0 and 2^-100 <= x < 2^126.  All pointers are device memory.

@@ -153,6 +153,44 @@ def test_inverse_kinematics_matches_reference_iterates():
             assert np.array_equal(idx.cpu().numpy(), g[f"idx_valid_{iters}"])
 
 
+def test_fused_ik_kernel_vs_oracle_and_torch_loop():
+    """trk_ik_adam (one kernel, state in registers) against the numpy restatement of the reference loop and
+    against the same loop run with torch.optim.Adam over the FK autograd.Function."""
+    from conftest import get_desc
+    from oracle import restatement as orc
+    from torch_robotics_b200._lib import DeviceModel
+    from torch_robotics_b200.torch_kinematics_tree.models.robots import DifferentiableFrankaPanda
+    g, d = load_golden("ik_panda"), get_desc("panda")
+    m = DeviceModel(d, DEV)
+    rng = np.random.default_rng(3)
+    S = 4096
+    q0 = (g["lower"] + rng.random((S, 7)) * (g["upper"] - g["lower"])).astype(np.float32)
+    q0[:64] += 0.2                                                     # some seeds start outside the limits
+    for iters in (1, 3, 10):
+        r = m.ik_adam(t(q0), g["H_target"], 10, g["lower"], g["upper"], n_iters=iters, lr=0.2, se3_eps=0.05)
+        qo, idxo = orc.ik_adam(d, 10, q0, g["H_target"], g["lower"], g["upper"], iters, 0.2, 0.05)
+        # Adam normalises by sqrt(v): fp32 differences grow with the iteration count, so bound the bulk
+        # tightly and the worst seed loosely
+        diff = np.abs(r["q"].cpu().numpy() - qo).max(axis=1)
+        assert np.quantile(diff, 0.99) < 2e-4 * iters and diff.max() < 2e-3 * iters
+        idx = torch.nonzero(r["valid"]).reshape(-1).cpu().numpy()
+        assert len(np.setxor1d(idx, idxo)) <= 2
+    # per-iteration valid counts and the "all valid" early stop: a batch made of one converged seed
+    panda = DifferentiableFrankaPanda(device=DEV)
+    Ht = t(g["H_target"])
+    q_ref, idx_ref = panda.inverse_kinematics(Ht, batch_size=24, max_iters=40, lr=0.2, se3_eps=5e-2, q0=t(g["q0"]).clone(),
+                                              q0_noise=0.0, eps_joint_lim=torch.pi / 64, print_freq=-1, debug=True)   # torch loop
+    q_fus, idx_fus = panda.inverse_kinematics(Ht, batch_size=24, max_iters=40, lr=0.2, se3_eps=5e-2, q0=t(g["q0"]).clone(),
+                                              q0_noise=0.0, eps_joint_lim=torch.pi / 64, print_freq=-1)              # fused kernel
+    assert q_fus.requires_grad and idx_fus.dtype == torch.int64
+    assert rel_err(q_fus.detach().cpu().numpy(), q_ref.detach().cpu().numpy()) < 5e-3
+    good = q_fus.detach()[idx_fus][:1]
+    if good.shape[0] == 1:
+        qs, idxs = panda.inverse_kinematics(Ht, batch_size=1, max_iters=50, lr=0.2, se3_eps=5e-2, q0=good.clone(), q0_noise=0.0,
+                                            eps_joint_lim=torch.pi / 64, print_freq=-1)
+        assert torch.equal(qs.detach(), torch.clamp(good, t(g["lower"]), t(g["upper"]))) and idxs.numel() == 1    # stopped at iteration 0
+
+
 def test_host_pipeline_matches_device_call(planning):
     from torch_robotics_b200.host_pipeline import HostObjectivePipeline
     robot, env, task = planning

@@ -41,13 +41,20 @@ class CostDesc(C.Structure):
                 ("clamp_self", C.c_int32), ("clamp_obj", C.c_int32), ("clamp_ws", C.c_int32), ("weights", C.c_float * 4)]
 
 
+class IKParamsC(C.Structure):
+    _fields_ = [("ee_link", C.c_int32), ("n_iters", C.c_int32), ("n_updates", C.c_int32),
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("w_se3", C.c_float), ("w_joint_limits", C.c_float), ("se3_eps", C.c_float),
+                ("lower", c_float_p), ("upper", c_float_p), ("H_target", c_float_p)]
+
+
 _lib = None
 _lib_lock = threading.Lock()
 
 EXPORTS = [
     "trk_abi_version", "trk_last_error", "trk_model_create", "trk_model_destroy", "trk_model_kernel_family",
     "trk_fk_forward", "trk_fk_backward", "trk_cost_create", "trk_cost_destroy", "trk_cost_set_ee_target",
-    "trk_cost_set_weights", "trk_objective", "trk_cost_stage", "trk_selftest_sqrt",
+    "trk_cost_set_weights", "trk_objective", "trk_cost_stage", "trk_selftest_sqrt", "trk_ik_adam",
 ]
 
 
@@ -82,6 +89,7 @@ def lib() -> C.CDLL:
         L.trk_objective.argtypes = [vp, vp, vp, i64, vp, f32, vp, vp, vp, vp, vp, vp]
         L.trk_cost_stage.argtypes = [vp, vp, vp, vp, i64, vp, f32, vp, vp, vp, vp, vp, vp, vp]
         L.trk_selftest_sqrt.argtypes = [vp, i64, vp, vp, vp]
+        L.trk_ik_adam.argtypes = [vp, C.POINTER(IKParamsC), vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
         for name in EXPORTS:
             fn = getattr(L, name)
             if fn.restype is C.c_int and name not in ("trk_abi_version",):
@@ -193,6 +201,46 @@ class DeviceModel:
         check(lib().trk_fk_backward(self.handle, q.data_ptr(), q.shape[0], p, n_sel, G.data_ptr(), grad.data_ptr(),
                                     stream_ptr(q.device)), "trk_fk_backward")
         return grad
+
+
+    def ik_adam(self, q0: torch.Tensor, H_target, ee_link: int, lower, upper, n_iters: int, n_updates: Optional[int] = None,
+                lr=1e-2, betas=(0.9, 0.999), eps=1e-8, w_se3=1.0, w_joint_limits=300.0, se3_eps=1e-1, want_loss_stats=False):
+        """Fused Adam IK (trk_ik_adam).  q0 [S, D] is not modified.  Returns dict(q, err, valid (bool), valid_count
+        [n_iters] int32, loss_sum / loss_sqsum [n_iters] or None).  Raises NotImplementedError for models without a
+        compiled-in kernel family (callers then iterate over fk / fk_backward)."""
+        if self.kernel_family == "generic":
+            raise NotImplementedError("fused IK is available for compiled-in robots only")
+        q = require_cuda_f32(q0, "q0").clone()
+        S, D = q.shape
+        dev = q.device
+        n_updates = n_iters if n_updates is None else n_updates
+        t = np.arange(1, n_iters + 1, dtype=np.float64)
+        step_size = torch.as_tensor((lr / (1.0 - betas[0] ** t)).astype(np.float32), device=dev)
+        bc2 = torch.as_tensor(np.sqrt(1.0 - betas[1] ** t).astype(np.float32), device=dev)
+        lo = _c32(lower.detach().cpu().numpy() if torch.is_tensor(lower) else lower, np.float32).reshape(-1)
+        hi = _c32(upper.detach().cpu().numpy() if torch.is_tensor(upper) else upper, np.float32).reshape(-1)
+        if lo.shape[0] != D or hi.shape[0] != D:
+            raise RuntimeError(f"lower/upper must have {D} entries")
+        tgt_seed, tgt_host = None, None
+        Ht = H_target.detach() if torch.is_tensor(H_target) else torch.as_tensor(np.asarray(H_target, np.float32))
+        Ht = Ht.reshape(-1, 4, 4)
+        if Ht.shape[0] == 1:
+            tgt_host = _c32(Ht[0].cpu().numpy(), np.float32).reshape(16)
+        elif Ht.shape[0] == S:
+            tgt_seed = require_cuda_f32(Ht.to(dev), "H_target")
+        else:
+            raise RuntimeError("H_target must be [4,4], [1,4,4] or [S,4,4]")
+        p = IKParamsC(int(ee_link), int(n_iters), int(n_updates), float(lr), float(betas[0]), float(betas[1]), float(eps),
+                      float(w_se3), float(w_joint_limits), float(se3_eps), _fp(lo), _fp(hi), None if tgt_host is None else _fp(tgt_host))
+        err = torch.empty(S, dtype=torch.float32, device=dev)
+        valid = torch.empty(S, dtype=torch.uint8, device=dev)
+        count = torch.empty(n_iters, dtype=torch.int32, device=dev)
+        ls = torch.empty(n_iters, dtype=torch.float32, device=dev) if want_loss_stats else None
+        lq = torch.empty(n_iters, dtype=torch.float32, device=dev) if want_loss_stats else None
+        ptr = lambda x: None if x is None else x.data_ptr()
+        check(lib().trk_ik_adam(self.handle, C.byref(p), step_size.data_ptr(), bc2.data_ptr(), ptr(tgt_seed), S, q.data_ptr(),
+                                err.data_ptr(), valid.data_ptr(), count.data_ptr(), ptr(ls), ptr(lq), stream_ptr(dev)), "trk_ik_adam")
+        return dict(q=q, err=err, valid=valid.bool(), valid_count=count, loss_sum=ls, loss_sqsum=lq)
 
 
 class DeviceCost:

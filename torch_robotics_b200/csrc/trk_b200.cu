@@ -651,6 +651,38 @@ int trk_objective(const trk_model* m, const trk_cost* c, const float* q, int64_t
     return e == cudaSuccess ? TRK_OK : cuda_fail(e, "objective launch");
 }
 
+int trk_ik_adam(const trk_model* m, const trk_ik_params* p, const float* step_size, const float* bc2_sqrt,
+                const float* target_seed, int64_t n, float* q_io, float* err_out, uint8_t* valid_out, int32_t* valid_count,
+                float* loss_sum, float* loss_sqsum, void* stream) {
+    TRK_CHECK_PTR(m, "model"); TRK_CHECK_PTR(p, "params");
+    if (!m->family) return fail(TRK_E_UNSUPPORTED, "fused IK needs a compiled-in robot (model is served by the runtime-tree family)");
+    if (n < 0) return fail(TRK_E_RANGE, "n=%lld", (long long)n);
+    if (p->n_iters < 1 || p->n_updates < 0 || p->n_updates > p->n_iters) return fail(TRK_E_RANGE, "n_iters=%d n_updates=%d", p->n_iters, p->n_updates);
+    if (p->ee_link < 0 || p->ee_link >= m->L) return fail(TRK_E_RANGE, "ee_link=%d", p->ee_link);
+    TRK_CHECK_PTR(p->lower, "lower"); TRK_CHECK_PTR(p->upper, "upper");
+    if (!target_seed) TRK_CHECK_PTR(p->H_target, "H_target");
+    TRK_CHECK_PTR(step_size, "step_size"); TRK_CHECK_PTR(bc2_sqrt, "bc2_sqrt"); TRK_CHECK_PTR(valid_count, "valid_count");
+    if (n == 0) return TRK_OK;
+    TRK_CHECK_PTR(q_io, "q_io");
+    IKParams P;
+    memset(&P, 0, sizeof(P));
+    P.ee_link = p->ee_link; P.n_iters = p->n_iters; P.n_updates = p->n_updates; P.per_seed_target = target_seed ? 1 : 0;
+    P.lr = p->lr; P.beta1 = p->beta1; P.beta2 = p->beta2; P.eps = p->eps;
+    P.w_se3 = p->w_se3; P.w_lim = p->w_joint_limits; P.se3_eps = p->se3_eps;
+    for (int c = 0; c < m->D; ++c) { P.lower[c] = p->lower[c]; P.upper[c] = p->upper[c]; }
+    if (p->H_target) memcpy(P.target, p->H_target, sizeof(P.target));
+    DeviceGuard guard(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(valid_count, 0, sizeof(int32_t) * p->n_iters, st);
+    if (e == cudaSuccess && loss_sum) e = cudaMemsetAsync(loss_sum, 0, sizeof(float) * p->n_iters, st);
+    if (e == cudaSuccess && loss_sqsum) e = cudaMemsetAsync(loss_sqsum, 0, sizeof(float) * p->n_iters, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(ik statistics)");
+    if (loss_sum && !loss_sqsum) return fail(TRK_E_NULL, "loss_sqsum is required with loss_sum");
+    e = trk::launch_static_ik(m->family, P, step_size, bc2_sqrt, target_seed, n, q_io, err_out, valid_out, valid_count, loss_sum,
+                              loss_sqsum, st);
+    return e == cudaSuccess ? TRK_OK : cuda_fail(e, "ik_adam launch");
+}
+
 int trk_selftest_sqrt(const float* x, int64_t n, float* y_core, float* y_ref, void* stream) {
     if (n <= 0) return TRK_OK;
     TRK_CHECK_PTR(x, "x"); TRK_CHECK_PTR(y_core, "y_core"); TRK_CHECK_PTR(y_ref, "y_ref");

@@ -59,6 +59,12 @@ template <class R>
 struct STree {
     static constexpr int L = R::L, D = R::D;
 
+    // position of body b in the parents-first tables
+    __host__ __device__ static constexpr int topo_index_of(int b) {
+        for (int i = 0; i < L; ++i) if (R::body[i] == b) return i;
+        return 0;
+    }
+
     // child pose from parent pose: rigid_body.py:162-192 + geometrics/utils.py:11-17, link I of the tables
     template <int I>
     static __device__ __forceinline__ void compose(const float (&Wp)[12], float theta, float (&Wc)[12]) {
@@ -551,6 +557,146 @@ __global__ void __launch_bounds__(kSBlock, 4) k_objective_cm(const float* __rest
             }, pass, [&](int c, float g) { grow[c] = g; });
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused batched Adam inverse kinematics (DifferentiableTree.inverse_kinematics, robot_tree.py:303-442):
+// one thread owns one seed and keeps q, the Adam moments and the gradient in registers for all iterations.
+// Per iteration, exactly as the reference loop:
+//   1. termination test on the current q (ik_termination :419-442): inside [lower, upper] and
+//      SE3_distance(FK(q)[ee], H_target) < se3_eps;  the number of valid seeds is accumulated per iteration
+//      (one atomic per block) so the host can find the iteration at which every seed was valid (:356);
+//   2. loss = w_se3 * SE3_distance + w_lim * sum(limit violation^2) (loss_fn_ik_per_q :386-417), analytic gradient;
+//   3. torch.optim.Adam step (defaults: betas, eps; bias corrections passed in per iteration).
+// The reference evaluates FK twice per iteration on the same q; here it is evaluated once.
+// ------------------------------------------------------------------------------------------
+struct IKParams {
+    int   ee_link, n_iters, n_updates, per_seed_target;
+    float lr, beta1, beta2, eps, w_se3, w_lim, se3_eps, pad;
+    float lower[TRK_MAX_DOFS], upper[TRK_MAX_DOFS];
+    float target[16];
+};
+
+template <class R>
+__global__ void __launch_bounds__(kSBlock) k_ik_adam_static(IKParams P, const float* __restrict__ step_size, const float* __restrict__ bc2_sqrt,
+                                                            const float* __restrict__ target_seed, long long n_seeds,
+                                                            float* __restrict__ q_io, float* __restrict__ err_out,
+                                                            uint8_t* __restrict__ valid_out, int* __restrict__ valid_count,
+                                                            float* __restrict__ loss_sum, float* __restrict__ loss_sqsum) {
+    constexpr int L = R::L, D = R::D;
+    __shared__ int s_cnt;
+    __shared__ float s_sum, s_sq;
+    const long long seed = (long long)blockIdx.x * kSBlock + threadIdx.x;
+    const bool live = seed < n_seeds;
+    const int lane = threadIdx.x & 31;
+    float qv[D], mom[D], var[D];
+    sfor<D>([&](auto c) { qv[c] = live ? q_io[seed * D + c] : 0.f; mom[c] = 0.f; var[c] = 0.f; });
+    float Rt[9], pt[3];
+    {
+        const float* Ht = (P.per_seed_target && live) ? target_seed + seed * 16 : P.target;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            Rt[i * 3 + 0] = Ht[i * 4 + 0]; Rt[i * 3 + 1] = Ht[i * 4 + 1]; Rt[i * 3 + 2] = Ht[i * 4 + 2]; pt[i] = Ht[i * 4 + 3];
+        }
+    }
+    EEParams ee;
+    ee.ee_w_rot = 1.f; ee.ee_w_pos = 1.f; ee.ee_square = 0; ee.w[3] = P.w_se3;
+    float err = 0.f;
+    bool valid = false;
+#pragma unroll 1
+    for (int it = 0; it < P.n_iters; ++it) {
+        if (threadIdx.x == 0) { s_cnt = 0; s_sum = 0.f; s_sq = 0.f; }
+        __syncthreads();
+        float W[L][12], JA[D][3], Wee[12], PJ[D][3];
+        sfor<12>([&](auto k) { Wee[k] = 0.f; });
+        unsigned pass;
+        STree<R>::forward([&](int c) { return qv[c]; }, W, pass, [&](auto ic, const float (&wp)[12], const float (&w)[12]) {
+            constexpr int i = decltype(ic)::value, b = R::body[i];
+            constexpr int qi = R::qidx[i];
+            if constexpr (qi >= 0) {
+                STree<R>::template joint_axis<i>(wp, w, JA[qi]);
+                PJ[qi][0] = w[9]; PJ[qi][1] = w[10]; PJ[qi][2] = w[11];
+            }
+            if (b == P.ee_link) sfor<12>([&](auto kc) { Wee[kc] = w[kc]; });
+        });
+        float gR[9], gp[3];
+        err = ee_term<true>(&ee, Wee, &Wee[9], Rt, pt, gR, gp);       // SE3_distance, un-squared, weights 1
+        bool in_lim = true;
+        float e_lim = 0.f;
+        sfor<D>([&](auto c) {
+            const float lo = P.lower[c], hi = P.upper[c];
+            in_lim = in_lim && (qv[c] >= lo) && (qv[c] <= hi);
+            const float dl = lo - qv[c], dh = hi - qv[c];
+            e_lim += (qv[c] < lo ? dl * dl : 0.f) + (qv[c] > hi ? dh * dh : 0.f);
+        });
+        valid = in_lim && (err < P.se3_eps);
+        const float loss = P.w_se3 * err + P.w_lim * e_lim;
+        // per-iteration statistics: warp reduce, one shared atomic per warp, one global atomic per block
+        const unsigned ball = __ballot_sync(0xffffffffu, valid && live);
+        float ls = live ? loss : 0.f, lq = live ? loss * loss : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { ls += __shfl_xor_sync(0xffffffffu, ls, o); lq += __shfl_xor_sync(0xffffffffu, lq, o); }
+        if (lane == 0) { atomicAdd(&s_cnt, __popc(ball)); atomicAdd(&s_sum, ls); atomicAdd(&s_sq, lq); }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicAdd(valid_count + it, s_cnt);
+            if (loss_sum) { atomicAdd(loss_sum + it, s_sum); atomicAdd(loss_sqsum + it, s_sq); }
+        }
+        if (it >= P.n_updates) continue;
+        // gradient of the loss: EE wrench applied at the EE body, projected on the joints above it.  The
+        // wrench enters every joint's subtree sum only if the joint is an ancestor of the EE body, which
+        // the leaf->root sweep of STree::backward handles through the body index.
+        float ax, ay, az;
+        axial_gR_Rt(gR, Wee, ax, ay, az);
+        const float eF[3] = {gp[0], gp[1], gp[2]};
+        const float eT[3] = {Wee[10] * gp[2] - Wee[11] * gp[1] + ax, Wee[11] * gp[0] - Wee[9] * gp[2] + ay,
+                             Wee[9] * gp[1] - Wee[10] * gp[0] + az};
+        float grad[D];
+        STree<R>::backward(JA, [&](auto bc, float (&f)[3], float (&t)[3], float (&pos)[3]) {
+            constexpr int b = decltype(bc)::value;
+            constexpr int qb = R::qidx[STree<R>::topo_index_of(b)];
+            if constexpr (qb >= 0) { sfor<3>([&](auto rc) { pos[rc] = PJ[qb][rc]; }); } else { sfor<3>([&](auto rc) { pos[rc] = 0.f; }); }
+            const bool is_e = (b == P.ee_link);
+            sfor<3>([&](auto rc) { f[rc] = is_e ? eF[rc] : 0.f; t[rc] = is_e ? eT[rc] : 0.f; });
+        }, pass, [&](int c, float g) { grad[c] = g; });
+        const float ss = step_size[it], b2s = bc2_sqrt[it];
+        sfor<D>([&](auto c) {
+            const float lo = P.lower[c], hi = P.upper[c];
+            float g = grad[c];
+            g += P.w_lim * ((qv[c] < lo ? -2.f * (lo - qv[c]) : 0.f) + (qv[c] > hi ? -2.f * (hi - qv[c]) : 0.f));
+            mom[c] = fmaf(1.f - P.beta1, g - mom[c], mom[c]);                 // exp_avg.lerp_(grad, 1 - beta1)
+            var[c] = fmaf((1.f - P.beta2) * g, g, var[c] * P.beta2);          // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+            const float denom = sqrtf(var[c]) / b2s + P.eps;
+            qv[c] = qv[c] - ss * (mom[c] / denom);                            // param.addcdiv_(exp_avg, denom, -step_size)
+        });
+    }
+    if (live) {
+        sfor<D>([&](auto c) { q_io[seed * D + c] = qv[c]; });
+        if (err_out) err_out[seed] = err;
+        if (valid_out) valid_out[seed] = valid ? 1 : 0;
+    }
+}
+
+template <class R>
+inline cudaError_t launch_ik_t(const IKParams& P, const float* step_size, const float* bc2_sqrt, const float* target_seed,
+                               long long n_seeds, float* q_io, float* err_out, uint8_t* valid_out, int* valid_count,
+                               float* loss_sum, float* loss_sqsum, cudaStream_t st) {
+    const long long blocks = (n_seeds + kSBlock - 1) / kSBlock;
+    k_ik_adam_static<R><<<(unsigned)blocks, kSBlock, 0, st>>>(P, step_size, bc2_sqrt, target_seed, n_seeds, q_io, err_out, valid_out,
+                                                             valid_count, loss_sum, loss_sqsum);
+    return cudaGetLastError();
+}
+
+inline cudaError_t launch_static_ik(int family, const IKParams& P, const float* step_size, const float* bc2_sqrt,
+                                    const float* target_seed, long long n_seeds, float* q_io, float* err_out, uint8_t* valid_out,
+                                    int* valid_count, float* loss_sum, float* loss_sqsum, cudaStream_t st) {
+    int id = 0;
+#define X(Rb) \
+    ++id;     \
+    if (family == id) return launch_ik_t<Rb>(P, step_size, bc2_sqrt, target_seed, n_seeds, q_io, err_out, valid_out, valid_count, loss_sum, loss_sqsum, st);
+    TRK_FOR_EACH_STATIC_ROBOT(X)
+#undef X
+    return cudaErrorInvalidValue;
 }
 
 // which compile-time collision model (if any) belongs to a compiled-in robot

@@ -131,6 +131,10 @@ class DifferentiableTree(torch.nn.Module):
             q0 = q0 + torch.randn(batch_size, self._n_dofs, device=device) * q0_noise
             q0 = torch.clamp(q0, lower, upper)
             assert q0.shape == (batch_size, self._n_dofs)
+        model = self.device_model(device)
+        if model.kernel_family != "generic" and not debug and max_iters >= 1:
+            return self._inverse_kinematics_fused(model, q0, H_target, link_name, batch_size, max_iters, lr, se3_eps,
+                                                  lower, upper, print_freq)
         q = q0.clone().requires_grad_(True)
         optimizer = torch.optim.Adam([q], lr=lr)
         idx_valid = torch.empty(0, dtype=torch.int64, device=device)
@@ -155,6 +159,39 @@ class DifferentiableTree(torch.nn.Module):
                 print("\nIK did not converge for all joint configurations!")
                 print(f"idx_valid: {len(idx_valid)}/{batch_size}")
         return q, idx_valid
+
+    def _inverse_kinematics_fused(self, model, q0, H_target, link_name, batch_size, max_iters, lr, se3_eps, lower, upper,
+                                  print_freq):
+        """The same loop inside one kernel (trk_ik_adam): q and the Adam moments stay in registers; the host
+        reads back one per-iteration valid-seed count at the end instead of synchronising every iteration."""
+        ee = self._name_to_idx_map[link_name]
+        kw = dict(lr=lr, se3_eps=se3_eps, w_se3=1.0, w_joint_limits=300.0)
+        want_stats = print_freq != -1
+        r = model.ik_adam(q0, H_target, ee, lower, upper, n_iters=max_iters, want_loss_stats=want_stats, **kw)
+        count = r["valid_count"].cpu()
+        hit = torch.nonzero(count == batch_size)
+        n_done = max_iters
+        if hit.numel() > 0:          # every seed was valid at iteration `it`: the reference stops before updating
+            n_done = int(hit[0])
+            r2 = model.ik_adam(q0, H_target, ee, lower, upper, n_iters=n_done + 1, n_updates=n_done, **kw)
+            r2["loss_sum"], r2["loss_sqsum"] = r["loss_sum"], r["loss_sqsum"]
+            r = r2
+        if want_stats:
+            ls, lq = r["loss_sum"].double().cpu(), r["loss_sqsum"].double().cpu()
+            for i in range(min(n_done, max_iters)):
+                if i == 0 or (i % print_freq) == 0:
+                    mean = ls[i] / batch_size
+                    std = ((lq[i] - batch_size * mean * mean).clamp_min(0) / max(batch_size - 1, 1)).sqrt()
+                    print(f"\n---> Iter {i}/{max_iters}")
+                    print(f"Error mean, std: {mean:.3f}, {std:.3f}")
+                    print(f"idx_valid: {int(count[i])}/{batch_size}")
+            if hit.numel() > 0:
+                print(f"\nIK converged for all joint configurations in {n_done} iterations")
+            else:
+                print("\nIK did not converge for all joint configurations!")
+                print(f"idx_valid: {int(count[max_iters - 1])}/{batch_size}")
+        idx_valid = torch.nonzero(r["valid"]).reshape(-1)
+        return r["q"].requires_grad_(True), idx_valid
 
     def loss_fn_ik_per_q(self, q, H_target, link_name, w_se3=1.0, w_joint_limits=1.0, lower=None, upper=None,
                          w_q_rest=1.0, q_rest=None, debug=False):
