@@ -251,6 +251,24 @@ __device__ __forceinline__ void warp_load_link(float4* stage, int lane, long lon
 #endif
 constexpr int kSBlock = TRK_SBLOCK;
 
+// asynchronous global->shared prefetch of one link's 32 upstream-gradient matrices (16 B per lane x 4)
+__device__ __forceinline__ void warp_prefetch_link(float4* stage, int lane, long long warp_cfg0, long long n, int n_sel, int s,
+                                                   const float* __restrict__ G) {
+    const int r = lane & 3;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int c = (lane >> 2) + 8 * it;
+        const long long g = warp_cfg0 + c;
+        const float4* src = reinterpret_cast<const float4*>(G) + (((g < n ? g : n - 1) * n_sel + s) * 4 + r);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(stage + stage_idx(c, r));
+        const int bytes = (g < n) ? 16 : 0;   // out-of-range rows are zero-filled
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------
@@ -261,14 +279,27 @@ __global__ void __launch_bounds__(kSBlock) k_fk_forward_static(const float* __re
     float4* stage = stage_all + (threadIdx.x >> 5) * 128;
     const int lane = threadIdx.x & 31;
     constexpr int L = R::L, D = R::D;
-    for (long long base = (long long)blockIdx.x * kSBlock; base < n; base += (long long)gridDim.x * kSBlock) {
+    const long long stride = (long long)gridDim.x * kSBlock;
+    long long base = (long long)blockIdx.x * kSBlock;
+    float qn[D > 0 ? D : 1];   // joint values of the NEXT tile, loaded while the current one is computed
+    {
         const long long cfg = base + threadIdx.x;
-        const long long warp_cfg0 = base + (threadIdx.x & ~31);
-        if (warp_cfg0 >= n) continue;
         const float* qrow = q + (cfg < n ? cfg : n - 1) * D;
+        sfor<D>([&](auto c) { qn[c] = (base < n) ? __ldg(qrow + c) : 0.f; });
+    }
+    for (; base < n; base += stride) {
+        const long long warp_cfg0 = base + (threadIdx.x & ~31);
+        float qc[D > 0 ? D : 1];
+        sfor<D>([&](auto c) { qc[c] = qn[c]; });
+        {
+            const long long nb = base + stride, cfg = nb + threadIdx.x;
+            const float* qrow = q + (cfg < n ? cfg : n - 1) * D;
+            if (nb < n) sfor<D>([&](auto c) { qn[c] = __ldg(qrow + c); });
+        }
+        if (warp_cfg0 >= n) continue;   // warp-uniform
         float W[L][12];
         unsigned pass;
-        STree<R>::forward([&](int c) { return __ldg(qrow + c); }, W, pass, [&](auto ic, const float (&)[12], const float (&w)[12]) {
+        STree<R>::forward([&](int c) { return qc[c]; }, W, pass, [&](auto ic, const float (&)[12], const float (&w)[12]) {
             constexpr int b = R::body[decltype(ic)::value];
             const int s = slots.slot[b];
             if (s >= 0)
@@ -278,11 +309,78 @@ __global__ void __launch_bounds__(kSBlock) k_fk_forward_static(const float* __re
     }
 }
 
+// FK forward, all links in body order (the default selection): each lane assembles its configuration's
+// link matrices in its own (padded, conflict-free) shared-memory row and hands the row to the TMA engine
+// with one bulk store (cp.async.bulk.global.shared::cta) per chunk of links.  A configuration's L x 64 B are
+// contiguous in H, so the bulk stores write whole lines and the SM issues ~L x 4 shared stores instead of
+// L x 12 staged load/store instructions.  Requires the parents-first order to be the body order.
+template <class R>
+struct FkTma {
+    static constexpr int L = R::L;
+    static constexpr int kChunk = L < 11 ? L : 11;                  // links per bulk store
+    static constexpr int kRowBytes = kChunk * 64 + 16;              // +16: rows land on distinct bank groups
+    static constexpr int kWarpBytes = 32 * kRowBytes;
+    static constexpr size_t smem_bytes = (size_t)(kSBlock / 32) * kWarpBytes;
+    __host__ __device__ static constexpr bool body_order() {
+        for (int i = 0; i < L; ++i) if (R::body[i] != i) return false;
+        return true;
+    }
+};
+
+template <class R>
+__global__ void __launch_bounds__(kSBlock) k_fk_forward_static_tma(const float* __restrict__ q, long long n, float* __restrict__ H) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using T = FkTma<R>;
+    constexpr int L = R::L, D = R::D, kChunk = T::kChunk;
+    const int lane = threadIdx.x & 31;
+    float4* row = reinterpret_cast<float4*>(smem_raw + (threadIdx.x >> 5) * T::kWarpBytes + lane * T::kRowBytes);
+    const unsigned row_s = (unsigned)__cvta_generic_to_shared(row);
+    const long long stride = (long long)gridDim.x * kSBlock;
+    long long base = (long long)blockIdx.x * kSBlock;
+    float qn[D > 0 ? D : 1];
+    {
+        const long long cfg = base + threadIdx.x;
+        const float* qrow = q + (cfg < n ? cfg : n - 1) * D;
+        sfor<D>([&](auto c) { qn[c] = (base < n) ? __ldg(qrow + c) : 0.f; });
+    }
+    for (; base < n; base += stride) {
+        const long long cfg = base + threadIdx.x;
+        float qc[D > 0 ? D : 1];
+        sfor<D>([&](auto c) { qc[c] = qn[c]; });
+        {
+            const long long nb = base + stride, ncfg = nb + threadIdx.x;
+            const float* qrow = q + (ncfg < n ? ncfg : n - 1) * D;
+            if (nb < n) sfor<D>([&](auto c) { qn[c] = __ldg(qrow + c); });
+        }
+        if (cfg >= n) continue;
+        float W[L][12];
+        unsigned pass;
+        STree<R>::forward([&](int c) { return qc[c]; }, W, pass, [&](auto ic, const float (&)[12], const float (&w)[12]) {
+            constexpr int i = decltype(ic)::value, j = i % kChunk, c0 = i - j;
+            if constexpr (j == 0)   // the previous bulk store must have finished READING this row
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            row[j * 4 + 0] = make_float4(w[0], w[1], w[2], w[9]);
+            row[j * 4 + 1] = make_float4(w[3], w[4], w[5], w[10]);
+            row[j * 4 + 2] = make_float4(w[6], w[7], w[8], w[11]);
+            row[j * 4 + 3] = make_float4(0.f, 0.f, 0.f, 1.f);
+            if constexpr (j == kChunk - 1 || i == L - 1) {
+                constexpr int bytes = (j + 1) * 64;
+                float* dst = H + (cfg * L + c0) * 16;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(row_s), "n"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        });
+    }
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 template <class R>
 __global__ void __launch_bounds__(kSBlock) k_fk_backward_static(const float* __restrict__ q, long long n, SlotMap slots, int n_sel,
                                                                 const float* __restrict__ G, float* __restrict__ grad_q) {
-    __shared__ __align__(16) float4 stage_all[(kSBlock / 32) * 128];
-    float4* stage = stage_all + (threadIdx.x >> 5) * 128;
+    // two 2-KB stages per warp: the next link's gradient tile streams in (cp.async) while the current one is consumed
+    __shared__ __align__(16) float4 stage_all[(kSBlock / 32) * 256];
+    float4* stage = stage_all + (threadIdx.x >> 5) * 256;
     const int lane = threadIdx.x & 31;
     constexpr int L = R::L, D = R::D;
     for (long long base = (long long)blockIdx.x * kSBlock; base < n; base += (long long)gridDim.x * kSBlock) {
@@ -290,19 +388,34 @@ __global__ void __launch_bounds__(kSBlock) k_fk_backward_static(const float* __r
         const long long warp_cfg0 = base + (threadIdx.x & ~31);
         if (warp_cfg0 >= n) continue;
         const float* qrow = q + (cfg < n ? cfg : n - 1) * D;
+        {
+            constexpr int b0 = R::body[0];
+            const int s0 = slots.slot[b0];
+            if (s0 >= 0) warp_prefetch_link(stage, lane, warp_cfg0, n, n_sel, s0, G);
+            cp_async_commit();
+        }
         float W[L][12], F[L][3], T[L][3], P[L][3], JA[D > 0 ? D : 1][3];
         unsigned pass;
         STree<R>::forward([&](int c) { return __ldg(qrow + c); }, W, pass, [&](auto ic, const float (&wp)[12], const float (&w)[12]) {
             constexpr int i = decltype(ic)::value, b = R::body[i];
             const int s = slots.slot[b];
+            if constexpr (i + 1 < L) {
+                constexpr int bn = R::body[i + 1];
+                const int sn = slots.slot[bn];
+                if (sn >= 0) warp_prefetch_link(stage + ((i + 1) & 1) * 128, lane, warp_cfg0, n, n_sel, sn, G);
+            }
+            cp_async_commit();
             P[b][0] = w[9]; P[b][1] = w[10]; P[b][2] = w[11];
             constexpr int qi = R::qidx[i];
             if constexpr (qi >= 0) STree<R>::template joint_axis<i>(wp, w, JA[qi]);
             F[b][0] = F[b][1] = F[b][2] = 0.f;
             T[b][0] = T[b][1] = T[b][2] = 0.f;
             if (s >= 0) {
-                float4 m0, m1, m2;
-                warp_load_link(stage, lane, warp_cfg0, n, n_sel, s, G, m0, m1, m2);
+                cp_async_wait<1>();
+                __syncwarp();
+                const float4* st = stage + (i & 1) * 128;
+                const float4 m0 = st[stage_idx(lane, 0)], m1 = st[stage_idx(lane, 1)], m2 = st[stage_idx(lane, 2)];
+                __syncwarp();
                 const float gR[9] = {m0.x, m0.y, m0.z, m1.x, m1.y, m1.z, m2.x, m2.y, m2.z};
                 float ax, ay, az;
                 axial_gR_Rt(gR, w, ax, ay, az);
@@ -312,6 +425,7 @@ __global__ void __launch_bounds__(kSBlock) k_fk_backward_static(const float* __r
                 T[b][2] = w[9] * m1.w - w[10] * m0.w + az;
             }
         });
+        cp_async_wait<0>();
         float* grow = grad_q + cfg * D;
         const bool valid = cfg < n;
         STree<R>::backward(JA, [&](auto bc, float (&f)[3], float (&t)[3], float (&pos)[3]) {
@@ -758,6 +872,20 @@ inline int persistent_grid(K kernel, int n_sms, size_t smem, long long n) {
 template <class R>
 inline cudaError_t launch_fk_forward_t(int n_sms, const float* q, long long n, const SlotMap& sm, int n_sel, float* H,
                                        cudaStream_t st) {
+    if constexpr (FkTma<R>::body_order()) {
+        bool identity = (n_sel == R::L);
+        for (int b = 0; identity && b < R::L; ++b) identity = (sm.slot[b] == b);
+        if (identity) {   // all links in body order: TMA bulk-store variant
+            auto kt = k_fk_forward_static_tma<R>;
+            constexpr size_t smem = FkTma<R>::smem_bytes;
+            if (smem > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+            }
+            kt<<<persistent_grid(kt, n_sms, smem, n), kSBlock, smem, st>>>(q, n, H);
+            return cudaGetLastError();
+        }
+    }
     auto k = k_fk_forward_static<R>;
     k<<<persistent_grid(k, n_sms, 0, n), kSBlock, 0, st>>>(q, n, sm, n_sel, H);
     return cudaGetLastError();
