@@ -792,25 +792,13 @@ __global__ void __launch_bounds__(kSBlock) k_ik_adam_static(IKParams P, const fl
 }
 
 template <class R>
-inline cudaError_t launch_ik_t(const IKParams& P, const float* step_size, const float* bc2_sqrt, const float* target_seed,
+cudaError_t launch_ik_t(const IKParams& P, const float* step_size, const float* bc2_sqrt, const float* target_seed,
                                long long n_seeds, float* q_io, float* err_out, uint8_t* valid_out, int* valid_count,
                                float* loss_sum, float* loss_sqsum, cudaStream_t st) {
     const long long blocks = (n_seeds + kSBlock - 1) / kSBlock;
     k_ik_adam_static<R><<<(unsigned)blocks, kSBlock, 0, st>>>(P, step_size, bc2_sqrt, target_seed, n_seeds, q_io, err_out, valid_out,
                                                              valid_count, loss_sum, loss_sqsum);
     return cudaGetLastError();
-}
-
-inline cudaError_t launch_static_ik(int family, const IKParams& P, const float* step_size, const float* bc2_sqrt,
-                                    const float* target_seed, long long n_seeds, float* q_io, float* err_out, uint8_t* valid_out,
-                                    int* valid_count, float* loss_sum, float* loss_sqsum, cudaStream_t st) {
-    int id = 0;
-#define X(Rb) \
-    ++id;     \
-    if (family == id) return launch_ik_t<Rb>(P, step_size, bc2_sqrt, target_seed, n_seeds, q_io, err_out, valid_out, valid_count, loss_sum, loss_sqsum, st);
-    TRK_FOR_EACH_STATIC_ROBOT(X)
-#undef X
-    return cudaErrorInvalidValue;
 }
 
 // which compile-time collision model (if any) belongs to a compiled-in robot
@@ -870,7 +858,7 @@ inline int persistent_grid(K kernel, int n_sms, size_t smem, long long n) {
 }
 
 template <class R>
-inline cudaError_t launch_fk_forward_t(int n_sms, const float* q, long long n, const SlotMap& sm, int n_sel, float* H,
+cudaError_t launch_fk_forward_t(int n_sms, const float* q, long long n, const SlotMap& sm, int n_sel, float* H,
                                        cudaStream_t st) {
     if constexpr (FkTma<R>::body_order()) {
         bool identity = (n_sel == R::L);
@@ -892,7 +880,7 @@ inline cudaError_t launch_fk_forward_t(int n_sms, const float* q, long long n, c
 }
 
 template <class R>
-inline cudaError_t launch_fk_backward_t(int n_sms, const float* q, long long n, const SlotMap& sm, int n_sel, const float* G,
+cudaError_t launch_fk_backward_t(int n_sms, const float* q, long long n, const SlotMap& sm, int n_sel, const float* G,
                                         float* grad_q, cudaStream_t st) {
     auto k = k_fk_backward_static<R>;
     k<<<persistent_grid(k, n_sms, 0, n), kSBlock, 0, st>>>(q, n, sm, n_sel, G, grad_q);
@@ -926,7 +914,7 @@ inline cudaError_t launch_objective_cm_k(int n_sms, const float* cost_words, int
 }
 
 template <class R>
-inline cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwords, int clamp_any, int cm_match, const float* q,
+cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwords, int clamp_any, int cm_match, const float* q,
                                       long long n, const float* ee_target_cfg, float margin_override, int use_override,
                                       float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin,
                                       cudaStream_t st) {
@@ -942,6 +930,35 @@ inline cudaError_t launch_objective_t(int n_sms, const float* cost_words, int co
     if (grad_q) return clamp_any ? launch_objective_k<R, true, true>(TRK_OBJ_ARGS) : launch_objective_k<R, true, false>(TRK_OBJ_ARGS);
     return clamp_any ? launch_objective_k<R, false, true>(TRK_OBJ_ARGS) : launch_objective_k<R, false, false>(TRK_OBJ_ARGS);
 #undef TRK_OBJ_ARGS
+}
+
+// ------------------------------------------------------------------------------------------
+// One translation unit per compiled-in robot: trk_static_inst.cu (compiled with -DTRK_INST_ROBOT=<robot>)
+// explicitly instantiates the four launchers below for that robot; every other unit only sees these
+// declarations, so the robots compile in parallel.
+// ------------------------------------------------------------------------------------------
+#define TRK_LAUNCHER_SIGNATURES(KW, Rb)                                                                                                   \
+    KW template cudaError_t launch_fk_forward_t<Rb>(int, const float*, long long, const SlotMap&, int, float*, cudaStream_t);           \
+    KW template cudaError_t launch_fk_backward_t<Rb>(int, const float*, long long, const SlotMap&, int, const float*, float*, cudaStream_t); \
+    KW template cudaError_t launch_objective_t<Rb>(int, const float*, int, int, int, const float*, long long, const float*, float, int,   \
+                                                   float*, float*, float*, uint8_t*, int*, cudaStream_t);                               \
+    KW template cudaError_t launch_ik_t<Rb>(const IKParams&, const float*, const float*, const float*, long long, float*, float*,        \
+                                            uint8_t*, int*, float*, float*, cudaStream_t);
+#ifndef TRK_INST_ROBOT   // family dispatch: main translation unit only
+#define TRK_DECLARE_EXTERN(Rb) TRK_LAUNCHER_SIGNATURES(extern, Rb)
+TRK_FOR_EACH_STATIC_ROBOT(TRK_DECLARE_EXTERN)
+#undef TRK_DECLARE_EXTERN
+
+inline cudaError_t launch_static_ik(int family, const IKParams& P, const float* step_size, const float* bc2_sqrt,
+                                    const float* target_seed, long long n_seeds, float* q_io, float* err_out, uint8_t* valid_out,
+                                    int* valid_count, float* loss_sum, float* loss_sqsum, cudaStream_t st) {
+    int id = 0;
+#define X(Rb) \
+    ++id;     \
+    if (family == id) return launch_ik_t<Rb>(P, step_size, bc2_sqrt, target_seed, n_seeds, q_io, err_out, valid_out, valid_count, loss_sum, loss_sqsum, st);
+    TRK_FOR_EACH_STATIC_ROBOT(X)
+#undef X
+    return cudaErrorInvalidValue;
 }
 
 inline cudaError_t launch_static_fk_forward(int family, int n_sms, const float* q, long long n, const SlotMap& sm, int n_sel,
@@ -995,5 +1012,7 @@ inline cudaError_t launch_static_objective(int family, int n_sms, const float* c
 #undef X
     return cudaErrorInvalidValue;
 }
+
+#endif   // TRK_INST_ROBOT
 
 }  // namespace trk
