@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kBlock) k_objective_generic(const float* __res
         float terms[4] = {0.f, 0.f, 0.f, 0.f};
         unsigned occ;
         collision_terms<WANT_GRAD, true>(
-            cv, [&](int b, float& x, float& y, float& z) { x = W[b][9]; y = W[b][10]; z = W[b][11]; },
+            cv, cv.pt_link, cv.pair_i, cv.pair_j, [&](int b, float& x, float& y, float& z) { x = W[b][9]; y = W[b][10]; z = W[b][11]; },
             [&](int b, float gx, float gy, float gz) { F[b][0] += gx; F[b][1] += gy; F[b][2] += gz; }, margin_override,
             use_override != 0, terms, occ, argmin ? argmin + cfg * (long long)(h->nObj * h->S) : nullptr);
         float gR[9], gp[3];
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kBlock) k_cost_stage(const float* __restrict__
         float terms[4] = {0.f, 0.f, 0.f, 0.f};
         unsigned occ;
         collision_terms<WANT_GRAD, true>(
-            cv, [&](int b, float& x, float& y, float& z) { x = __ldg(P + b * 3); y = __ldg(P + b * 3 + 1); z = __ldg(P + b * 3 + 2); },
+            cv, cv.pt_link, cv.pair_i, cv.pair_j, [&](int b, float& x, float& y, float& z) { x = __ldg(P + b * 3); y = __ldg(P + b * 3 + 1); z = __ldg(P + b * 3 + 2); },
             [&](int b, float gx, float gy, float gz) { F[b][0] += gx; F[b][1] += gy; F[b][2] += gz; }, margin_override,
             use_override != 0, terms, occ, argmin ? argmin + cfg * (long long)(h->nObj * h->S) : nullptr);
         if (h->ee_enabled && ee_pose) {
@@ -283,6 +283,7 @@ struct trk_cost {
     int L;
     int S, nObj, K, P;
     int ee_enabled;
+    int n_slots;                // bodies referenced by the tables
     int cm_match;               // cost table equals the compile-time collision model of the model's family
     float* d_words;
     int nwords;
@@ -514,7 +515,8 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
     int off = 64;
     auto take = [&](int nw) { int o = off; off = align4(off + nw); return o; };
     const int o_pt_link = take(S), o_mobj = take(S), o_mws = take(S), o_ostart = take(nObj + 1), o_oid = take(nObj),
-              o_oR = take(nObj * 9), o_opos = take(nObj * 3), o_sph = take(K * 4), o_pi = take(P), o_pj = take(P), o_pm = take(P), o_ormax = take(nObj), o_oc2 = take(nObj), o_sphq = take(K * 4);
+              o_oR = take(nObj * 9), o_opos = take(nObj * 3), o_sph = take(K * 4), o_pi = take(P), o_pj = take(P), o_pm = take(P), o_ormax = take(nObj), o_oc2 = take(nObj), o_sphq = take(K * 4),
+              o_sob = take(m->L), o_pts = take(S), o_psi = take(P), o_psj = take(P);
     const int nwords = off;
     trk_cost* c = new (std::nothrow) trk_cost();
     if (!c) return fail(TRK_E_RANGE, "out of host memory");
@@ -568,6 +570,15 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
         w[o_sph + 4 * k + 2] = d->sph_center[3 * k + 2]; w[o_sph + 4 * k + 3] = d->sph_radius[k];
     }
     for (int p = 0; p < P; ++p) { iw[o_pi + p] = d->pair_i[p]; iw[o_pj + p] = d->pair_j[p]; w[o_pm + p] = d->pair_margin[p]; }
+    {   // dense slots for the bodies the tables reference (per-thread shared-memory columns exist only for these)
+        int n_slots = 0;
+        for (int b = 0; b < m->L; ++b) iw[o_sob + b] = -1;
+        auto slot = [&](int b) { if (iw[o_sob + b] < 0) iw[o_sob + b] = n_slots++; return iw[o_sob + b]; };
+        for (int p = 0; p < P; ++p) { iw[o_psi + p] = slot(d->pair_i[p]); iw[o_psj + p] = slot(d->pair_j[p]); }
+        for (int s = 0; s < S; ++s) iw[o_pts + s] = slot(d->pt_link[s]);
+        h->n_slots = n_slots; h->off_slot_of_body = o_sob; h->off_pt_slot = o_pts; h->off_pair_si = o_psi; h->off_pair_sj = o_psj;
+        c->n_slots = n_slots;
+    }
     c->cm_match = trk::static_cm_match(m->family, w);
     c->device = m->device; c->L = m->L; c->S = S; c->nObj = nObj; c->K = K; c->P = P; c->ee_enabled = h->ee_enabled; c->nwords = nwords;
     DeviceGuard guard(m->device);
@@ -625,7 +636,7 @@ int trk_objective(const trk_model* m, const trk_cost* c, const float* q, int64_t
     if (m->family && trk::static_objective_supported(m->family)) {
         const CostHeader* hh = reinterpret_cast<const CostHeader*>(c->h_words.data());
         const int clamp_any = hh->clamp_self | hh->clamp_obj | hh->clamp_ws;
-        cudaError_t e = trk::launch_static_objective(m->family, m->n_sms, c->d_words, c->nwords, clamp_any, c->cm_match, q, n, ee_target_cfg,
+        cudaError_t e = trk::launch_static_objective(m->family, m->n_sms, c->d_words, c->nwords, c->n_slots, clamp_any, c->cm_match, q, n, ee_target_cfg,
                                                      margin_override, use_override, cost_total, cost_terms, grad_q,
                                                      occupancy, argmin, st);
         return e == cudaSuccess ? TRK_OK : cuda_fail(e, "objective(static)");

@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(kSBlock) k_fk_backward_static(const float* __r
 }
 
 template <class R, bool WANT_GRAD, bool CLAMP>
-__global__ void __launch_bounds__(kSBlock, R::L <= 16 ? TRK_OBJ_MINBLOCKS : 1) k_objective_static(const float* __restrict__ cost_words, int cost_nwords,
+__global__ void __launch_bounds__(kSBlock, 4) k_objective_static(const float* __restrict__ cost_words, int cost_nwords, int n_slots,
                                                               const float* __restrict__ q, long long n,
                                                               const float* __restrict__ ee_target_cfg, float margin_override,
                                                               int use_override, float* __restrict__ cost_total,
@@ -445,8 +445,8 @@ __global__ void __launch_bounds__(kSBlock, R::L <= 16 ? TRK_OBJ_MINBLOCKS : 1) k
     extern __shared__ __align__(16) float smem[];
     constexpr int L = R::L, D = R::D;
     float* cw = smem;
-    float* spos = smem + cost_nwords;                 // [3L][kSBlock]
-    float* sgrd = spos + 3 * L * kSBlock;             // [3L][kSBlock]
+    float* spos = smem + cost_nwords;                 // [3 n_slots][kSBlock] positions of the bodies the cost tables reference
+    float* sgrd = spos + 3 * n_slots * kSBlock;       // [3 n_slots][kSBlock] their position gradients
     block_copy_words(cw, cost_words, cost_nwords);
     __syncthreads();
     const CostView cv(cw);
@@ -472,20 +472,28 @@ __global__ void __launch_bounds__(kSBlock, R::L <= 16 ? TRK_OBJ_MINBLOCKS : 1) k
                 for (int i = 0; i < 3; ++i) pt[i] = h->ee_t[i];
             }
         }
-        float W[L][12], JA[D > 0 ? D : 1][3];
+        float W[L][12], JA[D > 0 ? D : 1][3], PJ[D > 0 ? D : 1][3];
         float eF[3] = {0.f, 0.f, 0.f}, eT[3] = {0.f, 0.f, 0.f}, Wee[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         unsigned pass;
         STree<R>::forward([&](int c) { return __ldg(qrow + c); }, W, pass, [&](auto ic, const float (&wp)[12], const float (&w)[12]) {
             constexpr int i = decltype(ic)::value, b = R::body[i];
-            spos[(b * 3 + 0) * kSBlock + tid] = w[9];
-            spos[(b * 3 + 1) * kSBlock + tid] = w[10];
-            spos[(b * 3 + 2) * kSBlock + tid] = w[11];
+            const int sl = cv.slot_of_body[b];
+            if (sl >= 0) {
+                spos[(sl * 3 + 0) * kSBlock + tid] = w[9];
+                spos[(sl * 3 + 1) * kSBlock + tid] = w[10];
+                spos[(sl * 3 + 2) * kSBlock + tid] = w[11];
+                if (WANT_GRAD) {
+                    sgrd[(sl * 3 + 0) * kSBlock + tid] = 0.f;
+                    sgrd[(sl * 3 + 1) * kSBlock + tid] = 0.f;
+                    sgrd[(sl * 3 + 2) * kSBlock + tid] = 0.f;
+                }
+            }
             if (WANT_GRAD) {
-                sgrd[(b * 3 + 0) * kSBlock + tid] = 0.f;
-                sgrd[(b * 3 + 1) * kSBlock + tid] = 0.f;
-                sgrd[(b * 3 + 2) * kSBlock + tid] = 0.f;
                 constexpr int qi = R::qidx[i];
-            if constexpr (qi >= 0) STree<R>::template joint_axis<i>(wp, w, JA[qi]);
+                if constexpr (qi >= 0) {
+                    STree<R>::template joint_axis<i>(wp, w, JA[qi]);
+                    PJ[qi][0] = w[9]; PJ[qi][1] = w[10]; PJ[qi][2] = w[11];
+                }
             }
             if (b == e) sfor<12>([&](auto kc) { Wee[kc] = w[kc]; });   // the EE body is chosen at run time: keep a copy
         });
@@ -503,7 +511,7 @@ __global__ void __launch_bounds__(kSBlock, R::L <= 16 ? TRK_OBJ_MINBLOCKS : 1) k
         }
         unsigned occ;
         collision_terms<WANT_GRAD, CLAMP>(
-            cv,
+            cv, cv.pt_slot, cv.pair_si, cv.pair_sj,
             [&](int b, float& x, float& y, float& z) {
                 x = spos[(b * 3 + 0) * kSBlock + tid]; y = spos[(b * 3 + 1) * kSBlock + tid]; z = spos[(b * 3 + 2) * kSBlock + tid];
             },
@@ -518,13 +526,19 @@ __global__ void __launch_bounds__(kSBlock, R::L <= 16 ? TRK_OBJ_MINBLOCKS : 1) k
             float* grow = grad_q + cfg * D;
             STree<R>::backward(JA, [&](auto bc, float (&f)[3], float (&t)[3], float (&pos)[3]) {
                 constexpr int b = decltype(bc)::value;
-                sfor<3>([&](auto rc) {
-                    pos[rc] = spos[(b * 3 + rc) * kSBlock + tid];
-                    f[rc] = sgrd[(b * 3 + rc) * kSBlock + tid];
-                });
-                t[0] = pos[1] * f[2] - pos[2] * f[1];
-                t[1] = pos[2] * f[0] - pos[0] * f[2];
-                t[2] = pos[0] * f[1] - pos[1] * f[0];
+                constexpr int qb = R::qidx[STree<R>::topo_index_of(b)];
+                const int sl = cv.slot_of_body[b];
+                sfor<3>([&](auto rc) { f[rc] = 0.f; t[rc] = 0.f; pos[rc] = 0.f; });
+                if constexpr (qb >= 0) sfor<3>([&](auto rc) { pos[rc] = PJ[qb][rc]; });
+                if (sl >= 0) {
+                    sfor<3>([&](auto rc) {
+                        pos[rc] = spos[(sl * 3 + rc) * kSBlock + tid];
+                        f[rc] = sgrd[(sl * 3 + rc) * kSBlock + tid];
+                    });
+                    t[0] = pos[1] * f[2] - pos[2] * f[1];
+                    t[1] = pos[2] * f[0] - pos[0] * f[2];
+                    t[2] = pos[0] * f[1] - pos[1] * f[0];
+                }
                 if (b == e) sfor<3>([&](auto rc) { f[rc] += eF[rc]; t[rc] += eT[rc]; });
             }, pass, [&](int c, float g) { grow[c] = g; });
         }
@@ -888,16 +902,16 @@ cudaError_t launch_fk_backward_t(int n_sms, const float* q, long long n, const S
 }
 
 template <class R, bool WANT_GRAD, bool CLAMP>
-inline cudaError_t launch_objective_k(int n_sms, const float* cost_words, int cost_nwords, const float* q, long long n,
+inline cudaError_t launch_objective_k(int n_sms, const float* cost_words, int cost_nwords, int n_slots, const float* q, long long n,
                                       const float* ee_target_cfg, float margin_override, int use_override, float* cost_total,
                                       float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin, cudaStream_t st) {
-    const size_t smem = ((size_t)cost_nwords + (size_t)6 * R::L * kSBlock) * sizeof(float);
+    const size_t smem = ((size_t)cost_nwords + (size_t)6 * n_slots * kSBlock) * sizeof(float);
     auto k = k_objective_static<R, WANT_GRAD, CLAMP>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k<<<persistent_grid(k, n_sms, smem, n), kSBlock, smem, st>>>(cost_words, cost_nwords, q, n, ee_target_cfg, margin_override,
+    k<<<persistent_grid(k, n_sms, smem, n), kSBlock, smem, st>>>(cost_words, cost_nwords, n_slots, q, n, ee_target_cfg, margin_override,
                                                                  use_override, cost_total, cost_terms, grad_q, occupancy, argmin);
     return cudaGetLastError();
 }
@@ -914,7 +928,7 @@ inline cudaError_t launch_objective_cm_k(int n_sms, const float* cost_words, int
 }
 
 template <class R>
-cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwords, int clamp_any, int cm_match, const float* q,
+cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwords, int n_slots, int clamp_any, int cm_match, const float* q,
                                       long long n, const float* ee_target_cfg, float margin_override, int use_override,
                                       float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin,
                                       cudaStream_t st) {
@@ -927,8 +941,11 @@ cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwor
             return clamp_any ? launch_objective_cm_k<R, CM, false, true>(TRK_OBJ_ARGS) : launch_objective_cm_k<R, CM, false, false>(TRK_OBJ_ARGS);
         }
     }
-    if (grad_q) return clamp_any ? launch_objective_k<R, true, true>(TRK_OBJ_ARGS) : launch_objective_k<R, true, false>(TRK_OBJ_ARGS);
-    return clamp_any ? launch_objective_k<R, false, true>(TRK_OBJ_ARGS) : launch_objective_k<R, false, false>(TRK_OBJ_ARGS);
+#define TRK_OBJ_ARGS_S n_sms, cost_words, cost_nwords, n_slots, q, n, ee_target_cfg, margin_override, use_override, cost_total, cost_terms, \
+                       grad_q, occupancy, argmin, st
+    if (grad_q) return clamp_any ? launch_objective_k<R, true, true>(TRK_OBJ_ARGS_S) : launch_objective_k<R, true, false>(TRK_OBJ_ARGS_S);
+    return clamp_any ? launch_objective_k<R, false, true>(TRK_OBJ_ARGS_S) : launch_objective_k<R, false, false>(TRK_OBJ_ARGS_S);
+#undef TRK_OBJ_ARGS_S
 #undef TRK_OBJ_ARGS
 }
 
@@ -940,7 +957,7 @@ cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwor
 #define TRK_LAUNCHER_SIGNATURES(KW, Rb)                                                                                                   \
     KW template cudaError_t launch_fk_forward_t<Rb>(int, const float*, long long, const SlotMap&, int, float*, cudaStream_t);           \
     KW template cudaError_t launch_fk_backward_t<Rb>(int, const float*, long long, const SlotMap&, int, const float*, float*, cudaStream_t); \
-    KW template cudaError_t launch_objective_t<Rb>(int, const float*, int, int, int, const float*, long long, const float*, float, int,   \
+    KW template cudaError_t launch_objective_t<Rb>(int, const float*, int, int, int, int, const float*, long long, const float*, float, int, \
                                                    float*, float*, float*, uint8_t*, int*, cudaStream_t);                               \
     KW template cudaError_t launch_ik_t<Rb>(const IKParams&, const float*, const float*, const float*, long long, float*, float*,        \
                                             uint8_t*, int*, float*, float*, cudaStream_t);
@@ -998,7 +1015,7 @@ inline int static_cm_match(int family, const float* host_cost_words) {
     return 0;
 }
 
-inline cudaError_t launch_static_objective(int family, int n_sms, const float* cost_words, int cost_nwords, int clamp_any, int cm_match,
+inline cudaError_t launch_static_objective(int family, int n_sms, const float* cost_words, int cost_nwords, int n_slots, int clamp_any, int cm_match,
                                            const float* q, long long n, const float* ee_target_cfg, float margin_override, int use_override,
                                            float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin,
                                            cudaStream_t st) {
@@ -1006,7 +1023,7 @@ inline cudaError_t launch_static_objective(int family, int n_sms, const float* c
 #define X(Rb) \
     ++id;     \
     if (family == id)  \
-        return launch_objective_t<Rb>(n_sms, cost_words, cost_nwords, clamp_any, cm_match, q, n, ee_target_cfg, margin_override, use_override, \
+        return launch_objective_t<Rb>(n_sms, cost_words, cost_nwords, n_slots, clamp_any, cm_match, q, n, ee_target_cfg, margin_override, use_override, \
                                       cost_total, cost_terms, grad_q, occupancy, argmin, st);
     TRK_FOR_EACH_STATIC_ROBOT(X)
 #undef X
