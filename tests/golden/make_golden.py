@@ -307,8 +307,51 @@ def golden_ik():
     print("ik: valid after 40 iters:", out["idx_valid_40"])
 
 
+
+
+def golden_trajectories():
+    """Trajectory collision classification (tasks.py:234-328) on Panda + EnvSpheres3D: interpolation between
+    waypoints, zero-margin collision flags, free / colliding index lists, joint-limit filter, statistics."""
+    from torch_robotics.trajectory.utils import interpolate_traj_via_points
+    gen = torch.Generator().manual_seed(2024)
+    robot = quiet(RobotPanda, tensor_args=TA)
+    env = quiet(EnvSpheres3D, tensor_args=TA)
+    task = quiet(PlanningTask, env=env, robot=robot, tensor_args=TA)
+    lo, hi = robot.q_min, robot.q_max
+    B, H = 24, 12
+    # short straight-line segments around random configurations: a mix of free and colliding trajectories
+    start = lo + torch.rand(B, 1, 7, generator=gen) * (hi - lo)
+    step = (torch.rand(B, 1, 7, generator=gen) - 0.5) * 0.04
+    trajs = (start + step * torch.arange(H).view(1, H, 1)).contiguous()
+    trajs[3, 5, 0] = hi[0] + 0.2          # leaves the joint limits
+    out = {"trajs": trajs.numpy()}
+    out["interp5"] = interpolate_traj_via_points(trajs, num_interpolation=5).numpy()
+    trajs_in_limits = torch.maximum(torch.minimum(trajs, hi), lo).contiguous()
+    out["trajs_in_limits"] = trajs_in_limits.numpy()
+    # the 4-D input path of the reference raises when a collision-free trajectory violates the joint limits
+    # (torch.cat of [n,2] and [m,1] index tensors, tasks.py:281-283), so it is recorded without such a trajectory
+    for tag, t in (("3d", trajs), ("4d", trajs_in_limits.reshape(2, 12, H, 7))):
+        coll, coll_idx, free, free_idx, wp = task.get_trajs_collision_and_free(t, return_indices=True, num_interpolation=5)
+        out[f"{tag}_coll_idx"] = coll_idx.numpy().astype(np.int64)
+        out[f"{tag}_free_idx"] = free_idx.numpy().astype(np.int64)
+        out[f"{tag}_waypoint_collisions"] = wp.numpy()
+        out[f"{tag}_n_coll"] = np.int64(0 if coll is None else coll.shape[-3])
+        out[f"{tag}_n_free"] = np.int64(0 if free is None else free.shape[-3])
+        out[f"{tag}_coll"] = np.zeros(0, np.float32) if coll is None else coll.numpy()
+        out[f"{tag}_free"] = np.zeros(0, np.float32) if free is None else free.numpy()
+    out["fraction_free"] = np.float64(task.compute_fraction_free_trajs(trajs))
+    out["collision_intensity"] = np.float64(task.compute_collision_intensity_trajs(trajs))
+    out["success"] = np.int64(task.compute_success_free_trajs(trajs))
+    np.savez_compressed(os.path.join(HERE, "planning_trajectories.npz"), **out)
+    print("trajectories: free", out["3d_free_idx"].reshape(-1), "coll", out["3d_coll_idx"].reshape(-1), "frac", out["fraction_free"])
+
+
 if __name__ == "__main__":
-    golden_fk()
-    golden_planning()
-    golden_stretch_objective()
-    golden_ik()
+    if os.environ.get("GOLDEN_ONLY") == "trajectories":
+        golden_trajectories()
+    else:
+        golden_fk()
+        golden_planning()
+        golden_stretch_objective()
+        golden_ik()
+        golden_trajectories()

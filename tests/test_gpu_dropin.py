@@ -191,6 +191,35 @@ def test_fused_ik_kernel_vs_oracle_and_torch_loop():
         assert torch.equal(qs.detach(), torch.clamp(good, t(g["lower"]), t(g["upper"]))) and idxs.numel() == 1    # stopped at iteration 0
 
 
+def test_trajectory_collision_classification(planning):
+    """get_trajs_collision_and_free and the statistics built on it (tasks.py:234-328): integer outputs equal
+    the reference's bit for bit."""
+    from torch_robotics_b200.trajectory.utils import interpolate_traj_via_points
+    robot, env, task = planning
+    g = load_golden("planning_trajectories")
+    trajs = t(g["trajs"])
+    assert rel_err(interpolate_traj_via_points(trajs, num_interpolation=5).cpu().numpy(), g["interp5"]) < 1e-6
+    coll, coll_idx, free, free_idx, wp = task.get_trajs_collision_and_free(trajs, return_indices=True, num_interpolation=5)
+    assert coll_idx.dtype == torch.int64 and np.array_equal(coll_idx.cpu().numpy(), g["3d_coll_idx"])
+    assert np.array_equal(free_idx.cpu().numpy(), g["3d_free_idx"])
+    assert np.array_equal(wp.cpu().numpy(), g["3d_waypoint_collisions"])
+    assert np.array_equal(coll.cpu().numpy(), g["3d_coll"]) and np.array_equal(free.cpu().numpy(), g["3d_free"])
+    t4 = t(g["trajs_in_limits"]).reshape(2, 12, 12, 7)
+    coll, coll_idx, free, free_idx, wp = task.get_trajs_collision_and_free(t4, return_indices=True, num_interpolation=5)
+    assert np.array_equal(coll_idx.cpu().numpy(), g["4d_coll_idx"]) and np.array_equal(free_idx.cpu().numpy(), g["4d_free_idx"])
+    assert np.array_equal(wp.cpu().numpy(), g["4d_waypoint_collisions"])
+    assert np.array_equal(coll.cpu().numpy(), g["4d_coll"]) and np.array_equal(free.cpu().numpy(), g["4d_free"])
+    assert task.compute_fraction_free_trajs(trajs) == pytest.approx(float(g["fraction_free"]))
+    assert float(task.compute_collision_intensity_trajs(trajs)) == pytest.approx(float(g["collision_intensity"]))
+    assert task.compute_success_free_trajs(trajs) == int(g["success"])
+    # 4-D input with a limit-violating free trajectory (the reference raises here): handled
+    t4v = trajs.reshape(2, 12, 12, 7)
+    coll, coll_idx, free, free_idx, _ = task.get_trajs_collision_and_free(t4v, return_indices=True)
+    assert coll_idx.shape[1] == 2 and coll_idx.shape[0] + free_idx.shape[0] == 24
+    q_free = task.random_coll_free_q(n_samples=16)
+    assert q_free.shape == (16, 7) and not bool(task.compute_collision(q_free).any())
+
+
 def test_host_pipeline_matches_device_call(planning):
     from torch_robotics_b200.host_pipeline import HostObjectivePipeline
     robot, env, task = planning

@@ -13,11 +13,14 @@ from abc import ABC
 
 import torch
 
+import sys
+
 from .. import ops
 from .._lib import DeviceCost
 from ..descriptor import build_cost_descriptor
 from ..torch_planning_objectives.fields.distance_fields import (
     CollisionObjectDistanceField, CollisionWorkspaceBoundariesDistanceField, _tree_of)
+from ..trajectory.utils import interpolate_traj_via_points
 
 
 class Task(ABC):
@@ -138,3 +141,70 @@ class PlanningTask(Task):
         q3, out_shape = self._as_bhd(self.robot.get_position(x))
         flat = q3.reshape(-1, q3.shape[-1])
         return ops.objective(self._fused_cost(flat.device, ee_field, ee_link_name), flat).reshape(out_shape)
+
+    # ---------------------------------------------------------------------------------- sampling
+    def sample_q(self, without_collision=True, **kwargs):
+        return self.random_coll_free_q(**kwargs) if without_collision else self.robot.random_q(**kwargs)
+
+    def random_coll_free_q(self, n_samples=1, max_samples=1000, max_tries=1000):
+        """Rejection sampling of collision-free configurations (reference: tasks.py:104-129)."""
+        samples = torch.zeros((n_samples, self.robot.q_dim), **self.tensor_args)
+        filled = 0
+        for _ in range(max_tries):
+            qs = self.robot.random_q(max_samples)
+            free = torch.nonzero(~self.compute_collision(qs).reshape(-1)).reshape(-1)
+            if free.numel() == 0:
+                continue
+            pick = free[torch.randperm(free.numel(), device=free.device)[:n_samples]]
+            take = min(pick.numel(), n_samples - filled)
+            samples[filled:filled + take] = qs[pick[:take]]
+            filled += take
+            if filled >= n_samples:
+                return samples.squeeze()
+        sys.exit("Could not find a collision free configuration")
+
+    # ---------------------------------------------------------------------------------- trajectories
+    def get_trajs_collision_and_free(self, trajs, return_indices=False, num_interpolation=5):
+        """Split a batch of trajectories [B, H, D] (or [N, B, H, D]) into colliding and collision-free ones
+        (reference: tasks.py:234-308).  Collisions are tested with zero margin on the points interpolated
+        between the waypoints; a collision-free trajectory that leaves the joint limits counts as colliding.
+        Index tensors are int64 [n, 1] ([n, 2] for 4-D input), in the reference's order: trajectories with a
+        colliding waypoint first, then the limit violators."""
+        assert trajs.ndim in (3, 4)
+        four_d = trajs.ndim == 4
+        flat = trajs.reshape(-1, trajs.shape[-2], trajs.shape[-1]) if four_d else trajs
+        waypoint_coll = self.compute_collision(interpolate_traj_via_points(flat, num_interpolation=num_interpolation), margin=0.)
+        if four_d:
+            waypoint_coll = waypoint_coll.reshape(trajs.shape[0], trajs.shape[1], -1)
+        free_idx = torch.argwhere(~waypoint_coll.any(dim=-1))
+        coll_idx = torch.argwhere(waypoint_coll.any(dim=-1))
+        if free_idx.numel() > 0:
+            sel = trajs[tuple(free_idx.t())]
+            pos = self.robot.get_position(sel)
+            inside = ((pos >= self.robot.q_min) & (pos <= self.robot.q_max)).all(dim=-1).all(dim=-1)
+            if not bool(inside.any()):
+                coll_idx, free_idx = free_idx.clone(), free_idx[:0]
+            else:
+                coll_idx = torch.cat((coll_idx, free_idx[~inside]))
+                free_idx = free_idx[inside]
+        trajs_free = trajs[tuple(free_idx.t())] if free_idx.numel() else None
+        trajs_coll = trajs[tuple(coll_idx.t())] if coll_idx.numel() else None
+        if four_d:
+            trajs_free = None if trajs_free is None else trajs_free
+            trajs_coll = None if trajs_coll is None else trajs_coll
+        if return_indices:
+            return trajs_coll, coll_idx, trajs_free, free_idx, waypoint_coll
+        return trajs_coll, trajs_free
+
+    def compute_fraction_free_trajs(self, trajs, **kwargs):
+        _, coll_idx, _, free_idx, _ = self.get_trajs_collision_and_free(trajs, return_indices=True)
+        n_free, n_coll = free_idx.nelement(), coll_idx.nelement()
+        return n_free / (n_free + n_coll)
+
+    def compute_collision_intensity_trajs(self, trajs, **kwargs):
+        wp = self.get_trajs_collision_and_free(trajs, return_indices=True)[4]
+        return torch.count_nonzero(wp) / wp.nelement()
+
+    def compute_success_free_trajs(self, trajs, **kwargs):
+        free = self.get_trajs_collision_and_free(trajs)[1]
+        return 1 if free is not None and free.nelement() >= 1 else 0
