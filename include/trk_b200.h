@@ -35,6 +35,7 @@ extern "C" {
 #define TRK_MAX_SPHERES 256
 #define TRK_MAX_OBJECTS 16
 #define TRK_MAX_PAIRS   128
+#define TRK_MAX_BOXES   64
 
 #define TRK_OK              0
 #define TRK_E_NULL         -1   /* required pointer is null */
@@ -100,6 +101,14 @@ typedef struct trk_cost_desc {
     int32_t        n_spheres;      /* K */
     const float*   sph_center;     /* [K*3] in the object frame */
     const float*   sph_radius;     /* [K] */
+    /* boxes (primitives.py:198-334): object o also owns boxes [obj_box_start[o], obj_box_start[o+1]); the object's
+       signed distance is the minimum over its spheres and boxes.  n_boxes may be 0 (all box pointers then unused). */
+    int32_t        n_boxes;        /* KB <= TRK_MAX_BOXES */
+    const int32_t* obj_box_start;  /* [n_objects + 1] */
+    const float*   box_center;     /* [KB*3] in the object frame */
+    const float*   box_half;       /* [KB*3] half sizes */
+    const float*   box_radius;     /* [KB] rounding radius of MultiBoxField (:309-334); ignored for sharp boxes */
+    const int32_t* box_rounded;    /* [KB] 1 = MultiBoxField (rounded), 0 = MultiSharpBoxField */
     int32_t        ws_enabled;
     float          ws_min[3];      /* distance_fields.py:326-332 */
     float          ws_max[3];
@@ -162,7 +171,8 @@ int  trk_cost_set_weights(trk_cost* cost, const float* weights4, void* stream);
  *   cost_terms [n, 4]     self, object, ws, ee                           (nullable)
  *   grad_q     [n, D]     d cost_total / d q                             (nullable: forward only)
  *   occupancy  [n] uint8  TRK_OCC_* bits (compute_collision, tasks.py:131) (nullable)
- *   argmin     [n, n_objects, S] int32 nearest sphere per object and point, index within the object (nullable)
+ *   argmin     [n, n_objects, S] int32 nearest primitive per object and point, index within the object
+ *                             (its spheres first, then its boxes) (nullable)
  */
 int trk_objective(const trk_model* model, const trk_cost* cost, const float* q, int64_t n,
                   const float* ee_target_cfg, float margin_override,

@@ -25,6 +25,7 @@ class OrcCost(C.Structure):
     _fields_ = [("n_points", C.c_int32), ("pt_link", ip), ("pt_margin_obj", fp), ("pt_margin_ws", fp),
                 ("n_objects", C.c_int32), ("obj_start", ip), ("obj_identity", ip), ("obj_R", fp), ("obj_pos", fp),
                 ("n_spheres", C.c_int32), ("sph_center", fp), ("sph_radius", fp),
+                ("n_boxes", C.c_int32), ("obj_box_start", ip), ("box_center", fp), ("box_half", fp), ("box_radius", fp), ("box_rounded", ip),
                 ("ws_enabled", C.c_int32), ("ws_min", C.c_float * 3), ("ws_max", C.c_float * 3),
                 ("n_pairs", C.c_int32), ("pair_i", ip), ("pair_j", ip), ("pair_margin", fp),
                 ("ee_enabled", C.c_int32), ("ee_link", C.c_int32), ("ee_w_pos", C.c_float), ("ee_w_rot", C.c_float),
@@ -74,12 +75,16 @@ class Cost:
         k = self.keep = dict(pt_link=_a(c.pt_link, np.int32), mobj=_a(c.pt_margin_obj, np.float32), mws=_a(c.pt_margin_ws, np.float32),
                              obj_start=_a(c.obj_start, np.int32), obj_ident=_a(c.obj_identity, np.int32), obj_R=_a(c.obj_R, np.float32),
                              obj_pos=_a(c.obj_pos, np.float32), sc=_a(c.sph_center, np.float32), sr=_a(c.sph_radius, np.float32),
-                             pi=_a(c.pair_i, np.int32), pj=_a(c.pair_j, np.int32), pm=_a(c.pair_margin, np.float32))
+                             pi=_a(c.pair_i, np.int32), pj=_a(c.pair_j, np.int32), pm=_a(c.pair_margin, np.float32),
+                             obs=_a(c.obj_box_start, np.int32), bc=_a(c.box_center, np.float32), bh=_a(c.box_half, np.float32),
+                             br=_a(c.box_radius, np.float32), bf=_a(c.box_rounded, np.int32))
         P = lambda n: k[n].ctypes.data_as(ip if k[n].dtype == np.int32 else fp)
         s = self.s = OrcCost()
         s.n_points, s.pt_link, s.pt_margin_obj, s.pt_margin_ws = c.n_points, P("pt_link"), P("mobj"), P("mws")
         s.n_objects, s.obj_start, s.obj_identity, s.obj_R, s.obj_pos = c.n_objects, P("obj_start"), P("obj_ident"), P("obj_R"), P("obj_pos")
         s.n_spheres, s.sph_center, s.sph_radius = c.n_spheres, P("sc"), P("sr")
+        s.n_boxes, s.obj_box_start, s.box_center, s.box_half = c.n_boxes, P("obs"), P("bc"), P("bh")
+        s.box_radius, s.box_rounded = P("br"), P("bf")
         s.ws_enabled = int(c.ws_enabled)
         s.ws_min = (C.c_float * 3)(*[float(v) for v in c.ws_min])
         s.ws_max = (C.c_float * 3)(*[float(v) for v in c.ws_max])

@@ -213,6 +213,33 @@ def fk_backward(desc, q, G, sel=None, dtype=np.float32):
 # ----------------------------------------------------------------------------------------------
 # planning objective on link positions
 # ----------------------------------------------------------------------------------------------
+def _box_sdf_and_grad(cost, kb, xo, dtype):
+    """One box primitive at points xo [N,S,3] (object frame): signed distance and its gradient.
+    primitives.py:219-223 (sharp: max_c(|x-c| - h)), :326-334 (rounded: min(max q, 0) + |relu(q)| - r,
+    q = |x-c| - h + r).  Gradient = autograd of those expressions (first maximal component gets the max's share)."""
+    c, hh, r = cost.box_center[kb].astype(dtype), cost.box_half[kb].astype(dtype), dtype(cost.box_radius[kb])
+    v = (xo - c).astype(dtype)
+    q = (np.abs(v) - hh).astype(dtype)
+    sgn = np.sign(v).astype(dtype)
+    w = np.zeros_like(q)
+    if cost.box_rounded[kb]:
+        q = (q + r).astype(dtype)
+        mq = q.max(-1)
+        rq = np.maximum(q, 0)
+        nrm = norm3(rq[..., 0], rq[..., 1], rq[..., 2], dtype)
+        sd = ((np.minimum(mq, 0) + nrm).astype(dtype) - r).astype(dtype)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            w = np.where(nrm[..., None] > 0, rq / nrm[..., None], 0).astype(dtype)
+        max_active = mq < 0
+    else:
+        mq = q.max(-1)
+        sd = mq.astype(dtype)
+        max_active = np.ones(mq.shape, bool)
+    amax = np.argmax(q, -1)
+    onehot = (np.arange(3)[None, None, :] == amax[..., None]) & max_active[..., None]
+    return sd, (sgn * (w + onehot.astype(dtype))).astype(dtype)
+
+
 def object_term(cost, x, dtype=np.float32, margin_override=None):
     """Object-collision term on collision points x [N,S,3].
 
@@ -249,6 +276,13 @@ def object_term(cost, x, dtype=np.float32, margin_override=None):
             with np.errstate(invalid="ignore", divide="ignore"):
                 dirk = np.where(dist[..., None] > 0, v / dist[..., None], 0).astype(dtype)
             bdir = np.where(take[..., None], dirk, bdir)
+        kb0, kb1 = (int(cost.obj_box_start[o]), int(cost.obj_box_start[o + 1])) if getattr(cost, "n_boxes", 0) else (0, 0)
+        for kb in range(kb0, kb1):   # boxes come after the object's spheres; strict < keeps the earlier primitive
+            sd, gd = _box_sdf_and_grad(cost, kb, xo, dtype)
+            take = sd < best
+            best = np.where(take, sd, best)
+            bidx = np.where(take, (k1 - k0) + (kb - kb0), bidx)
+            bdir = np.where(take[..., None], gd, bdir)
         sdf[:, o], amin[:, o] = best, bidx
         gdir[:, o] = bdir if cost.obj_identity[o] else (bdir @ cost.obj_R[o].astype(dtype).T)
     margin = cost.pt_margin_obj.astype(dtype)[None, None, :]

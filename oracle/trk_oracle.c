@@ -45,6 +45,10 @@ typedef struct {
     const float *obj_R, *obj_pos;
     int32_t n_spheres;
     const float *sph_center, *sph_radius;
+    int32_t n_boxes;
+    const int32_t *obj_box_start;
+    const float *box_center, *box_half, *box_radius;
+    const int32_t *box_rounded;
     int32_t ws_enabled;
     float ws_min[3], ws_max[3];
     int32_t n_pairs;
@@ -63,6 +67,30 @@ static float norm3(float x, float y, float z) {
     s = fmaf(y, y, s);
     s = fmaf(z, z, s);
     return sqrtf(s);
+}
+
+/* one box primitive (primitives.py:219-223 sharp, :326-334 rounded): signed distance, optionally its gradient */
+static float box_sdf(const orc_cost *k, int kb, const float *x, float *g) {
+    const float *c = k->box_center + 3 * kb, *hh = k->box_half + 3 * kb;
+    const float r = k->box_radius[kb];
+    const int rounded = k->box_rounded[kb];
+    float v[3], q[3], w[3] = {0.f, 0.f, 0.f};
+    for (int i = 0; i < 3; ++i) { v[i] = x[i] - c[i]; q[i] = fabsf(v[i]) - hh[i]; if (rounded) q[i] = q[i] + r; }
+    const float mq = fmaxf(fmaxf(q[0], q[1]), q[2]);
+    float sd = mq;
+    int max_active = 1;
+    if (rounded) {
+        const float rq[3] = {fmaxf(q[0], 0.f), fmaxf(q[1], 0.f), fmaxf(q[2], 0.f)};
+        const float nrm = norm3(rq[0], rq[1], rq[2]);
+        sd = (fminf(mq, 0.f) + nrm) - r;
+        if (nrm > 0.f) for (int i = 0; i < 3; ++i) w[i] = rq[i] / nrm;
+        max_active = mq < 0.f;
+    }
+    if (g) {
+        if (max_active) { if (q[0] == mq) w[0] += 1.f; else if (q[1] == mq) w[1] += 1.f; else w[2] += 1.f; }
+        for (int i = 0; i < 3; ++i) g[i] = (v[i] > 0.f ? 1.f : (v[i] < 0.f ? -1.f : 0.f)) * w[i];
+    }
+    return sd;
 }
 
 /* rigid_body.py:146-211 for one configuration; W[b] = R (9) | p (3); pass[b] = clamp passes gradient */
@@ -230,6 +258,13 @@ static void objective_one(const orc_tree *t, const orc_cost *k, const float *q, 
                     const float d = norm3(vx, vy, vz), sd = d - k->sph_radius[kk];
                     if (sd < best) { best = sd; bidx = kk - k->obj_start[o]; bvx = vx; bvy = vy; bvz = vz; bd = d; }
                 }
+                int bbox = -1;
+                const float xob[3] = {xo, yo, zo};
+                if (k->n_boxes > 0)
+                    for (int kb = k->obj_box_start[o]; kb < k->obj_box_start[o + 1]; ++kb) {
+                        const float sd = box_sdf(k, kb, xob, 0);
+                        if (sd < best) { best = sd; bbox = kb; bidx = (k->obj_start[o + 1] - k->obj_start[o]) + (kb - k->obj_box_start[o]); }
+                    }
                 if (argmin) argmin[o * S + s] = bidx;
                 if (best < (use_mo ? mo : m)) occ |= 2u;
                 float val = -(best - m);
@@ -237,8 +272,10 @@ static void objective_one(const orc_tree *t, const orc_cost *k, const float *q, 
                 if (k->clamp_obj) { act = val > 0.f; val = fmaxf(val, 0.f); }
                 if (o == 0 || val > vmax) {
                     vmax = val;
-                    if (act && bd > 0.f) {
-                        float ux = bvx / bd, uy = bvy / bd, uz = bvz / bd;
+                    if (act && (bd > 0.f || bbox >= 0)) {
+                        float ux = 0.f, uy = 0.f, uz = 0.f;
+                        if (bbox >= 0) { float gb[3]; box_sdf(k, bbox, xob, gb); ux = gb[0]; uy = gb[1]; uz = gb[2]; }
+                        else { ux = bvx / bd; uy = bvy / bd; uz = bvz / bd; }
                         if (!k->obj_identity[o]) {
                             const float wx = Ro[0] * ux + Ro[1] * uy + Ro[2] * uz, wy = Ro[3] * ux + Ro[4] * uy + Ro[5] * uz,
                                         wz = Ro[6] * ux + Ro[7] * uy + Ro[8] * uz;

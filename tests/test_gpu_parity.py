@@ -68,7 +68,7 @@ def test_autograd_function_matches_raw(models):
     assert rel_err(q.grad.cpu().numpy(), g["grad_q"]) < GRAD_TOL
 
 
-@pytest.mark.parametrize("case", ["panda_spheres3d", "panda_two_objects"])
+@pytest.mark.parametrize("case", ["panda_spheres3d", "panda_two_objects", "panda_boxes"])
 def test_objective_vs_golden(models, case):
     from torch_robotics_b200._lib import DeviceCost
     g, m = load_golden(f"planning_{case}"), models["panda"]
@@ -99,7 +99,7 @@ def test_objective_vs_golden(models, case):
     assert np.array_equal((occ0 & 4) != 0, g["occ_ws_zero"].reshape(-1))
 
 
-@pytest.mark.parametrize("case", ["panda_spheres3d", "panda_two_objects"])
+@pytest.mark.parametrize("case", ["panda_spheres3d", "panda_two_objects", "panda_boxes"])
 def test_cost_stage_bit_exact_on_reference_positions(models, case):
     """Stage-wise exactness: fed the reference's link positions, masks, arg-min
     and the decision-chain costs are bit-identical with the oracle, and the masks with the reference."""
@@ -236,4 +236,28 @@ def test_posed_nonuniform_objects_bit_exact_vs_oracle(models):
     assert np.array_equal((occ & 2) != 0, ro["occ"]) and np.array_equal((occ & 4) != 0, rw["occ"])
     gp = np.zeros_like(pw)
     np.add.at(gp, (slice(None), cost.pt_link), ro["gx"] + rw["gx"])
+    assert rel_err(r["grad_pos"].cpu().numpy(), gp) < 1e-5
+
+
+def test_box_obstacles_bit_exact_vs_oracle_at_scale(models):
+    """Rounded and sharp boxes mixed with spheres in posed objects: decision chain bit-identical with the oracle
+    on 200k random position sets, including points inside boxes and exactly on faces / centres."""
+    from torch_robotics_b200._lib import DeviceCost
+    g, m = load_golden("planning_panda_boxes"), models["panda"]
+    cost = planning_cost_from_golden(g, with_ee=False)
+    cost.weights = np.array([0, 1, 0, 0], np.float32)
+    dc = DeviceCost(m, cost)
+    rng = np.random.default_rng(21)
+    n = 200_000
+    pw = rng.uniform(-0.9, 0.9, (n, 11, 3)).astype(np.float32)
+    pw[:500, 2] = cost.box_center[0]                                  # box centre
+    pw[500:1000, 3] = cost.box_center[1] + cost.box_half[1] * np.array([1, 0, 0], np.float32)   # on a face
+    r = dc.cost_stage(t(pw), want_grad=True, want_occupancy=True, want_argmin=True)
+    x = pw[:, cost.pt_link]
+    ro = orc.object_term(cost, x, np.float32)
+    assert np.array_equal(r["argmin"].cpu().numpy(), ro["argmin"])
+    assert np.array_equal(r["terms"].cpu().numpy()[:, 1], ro["cost"])
+    assert np.array_equal((r["occupancy"].cpu().numpy() & 2) != 0, ro["occ"])
+    gp = np.zeros_like(pw)
+    np.add.at(gp, (slice(None), cost.pt_link), ro["gx"])
     assert rel_err(r["grad_pos"].cpu().numpy(), gp) < 1e-5

@@ -41,7 +41,7 @@ def test_fk_forward_and_backward(robot, dtype):
     assert rel_err(grad, g["grad_q"]) < GRAD_TOL
 
 
-@pytest.mark.parametrize("case", ["panda_spheres3d", "panda_two_objects"])
+@pytest.mark.parametrize("case", ["panda_spheres3d", "panda_two_objects", "panda_boxes"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_planning_terms(case, dtype):
     g, d = load_golden(f"planning_{case}"), get_desc("panda")
@@ -62,7 +62,7 @@ def test_planning_terms(case, dtype):
     assert rel_err(rc["grad_q"], g["grad_collision"].reshape(-1, 7)) < GRAD_TOL
 
 
-@pytest.mark.parametrize("case", ["panda_spheres3d", "panda_two_objects"])
+@pytest.mark.parametrize("case", ["panda_spheres3d", "panda_two_objects", "panda_boxes"])
 def test_planning_masks_and_argmin_bit_exact(case):
     """Stage-wise exactness: fed the reference's own link positions, the cost stage reproduces the
     reference's occupancy masks and nearest-sphere indices exactly."""
@@ -79,6 +79,8 @@ def test_planning_masks_and_argmin_bit_exact(case):
     identity = [bool(cost.obj_identity[o]) for o in range(n_obj)]
     am = g["obj_argmin"].reshape(-1, n_obj, cost.n_points)
     for o in range(n_obj):
+        if (am[:, o] < 0).all():
+            continue            # arg-min fixtures exist for sphere-only objects
         if identity[o]:
             assert np.array_equal(ro["argmin"][:, o], am[:, o])
         else:   # posed object: the reference goes through a BLAS matmul, allow near-tie flips only

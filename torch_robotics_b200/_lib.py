@@ -34,6 +34,8 @@ class CostDesc(C.Structure):
     _fields_ = [("n_points", C.c_int32), ("pt_link", c_int32_p), ("pt_margin_obj", c_float_p), ("pt_margin_ws", c_float_p),
                 ("n_objects", C.c_int32), ("obj_start", c_int32_p), ("obj_identity", c_int32_p), ("obj_R", c_float_p),
                 ("obj_pos", c_float_p), ("n_spheres", C.c_int32), ("sph_center", c_float_p), ("sph_radius", c_float_p),
+                ("n_boxes", C.c_int32), ("obj_box_start", c_int32_p), ("box_center", c_float_p), ("box_half", c_float_p),
+                ("box_radius", c_float_p), ("box_rounded", c_int32_p),
                 ("ws_enabled", C.c_int32), ("ws_min", C.c_float * 3), ("ws_max", C.c_float * 3),
                 ("n_pairs", C.c_int32), ("pair_i", c_int32_p), ("pair_j", c_int32_p), ("pair_margin", c_float_p),
                 ("ee_enabled", C.c_int32), ("ee_link", C.c_int32), ("ee_w_pos", C.c_float), ("ee_w_rot", C.c_float),
@@ -254,12 +256,16 @@ class DeviceCost:
             obj_start=_c32(cost.obj_start, np.int32), obj_ident=_c32(cost.obj_identity, np.int32),
             obj_R=_c32(cost.obj_R, np.float32), obj_pos=_c32(cost.obj_pos, np.float32),
             sph_c=_c32(cost.sph_center, np.float32), sph_r=_c32(cost.sph_radius, np.float32),
-            pi=_c32(cost.pair_i, np.int32), pj=_c32(cost.pair_j, np.int32), pm=_c32(cost.pair_margin, np.float32))
+            pi=_c32(cost.pair_i, np.int32), pj=_c32(cost.pair_j, np.int32), pm=_c32(cost.pair_margin, np.float32),
+            obs=_c32(cost.obj_box_start, np.int32), bc=_c32(cost.box_center, np.float32), bh=_c32(cost.box_half, np.float32),
+            br=_c32(cost.box_radius, np.float32), bf=_c32(cost.box_rounded, np.int32))
         cd = CostDesc()
         cd.n_points, cd.pt_link, cd.pt_margin_obj, cd.pt_margin_ws = cost.n_points, _ip(k["pt_link"]), _fp(k["mobj"]), _fp(k["mws"])
         cd.n_objects, cd.obj_start, cd.obj_identity = cost.n_objects, _ip(k["obj_start"]), _ip(k["obj_ident"])
         cd.obj_R, cd.obj_pos = _fp(k["obj_R"]), _fp(k["obj_pos"])
         cd.n_spheres, cd.sph_center, cd.sph_radius = cost.n_spheres, _fp(k["sph_c"]), _fp(k["sph_r"])
+        cd.n_boxes, cd.obj_box_start, cd.box_center, cd.box_half = cost.n_boxes, _ip(k["obs"]), _fp(k["bc"]), _fp(k["bh"])
+        cd.box_radius, cd.box_rounded = _fp(k["br"]), _ip(k["bf"])
         cd.ws_enabled = int(cost.ws_enabled)
         cd.ws_min = (C.c_float * 3)(*[float(v) for v in cost.ws_min])
         cd.ws_max = (C.c_float * 3)(*[float(v) for v in cost.ws_max])

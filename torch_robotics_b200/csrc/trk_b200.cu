@@ -491,11 +491,14 @@ static int align4(int x) { return (x + 3) & ~3; }
 int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) {
     TRK_CHECK_PTR(m, "model"); TRK_CHECK_PTR(d, "desc"); TRK_CHECK_PTR(out, "out");
     *out = nullptr;
-    const int S = d->n_points, nObj = d->n_objects, K = d->n_spheres, P = d->n_pairs;
+    const int S = d->n_points, nObj = d->n_objects, K = d->n_spheres, P = d->n_pairs, KB = d->n_boxes;
     if (S < 0 || S > TRK_MAX_POINTS) return fail(TRK_E_RANGE, "n_points=%d", S);
     if (nObj < 0 || nObj > TRK_MAX_OBJECTS) return fail(TRK_E_RANGE, "n_objects=%d", nObj);
     if (K < 0 || K > TRK_MAX_SPHERES) return fail(TRK_E_RANGE, "n_spheres=%d", K);
     if (P < 0 || P > TRK_MAX_PAIRS) return fail(TRK_E_RANGE, "n_pairs=%d", P);
+    if (KB < 0 || KB > TRK_MAX_BOXES) return fail(TRK_E_RANGE, "n_boxes=%d", KB);
+    if (KB) { TRK_CHECK_PTR(d->obj_box_start, "obj_box_start"); TRK_CHECK_PTR(d->box_center, "box_center"); TRK_CHECK_PTR(d->box_half, "box_half");
+              TRK_CHECK_PTR(d->box_radius, "box_radius"); TRK_CHECK_PTR(d->box_rounded, "box_rounded"); }
     if (S) { TRK_CHECK_PTR(d->pt_link, "pt_link"); TRK_CHECK_PTR(d->pt_margin_obj, "pt_margin_obj"); TRK_CHECK_PTR(d->pt_margin_ws, "pt_margin_ws"); }
     if (nObj) { TRK_CHECK_PTR(d->obj_start, "obj_start"); TRK_CHECK_PTR(d->obj_identity, "obj_identity"); TRK_CHECK_PTR(d->obj_R, "obj_R"); TRK_CHECK_PTR(d->obj_pos, "obj_pos"); }
     if (K) { TRK_CHECK_PTR(d->sph_center, "sph_center"); TRK_CHECK_PTR(d->sph_radius, "sph_radius"); }
@@ -508,7 +511,13 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
     if (nObj) {
         if (d->obj_start[0] != 0 || d->obj_start[nObj] != K) return fail(TRK_E_RANGE, "obj_start must span [0, n_spheres]");
         for (int o = 0; o < nObj; ++o)
-            if (d->obj_start[o + 1] <= d->obj_start[o]) return fail(TRK_E_RANGE, "every object needs at least one sphere");
+            if (d->obj_start[o + 1] < d->obj_start[o]) return fail(TRK_E_RANGE, "obj_start must be non-decreasing");
+        if (KB && (d->obj_box_start[0] != 0 || d->obj_box_start[nObj] != KB)) return fail(TRK_E_RANGE, "obj_box_start must span [0, n_boxes]");
+        for (int o = 0; o < nObj; ++o) {
+            const int nb = KB ? d->obj_box_start[o + 1] - d->obj_box_start[o] : 0;
+            if (nb < 0) return fail(TRK_E_RANGE, "obj_box_start must be non-decreasing");
+            if (d->obj_start[o + 1] - d->obj_start[o] + nb < 1) return fail(TRK_E_RANGE, "object %d has no primitive", o);
+        }
     }
     if (d->ee_enabled && (d->ee_link < 0 || d->ee_link >= m->L)) return fail(TRK_E_RANGE, "ee_link=%d", d->ee_link);
 
@@ -516,7 +525,8 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
     auto take = [&](int nw) { int o = off; off = align4(off + nw); return o; };
     const int o_pt_link = take(S), o_mobj = take(S), o_mws = take(S), o_ostart = take(nObj + 1), o_oid = take(nObj),
               o_oR = take(nObj * 9), o_opos = take(nObj * 3), o_sph = take(K * 4), o_pi = take(P), o_pj = take(P), o_pm = take(P), o_ormax = take(nObj), o_oc2 = take(nObj), o_sphq = take(K * 4),
-              o_sob = take(m->L), o_pts = take(S), o_psi = take(P), o_psj = take(P);
+              o_sob = take(m->L), o_pts = take(S), o_psi = take(P), o_psj = take(P),
+              o_obs = take(nObj + 1), o_box = take(KB * 8);
     const int nwords = off;
     trk_cost* c = new (std::nothrow) trk_cost();
     if (!c) return fail(TRK_E_RANGE, "out of host memory");
@@ -557,6 +567,7 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
             w[o_oc2 + o] = c2max;
             int bits = 1;
             while ((1 << bits) < (k1 - k0)) ++bits;
+            if (k1 == k0) uniform = false;
             iw[o_oid + o] = (d->obj_identity[o] ? OBJ_IDENTITY : 0) | (uniform ? OBJ_UNIFORM_RADIUS : 0) | (bits << OBJ_BITS_SHIFT);
             w[o_ormax + o] = rmax;
         }
@@ -576,6 +587,13 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
         auto slot = [&](int b) { if (iw[o_sob + b] < 0) iw[o_sob + b] = n_slots++; return iw[o_sob + b]; };
         for (int p = 0; p < P; ++p) { iw[o_psi + p] = slot(d->pair_i[p]); iw[o_psj + p] = slot(d->pair_j[p]); }
         for (int s = 0; s < S; ++s) iw[o_pts + s] = slot(d->pt_link[s]);
+        h->KB = KB; h->off_obj_box_start = o_obs; h->off_box = o_box;
+        for (int o = 0; o <= nObj; ++o) iw[o_obs + o] = KB ? d->obj_box_start[o] : 0;
+        for (int kb = 0; kb < KB; ++kb) {
+            float* bw = w + o_box + 8 * kb;
+            bw[0] = d->box_center[3 * kb]; bw[1] = d->box_center[3 * kb + 1]; bw[2] = d->box_center[3 * kb + 2]; bw[3] = d->box_radius[kb];
+            bw[4] = d->box_half[3 * kb]; bw[5] = d->box_half[3 * kb + 1]; bw[6] = d->box_half[3 * kb + 2]; bw[7] = d->box_rounded[kb] ? 1.f : 0.f;
+        }
         h->n_slots = n_slots; h->off_slot_of_body = o_sob; h->off_pt_slot = o_pts; h->off_pair_si = o_psi; h->off_pair_sj = o_psj;
         c->n_slots = n_slots;
     }
@@ -635,7 +653,7 @@ int trk_objective(const trk_model* m, const trk_cost* c, const float* q, int64_t
     cudaStream_t st = (cudaStream_t)stream;
     if (m->family && trk::static_objective_supported(m->family)) {
         const CostHeader* hh = reinterpret_cast<const CostHeader*>(c->h_words.data());
-        const int clamp_any = hh->clamp_self | hh->clamp_obj | hh->clamp_ws;
+        const int clamp_any = hh->clamp_self | hh->clamp_obj | hh->clamp_ws | (hh->KB > 0 ? 1 : 0);   // general-tables variant
         cudaError_t e = trk::launch_static_objective(m->family, m->n_sms, c->d_words, c->nwords, c->n_slots, clamp_any, c->cm_match, q, n, ee_target_cfg,
                                                      margin_override, use_override, cost_total, cost_terms, grad_q,
                                                      occupancy, argmin, st);

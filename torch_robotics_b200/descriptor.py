@@ -226,6 +226,7 @@ MAX_POINTS = 64     # TRK_MAX_POINTS
 MAX_SPHERES = 256   # TRK_MAX_SPHERES
 MAX_OBJECTS = 16    # TRK_MAX_OBJECTS
 MAX_PAIRS = 128     # TRK_MAX_PAIRS
+MAX_BOXES = 64      # TRK_MAX_BOXES
 
 
 @dataclass
@@ -254,6 +255,12 @@ class CostDescriptor:
     obj_identity: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
     sph_center: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.float32))
     sph_radius: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))
+    # boxes: object o also owns boxes [obj_box_start[o], obj_box_start[o+1]) (primitives.py:198-334)
+    obj_box_start: np.ndarray = field(default_factory=lambda: np.zeros(1, np.int32))
+    box_center: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.float32))
+    box_half: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.float32))
+    box_radius: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))     # MultiBoxField rounding radius
+    box_rounded: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))      # 1 rounded, 0 sharp
     # workspace box
     ws_enabled: int = 0
     ws_min: np.ndarray = field(default_factory=lambda: np.zeros(3, np.float32))
@@ -292,9 +299,13 @@ class CostDescriptor:
     def n_pairs(self) -> int:
         return int(self.pair_i.shape[0])
 
+    @property
+    def n_boxes(self) -> int:
+        return int(self.box_radius.shape[0])
+
     def validate(self, n_links: int) -> None:
         if self.n_points > MAX_POINTS or self.n_spheres > MAX_SPHERES or self.n_objects > MAX_OBJECTS \
-                or self.n_pairs > MAX_PAIRS:
+                or self.n_pairs > MAX_PAIRS or self.n_boxes > MAX_BOXES:
             raise ValueError("cost descriptor exceeds compiled table sizes")
         for arr in (self.pt_link, self.pair_i, self.pair_j):
             if arr.size and (arr.min() < 0 or arr.max() >= n_links):
@@ -336,9 +347,10 @@ def build_cost_descriptor(
         link_idxs_for_object_collision_checking / link_margins_..._tensor (robot_base.py:57-85).
     cutoff_*: the fields' cutoff_margin; the per-point margin is the fp32 sum radius + cutoff
         (distance_fields.py:113).
-    objects: iterable of (centers [K,3], radii [K], pos [3] | None, ori_wxyz [4] | None) - one entry
+    objects: iterable of (centers [K,3], radii [K], pos [3] | None, ori_wxyz [4] | None[, boxes]) - one entry
         per ObjectField; several primitive sphere fields of one object are simply concatenated
-        (min over fields of min over spheres, primitives.py:402-405).
+        (min over fields of min over spheres, primitives.py:402-405).  `boxes` is an optional list of
+        (centers [KB,3], sizes [KB,3], rounded: bool) for MultiBoxField (rounded) / MultiSharpBoxField entries.
     self_pairs: (body_i, body_j) pairs, self_margin their margins (robot_base.py:105-141).
     """
     c = CostDescriptor()
@@ -348,8 +360,18 @@ def build_cost_descriptor(
     c.pt_margin_obj = (rad + cutoff_obj).numpy().astype(np.float32) if rad.numel() else np.zeros(0, np.float32)
     c.pt_margin_ws = (rad + cutoff_ws).numpy().astype(np.float32) if rad.numel() else np.zeros(0, np.float32)
     starts, Rs, poss, idents, cs, rs = [0], [], [], [], [], []
+    bstarts, bc, bh, br, bf = [0], [], [], [], []
     for obj in objects:
         centers, radii = _f32(obj[0]).reshape(-1, 3), _f32(obj[1]).reshape(-1)
+        nb = 0
+        for bcen, bsize, rounded in (obj[4] if len(obj) > 4 and obj[4] is not None else []):
+            sizes = torch.as_tensor(_f32(bsize).reshape(-1, 3))
+            bc.append(_f32(bcen).reshape(-1, 3))
+            bh.append((sizes / 2).numpy())                                        # primitives.py:214
+            br.append((torch.min(sizes, dim=-1)[0] * 0.15).numpy() if rounded else np.zeros(len(sizes), np.float32))   # :325
+            bf.append(np.full(len(sizes), 1 if rounded else 0, np.int32))
+            nb += len(sizes)
+        bstarts.append(bstarts[-1] + nb)
         pos = None if len(obj) < 3 or obj[2] is None else _f32(obj[2]).reshape(3)
         ori = None if len(obj) < 4 or obj[3] is None else _f32(obj[3]).reshape(4)
         ident = (pos is None or not np.any(pos)) and (ori is None or (ori[0] == 1 and not np.any(ori[1:])))
@@ -365,6 +387,10 @@ def build_cost_descriptor(
     c.obj_identity = np.asarray(idents, np.int32)
     c.sph_center = np.concatenate(cs).astype(np.float32) if cs else np.zeros((0, 3), np.float32)
     c.sph_radius = np.concatenate(rs).astype(np.float32) if rs else np.zeros(0, np.float32)
+    c.obj_box_start = np.asarray(bstarts, np.int32)
+    if bc:
+        c.box_center, c.box_half = np.concatenate(bc).astype(np.float32), np.concatenate(bh).astype(np.float32)
+        c.box_radius, c.box_rounded = np.concatenate(br).astype(np.float32), np.concatenate(bf).astype(np.int32)
     if ws_min is not None:
         c.ws_enabled, c.ws_min, c.ws_max = 1, _f32(ws_min).reshape(3), _f32(ws_max).reshape(3)
     pairs = np.asarray(self_pairs, np.int32).reshape(-1, 2)

@@ -47,6 +47,42 @@ class MultiSphereField(PrimitiveShapeField):
         self.radii.grad = None
 
 
+class MultiSharpBoxField(PrimitiveShapeField):
+    """Axis-aligned boxes, Chebyshev-style signed distance (reference: primitives.py:198-223)."""
+    ROUNDED = False
+
+    def __init__(self, centers, sizes, tensor_args=None):
+        super().__init__(dim=centers.shape[-1], tensor_args=tensor_args)
+        self.centers = to_torch(centers, **self.tensor_args)
+        self.sizes = to_torch(sizes, **self.tensor_args)
+        self.half_sizes = self.sizes / 2
+
+    def __repr__(self):
+        return f"{type(self).__name__}(centers={self.centers}, sizes={self.sizes})"
+
+    def compute_signed_distance_impl(self, x):
+        d = torch.abs(x.unsqueeze(-2) - self.centers) - self.half_sizes
+        return d.max(dim=-1)[0].min(dim=-1)[0]
+
+
+class MultiBoxField(MultiSharpBoxField):
+    """Rounded boxes, radius 0.15 x the smallest side (reference: primitives.py:309-334)."""
+    ROUNDED = True
+
+    def __init__(self, centers, sizes, tensor_args=None):
+        super().__init__(centers, sizes, tensor_args=tensor_args)
+        self.radius = torch.min(self.sizes, dim=-1)[0] * 0.15
+
+    def compute_signed_distance_impl(self, x):
+        q = torch.abs(x.unsqueeze(-2) - self.centers) - self.half_sizes + self.radius.unsqueeze(-1)
+        mq = torch.amax(q, dim=-1)
+        sdf = torch.minimum(mq, torch.zeros_like(mq)) + torch.linalg.norm(torch.relu(q), dim=-1) - self.radius
+        return sdf.min(dim=-1)[0]
+
+
+MultiRoundedBoxField = MultiBoxField
+
+
 class ObjectField(PrimitiveShapeField):
     """A posed group of primitive fields (pose = pos + wxyz quaternion in the world frame)."""
 
@@ -83,13 +119,16 @@ class ObjectField(PrimitiveShapeField):
             f.zero_grad()
 
     def as_sphere_table(self):
-        """(centers [K,3], radii [K], pos [3], ori_wxyz [4]) for the cost descriptor."""
-        cs, rs = [], []
+        """(centers [K,3], radii [K], pos [3], ori_wxyz [4], boxes) for the cost descriptor: sphere fields are
+        concatenated; box fields are listed as (centers, sizes, rounded)."""
+        cs, rs, boxes = [torch.zeros(0, 3)], [torch.zeros(0)], []
         for f in self.fields:
-            if not isinstance(f, MultiSphereField):
-                raise NotImplementedError(f"{type(f).__name__} obstacles are not ingested by the fused kernel yet "
-                                          "(spheres only; boxes: SURVEY.md section 8 row f2)")
-            cs.append(f.centers.detach().float().cpu().reshape(-1, 3))
-            rs.append(f.radii.detach().float().cpu().reshape(-1))
+            if isinstance(f, MultiSphereField):
+                cs.append(f.centers.detach().float().cpu().reshape(-1, 3))
+                rs.append(f.radii.detach().float().cpu().reshape(-1))
+            elif isinstance(f, MultiSharpBoxField):
+                boxes.append((f.centers.detach().float().cpu().numpy(), f.sizes.detach().float().cpu().numpy(), f.ROUNDED))
+            else:
+                raise NotImplementedError(f"{type(f).__name__} obstacles are not ingested by the fused kernel")
         return torch.cat(cs).numpy(), torch.cat(rs).numpy(), self.pos.detach().float().cpu().numpy(), \
-            self.ori.detach().float().cpu().numpy()
+            self.ori.detach().float().cpu().numpy(), boxes

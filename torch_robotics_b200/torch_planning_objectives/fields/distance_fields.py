@@ -159,7 +159,7 @@ class CollisionObjectDistanceField(CollisionObjectBase):
         sig = []
         for obj in self._objects():
             sig.append((id(obj), obj.pos._version, obj.ori._version, id(obj.pos), id(obj.ori),
-                        tuple((id(f.centers), f.centers._version, f.radii._version) for f in obj.fields)))
+                        tuple((id(f.centers), f.centers._version, getattr(f, 'radii', getattr(f, 'sizes', None))._version) for f in obj.fields)))
         return tuple(sig)
 
     def _descriptor(self):
