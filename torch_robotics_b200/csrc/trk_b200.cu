@@ -521,10 +521,12 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
     }
     if (d->ee_enabled && (d->ee_link < 0 || d->ee_link >= m->L)) return fail(TRK_E_RANGE, "ee_link=%d", d->ee_link);
 
+    int KQ = 0;   // spheres padded per object to a multiple of four (scan table)
+    for (int o = 0; o < nObj; ++o) KQ += (d->obj_start[o + 1] - d->obj_start[o] + 3) & ~3;
     int off = 64;
     auto take = [&](int nw) { int o = off; off = align4(off + nw); return o; };
     const int o_pt_link = take(S), o_mobj = take(S), o_mws = take(S), o_ostart = take(nObj + 1), o_oid = take(nObj),
-              o_oR = take(nObj * 9), o_opos = take(nObj * 3), o_sph = take(K * 4), o_pi = take(P), o_pj = take(P), o_pm = take(P), o_ormax = take(nObj), o_oc2 = take(nObj), o_sphq = take(K * 4),
+              o_oR = take(nObj * 9), o_opos = take(nObj * 3), o_sph = take(K * 4), o_pi = take(P), o_pj = take(P), o_pm = take(P), o_ormax = take(nObj), o_oc2 = take(nObj), o_sphq = take(KQ * 4), o_oqs = take(nObj + 1), o_otol = take(nObj),
               o_sob = take(m->L), o_pts = take(S), o_psi = take(P), o_psj = take(P),
               o_obs = take(nObj + 1), o_box = take(KB * 8);
     const int nwords = off;
@@ -546,10 +548,11 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
     }
     h->off_pt_link = o_pt_link; h->off_pt_mobj = o_mobj; h->off_pt_mws = o_mws; h->off_obj_start = o_ostart;
     h->off_obj_ident = o_oid; h->off_obj_R = o_oR; h->off_obj_pos = o_opos; h->off_sph = o_sph;
-    h->off_pair_i = o_pi; h->off_pair_j = o_pj; h->off_pair_m = o_pm; h->off_obj_rmax = o_ormax; h->off_obj_c2max = o_oc2; h->off_sphq = o_sphq;
+    h->off_pair_i = o_pi; h->off_pair_j = o_pj; h->off_pair_m = o_pm; h->off_obj_rmax = o_ormax; h->off_obj_c2max = o_oc2; h->off_sphq = o_sphq; h->off_obj_qstart = o_oqs; h->off_obj_tol = o_otol;
     for (int s = 0; s < S; ++s) { iw[o_pt_link + s] = d->pt_link[s]; w[o_mobj + s] = d->pt_margin_obj[s]; w[o_mws + s] = d->pt_margin_ws[s]; }
     if (nObj) {
         for (int o = 0; o <= nObj; ++o) iw[o_ostart + o] = d->obj_start[o];
+        int qpos = 0;
         for (int o = 0; o < nObj; ++o) {
             // per-object scan parameters: equal radii -> squared-distance keys; bits = index width packed in the key
             const int k0 = d->obj_start[o], k1 = d->obj_start[o + 1];
@@ -561,15 +564,24 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
                 const float* cc = d->sph_center + 3 * k;
                 const float c2 = cc[0] * cc[0] + cc[1] * cc[1] + cc[2] * cc[2];
                 c2max = fmaxf(c2max, c2);
-                w[o_sphq + 4 * k + 0] = -2.f * cc[0]; w[o_sphq + 4 * k + 1] = -2.f * cc[1];
-                w[o_sphq + 4 * k + 2] = -2.f * cc[2]; w[o_sphq + 4 * k + 3] = c2;
+                float* qw = w + o_sphq + 4 * (qpos + (k - k0));
+                qw[0] = -2.f * cc[0]; qw[1] = -2.f * cc[1]; qw[2] = -2.f * cc[2]; qw[3] = c2;
             }
+            iw[o_oqs + o] = qpos;
+            const int padded = (k1 - k0 + 3) & ~3;
+            for (int k = k1 - k0; k < padded; ++k) {   // dummies that can never be nearest
+                float* qw = w + o_sphq + 4 * (qpos + k);
+                qw[0] = qw[1] = qw[2] = 0.f; qw[3] = 1e30f;
+            }
+            qpos += padded;
+            iw[o_oqs + o + 1] = qpos;
             w[o_oc2 + o] = c2max;
             int bits = 1;
             while ((1 << bits) < (k1 - k0)) ++bits;
             if (k1 == k0) uniform = false;
             iw[o_oid + o] = (d->obj_identity[o] ? OBJ_IDENTITY : 0) | (uniform ? OBJ_UNIFORM_RADIUS : 0) | (bits << OBJ_BITS_SHIFT);
             w[o_ormax + o] = rmax;
+            w[o_otol + o] = ldexpf(1.f, bits - 19);
         }
         memcpy(w + o_oR, d->obj_R, nObj * 9 * sizeof(float));
         memcpy(w + o_opos, d->obj_pos, nObj * 3 * sizeof(float));
