@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Join an ncu report's per-SASS-instruction counters with nvdisasm line info -> per source line.
 
-usage: python tools/ncu_by_line.py <report.ncu-rep> <library.so> <kernel-mangled-substring> [n_warps]
+usage: python tools/ncu_by_line.py <report.ncu-rep> <library.so | object.o> <kernel-mangled-substring> [n_warps]
+(for kernels of the compiled-in family pass the robot's object file, e.g. csrc/build/trk_static_Panda.o: the
+per-robot cubins inside libtrk_b200.so share one file name and overwrite each other when extracted)
 Needs ncu, cuobjdump and nvdisasm on PATH (no GPU)."""
 import collections
 import csv
@@ -22,8 +24,10 @@ def main():
     counts = [(int(r[ia]), int(r[iw]), r[1].strip()) for r in rows[2:] if len(r) > ia]
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-    cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "-g", cubin], capture_output=True, text=True).stdout.splitlines()
+    dis = []
+    for f in sorted(os.listdir(tmp)):      # the library holds one cubin per translation unit
+        if f.endswith(".cubin"):
+            dis += subprocess.run(["nvdisasm", "-g", os.path.join(tmp, f)], capture_output=True, text=True).stdout.splitlines()
     lines, on, cur = [], False, ("?", 0)
     for ln in dis:
         if ln.startswith(".text."):
@@ -48,7 +52,8 @@ def main():
     src = {}
     for (f, l), c in agg.most_common(70):
         if f not in src:
-            for root in (os.path.dirname(os.path.abspath(lib)), "."):
+            libdir = os.path.dirname(os.path.abspath(lib))
+            for root in (libdir, os.path.dirname(libdir), "."):
                 p = os.path.join(root, f)
                 if os.path.exists(p):
                     src[f] = open(p).read().splitlines()
