@@ -106,6 +106,7 @@ class ClockSampler(threading.Thread):
 def cpu_port_rate(desc, cost, n_sample, min_seconds, seed=11):
     """configs/s of the C port of the reference path (oracle/trk_oracle.c) on all host threads."""
     from oracle import c_oracle as co
+    co.set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread
     tree, cc = co.Tree(desc), co.Cost(cost)
     q = sample_q(desc, n_sample, seed)
     out = dict(total=np.empty(n_sample, np.float32), terms=None, grad_q=np.empty_like(q), occ=None, argmin=None)
@@ -126,6 +127,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import c_oracle as co
+    co.set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host thread
     desc, cost = panda_objective_descriptors()
     tree, cc = co.Tree(desc), co.Cost(cost)
     q = sample_q(desc, CPU_SAMPLE, 11)
