@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Small invocations of every kernel family for compute-sanitizer (memcheck / racecheck / initcheck):
+    compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import numpy as np, torch
+from conftest import get_desc, load_golden, planning_cost_from_golden, stretch_cost_from_golden
+from torch_robotics_b200._lib import DeviceCost, DeviceModel
+from torch_robotics_b200.descriptor import compile_urdf
+
+dev = "cuda:0"
+rng = np.random.default_rng(0)
+for robot, n in (("panda", 1000), ("stretch", 333), ("shadow_hand", 97)):
+    d = get_desc(robot)
+    m = DeviceModel(d, dev)
+    q = torch.as_tensor(rng.uniform(-3, 3, (n, d.n_dofs)).astype(np.float32), device=dev)
+    H = m.fk_forward(q)                                   # TMA bulk-store kernel
+    sel = [int(v) for v in rng.permutation(d.n_links)[:3]]
+    Hs = m.fk_forward(q, sel)                             # staged-store kernel
+    g = m.fk_backward(q, torch.randn_like(H))             # cp.async double-buffered kernel
+    gs = m.fk_backward(q, torch.randn_like(Hs), sel)
+# a URDF outside the compiled-in set -> runtime-tree family
+import tempfile
+urdf = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "torch_robotics_b200", "data", "urdf", "robots", "kuka_iiwa", "urdf", "iiwa7_allegro.urdf")
+dg = compile_urdf(urdf, "iiwa7_allegro")
+mg = DeviceModel(dg, dev)
+assert mg.kernel_family == "generic"
+qg = torch.as_tensor(rng.uniform(-1, 1, (515, dg.n_dofs)).astype(np.float32), device=dev)
+Hg = mg.fk_forward(qg); gg = mg.fk_backward(qg, torch.randn_like(Hg))
+for case, robot in (("planning_panda_spheres3d", "panda"), ("planning_panda_two_objects", "panda"), ("planning_panda_boxes", "panda")):
+    g = load_golden(case); d = get_desc(robot); m = DeviceModel(d, dev)
+    dc = DeviceCost(m, planning_cost_from_golden(g))
+    q = torch.as_tensor(g["q"].reshape(-1, 7), device=dev)
+    r = dc.objective(q, want_terms=True, want_occupancy=True, want_argmin=True)
+    H = m.fk_forward(q)
+    r2 = dc.cost_stage(H[:, :, :3, 3].contiguous(), H[:, 10].contiguous(), want_occupancy=True, want_argmin=True)
+g = load_golden("objective_stretch"); d = get_desc("stretch"); m = DeviceModel(d, dev)
+DeviceCost(m, stretch_cost_from_golden(g)).objective(torch.as_tensor(g["q"], device=dev))
+g = load_golden("ik_panda"); m = DeviceModel(get_desc("panda"), dev)
+m.ik_adam(torch.as_tensor(g["q0"], device=dev), g["H_target"], 10, g["lower"], g["upper"], n_iters=5, lr=0.2, se3_eps=0.05, want_loss_stats=True)
+torch.cuda.synchronize()
+print("sanitize_smoke: all kernel families ran")

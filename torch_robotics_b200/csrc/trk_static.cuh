@@ -13,6 +13,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 #include <utility>
@@ -875,7 +876,9 @@ template <class R>
 cudaError_t launch_fk_forward_t(int n_sms, const float* q, long long n, const SlotMap& sm, int n_sel, float* H,
                                        cudaStream_t st) {
     if constexpr (FkTma<R>::body_order()) {
-        bool identity = (n_sel == R::L);
+        static const bool no_tma = std::getenv("TRK_B200_NO_TMA") != nullptr;   // diagnostic switch (compute-sanitizer initcheck
+                                                                                 // does not track async-proxy writes)
+        bool identity = (n_sel == R::L) && !no_tma;
         for (int b = 0; identity && b < R::L; ++b) identity = (sm.slot[b] == b);
         if (identity) {   // all links in body order: TMA bulk-store variant
             auto kt = k_fk_forward_static_tma<R>;
