@@ -562,8 +562,11 @@ struct CMInfo {
     }
 };
 
+#ifndef TRK_CM_MINBLOCKS
+#define TRK_CM_MINBLOCKS 4
+#endif
 template <class R, class CM, bool WANT_GRAD, bool CLAMP>
-__global__ void __launch_bounds__(kSBlock, 4) k_objective_cm(const float* __restrict__ cost_words, int cost_nwords,
+__global__ void __launch_bounds__(kSBlock, TRK_CM_MINBLOCKS) k_objective_cm(const float* __restrict__ cost_words, int cost_nwords,
                                                              const float* __restrict__ q, long long n,
                                                              const float* __restrict__ ee_target_cfg, float margin_override,
                                                              int use_override, float* __restrict__ cost_total,
