@@ -316,7 +316,7 @@ def main():
                                  "frac": kernel_rate * BYTES_PER_CFG / 1e9 / peaks["hbm_gbs"]}},
             "e2e": {"value": world * n / e2e_s, "unit": "configs/s", "h2d_bytes_per_step": n * desc.n_dofs * 4,
                     "d2h_bytes_per_step": n * (desc.n_dofs + 1) * 4, "ms_per_step": e2e_s * 1e3,
-                    "api": "HostObjectivePipeline.run(pinned q) -> pinned cost, grad_q (chunked, copy/compute overlap)"},
+                    "api": "C ABI trk_objective_host(pinned q) -> pinned cost, grad_q (8 chunks, H2D / kernel / D2H on three streams)"},
             "gpu_launches": args.steps,
             "extra_kernels": extra,
             "clocks": sampler.result(),

@@ -180,6 +180,18 @@ int trk_objective(const trk_model* model, const trk_cost* cost, const float* q, 
                   uint8_t* occupancy, int32_t* argmin, void* stream);
 
 /*
+ * Host-buffer form of trk_objective: q, cost_total and grad_q are HOST pointers (page-locked memory gives
+ * asynchronous, overlapped copies; pageable memory works but serialises).  The batch is cut into `n_chunks`
+ * pieces that flow through three internal streams - H2D copy, kernel, D2H copy - so both PCIe directions and the
+ * compute overlap.  Device staging buffers live in the cost handle and are grown on demand (the only
+ * allocation this library performs after handle creation).  The call returns when the results are in host
+ * memory.  Not re-entrant for one cost handle.
+ *   q_host [n, D], cost_total_host [n] (nullable), grad_q_host [n, D] (nullable: forward only)
+ */
+int trk_objective_host(const trk_model* model, trk_cost* cost, const float* q_host, int64_t n, int32_t n_chunks,
+                       float* cost_total_host, float* grad_q_host);
+
+/*
  * Cost stage alone, on caller-supplied link positions - the DistanceField.compute_cost entry
  * (distance_fields.py:26-55) which receives FK output as a tensor.
  *   link_pos [n, L, 3]  world positions of all bodies (RobotBase.fk_map_collision, robot_base.py:171)

@@ -56,7 +56,7 @@ _lib_lock = threading.Lock()
 EXPORTS = [
     "trk_abi_version", "trk_last_error", "trk_model_create", "trk_model_destroy", "trk_model_kernel_family",
     "trk_fk_forward", "trk_fk_backward", "trk_cost_create", "trk_cost_destroy", "trk_cost_set_ee_target",
-    "trk_cost_set_weights", "trk_objective", "trk_cost_stage", "trk_selftest_sqrt", "trk_ik_adam",
+    "trk_cost_set_weights", "trk_objective", "trk_objective_host", "trk_cost_stage", "trk_selftest_sqrt", "trk_ik_adam",
 ]
 
 
@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
         L.trk_objective.argtypes = [vp, vp, vp, i64, vp, f32, vp, vp, vp, vp, vp, vp]
         L.trk_cost_stage.argtypes = [vp, vp, vp, vp, i64, vp, f32, vp, vp, vp, vp, vp, vp, vp]
         L.trk_selftest_sqrt.argtypes = [vp, i64, vp, vp, vp]
+        L.trk_objective_host.argtypes = [vp, vp, vp, i64, i32, vp, vp]
         L.trk_ik_adam.argtypes = [vp, C.POINTER(IKParamsC), vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
         for name in EXPORTS:
             fn = getattr(L, name)
@@ -330,6 +331,20 @@ class DeviceCost:
         check(lib().trk_objective(m.handle, self.handle, q.data_ptr(), n, ptr(tgt), mo, ptr(total), ptr(terms), ptr(grad),
                                   ptr(occ), ptr(amin), stream_ptr(dev)), "trk_objective")
         return dict(total=total, terms=terms, grad_q=grad, occupancy=occ, argmin=amin)
+
+    def objective_host(self, q_host: torch.Tensor, cost_host: torch.Tensor, grad_host: Optional[torch.Tensor] = None,
+                       n_chunks: int = 8) -> None:
+        """trk_objective_host: contiguous fp32 HOST tensors in and out (pin them for overlapped copies); returns
+        when cost_host / grad_host are filled."""
+        for t, name in ((q_host, "q_host"), (cost_host, "cost_host"), (grad_host, "grad_host")):
+            if t is not None and (t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
+                raise RuntimeError(f"{name} must be a contiguous float32 host tensor")
+        n = q_host.shape[0]
+        if q_host.ndim != 2 or q_host.shape[1] != self.model.n_dofs or cost_host.shape != (n,) or \
+                (grad_host is not None and tuple(grad_host.shape) != (n, self.model.n_dofs)):
+            raise RuntimeError("objective_host: shape mismatch")
+        check(lib().trk_objective_host(self.model.handle, self.handle, q_host.data_ptr(), n, int(n_chunks), cost_host.data_ptr(),
+                                       None if grad_host is None else grad_host.data_ptr()), "trk_objective_host")
 
     def cost_stage(self, link_pos: torch.Tensor, ee_pose: Optional[torch.Tensor] = None, want_grad=True,
                    want_occupancy=False, want_argmin=False, ee_target_cfg=None, margin_override: Optional[float] = None):

@@ -288,6 +288,12 @@ struct trk_cost {
     float* d_words;
     int nwords;
     std::vector<float> h_words;  // host mirror, for the setters
+    // host-buffer pipeline (trk_objective_host): staging buffers, streams and events, created on first use
+    float* hp_q = nullptr; float* hp_cost = nullptr; float* hp_grad = nullptr;
+    int64_t hp_cap = 0;
+    cudaStream_t hp_s[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t hp_in[64], hp_k[64];
+    int hp_events = 0;
 };
 
 struct DeviceGuard {
@@ -623,6 +629,9 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
 void trk_cost_destroy(trk_cost* c) {
     if (!c) return;
     DeviceGuard guard(c->device);
+    cudaFree(c->hp_q); cudaFree(c->hp_cost); cudaFree(c->hp_grad);
+    for (int i = 0; i < 3; ++i) if (c->hp_s[i]) cudaStreamDestroy(c->hp_s[i]);
+    for (int i = 0; i < c->hp_events; ++i) { cudaEventDestroy(c->hp_in[i]); cudaEventDestroy(c->hp_k[i]); }
     cudaFree(c->d_words);
     delete c;
 }
@@ -730,6 +739,58 @@ int trk_selftest_sqrt(const float* x, int64_t n, float* y_core, float* y_ref, vo
     k_selftest_sqrt<<<1184, 256, 0, (cudaStream_t)stream>>>(x, n, y_core, y_ref);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? TRK_OK : cuda_fail(e, "selftest_sqrt launch");
+}
+
+int trk_objective_host(const trk_model* m, trk_cost* c, const float* q_host, int64_t n, int32_t n_chunks, float* cost_host,
+                       float* grad_host) {
+    TRK_CHECK_PTR(m, "model"); TRK_CHECK_PTR(c, "cost");
+    if (c->device != m->device || c->L != m->L) return fail(TRK_E_RANGE, "cost tables were built for a different model");
+    if (n < 0) return fail(TRK_E_RANGE, "n=%lld", (long long)n);
+    if (n == 0) return TRK_OK;
+    TRK_CHECK_PTR(q_host, "q_host");
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > 64) n_chunks = 64;
+    DeviceGuard guard(m->device);
+    const int D = m->D;
+    cudaError_t e = cudaSuccess;
+    if (!c->hp_s[0]) {
+        for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&c->hp_s[i], cudaStreamNonBlocking);
+        for (; c->hp_events < 64 && e == cudaSuccess; ++c->hp_events) {
+            e = cudaEventCreateWithFlags(&c->hp_in[c->hp_events], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->hp_k[c->hp_events], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "objective_host: stream/event creation");
+    }
+    if (n > c->hp_cap) {
+        cudaFree(c->hp_q); cudaFree(c->hp_cost); cudaFree(c->hp_grad);
+        c->hp_q = c->hp_cost = c->hp_grad = nullptr; c->hp_cap = 0;
+        e = cudaMalloc(&c->hp_q, (size_t)n * D * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&c->hp_cost, (size_t)n * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&c->hp_grad, (size_t)n * D * sizeof(float));
+        if (e != cudaSuccess) return cuda_fail(e, "objective_host: staging allocation");
+        c->hp_cap = n;
+    }
+    const int64_t step = (n + n_chunks - 1) / n_chunks;
+    int ci = 0;
+    for (int64_t lo = 0; lo < n; lo += step, ++ci) {
+        const int64_t cnt = (lo + step <= n) ? step : n - lo;
+        e = cudaMemcpyAsync(c->hp_q + lo * D, q_host + lo * D, (size_t)cnt * D * sizeof(float), cudaMemcpyHostToDevice, c->hp_s[0]);
+        if (e == cudaSuccess) e = cudaEventRecord(c->hp_in[ci], c->hp_s[0]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->hp_s[1], c->hp_in[ci], 0);
+        if (e != cudaSuccess) return cuda_fail(e, "objective_host: H2D");
+        const int rc = trk_objective(m, c, c->hp_q + lo * D, cnt, nullptr, NAN, c->hp_cost + lo, nullptr,
+                                     grad_host ? c->hp_grad + lo * D : nullptr, nullptr, nullptr, c->hp_s[1]);
+        if (rc) return rc;
+        e = cudaEventRecord(c->hp_k[ci], c->hp_s[1]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->hp_s[2], c->hp_k[ci], 0);
+        if (e == cudaSuccess && cost_host)
+            e = cudaMemcpyAsync(cost_host + lo, c->hp_cost + lo, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToHost, c->hp_s[2]);
+        if (e == cudaSuccess && grad_host)
+            e = cudaMemcpyAsync(grad_host + lo * D, c->hp_grad + lo * D, (size_t)cnt * D * sizeof(float), cudaMemcpyDeviceToHost, c->hp_s[2]);
+        if (e != cudaSuccess) return cuda_fail(e, "objective_host: D2H");
+    }
+    e = cudaStreamSynchronize(c->hp_s[2]);
+    return e == cudaSuccess ? TRK_OK : cuda_fail(e, "objective_host: synchronize");
 }
 
 int trk_cost_stage(const trk_model* m, const trk_cost* c, const float* link_pos, const float* ee_pose, int64_t n,
