@@ -276,6 +276,7 @@ struct trk_model {
     int nwords;
     int family;                 // trk::StaticFamily id, 0 = generic
     int32_t parent[TRK_MAX_LINKS];
+    int32_t qidx[TRK_MAX_LINKS];
 };
 
 struct trk_cost {
@@ -418,6 +419,7 @@ int trk_model_create(const trk_model_desc* d, int device, trk_model** out) {
     m->device = device; m->L = L; m->D = D; m->nwords = nwords;
     m->maxl_bucket = L <= 16 ? 16 : (L <= 32 ? 32 : 64);
     memcpy(m->parent, d->parent, L * sizeof(int32_t));
+    memcpy(m->qidx, d->q_index, L * sizeof(int32_t));
     cudaError_t e = cudaDeviceGetAttribute(&m->n_sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) { delete m; return cuda_fail(e, "cudaDeviceGetAttribute"); }
     e = cudaMalloc(&m->d_words, nwords * sizeof(float));
@@ -721,6 +723,8 @@ int trk_ik_adam(const trk_model* m, const trk_ik_params* p, const float* step_si
     P.w_se3 = p->w_se3; P.w_lim = p->w_joint_limits; P.se3_eps = p->se3_eps;
     for (int c = 0; c < m->D; ++c) { P.lower[c] = p->lower[c]; P.upper[c] = p->upper[c]; }
     if (p->H_target) memcpy(P.target, p->H_target, sizeof(P.target));
+    for (int b = p->ee_link; b >= 0; b = m->parent[b])   // q columns of the joints between the root and the EE body
+        if (m->qidx[b] >= 0) P.anc_mask |= 1u << m->qidx[b];
     DeviceGuard guard(m->device);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(valid_count, 0, sizeof(int32_t) * p->n_iters, st);

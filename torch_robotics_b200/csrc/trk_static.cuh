@@ -704,6 +704,8 @@ __global__ void __launch_bounds__(kSBlock, TRK_CM_MINBLOCKS) k_objective_cm(cons
 // ------------------------------------------------------------------------------------------
 struct IKParams {
     int   ee_link, n_iters, n_updates, per_seed_target;
+    unsigned anc_mask;      // bit c set when q column c drives an ancestor (or the body itself) of ee_link
+    int   pad_i[3];
     float lr, beta1, beta2, eps, w_se3, w_lim, se3_eps, pad;
     float lower[TRK_MAX_DOFS], upper[TRK_MAX_DOFS];
     float target[16];
@@ -775,22 +777,31 @@ __global__ void __launch_bounds__(kSBlock) k_ik_adam_static(IKParams P, const fl
             if (loss_sum) { atomicAdd(loss_sum + it, s_sum); atomicAdd(loss_sqsum + it, s_sq); }
         }
         if (it >= P.n_updates) continue;
-        // gradient of the loss: EE wrench applied at the EE body, projected on the joints above it.  The
-        // wrench enters every joint's subtree sum only if the joint is an ancestor of the EE body, which
-        // the leaf->root sweep of STree::backward handles through the body index.
+        // gradient of the loss: the only wrench is the EE one, so every joint above the EE body sees the same
+        // (F, T) and no tree sweep is needed: d loss / d q_j = a_j . (T - p_j x F) for ancestors, 0 otherwise
+        // (revolute; prismatic: a_j . F); the clamp mask of FK applies as in STree::backward.
         float ax, ay, az;
         axial_gR_Rt(gR, Wee, ax, ay, az);
         const float eF[3] = {gp[0], gp[1], gp[2]};
         const float eT[3] = {Wee[10] * gp[2] - Wee[11] * gp[1] + ax, Wee[11] * gp[0] - Wee[9] * gp[2] + ay,
                              Wee[9] * gp[1] - Wee[10] * gp[0] + az};
         float grad[D];
-        STree<R>::backward(JA, [&](auto bc, float (&f)[3], float (&t)[3], float (&pos)[3]) {
-            constexpr int b = decltype(bc)::value;
-            constexpr int qb = R::qidx[STree<R>::topo_index_of(b)];
-            if constexpr (qb >= 0) { sfor<3>([&](auto rc) { pos[rc] = PJ[qb][rc]; }); } else { sfor<3>([&](auto rc) { pos[rc] = 0.f; }); }
-            const bool is_e = (b == P.ee_link);
-            sfor<3>([&](auto rc) { f[rc] = is_e ? eF[rc] : 0.f; t[rc] = is_e ? eT[rc] : 0.f; });
-        }, pass, [&](int c, float g) { grad[c] = g; });
+        sfor<L>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int qi = R::qidx[i];
+            if constexpr (qi >= 0) {
+                float g;
+                if constexpr (R::kind[i] == TRK_KIND_REVOLUTE) {
+                    const float mx = eT[0] - (PJ[qi][1] * eF[2] - PJ[qi][2] * eF[1]);
+                    const float my = eT[1] - (PJ[qi][2] * eF[0] - PJ[qi][0] * eF[2]);
+                    const float mz = eT[2] - (PJ[qi][0] * eF[1] - PJ[qi][1] * eF[0]);
+                    g = JA[qi][0] * mx + JA[qi][1] * my + JA[qi][2] * mz;
+                } else {
+                    g = JA[qi][0] * eF[0] + JA[qi][1] * eF[1] + JA[qi][2] * eF[2];
+                }
+                grad[qi] = (((P.anc_mask & pass) >> qi) & 1u) ? g : 0.f;
+            }
+        });
         const float ss = step_size[it], b2s = bc2_sqrt[it];
         sfor<D>([&](auto c) {
             const float lo = P.lower[c], hi = P.upper[c];
