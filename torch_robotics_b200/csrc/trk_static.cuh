@@ -802,15 +802,16 @@ __global__ void __launch_bounds__(kSBlock) k_ik_adam_static(IKParams P, const fl
                 grad[qi] = (((P.anc_mask & pass) >> qi) & 1u) ? g : 0.f;
             }
         });
-        const float ss = step_size[it], b2s = bc2_sqrt[it];
+        const float ss = step_size[it], inv_b2s = 1.f / bc2_sqrt[it];
         sfor<D>([&](auto c) {
             const float lo = P.lower[c], hi = P.upper[c];
             float g = grad[c];
             g += P.w_lim * ((qv[c] < lo ? -2.f * (lo - qv[c]) : 0.f) + (qv[c] > hi ? -2.f * (hi - qv[c]) : 0.f));
             mom[c] = fmaf(1.f - P.beta1, g - mom[c], mom[c]);                 // exp_avg.lerp_(grad, 1 - beta1)
             var[c] = fmaf((1.f - P.beta2) * g, g, var[c] * P.beta2);          // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
-            const float denom = sqrtf(var[c]) / b2s + P.eps;
-            qv[c] = qv[c] - ss * (mom[c] / denom);                            // param.addcdiv_(exp_avg, denom, -step_size)
+            float rs_unused;
+            const float denom = sqrt_rn_core(var[c], rs_unused) * inv_b2s + P.eps;   // sqrt(v) / sqrt(1 - beta2^t) + eps
+            qv[c] = qv[c] - ss * __fdividef(mom[c], denom);                        // param.addcdiv_(exp_avg, denom, -step_size)
         });
     }
     if (live) {
