@@ -184,6 +184,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from torch_robotics_b200.distributed import bind_to_gpu_numa_node
+    numa_bound = bind_to_gpu_numa_node(local_rank) if world > 1 else False
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -318,6 +320,7 @@ def main():
                     "d2h_bytes_per_step": n * (desc.n_dofs + 1) * 4, "ms_per_step": e2e_s * 1e3,
                     "api": "C ABI trk_objective_host(pinned q) -> pinned cost, grad_q (8 chunks, H2D / kernel / D2H on three streams)"},
             "gpu_launches": args.steps,
+            "numa_bound": numa_bound,
             "extra_kernels": extra,
             "clocks": sampler.result(),
             "wall_s_timed_region": t_wall,

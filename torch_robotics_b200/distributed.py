@@ -92,3 +92,17 @@ def gather_best_solutions(q_local: torch.Tensor, err_local: torch.Tensor, valid_
     top = torch.argsort(gkey, stable=True)[:k]
     sel = allb[top]
     return sel[:, :D], sel[:, D], sel[:, D + 1] > 0
+
+
+def bind_to_gpu_numa_node(device_index: int) -> bool:
+    """Pin the calling process to the CPU cores NVML reports as local to GPU `device_index`, so that page-locked
+    host buffers allocated afterwards (first touch) and the copy threads sit on the GPU's NUMA node.  Matters for
+    the host-buffer path when several ranks share one host: without it, ranks contend for one socket's memory
+    and the inter-socket link.  Returns False when NVML is unavailable (the call is then a no-op)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(int(device_index)))
+        return True
+    except Exception:
+        return False
