@@ -109,6 +109,18 @@ typedef struct trk_cost_desc {
     const float*   box_half;       /* [KB*3] half sizes */
     const float*   box_radius;     /* [KB] rounding radius of MultiBoxField (:309-334); ignored for sharp boxes */
     const int32_t* box_rounded;    /* [KB] 1 = MultiBoxField (rounded), 0 = MultiSharpBoxField */
+    /* precomputed voxel SDF (environments/grid_map_sdf.py:9-114; EnvBase(precompute_sdf_obj_fixed=True), env_base.py:59-65):
+       at most one object may be a grid instead of primitives.  grid_obj = its object index (the object then owns no
+       spheres or boxes and must have the identity pose), -1 = none.  Cell of a point x (grid_map_sdf.py:96-101):
+       i = clamp(int(floor((x - grid_lo) / grid_extent * grid_n)), 0, grid_n - 1) per axis, in fp32.  grid_data is a
+       DEVICE pointer to [n0, n1, n2, 4] fp32 = (sdf, d sdf/dx, d sdf/dy, d sdf/dz) per cell, 16-byte aligned, owned by
+       the caller and kept alive as long as the cost handle; the value is sdf[cell], its gradient the stored one (the
+       reference's surrogate, grid_map_sdf.py:103-112). */
+    int32_t        grid_obj;
+    int32_t        grid_n[3];
+    float          grid_lo[3];
+    float          grid_extent[3];
+    const float*   grid_data;
     int32_t        ws_enabled;
     float          ws_min[3];      /* distance_fields.py:326-332 */
     float          ws_max[3];

@@ -26,6 +26,7 @@ class OrcCost(C.Structure):
                 ("n_objects", C.c_int32), ("obj_start", ip), ("obj_identity", ip), ("obj_R", fp), ("obj_pos", fp),
                 ("n_spheres", C.c_int32), ("sph_center", fp), ("sph_radius", fp),
                 ("n_boxes", C.c_int32), ("obj_box_start", ip), ("box_center", fp), ("box_half", fp), ("box_radius", fp), ("box_rounded", ip),
+                ("grid_obj", C.c_int32), ("grid_n", C.c_int32 * 3), ("grid_lo", C.c_float * 3), ("grid_extent", C.c_float * 3), ("grid_data", fp),
                 ("ws_enabled", C.c_int32), ("ws_min", C.c_float * 3), ("ws_max", C.c_float * 3),
                 ("n_pairs", C.c_int32), ("pair_i", ip), ("pair_j", ip), ("pair_margin", fp),
                 ("ee_enabled", C.c_int32), ("ee_link", C.c_int32), ("ee_w_pos", C.c_float), ("ee_w_rot", C.c_float),
@@ -85,6 +86,14 @@ class Cost:
         s.n_spheres, s.sph_center, s.sph_radius = c.n_spheres, P("sc"), P("sr")
         s.n_boxes, s.obj_box_start, s.box_center, s.box_half = c.n_boxes, P("obs"), P("bc"), P("bh")
         s.box_radius, s.box_rounded = P("br"), P("bf")
+        s.grid_obj = int(getattr(c, "grid_obj", -1))
+        if s.grid_obj >= 0:
+            g = c.grid_data
+            k["grid"] = _a(g if isinstance(g, np.ndarray) else g.detach().cpu().numpy(), np.float32)
+            s.grid_n = (C.c_int32 * 3)(*[int(v) for v in c.grid_n])
+            s.grid_lo = (C.c_float * 3)(*[float(v) for v in c.grid_lo])
+            s.grid_extent = (C.c_float * 3)(*[float(v) for v in c.grid_extent])
+            s.grid_data = k["grid"].ctypes.data_as(fp)
         s.ws_enabled = int(c.ws_enabled)
         s.ws_min = (C.c_float * 3)(*[float(v) for v in c.ws_min])
         s.ws_max = (C.c_float * 3)(*[float(v) for v in c.ws_max])

@@ -240,6 +240,24 @@ def _box_sdf_and_grad(cost, kb, xo, dtype):
     return sd, (sgn * (w + onehot.astype(dtype))).astype(dtype)
 
 
+def grid_cells(cost, x):
+    """Cell index of points x [..., 3]: clamp(int(floor((x - lo) / extent * n)), 0, n - 1), every step rounded to fp32
+    (grid_map_sdf.py:96-101: the grid shape enters as an int64 tensor that type promotion turns into fp32)."""
+    x = np.asarray(x, np.float32)
+    t = ((x - cost.grid_lo.astype(np.float32)) / cost.grid_extent.astype(np.float32)).astype(np.float32)
+    t = np.floor((t * cost.grid_n.astype(np.float32)).astype(np.float32))
+    with np.errstate(invalid="ignore"):
+        i = np.where(np.isfinite(t), np.clip(t, -1.0, 2.0 ** 30), -1.0).astype(np.int64)
+    return np.clip(i, 0, cost.grid_n.astype(np.int64) - 1)
+
+
+def _grid_host(cost):
+    g = cost.grid_data
+    if not isinstance(g, np.ndarray):
+        g = g.detach().cpu().numpy()
+    return np.asarray(g, np.float32)
+
+
 def object_term(cost, x, dtype=np.float32, margin_override=None):
     """Object-collision term on collision points x [N,S,3].
 
@@ -283,6 +301,12 @@ def object_term(cost, x, dtype=np.float32, margin_override=None):
             best = np.where(take, sd, best)
             bidx = np.where(take, (k1 - k0) + (kb - kb0), bidx)
             bdir = np.where(take[..., None], gd, bdir)
+        if o == getattr(cost, "grid_obj", -1):   # voxel SDF lookup, grid_map_sdf.py:96-112 (index always in fp32)
+            ci = grid_cells(cost, xo)
+            n1, n2 = int(cost.grid_n[1]), int(cost.grid_n[2])
+            cell = _grid_host(cost)[ci[..., 0], ci[..., 1], ci[..., 2]]
+            best, bdir = cell[..., 0].astype(dtype), cell[..., 1:4].astype(dtype)
+            bidx = ((ci[..., 0] * n1 + ci[..., 1]) * n2 + ci[..., 2]).astype(np.int32)
         sdf[:, o], amin[:, o] = best, bidx
         gdir[:, o] = bdir if cost.obj_identity[o] else (bdir @ cost.obj_R[o].astype(dtype).T)
     margin = cost.pt_margin_obj.astype(dtype)[None, None, :]

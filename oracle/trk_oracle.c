@@ -49,6 +49,10 @@ typedef struct {
     const int32_t *obj_box_start;
     const float *box_center, *box_half, *box_radius;
     const int32_t *box_rounded;
+    int32_t grid_obj;                  /* voxel SDF object (grid_map_sdf.py), -1 = none */
+    int32_t grid_n[3];
+    float grid_lo[3], grid_extent[3];
+    const float *grid_data;            /* HOST [n0][n1][n2][4] = (sdf, grad) */
     int32_t ws_enabled;
     float ws_min[3], ws_max[3];
     int32_t n_pairs;
@@ -70,6 +74,14 @@ static float norm3(float x, float y, float z) {
 }
 
 /* one box primitive (primitives.py:219-223 sharp, :326-334 rounded): signed distance, optionally its gradient */
+/* cell index along one axis: clamp(int(floor((x - lo) / extent * n)), 0, n - 1) in fp32 (grid_map_sdf.py:96-101) */
+static int grid_cell(float x, const orc_cost *k, int a) {
+    const float t = floorf(((x - k->grid_lo[a]) / k->grid_extent[a]) * (float)k->grid_n[a]);
+    if (!(t >= 0.f)) return 0;
+    if (t >= (float)k->grid_n[a]) return k->grid_n[a] - 1;
+    return (int)t;
+}
+
 static float box_sdf(const orc_cost *k, int kb, const float *x, float *g) {
     const float *c = k->box_center + 3 * kb, *hh = k->box_half + 3 * kb;
     const float r = k->box_radius[kb];
@@ -265,6 +277,12 @@ static void objective_one(const orc_tree *t, const orc_cost *k, const float *q, 
                         const float sd = box_sdf(k, kb, xob, 0);
                         if (sd < best) { best = sd; bbox = kb; bidx = (k->obj_start[o + 1] - k->obj_start[o]) + (kb - k->obj_box_start[o]); }
                     }
+                const float *cell = 0;
+                if (o == k->grid_obj) { /* grid_map_sdf.py:96-112: cell lookup, stored gradient */
+                    bidx = (grid_cell(xo, k, 0) * k->grid_n[1] + grid_cell(yo, k, 1)) * k->grid_n[2] + grid_cell(zo, k, 2);
+                    cell = k->grid_data + 4 * (int64_t)bidx;
+                    best = cell[0];
+                }
                 if (argmin) argmin[o * S + s] = bidx;
                 if (best < (use_mo ? mo : m)) occ |= 2u;
                 float val = -(best - m);
@@ -272,9 +290,10 @@ static void objective_one(const orc_tree *t, const orc_cost *k, const float *q, 
                 if (k->clamp_obj) { act = val > 0.f; val = fmaxf(val, 0.f); }
                 if (o == 0 || val > vmax) {
                     vmax = val;
-                    if (act && (bd > 0.f || bbox >= 0)) {
+                    if (act && (bd > 0.f || bbox >= 0 || cell)) {
                         float ux = 0.f, uy = 0.f, uz = 0.f;
-                        if (bbox >= 0) { float gb[3]; box_sdf(k, bbox, xob, gb); ux = gb[0]; uy = gb[1]; uz = gb[2]; }
+                        if (cell) { ux = cell[1]; uy = cell[2]; uz = cell[3]; }
+                        else if (bbox >= 0) { float gb[3]; box_sdf(k, bbox, xob, gb); ux = gb[0]; uy = gb[1]; uz = gb[2]; }
                         else { ux = bvx / bd; uy = bvy / bd; uz = bvz / bd; }
                         if (!k->obj_identity[o]) {
                             const float wx = Ro[0] * ux + Ro[1] * uy + Ro[2] * uz, wy = Ro[3] * ux + Ro[4] * uy + Ro[5] * uz,

@@ -375,8 +375,155 @@ def golden_trajectories():
     print("trajectories: free", out["3d_free_idx"].reshape(-1), "coll", out["3d_coll_idx"].reshape(-1), "frac", out["fraction_free"])
 
 
+class _NoGrasp:   # the generic fields only read robot.grasped_object (distance_fields.py:137)
+    grasped_object = None
+
+
+def _point_model_case(tag, q, pos_fn, pt_cols, pt_radius, env, cutoff, self_rows=None, self_pairs=None, self_margin=None, extra=None):
+    """Objective over collision points that are columns of pos_fn(q) [..., C, 3], composed from the reference's
+    generic field classes (the pattern of golden_stretch_objective)."""
+    f_obj = CollisionObjectDistanceField(_NoGrasp(), df_obj_list_fn=env.get_df_obj_list,
+                                         link_idxs_for_collision_checking=pt_cols,
+                                         link_margins_for_object_collision_checking_tensor=pt_radius,
+                                         cutoff_margin=cutoff, tensor_args=TA)
+    f_ws = CollisionWorkspaceBoundariesDistanceField(_NoGrasp(), link_idxs_for_collision_checking=pt_cols,
+                                                     link_margins_for_object_collision_checking_tensor=pt_radius,
+                                                     cutoff_margin=cutoff, ws_bounds_min=env.limits[0],
+                                                     ws_bounds_max=env.limits[1], tensor_args=TA)
+    f_self = None
+    if self_rows is not None:
+        from torch_robotics.torch_planning_objectives.fields.distance_fields import CollisionSelfField
+        f_self = CollisionSelfField(_NoGrasp(), link_idxs_for_collision_checking=self_rows,
+                                    idxs_links_distance_matrix=self_pairs, cutoff_margin=self_margin, tensor_args=TA)
+    fields = dict(obj=f_obj, ws=f_ws)
+    if f_self is not None:
+        fields["self"] = f_self
+    out = dict(q=q.numpy(), pt_cols=np.array(pt_cols, np.int32), pt_radius=pt_radius.numpy(), cutoff=np.float64(cutoff),
+               centers=env.obj_fixed_list[0].fields[0].centers.numpy(), radii=env.obj_fixed_list[0].fields[0].radii.numpy(),
+               ws_min=env.limits[0].numpy(), ws_max=env.limits[1].numpy())
+    if f_self is not None:
+        out.update(self_rows=np.array(self_rows, np.int32), self_pairs_local=np.array(self_pairs, np.int32),
+                   self_margin=self_margin.numpy())
+    out.update(extra or {})
+    for which in list(fields) + ["total"]:
+        qq = q.clone().requires_grad_(True)
+        pos = pos_fn(qq)
+        cs = {k: f.compute_cost(qq, pos, field_type="sdf") for k, f in fields.items()}
+        c = sum(cs.values()) if which == "total" else cs[which]
+        c.sum().backward()
+        out[f"cost_{which}"] = c.detach().numpy()
+        out[f"grad_{which}"] = qq.grad.numpy()
+    with torch.no_grad():
+        pos = pos_fn(q)
+        out["link_pos"] = pos.numpy()
+        for k, f in fields.items():
+            out[f"occ_{k}"] = f.compute_cost(q, pos, field_type="occupancy").numpy()
+    np.savez_compressed(os.path.join(HERE, f"points_{tag}.npz"), **out)
+    print("points", tag, "cost_total[0,:3]", out["cost_total"].reshape(-1)[:3], "occ", {k: int(out[f"occ_{k}"].sum()) for k in fields})
+
+
+def golden_attached_points():
+    """collision points that are not link origins.
+    (1) the grasped box of environments/objects.py:37-89 on RobotPanda.  The reference's PlanningTask raises
+        IndexError for it (distance_fields.py:137-154 selects the link columns twice), so the objective is composed
+        from its generic field classes over the columns robot_base.py:75-127 sets up: the five link spheres + the 14
+        box points against the obstacles / workspace, the ten robot pairs + 14 x 4 box-link pairs for self-collision.
+    (2) the per-link multi-sphere model of data/configs/panda/panda_sphere_config.yaml (unused by the reference's
+        own code): sphere centres are Frame.transform_point() of the link frames."""
+    import yaml
+    from pathlib import Path
+    from torch_robotics.environments.objects import GraspedObjectPandaBox
+    gen = torch.Generator().manual_seed(2718)
+    env = quiet(EnvSpheres3D, tensor_args=TA)
+
+    # (1) the reference rewrites the URDF next to the original; the tree is read-only here and already holds the
+    # result of that rewriting for this very object, so hand its path back instead of writing.
+    R.modidy_franka_panda_urdf_grasped_object = lambda f, g: Path(str(f).replace(".urdf", "_grasped_object.urdf"))
+    go = GraspedObjectPandaBox(tensor_args=TA)
+    robot = quiet(RobotPanda, grasped_object=go, tensor_args=TA)
+    n_links = len(robot.diff_panda.get_link_names())
+    n_pts = go.n_base_points_for_collision
+    grasp_cols = list(range(n_links, n_links + n_pts))
+    q = (robot.q_min + torch.rand(16, 8, 7, generator=gen) * (robot.q_max - robot.q_min)).contiguous()
+    _point_model_case("panda_grasped_box", q, robot.fk_map_collision,
+                      list(robot.link_idxs_for_object_collision_checking) + grasp_cols,
+                      robot.link_margins_for_object_collision_checking_tensor, env, 0.02,
+                      self_rows=list(robot.link_idxs_for_self_collision_checking) + grasp_cols,
+                      self_pairs=robot.df_collision_self.idxs_links_distance_matrix,
+                      self_margin=robot.df_collision_self.cutoff_margin,
+                      extra=dict(base_points=go.base_points_for_collision.numpy(), grasp_pos=go.pos.numpy(), grasp_ori=go.ori.numpy(),
+                                 link_names=np.array(robot.diff_panda.get_link_names())))
+
+    # (2)
+    cfg = yaml.safe_load(open("/root/reference/torch_robotics/data/configs/panda/panda_sphere_config.yaml"))
+    robot = quiet(RobotPanda, tensor_args=TA)
+    names = robot.diff_panda.get_link_names()
+    spheres = [(l, s) for l, lst in cfg.items() if l in names for s in lst]
+    offs = torch.tensor([s[:3] for _, s in spheres], **TA)
+    radii = torch.tensor([s[3] for _, s in spheres], **TA)
+
+    def pos_fn(qq):
+        shp = qq.shape
+        frames = robot.diff_panda.compute_forward_kinematics_all_links(qq.reshape(-1, 7), return_dict=True)
+        link_pos = torch.stack([frames[n].translation for n in names], dim=-2)
+        pts = torch.stack([frames[l].transform_point(offs[i:i + 1]).reshape(-1, 3) for i, (l, _) in enumerate(spheres)], dim=-2)
+        return torch.cat((link_pos, pts), dim=-2).reshape(*shp[:-1], len(names) + len(spheres), 3)
+
+    q = (robot.q_min + torch.rand(12, 8, 7, generator=gen) * (robot.q_max - robot.q_min)).contiguous()
+    _point_model_case("panda_sphere_model", q, pos_fn, list(range(len(names), len(names) + len(spheres))), radii, env, 0.01,
+                      extra=dict(sphere_links=np.array([l for l, _ in spheres]), sphere_offsets=offs.numpy()))
+
+
+def golden_voxel_sdf():
+    """EnvBase(precompute_sdf_obj_fixed=True) replaces the fixed objects by a GridMapSDF
+    (grid_map_sdf.py:9-114).  Coarse cells (0.05 m -> 40^3) keep the fixture small; one extra (non-grid) object is
+    added so that the max over objects (distance_fields.py:121) sees both kinds."""
+    gen = torch.Generator().manual_seed(1618)
+    robot = quiet(RobotPanda, tensor_args=TA)
+    extra = ObjectField([MultiSphereField(torch.tensor([[0.3, 0.3, 0.6], [-0.2, -0.4, 0.7]]), torch.tensor([0.2, 0.15]), tensor_args=TA)], "extra")
+    env = quiet(EnvSpheres3D, precompute_sdf_obj_fixed=True, sdf_cell_size=0.05, obj_extra_list=[extra], tensor_args=TA)
+    grid = env.grid_map_sdf_obj_fixed
+    task = quiet(PlanningTask, env=env, robot=robot, tensor_args=TA)
+    q = (robot.q_min + torch.rand(8, 16, 7, generator=gen) * (robot.q_max - robot.q_min)).contiguous()
+    out = dict(q=q.numpy(), sdf_tensor=grid.sdf_tensor.numpy(), grad_sdf_tensor=grid.grad_sdf_tensor.numpy(),
+               cmap_dim=grid.cmap_dim.numpy().astype(np.int32), limits=env.limits.numpy(), cell_size=np.float64(0.05),
+               extra_centers=extra.fields[0].centers.numpy(), extra_radii=extra.fields[0].radii.numpy(),
+               pt_link=np.array(robot.link_idxs_for_object_collision_checking, np.int32),
+               pt_radius=robot.link_margins_for_object_collision_checking_tensor.numpy(),
+               obstacle_cutoff_margin=np.float64(task.df_collision_objects.cutoff_margin))
+    for which in ("obj", "collision"):
+        qq = q.clone().requires_grad_(True)
+        pos = robot.fk_map_collision(qq)
+        c = task.df_collision_objects.compute_cost(qq, pos, field_type="sdf") if which == "obj" else task.compute_collision_cost(qq)
+        c.sum().backward()
+        out[f"cost_{which}"], out[f"grad_{which}"] = c.detach().numpy(), qq.grad.numpy()
+    with torch.no_grad():
+        pos = robot.fk_map_collision(q)
+        out["link_pos"] = pos.numpy()
+        out["occ_obj"] = task.df_collision_objects.compute_cost(q, pos, field_type="occupancy").numpy()
+        out["occ_obj_zero"] = task.df_collision_objects.compute_cost(q, pos, field_type="occupancy", margin=0.0).numpy()
+        out["occ_all"] = task.compute_collision(q).numpy()
+        pts = pos[..., robot.link_idxs_for_object_collision_checking, :]
+        cells = ((pts - grid.limits[0]) / grid.map_dim * grid.cmap_dim).floor().to(torch.int)
+        hi = torch.tensor(grid.points_for_sdf.shape[:-1]).type_as(cells) - 1
+        out["cells"] = cells.clamp(torch.zeros_like(hi), hi).numpy()
+        # standalone queries incl. points outside the workspace (clamped to the border cells, grid_map_sdf.py:99-100)
+        X = (torch.rand(512, 3, generator=gen) * 2.6 - 1.3).requires_grad_(False)
+        out["query_x"] = X.numpy()
+        out["query_sdf"] = grid(X.clone()).numpy()
+    Xg = torch.tensor(out["query_x"]).requires_grad_(True)
+    grid(Xg).sum().backward()
+    out["query_grad"] = Xg.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "planning_panda_voxel_sdf.npz"), **out)
+    print("voxel sdf", tuple(out["cmap_dim"]), "cost_collision[0,:3]", out["cost_collision"][0, :3], "occ", int(out["occ_obj"].sum()))
+
+
 if __name__ == "__main__":
-    if os.environ.get("GOLDEN_ONLY") == "trajectories":
+    if os.environ.get("GOLDEN_ONLY") == "voxel":
+        golden_voxel_sdf()
+    elif os.environ.get("GOLDEN_ONLY") == "points":
+        golden_attached_points()
+    elif os.environ.get("GOLDEN_ONLY") == "trajectories":
         golden_trajectories()
     elif os.environ.get("GOLDEN_ONLY") == "boxes":
         golden_planning_boxes()
@@ -387,3 +534,5 @@ if __name__ == "__main__":
         golden_stretch_objective()
         golden_ik()
         golden_trajectories()
+        golden_attached_points()
+        golden_voxel_sdf()

@@ -36,6 +36,8 @@ class CostDesc(C.Structure):
                 ("obj_pos", c_float_p), ("n_spheres", C.c_int32), ("sph_center", c_float_p), ("sph_radius", c_float_p),
                 ("n_boxes", C.c_int32), ("obj_box_start", c_int32_p), ("box_center", c_float_p), ("box_half", c_float_p),
                 ("box_radius", c_float_p), ("box_rounded", c_int32_p),
+                ("grid_obj", C.c_int32), ("grid_n", C.c_int32 * 3), ("grid_lo", C.c_float * 3), ("grid_extent", C.c_float * 3),
+                ("grid_data", C.c_void_p),
                 ("ws_enabled", C.c_int32), ("ws_min", C.c_float * 3), ("ws_max", C.c_float * 3),
                 ("n_pairs", C.c_int32), ("pair_i", c_int32_p), ("pair_j", c_int32_p), ("pair_margin", c_float_p),
                 ("ee_enabled", C.c_int32), ("ee_link", C.c_int32), ("ee_w_pos", C.c_float), ("ee_w_rot", C.c_float),
@@ -267,6 +269,18 @@ class DeviceCost:
         cd.n_spheres, cd.sph_center, cd.sph_radius = cost.n_spheres, _fp(k["sph_c"]), _fp(k["sph_r"])
         cd.n_boxes, cd.obj_box_start, cd.box_center, cd.box_half = cost.n_boxes, _ip(k["obs"]), _fp(k["bc"]), _fp(k["bh"])
         cd.box_radius, cd.box_rounded = _fp(k["br"]), _ip(k["bf"])
+        cd.grid_obj = int(getattr(cost, "grid_obj", -1))
+        if cd.grid_obj >= 0:     # the voxel grid stays in HBM; the handle only records its address
+            g = cost.grid_data
+            g = g if torch.is_tensor(g) else torch.as_tensor(np.ascontiguousarray(g, np.float32))
+            g = g.detach().to(device=model.device, dtype=torch.float32).contiguous()
+            if tuple(g.shape) != (*[int(v) for v in cost.grid_n], 4):
+                raise RuntimeError(f"voxel SDF data must be [n0, n1, n2, 4] = {tuple(cost.grid_n)} + (4,), got {tuple(g.shape)}")
+            k["grid"] = g
+            cd.grid_n = (C.c_int32 * 3)(*[int(v) for v in cost.grid_n])
+            cd.grid_lo = (C.c_float * 3)(*[float(v) for v in cost.grid_lo])
+            cd.grid_extent = (C.c_float * 3)(*[float(v) for v in cost.grid_extent])
+            cd.grid_data = g.data_ptr()
         cd.ws_enabled = int(cost.ws_enabled)
         cd.ws_min = (C.c_float * 3)(*[float(v) for v in cost.ws_min])
         cd.ws_max = (C.c_float * 3)(*[float(v) for v in cost.ws_max])

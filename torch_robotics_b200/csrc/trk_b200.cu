@@ -524,14 +524,34 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
         for (int o = 0; o < nObj; ++o) {
             const int nb = KB ? d->obj_box_start[o + 1] - d->obj_box_start[o] : 0;
             if (nb < 0) return fail(TRK_E_RANGE, "obj_box_start must be non-decreasing");
-            if (d->obj_start[o + 1] - d->obj_start[o] + nb < 1) return fail(TRK_E_RANGE, "object %d has no primitive", o);
+            const int nprim = d->obj_start[o + 1] - d->obj_start[o] + nb;
+            if (o == d->grid_obj ? nprim != 0 : nprim < 1)
+                return fail(TRK_E_RANGE, o == d->grid_obj ? "object %d is the voxel SDF and must own no primitives" : "object %d has no primitive", o);
         }
     }
     if (d->ee_enabled && (d->ee_link < 0 || d->ee_link >= m->L)) return fail(TRK_E_RANGE, "ee_link=%d", d->ee_link);
+    const int grid_obj = nObj ? d->grid_obj : -1;
+    if (grid_obj >= nObj) return fail(TRK_E_RANGE, "grid_obj=%d", grid_obj);
+    if (grid_obj >= 0) {
+        TRK_CHECK_PTR(d->grid_data, "grid_data");
+        if (reinterpret_cast<uintptr_t>(d->grid_data) % 16) return fail(TRK_E_ALIGN, "grid_data must be 16-byte aligned");
+        if (!d->obj_identity[grid_obj]) return fail(TRK_E_RANGE, "the voxel-SDF object must have the identity pose");
+        long long cells = 1;
+        for (int i = 0; i < 3; ++i) {
+            if (d->grid_n[i] < 1 || !(d->grid_extent[i] > 0.f)) return fail(TRK_E_RANGE, "grid axis %d: n=%d extent=%g", i, d->grid_n[i], d->grid_extent[i]);
+            cells *= d->grid_n[i];
+        }
+        if (cells > 0x7fffffffLL) return fail(TRK_E_RANGE, "voxel SDF has %lld cells (limit 2^31 - 1)", cells);
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, d->grid_data) != cudaSuccess || attr.type != cudaMemoryTypeDevice || attr.device != m->device) {
+            cudaGetLastError();
+            return fail(TRK_E_RANGE, "grid_data must be device memory on the model's device");
+        }
+    }
 
     int KQ = 0;   // spheres padded per object to a multiple of four (scan table)
     for (int o = 0; o < nObj; ++o) KQ += (d->obj_start[o + 1] - d->obj_start[o] + 3) & ~3;
-    int off = 64;
+    int off = (int)(sizeof(CostHeader) / 4);
     auto take = [&](int nw) { int o = off; off = align4(off + nw); return o; };
     const int o_pt_link = take(S), o_mobj = take(S), o_mws = take(S), o_ostart = take(nObj + 1), o_oid = take(nObj),
               o_oR = take(nObj * 9), o_opos = take(nObj * 3), o_sph = take(K * 4), o_pi = take(P), o_pj = take(P), o_pm = take(P), o_ormax = take(nObj), o_oc2 = take(nObj), o_sphq = take(KQ * 4), o_oqs = take(nObj + 1), o_otol = take(nObj),
@@ -587,7 +607,8 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
             int bits = 1;
             while ((1 << bits) < (k1 - k0)) ++bits;
             if (k1 == k0) uniform = false;
-            iw[o_oid + o] = (d->obj_identity[o] ? OBJ_IDENTITY : 0) | (uniform ? OBJ_UNIFORM_RADIUS : 0) | (bits << OBJ_BITS_SHIFT);
+            iw[o_oid + o] = (d->obj_identity[o] ? OBJ_IDENTITY : 0) | (uniform ? OBJ_UNIFORM_RADIUS : 0) | (o == grid_obj ? OBJ_GRID : 0) |
+                            (bits << OBJ_BITS_SHIFT);
             w[o_ormax + o] = rmax;
             w[o_otol + o] = ldexpf(1.f, bits - 19);
         }
@@ -613,6 +634,14 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
             float* bw = w + o_box + 8 * kb;
             bw[0] = d->box_center[3 * kb]; bw[1] = d->box_center[3 * kb + 1]; bw[2] = d->box_center[3 * kb + 2]; bw[3] = d->box_radius[kb];
             bw[4] = d->box_half[3 * kb]; bw[5] = d->box_half[3 * kb + 1]; bw[6] = d->box_half[3 * kb + 2]; bw[7] = d->box_rounded[kb] ? 1.f : 0.f;
+        }
+        h->grid_obj = grid_obj;
+        if (grid_obj >= 0) {
+            for (int i = 0; i < 3; ++i) {
+                h->grid_n[i] = d->grid_n[i]; h->grid_lo[i] = d->grid_lo[i]; h->grid_extent[i] = d->grid_extent[i];
+                h->grid_nf[i] = (float)d->grid_n[i];
+            }
+            h->grid_data = reinterpret_cast<const float4*>(d->grid_data);
         }
         h->n_slots = n_slots; h->off_slot_of_body = o_sob; h->off_pt_slot = o_pts; h->off_pair_si = o_psi; h->off_pair_sj = o_psj;
         c->n_slots = n_slots;
@@ -676,7 +705,7 @@ int trk_objective(const trk_model* m, const trk_cost* c, const float* q, int64_t
     cudaStream_t st = (cudaStream_t)stream;
     if (m->family && trk::static_objective_supported(m->family)) {
         const CostHeader* hh = reinterpret_cast<const CostHeader*>(c->h_words.data());
-        const int clamp_any = hh->clamp_self | hh->clamp_obj | hh->clamp_ws | (hh->KB > 0 ? 1 : 0);   // general-tables variant
+        const int clamp_any = hh->clamp_self | hh->clamp_obj | hh->clamp_ws | (hh->KB > 0 ? 1 : 0) | (hh->grid_obj >= 0 ? 1 : 0);   // general-tables variant
         cudaError_t e = trk::launch_static_objective(m->family, m->n_sms, c->d_words, c->nwords, c->n_slots, clamp_any, c->cm_match, q, n, ee_target_cfg,
                                                      margin_override, use_override, cost_total, cost_terms, grad_q,
                                                      occupancy, argmin, st);

@@ -219,6 +219,83 @@ def compile_urdf(path: str, name: str = "") -> TreeDescriptor:
         topo=np.asarray(topo, np.int32), depth=depth, limits=limits, controlled=controlled)
 
 
+def attach_bodies(desc: TreeDescriptor, bodies) -> "tuple[TreeDescriptor, list]":
+    """Descriptor with extra FIXED bodies appended after the existing ones.
+
+    bodies: iterable of (name, parent link name or body index, xyz, rpy-or-None).  A body with rpy=None and offset
+    xyz has its origin at R_w[parent] @ xyz + p_w[parent] - exactly what Frame.transform_point computes for
+    grasped-object points (robots/robot_panda.py:155-159, geometrics/frame.py:116) and what a per-link multi-sphere
+    collision model (data/configs/*_sphere_config.yaml) needs.  A body with an rpy is what the reference gets by
+    rewriting the URDF with a fixed joint (models/robots.py:24-53).  Because they are ordinary bodies, every kernel
+    (FK, fused objective, reverse mode) handles them without special code: a force on an attached point produces
+    the torque x_point x f on the chain automatically.  Parents may be bodies added earlier in the same call.
+    Returns (new descriptor, body indices of the additions)."""
+    import copy
+    d = copy.deepcopy(desc)
+    new_ids = []
+    for name, link, xyz, rpy in bodies:
+        idx = d.name_to_idx()
+        n0 = d.n_links
+        if n0 + 1 > MAX_LINKS:
+            raise ValueError(f"more than the compiled maximum of {MAX_LINKS} bodies after attaching {name!r}")
+        b = idx.get(link, -1) if isinstance(link, str) else int(link)
+        if not 0 <= b < n0:
+            raise ValueError(f"attached body {name!r}: unknown parent link {link!r}")
+        R = np.eye(3, dtype=np.float32) if rpy is None else fixed_rotation_from_rpy([float(v) for v in rpy])
+        new_ids.append(n0)
+        d.link_names.append(name)
+        d.joint_names.append(name + "_fixed_joint")
+        d.joint_types.append("fixed")
+        d.limits.append(None)
+        d.parent = np.append(d.parent, b).astype(np.int32)
+        d.kind = np.append(d.kind, KIND_FIXED).astype(np.int32)
+        d.axis_k = np.append(d.axis_k, 2).astype(np.int32)
+        d.axis_s = np.append(d.axis_s, 0).astype(np.float32)
+        d.axis = np.concatenate([d.axis, np.zeros((1, 3), np.float32)]).astype(np.float32)
+        d.q_index = np.append(d.q_index, -1).astype(np.int32)
+        d.R_fixed = np.concatenate([d.R_fixed, R[None].astype(np.float32)]).astype(np.float32)
+        d.trans = np.concatenate([d.trans, np.asarray(xyz, np.float32).reshape(1, 3)]).astype(np.float32)
+        d.lo = np.append(d.lo, 0).astype(np.float32)
+        d.hi = np.append(d.hi, 0).astype(np.float32)
+        d.has_lim = np.append(d.has_lim, 0).astype(np.int32)
+        d.topo = np.append(d.topo, n0).astype(np.int32)
+        d.depth = np.append(d.depth, d.depth[b] + 1).astype(np.int32)
+    return d, new_ids
+
+
+def attach_points(desc: TreeDescriptor, points, suffix: str = "__pt") -> "tuple[TreeDescriptor, list]":
+    """attach_bodies() for plain points: iterable of (link name or body index, (x, y, z) in the link frame)."""
+    names = desc.link_names
+    idx = desc.name_to_idx()
+    bodies = []
+    for k, (link, off) in enumerate(points):
+        base = link if isinstance(link, str) else names[int(link)]
+        if isinstance(link, str) and link not in idx:
+            raise ValueError(f"attached point {k}: unknown link {link!r}")
+        bodies.append((f"{base}{suffix}{k}", link, off, None))
+    return attach_bodies(desc, bodies)
+
+
+def point_descriptor() -> TreeDescriptor:
+    """One fixed body at the world origin: the 'model' used when the cost-stage kernel is run on free points (SDF grid
+    precomputation and standalone grid queries, environments/grid_map_sdf.py)."""
+    z = lambda dt: np.zeros(1, dt)
+    return TreeDescriptor(
+        name="point", link_names=["world"], joint_names=["world_joint"], joint_types=["fixed"],
+        parent=np.array([-1], np.int32), kind=np.array([KIND_FIXED], np.int32), axis_k=np.array([2], np.int32), axis_s=z(np.float32),
+        axis=np.zeros((1, 3), np.float32), q_index=np.array([-1], np.int32), R_fixed=np.eye(3, dtype=np.float32)[None].copy(),
+        trans=np.zeros((1, 3), np.float32), lo=z(np.float32), hi=z(np.float32), has_lim=z(np.int32), topo=z(np.int32),
+        depth=z(np.int32), limits=[None], controlled=[])
+
+
+def load_sphere_config(path) -> "list[tuple[str, list, float]]":
+    """[(link name, [x, y, z], radius), ...] from a data/configs/**/*_sphere_config.json file (converted from the
+    reference's YAML by tools/convert_sphere_config.py)."""
+    import json
+    with open(path) as f:
+        return [(s["link"], s["offset"], float(s["radius"])) for s in json.load(f)["spheres"]]
+
+
 # ----------------------------------------------------------------------------------------------
 # Planning-objective descriptor (collision points, obstacle spheres, self pairs, ws bounds, EE)
 # ----------------------------------------------------------------------------------------------
@@ -261,6 +338,12 @@ class CostDescriptor:
     box_half: np.ndarray = field(default_factory=lambda: np.zeros((0, 3), np.float32))
     box_radius: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float32))     # MultiBoxField rounding radius
     box_rounded: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))      # 1 rounded, 0 sharp
+    # precomputed voxel SDF (grid_map_sdf.py): at most one object is a grid; see VoxelSDF
+    grid_obj: int = -1
+    grid_n: np.ndarray = field(default_factory=lambda: np.zeros(3, np.int32))
+    grid_lo: np.ndarray = field(default_factory=lambda: np.zeros(3, np.float32))
+    grid_extent: np.ndarray = field(default_factory=lambda: np.ones(3, np.float32))
+    grid_data: object = None      # [n0, n1, n2, 4] fp32 (sdf, grad): torch tensor (any device) or numpy array
     # workspace box
     ws_enabled: int = 0
     ws_min: np.ndarray = field(default_factory=lambda: np.zeros(3, np.float32))
@@ -335,6 +418,30 @@ def _f32(x) -> np.ndarray:
     return np.ascontiguousarray(np.asarray(x, np.float32))
 
 
+@dataclass
+class VoxelSDF:
+    """A precomputed signed-distance grid standing in for an object list (GridMapSDF, grid_map_sdf.py:9-114).
+    data: [n0, n1, n2, 4] fp32 = (sdf, d/dx, d/dy, d/dz) at the cell's sample point; lo/extent: limits[0] and
+    |limits[1] - limits[0]|.  Pass an instance in build_cost_descriptor(objects=[...]) in place of a primitive tuple."""
+    n: tuple
+    lo: np.ndarray
+    extent: np.ndarray
+    data: object
+
+    def host_data(self) -> np.ndarray:
+        d = self.data
+        return np.ascontiguousarray(d.detach().cpu().numpy() if torch.is_tensor(d) else d, np.float32)
+
+
+def grid_cell_index(x, lo, extent, n):
+    """Cell of the points x [..., 3] exactly as GridMapSDF.get_sdf computes it (grid_map_sdf.py:96-101), fp32 torch."""
+    x = torch.as_tensor(x, dtype=torch.float32)
+    nf = torch.as_tensor(np.asarray(n, np.int64))
+    idx = ((x - torch.as_tensor(lo, dtype=torch.float32)) / torch.as_tensor(extent, dtype=torch.float32) * nf).floor().to(torch.int)
+    hi = (nf - 1).to(torch.int)
+    return idx.clamp(torch.zeros_like(hi), hi)
+
+
 def build_cost_descriptor(
         pt_link=(), pt_radius=(), cutoff_obj=0.0, cutoff_ws=None,
         objects=(), ws_min=None, ws_max=None,
@@ -361,7 +468,13 @@ def build_cost_descriptor(
     c.pt_margin_ws = (rad + cutoff_ws).numpy().astype(np.float32) if rad.numel() else np.zeros(0, np.float32)
     starts, Rs, poss, idents, cs, rs = [0], [], [], [], [], []
     bstarts, bc, bh, br, bf = [0], [], [], [], []
-    for obj in objects:
+    for oi, obj in enumerate(objects):
+        if isinstance(obj, VoxelSDF):
+            if c.grid_obj >= 0:
+                raise ValueError("at most one voxel SDF per objective (EnvBase builds one for its fixed objects)")
+            c.grid_obj, c.grid_n = oi, np.asarray(obj.n, np.int32).reshape(3)
+            c.grid_lo, c.grid_extent, c.grid_data = _f32(obj.lo).reshape(3), _f32(obj.extent).reshape(3), obj.data
+            obj = (np.zeros((0, 3), np.float32), np.zeros(0, np.float32), None, None)
         centers, radii = _f32(obj[0]).reshape(-1, 3), _f32(obj[1]).reshape(-1)
         nb = 0
         for bcen, bsize, rounded in (obj[4] if len(obj) > 4 and obj[4] is not None else []):

@@ -1,6 +1,6 @@
 """EnvBase: workspace limits + obstacle object lists (reference: environments/env_base.py:17-88).
-Only what feeds the distance fields is kept; occupancy maps, voxel SDF precomputation and rendering
-are outside the hot path."""
+Only what feeds the distance fields is kept - including the optional precomputed voxel SDF of the fixed objects
+(env_base.py:57-65); occupancy maps and rendering are outside the hot path."""
 import itertools
 from abc import ABC
 
@@ -12,8 +12,6 @@ class EnvBase(ABC):
     def __init__(self, name="NameEnvBase", limits=None, obj_fixed_list=None, obj_extra_list=None,
                  precompute_sdf_obj_fixed=False, sdf_cell_size=0.005, tensor_args=None, **kwargs):
         assert limits is not None
-        if precompute_sdf_obj_fixed:
-            raise NotImplementedError("precomputed voxel SDFs (grid_map_sdf.py) are SURVEY.md section 8 row f4")
         self.tensor_args = tensor_args
         self.name = name
         self.limits = limits
@@ -26,6 +24,9 @@ class EnvBase(ABC):
         self.obj_extra_list = obj_extra_list
         self.obj_all_list = set(itertools.chain(obj_fixed_list or [], obj_extra_list or []))
         self.grid_map_sdf_obj_fixed = None
+        if precompute_sdf_obj_fixed:
+            from .grid_map_sdf import GridMapSDF
+            self.grid_map_sdf_obj_fixed = GridMapSDF(self.limits, sdf_cell_size, self.obj_fixed_list, tensor_args=tensor_args)
         self.occupancy_map = None
 
     def get_obj_list(self):
@@ -34,7 +35,10 @@ class EnvBase(ABC):
     def get_df_obj_list(self, return_extra_objects_only=False):
         objs = []
         if not return_extra_objects_only:
-            objs.extend(self.obj_fixed_list or [])
+            if self.grid_map_sdf_obj_fixed is not None:      # the grid stands in for all fixed objects (env_base.py:80-84)
+                objs.append(self.grid_map_sdf_obj_fixed)
+            else:
+                objs.extend(self.obj_fixed_list or [])
         if self.obj_extra_list is not None:
             objs.extend(self.obj_extra_list)
         return objs

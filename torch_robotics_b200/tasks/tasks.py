@@ -40,7 +40,7 @@ class PlanningTask(Task):
         self.use_occupancy_map = False
         self.obstacle_cutoff_margin = obstacle_cutoff_margin
         r = self.robot
-        common = dict(link_idxs_for_collision_checking=r.link_idxs_for_object_collision_checking,
+        common = dict(link_idxs_for_collision_checking=r.point_idxs_for_object_collision_checking,
                       num_interpolated_points=r.num_interpolated_points_for_object_collision_checking,
                       link_margins_for_object_collision_checking_tensor=r.link_margins_for_object_collision_checking_tensor,
                       cutoff_margin=obstacle_cutoff_margin, tensor_args=self.tensor_args)
@@ -84,7 +84,7 @@ class PlanningTask(Task):
             ee = dict(ee_link=tree._name_to_idx_map[name], ee_target=torch.as_tensor(ee_field.target_H).reshape(4, 4),
                       ee_w_pos=ee_field.w_pos, ee_w_rot=ee_field.w_rot, ee_square=ee_field.square)
         return build_cost_descriptor(
-            pt_link=r.link_idxs_for_object_collision_checking,
+            pt_link=r.point_idxs_for_object_collision_checking,
             pt_radius=r.link_margins_for_object_collision_checking_tensor.detach().float().cpu(),
             cutoff_obj=self.obstacle_cutoff_margin, objects=[o.as_sphere_table() for o in f_obj._objects()],
             ws_min=self.ws_min, ws_max=self.ws_max, self_pairs=pairs, self_margin=self_margin,

@@ -19,7 +19,7 @@ import torch
 
 from ... import ops
 from ..._lib import DeviceModel
-from ...descriptor import TreeDescriptor, compile_urdf, quat_wxyz_to_matrix
+from ...descriptor import TreeDescriptor, attach_bodies, attach_points, compile_urdf, quat_wxyz_to_matrix
 from ...torch_utils.torch_utils import to_torch, torch_intersect_1d
 from ..geometrics.frame import Frame
 from ..geometrics.utils import SE3_distance
@@ -62,6 +62,7 @@ class DifferentiableTree(torch.nn.Module):
             raise NotImplementedError(f"{self.model_type} is not supported (the reference's MJCF loader is "
                                       "self-declared broken, models/utils.py:43)")
         self._desc = compile_urdf(model_path, name)
+        self._n_point_bodies = 0      # trailing bodies that are attached points (hidden from get_link_names)
         self._bodies = [BodyView(self._desc, i) for i in range(self._desc.n_links)]
         self._n_dofs = self._desc.n_dofs
         self._controlled_joints = list(self._desc.controlled)
@@ -78,6 +79,28 @@ class DifferentiableTree(torch.nn.Module):
         if idx not in self._device_models:
             self._device_models[idx] = DeviceModel(self._desc, torch.device("cuda", idx))
         return self._device_models[idx]
+
+    def _refresh_after_attach(self):
+        self._bodies = [BodyView(self._desc, i) for i in range(self._desc.n_links)]
+        self._name_to_idx_map = self._desc.name_to_idx()
+        self._device_models.clear()
+
+    def attach_link(self, name, parent, xyz, rpy=(0.0, 0.0, 0.0)):
+        """Append a fixed link `name` under `parent` with the given joint origin - the in-memory equivalent of the
+        reference's URDF rewriting for grasped objects (models/robots.py:24-53).  Must precede attach_points()."""
+        assert self._n_point_bodies == 0, "attach links before points"
+        self._desc, ids = attach_bodies(self._desc, [(name, parent, xyz, rpy)])
+        self._refresh_after_attach()
+        return ids[0]
+
+    def attach_points(self, points):
+        """Rigidly attach points to links: (link name, (x, y, z) in the link frame) pairs become extra fixed bodies
+        whose origins are the points' world positions (grasped-object points, multi-sphere link models).  They are
+        hidden from get_link_names(); get_all_body_names() lists them after the links.  Returns (names, indices)."""
+        self._desc, ids = attach_points(self._desc, points)
+        self._n_point_bodies += len(ids)
+        self._refresh_after_attach()
+        return [self._desc.link_names[i] for i in ids], ids
 
     def update_base_pose(self, pose_vec):
         """pose_vec: x, y, z, qw, qx, qy, qz (reference: robot_tree.py:133, frame.py:42-51)."""
@@ -223,6 +246,10 @@ class DifferentiableTree(torch.nn.Module):
         return lo, hi, -vel, vel
 
     def get_link_names(self) -> List[str]:
+        return list(self._desc.link_names[:self._desc.n_links - self._n_point_bodies])
+
+    def get_all_body_names(self) -> List[str]:
+        """Links followed by the attached points."""
         return list(self._desc.link_names)
 
     def print_link_names(self) -> None:

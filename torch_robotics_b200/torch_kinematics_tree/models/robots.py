@@ -31,12 +31,16 @@ class DifferentiableFrankaPanda(DifferentiableTree):
     """Franka Panda with or without gripper (robots.py:56-69)."""
 
     def __init__(self, link_list: Optional[str] = None, gripper=False, device="cpu", grasped_object=None):
-        if grasped_object is not None:
-            raise NotImplementedError("grasped-object URDF rewriting (robots.py:24-53) is outside the hot path "
-                                      "(SURVEY.md section 8 f4)")
         fname = "panda_arm_hand.urdf" if gripper else "panda_arm_no_gripper.urdf"
         self.model_path = (get_robot_path() / "franka_description" / "robots" / fname).as_posix()
         super().__init__(self.model_path, "differentiable_franka_panda", link_list=link_list, device=device)
+        if grasped_object is not None:
+            # The reference writes a second URDF with a fixed joint panda_hand -> grasped_object whose origin is
+            # (pos, q_to_euler(ori)) printed as fp32 (robots.py:24-53); the same link is appended in memory here.
+            from ..geometrics.quaternion import q_to_euler
+            xyz = grasped_object.pos.detach().float().cpu().reshape(-1).tolist()
+            rpy = q_to_euler(grasped_object.ori.detach().float().cpu()).reshape(-1).tolist()
+            self.attach_link("grasped_object", "panda_hand", xyz, rpy)
 
 
 class DifferentiableUR10(DifferentiableTree):

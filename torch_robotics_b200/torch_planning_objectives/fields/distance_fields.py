@@ -101,8 +101,8 @@ class EmbodimentDistanceFieldBase(DistanceField):
         return dc
 
     def compute_costs_impl(self, q, link_pos, field_type=None, **kwargs):
-        if getattr(self.robot, "grasped_object", None) is not None:
-            raise NotImplementedError("grasped-object collision points are SURVEY.md section 8 row f4")
+        # grasped-object points are ordinary columns of link_pos here (bodies attached to the tree, robot_base.py), so
+        # the reference's split / re-concatenation (distance_fields.py:137-152) has nothing to do
         field_type = self.field_type if field_type is None else field_type
         dc = self._device_cost(link_pos.device)
         if field_type == "sdf":
@@ -158,6 +158,9 @@ class CollisionObjectDistanceField(CollisionObjectBase):
     def _signature(self):
         sig = []
         for obj in self._objects():
+            if not hasattr(obj, "fields"):      # GridMapSDF
+                sig.append((id(obj), id(obj.grid)))
+                continue
             sig.append((id(obj), obj.pos._version, obj.ori._version, id(obj.pos), id(obj.ori),
                         tuple((id(f.centers), f.centers._version, getattr(f, 'radii', getattr(f, 'sizes', None))._version) for f in obj.fields)))
         return tuple(sig)
