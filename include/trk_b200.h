@@ -251,6 +251,15 @@ int trk_ik_adam(const trk_model* model, const trk_ik_params* params, const float
                 int32_t* valid_count, float* loss_sum, float* loss_sqsum, void* stream);
 
 /*
+ * Replaces DifferentiableTree.compute_analytical_jacobian_all_links (robot_tree.py:250-265), which differentiates
+ * FK + rotation_matrix_to_q (geometrics/quaternion.py:135-166) with torch.autograd.functional.jacobian.
+ * q [N, D] -> J [N, L, 7, D]: rows 0-2 d position / d q, rows 3-6 d quaternion (w, x, y, z) / d q, bodies in <link>
+ * order; columns of clamped joints and of joints not on the path root -> body are zero.  The quaternion is the
+ * representative rotation_matrix_to_q returns (its largest-magnitude component positive).
+ */
+int trk_link_jacobian(const trk_model* model, const float* q, int64_t n, float* J, void* stream);
+
+/*
  * Self-test of the branch-free correctly-rounded square root used for every distance that feeds a
  * comparison (trk_device.cuh: sqrt_rn_core): y_core[i] from that routine, y_ref[i] from sqrt.rn.f32.
  * The two must be bit-identical for x == 0 and 2^-100 <= x < 2^126.  All pointers are device memory.

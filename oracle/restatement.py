@@ -213,6 +213,56 @@ def fk_backward(desc, q, G, sel=None, dtype=np.float32):
 # ----------------------------------------------------------------------------------------------
 # planning objective on link positions
 # ----------------------------------------------------------------------------------------------
+def rotation_to_quaternion(R, dtype=np.float32):
+    """(w, x, y, z) of rotation matrices R [..., 3, 3] as geometrics/quaternion.py:135-166 picks it: of the four
+    candidates, the one whose own component sqrt(1 +- m00 +- m11 +- m22) is largest (first on ties), so that
+    component is positive."""
+    R = np.asarray(R, dtype)
+    m = [[R[..., i, j] for j in range(3)] for i in range(3)]
+    t = np.stack([1 + m[0][0] + m[1][1] + m[2][2], 1 + m[0][0] - m[1][1] - m[2][2],
+                  1 - m[0][0] + m[1][1] - m[2][2], 1 - m[0][0] - m[1][1] + m[2][2]], -1).astype(dtype)
+    qa = np.sqrt(np.maximum(t, 0)).astype(dtype)
+    rows = np.stack([
+        np.stack([qa[..., 0] ** 2, m[2][1] - m[1][2], m[0][2] - m[2][0], m[1][0] - m[0][1]], -1),
+        np.stack([m[2][1] - m[1][2], qa[..., 1] ** 2, m[1][0] + m[0][1], m[0][2] + m[2][0]], -1),
+        np.stack([m[0][2] - m[2][0], m[1][0] + m[0][1], qa[..., 2] ** 2, m[1][2] + m[2][1]], -1),
+        np.stack([m[1][0] - m[0][1], m[2][0] + m[0][2], m[2][1] + m[1][2], qa[..., 3] ** 2], -1)], -2).astype(dtype)
+    cand = rows / (2 * np.maximum(qa[..., None], dtype(0.1)))
+    i = np.argmax(qa, -1)
+    return np.take_along_axis(cand, i[..., None, None], -2)[..., 0, :].astype(dtype)
+
+
+def link_jacobian(desc, q, dtype=np.float32):
+    """J [N, L, 7, D]: d (position xyz, quaternion wxyz) of every body / d q - what
+    DifferentiableTree.compute_analytical_jacobian_all_links (robot_tree.py:250-265) obtains by autograd through FK and
+    rotation_matrix_to_q.  For joint j on the path root -> l with world axis a_j and origin p_j:
+      revolute : d p_l = a_j x (p_l - p_j),  d quat_l = 1/2 (0, a_j) (x) quat_l     (world-frame angular velocity)
+      prismatic: d p_l = R_w[parent(j)] a_raw, d quat_l = 0
+    times the clamp mask of joint j; all other columns are zero."""
+    q = np.asarray(q, dtype)
+    if q.ndim == 1:
+        q = q[None]
+    N, L, D = q.shape[0], desc.n_links, desc.n_dofs
+    Rw, pw = fk_forward(desc, q, dtype)
+    _, mask = joint_angles(desc, q, dtype)
+    quat = rotation_to_quaternion(Rw, dtype)
+    J = np.zeros((N, L, 7, D), dtype)
+    for l in range(L):
+        w, v = quat[:, l, 0], quat[:, l, 1:]
+        b = l
+        while b >= 0 and desc.parent[b] >= 0:
+            qi, kind = int(desc.q_index[b]), int(desc.kind[b])
+            if kind == KIND_REVOLUTE:
+                a = dtype(desc.axis_s[b]) * Rw[:, b, :, int(desc.axis_k[b])]
+                J[:, l, 0:3, qi] = mask[:, b, None] * np.cross(a, pw[:, l] - pw[:, b])
+                J[:, l, 3, qi] = mask[:, b] * dtype(-0.5) * np.sum(a * v, -1)
+                J[:, l, 4:7, qi] = mask[:, b, None] * dtype(0.5) * (w[:, None] * a + np.cross(a, v))
+            elif kind == KIND_PRISMATIC:
+                J[:, l, 0:3, qi] = mask[:, b, None] * (Rw[:, int(desc.parent[b])] @ desc.axis[b].astype(dtype))
+            b = int(desc.parent[b])
+    return J
+
+
 def _box_sdf_and_grad(cost, kb, xo, dtype):
     """One box primitive at points xo [N,S,3] (object frame): signed distance and its gradient.
     primitives.py:219-223 (sharp: max_c(|x-c| - h)), :326-334 (rounded: min(max q, 0) + |relu(q)| - r,

@@ -518,8 +518,26 @@ def golden_voxel_sdf():
     print("voxel sdf", tuple(out["cmap_dim"]), "cost_collision[0,:3]", out["cost_collision"][0, :3], "occ", int(out["occ_obj"].sum()))
 
 
+def golden_link_jacobians():
+    """compute_analytical_jacobian_all_links (robot_tree.py:250-265) for a chain (Panda), a tree with prismatic
+    joints and many fixed links (Stretch) and a branching hand with an oblique axis (Shadow); rows cover in-limit,
+    [0,1), out-of-limit (clamped -> zero columns) and at-limit configurations."""
+    gen = torch.Generator().manual_seed(577)
+    out = {}
+    for name in ("panda", "stretch", "shadow_hand"):
+        model = quiet(ROBOTS[name])
+        q = sample_q(model, 8, gen)
+        J = model.compute_analytical_jacobian_all_links(q)
+        H = model.compute_forward_kinematics_all_links(q)
+        out[f"{name}_q"], out[f"{name}_J"], out[f"{name}_H"] = q.numpy(), J.numpy(), H.numpy()
+        print("jacobian", name, tuple(J.shape), float(J.abs().max()))
+    np.savez_compressed(os.path.join(HERE, "link_jacobians.npz"), **out)
+
+
 if __name__ == "__main__":
-    if os.environ.get("GOLDEN_ONLY") == "voxel":
+    if os.environ.get("GOLDEN_ONLY") == "jacobian":
+        golden_link_jacobians()
+    elif os.environ.get("GOLDEN_ONLY") == "voxel":
         golden_voxel_sdf()
     elif os.environ.get("GOLDEN_ONLY") == "points":
         golden_attached_points()
@@ -536,3 +554,4 @@ if __name__ == "__main__":
         golden_trajectories()
         golden_attached_points()
         golden_voxel_sdf()
+        golden_link_jacobians()

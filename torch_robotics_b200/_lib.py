@@ -59,6 +59,7 @@ EXPORTS = [
     "trk_abi_version", "trk_last_error", "trk_model_create", "trk_model_destroy", "trk_model_kernel_family",
     "trk_fk_forward", "trk_fk_backward", "trk_cost_create", "trk_cost_destroy", "trk_cost_set_ee_target",
     "trk_cost_set_weights", "trk_objective", "trk_objective_host", "trk_cost_stage", "trk_selftest_sqrt", "trk_ik_adam",
+    "trk_link_jacobian",
 ]
 
 
@@ -93,6 +94,7 @@ def lib() -> C.CDLL:
         L.trk_objective.argtypes = [vp, vp, vp, i64, vp, f32, vp, vp, vp, vp, vp, vp]
         L.trk_cost_stage.argtypes = [vp, vp, vp, vp, i64, vp, f32, vp, vp, vp, vp, vp, vp, vp]
         L.trk_selftest_sqrt.argtypes = [vp, i64, vp, vp, vp]
+        L.trk_link_jacobian.argtypes = [vp, vp, i64, vp, vp]
         L.trk_objective_host.argtypes = [vp, vp, vp, i64, i32, vp, vp]
         L.trk_ik_adam.argtypes = [vp, C.POINTER(IKParamsC), vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
         for name in EXPORTS:
@@ -195,6 +197,17 @@ class DeviceModel:
         check(lib().trk_fk_forward(self.handle, q.data_ptr(), q.shape[0], p, n_sel, H.data_ptr(), stream_ptr(q.device)),
               "trk_fk_forward")
         return H
+
+    def link_jacobian(self, q: torch.Tensor) -> torch.Tensor:
+        """q [N, D] -> J [N, L, 7, D] = d (position, quaternion wxyz) of every body / d q (trk_link_jacobian)."""
+        q = require_cuda_f32(q, "q")
+        if q.ndim != 2 or q.shape[1] != self.n_dofs:
+            raise RuntimeError(f"q must be [N, {self.n_dofs}], got {tuple(q.shape)}")
+        if q.device != self.device:
+            raise RuntimeError(f"q is on {q.device} but the model lives on {self.device}")
+        J = torch.empty((q.shape[0], self.n_links, 7, self.n_dofs), dtype=torch.float32, device=q.device)
+        check(lib().trk_link_jacobian(self.handle, q.data_ptr(), q.shape[0], J.data_ptr(), stream_ptr(q.device)), "trk_link_jacobian")
+        return J
 
     def fk_backward(self, q: torch.Tensor, G: torch.Tensor, link_sel=None) -> torch.Tensor:
         q = require_cuda_f32(q, "q")

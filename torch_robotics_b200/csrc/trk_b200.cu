@@ -179,6 +179,129 @@ __global__ void __launch_bounds__(kBlock) k_objective_generic(const float* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Link Jacobians (DifferentiableTree.compute_analytical_jacobian_all_links, robot_tree.py:250-265):
+// J[cfg][body][7][D] = d (position xyz, quaternion wxyz) / d q.  The reference differentiates FK +
+// rotation_matrix_to_q (quaternion.py:135-166) by autograd; in closed form, for joint j on the path root -> body,
+//   revolute : d p = a_j x (p - p_j),  d quat = 1/2 (0, a_j) (x) quat        prismatic: d p = a_j, d quat = 0
+// with a_j the world joint axis times the clamp mask, zero elsewhere.  Output-bound (L*7*D*4 B per configuration):
+// phase 1, one thread per configuration: FK, quaternions and masked axes into a per-warp shared-memory record;
+// phase 2, the warp writes its 32 configurations' blocks cooperatively, consecutive lanes -> consecutive floats.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void quat_of_rotation(const float* R, float* qo) {
+    const float t[4] = {1.f + R[0] + R[4] + R[8], 1.f + R[0] - R[4] - R[8], 1.f - R[0] + R[4] - R[8], 1.f - R[0] - R[4] + R[8]};
+    float qa[4];
+    int im = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qa[i] = sqrtf(fmaxf(t[i], 0.f));
+#pragma unroll
+    for (int i = 1; i < 4; ++i) if (qa[i] > qa[im]) im = i;     // first maximum wins (argmax)
+    const float m21 = R[7], m12 = R[5], m02 = R[2], m20 = R[6], m10 = R[3], m01 = R[1];
+    float c[4];
+    if (im == 0)      { c[0] = qa[0] * qa[0]; c[1] = m21 - m12; c[2] = m02 - m20; c[3] = m10 - m01; }
+    else if (im == 1) { c[0] = m21 - m12; c[1] = qa[1] * qa[1]; c[2] = m10 + m01; c[3] = m02 + m20; }
+    else if (im == 2) { c[0] = m02 - m20; c[1] = m10 + m01; c[2] = qa[2] * qa[2]; c[3] = m12 + m21; }
+    else              { c[0] = m10 - m01; c[1] = m20 + m02; c[2] = m21 + m12; c[3] = qa[3] * qa[3]; }
+    const float inv = 1.f / (2.f * fmaxf(qa[im], 0.1f));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qo[i] = c[i] * inv;
+}
+
+template <int MAXL>
+__global__ void __launch_bounds__(kBlock) k_link_jacobian(const float* __restrict__ tree_words, int tree_nwords,
+                                                          const float* __restrict__ q, long long n, int rec_stride,
+                                                          float* __restrict__ J) {
+    extern __shared__ __align__(16) float smem[];
+    float* tw = smem;
+    block_copy_words(tw, tree_words, tree_nwords);
+    unsigned* anc = reinterpret_cast<unsigned*>(smem + tree_nwords);          // [MAXL] q columns on the path root -> body
+    int* jbody = reinterpret_cast<int*>(anc + MAXL);                          // [32] body driven by q column j
+    int* jprism = jbody + 32;                                                  // [32] 1 = prismatic
+    float* stage = reinterpret_cast<float*>(jprism + 32);
+    __syncthreads();
+    const TreeHeader* hdr = reinterpret_cast<const TreeHeader*>(tw);
+    const LinkRec* recs = reinterpret_cast<const LinkRec*>(tw + 16);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, D = hdr->D, L = hdr->L;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < L; ++i) {
+            const LinkRec& r = recs[i];
+            anc[r.body] = (r.parent < 0 ? 0u : anc[r.parent]) | (r.qidx >= 0 ? 1u << r.qidx : 0u);
+            if (r.qidx >= 0) { jbody[r.qidx] = r.body; jprism[r.qidx] = (r.flags & F_KIND_MASK) == TRK_KIND_PRISMATIC; }
+        }
+    }
+    __syncthreads();
+    float* wst = stage + (size_t)warp * 32 * rec_stride;
+    const int row = 7 * D, per_cfg = L * row;
+    const float invD = 1.f / (float)D;
+    for (long long base = ((long long)blockIdx.x * nwarps + warp) * 32; base < n; base += (long long)gridDim.x * nwarps * 32) {
+        {   // phase 1
+            const long long cfg = base + lane;
+            float W[MAXL][12];
+            unsigned long long pass;
+            fk_generic<MAXL>(hdr, recs, q + (cfg < n ? cfg : n - 1) * D, W, pass);
+            float* rec = wst + lane * rec_stride;
+            for (int i = 0; i < L; ++i) {
+                const LinkRec& r = recs[i];
+                const int b = r.body;
+                const float* w = W[b];
+                float qt[4];
+                quat_of_rotation(w, qt);
+                rec[b * 7 + 0] = w[9]; rec[b * 7 + 1] = w[10]; rec[b * 7 + 2] = w[11];
+                rec[b * 7 + 3] = qt[0]; rec[b * 7 + 4] = qt[1]; rec[b * 7 + 5] = qt[2]; rec[b * 7 + 6] = qt[3];
+                if (r.qidx >= 0) {
+                    const float mk = (pass >> b) & 1ull ? 1.f : 0.f;
+                    float ax, ay, az;
+                    if ((r.flags & F_KIND_MASK) == TRK_KIND_REVOLUTE) {
+                        const int k = (r.flags >> F_AXIS_SHIFT) & 3;
+                        ax = r.s * w[k]; ay = r.s * w[3 + k]; az = r.s * w[6 + k];
+                    } else {
+                        const float* wp = W[r.parent];
+                        ax = wp[0] * r.ax[0] + wp[1] * r.ax[1] + wp[2] * r.ax[2];
+                        ay = wp[3] * r.ax[0] + wp[4] * r.ax[1] + wp[5] * r.ax[2];
+                        az = wp[6] * r.ax[0] + wp[7] * r.ax[1] + wp[8] * r.ax[2];
+                    }
+                    float* a = rec + L * 7 + r.qidx * 3;
+                    a[0] = mk * ax; a[1] = mk * ay; a[2] = mk * az;
+                }
+            }
+        }
+        __syncwarp();
+        const int ncfg = (int)((n - base) < 32 ? (n - base) : 32);
+        for (int c = 0; c < ncfg; ++c) {   // phase 2
+            const float* rec = wst + c * rec_stride;
+            const float* axes = rec + L * 7;
+            float* out = J + (base + c) * (long long)per_cfg;
+            for (int l = 0; l < L; ++l) {
+                const unsigned al = anc[l];
+                const float px = rec[l * 7], py = rec[l * 7 + 1], pz = rec[l * 7 + 2];
+                const float qw = rec[l * 7 + 3], qx = rec[l * 7 + 4], qy = rec[l * 7 + 5], qz = rec[l * 7 + 6];
+                for (int e = lane; e < row; e += 32) {
+                    const int r = __float2int_rz(((float)e + 0.5f) * invD);
+                    const int j = e - r * D;
+                    float val = 0.f;
+                    if ((al >> j) & 1u) {
+                        const float ax = axes[j * 3], ay = axes[j * 3 + 1], az = axes[j * 3 + 2];
+                        if (jprism[j]) {
+                            val = r == 0 ? ax : (r == 1 ? ay : (r == 2 ? az : 0.f));
+                        } else if (r < 3) {
+                            const float* pj = rec + jbody[j] * 7;
+                            const float dx = px - pj[0], dy = py - pj[1], dz = pz - pj[2];
+                            val = r == 0 ? ay * dz - az * dy : (r == 1 ? az * dx - ax * dz : ax * dy - ay * dx);
+                        } else if (r == 3) {
+                            val = -0.5f * (ax * qx + ay * qy + az * qz);
+                        } else {
+                            const float cx = ay * qz - az * qy, cy = az * qx - ax * qz, cz = ax * qy - ay * qx;
+                            val = 0.5f * (r == 4 ? qw * ax + cx : (r == 5 ? qw * ay + cy : qw * az + cz));
+                        }
+                    }
+                    __stcs(out + l * row + e, val);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // cost stage on caller-supplied positions (DistanceField.compute_cost, distance_fields.py:26-55)
 template <int MAXL, bool WANT_GRAD>
 __global__ void __launch_bounds__(kBlock) k_cost_stage(const float* __restrict__ cost_words, int cost_nwords, int L,
@@ -764,6 +887,39 @@ int trk_ik_adam(const trk_model* m, const trk_ik_params* p, const float* step_si
     e = trk::launch_static_ik(m->family, P, step_size, bc2_sqrt, target_seed, n, q_io, err_out, valid_out, valid_count, loss_sum,
                               loss_sqsum, st);
     return e == cudaSuccess ? TRK_OK : cuda_fail(e, "ik_adam launch");
+}
+
+int trk_link_jacobian(const trk_model* m, const float* q, int64_t n, float* J, void* stream) {
+    TRK_CHECK_PTR(m, "model");
+    if (n < 0) return fail(TRK_E_RANGE, "n=%lld", (long long)n);
+    if (m->D < 1) return fail(TRK_E_RANGE, "the model has no movable joint");
+    if (n == 0) return TRK_OK;
+    TRK_CHECK_PTR(q, "q"); TRK_CHECK_PTR(J, "J");
+    DeviceGuard guard(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rec_stride = (m->L * 7 + m->D * 3) | 1;                       // odd: lanes hit distinct banks in phase 1
+    const size_t fixed = (size_t)m->nwords * 4 + (size_t)(m->maxl_bucket + 64) * 4;
+    const size_t per_warp = (size_t)32 * rec_stride * 4;
+    int warps = kWarps;
+    while (warps > 1 && fixed + warps * per_warp > 100 * 1024) --warps;     // two blocks per SM where possible
+    const size_t smem = fixed + warps * per_warp;
+    long long tiles = (n + 32LL * warps - 1) / (32LL * warps);
+    const long long cap = (long long)m->n_sms * 8;
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    cudaError_t e = cudaSuccess;
+#define LAUNCH_JAC(MAXL)                                                                                  \
+    do {                                                                                                  \
+        e = allow_smem(k_link_jacobian<MAXL>, smem);                                                      \
+        if (e == cudaSuccess) k_link_jacobian<MAXL><<<grid, warps * 32, smem, st>>>(m->d_words, m->nwords, q, n, rec_stride, J); \
+    } while (0)
+    switch (m->maxl_bucket) {
+        case 16: LAUNCH_JAC(16); break;
+        case 32: LAUNCH_JAC(32); break;
+        default: LAUNCH_JAC(64); break;
+    }
+#undef LAUNCH_JAC
+    if (e == cudaSuccess) e = cudaGetLastError();
+    return e == cudaSuccess ? TRK_OK : cuda_fail(e, "link_jacobian launch");
 }
 
 int trk_selftest_sqrt(const float* x, int64_t n, float* y_core, float* y_ref, void* stream) {

@@ -6,7 +6,7 @@ Kept: constructor signature, `compute_forward_kinematics_all_links`, `inverse_ki
 `get_joint_limit_array`, `print_link_names`, `update_base_pose`) and the attributes callers read
 (`_n_dofs`, `_controlled_joints`, `_name_to_idx_map`, `_bodies`, `link_list`).
 Not provided (out of the hot path): the stateful velocity
-propagation (`update_kinematic_state`) and the Jacobian helpers built on it.
+propagation (`update_kinematic_state`) and the stateful geometric-Jacobian helper built on it.
 
 q must be a float32 CUDA tensor: there is no CPU fallback.
 """
@@ -131,6 +131,18 @@ class DifferentiableTree(torch.nn.Module):
         if not return_dict:
             return H
         return {n: Frame(rot=H[:, k, :3, :3], trans=H[:, k, :3, 3], device=q.device) for k, n in enumerate(link_list)}
+
+    def compute_analytical_jacobian_all_links(self, q: torch.Tensor) -> torch.Tensor:
+        """q [B, n_dofs] (or [n_dofs]) -> [B, n_links, 7, n_dofs]: d (position xyz, quaternion wxyz) of every link /
+        d q.  The reference gets it from torch.autograd.functional.jacobian over FK + rotation_matrix_to_q
+        (robot_tree.py:250-265); here it is one kernel evaluating the closed form (trk_link_jacobian).  Links follow
+        self.link_list when set, like the FK call inside the reference's surrogate."""
+        if q.ndim == 1:
+            q = q.unsqueeze(0)
+        J = self.device_model(q.device).link_jacobian(q.detach())
+        names = self.link_list if self.link_list is not None else self.get_link_names()
+        idx = [self._name_to_idx_map[n] for n in names]
+        return J if idx == list(range(self._desc.n_links)) else J[:, idx]
 
     def compute_forward_kinematics(self, q, qd=None, link_name=None, state_less=True):
         if not state_less:
