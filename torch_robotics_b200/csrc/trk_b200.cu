@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -207,15 +208,14 @@ __device__ __forceinline__ void quat_of_rotation(const float* R, float* qo) {
     for (int i = 0; i < 4; ++i) qo[i] = c[i] * inv;
 }
 
-template <int MAXL>
 __global__ void __launch_bounds__(kBlock) k_link_jacobian(const float* __restrict__ tree_words, int tree_nwords,
-                                                          const float* __restrict__ q, long long n, int rec_stride,
-                                                          float* __restrict__ J) {
+                                                          const LiveSlots live, const float* __restrict__ q, long long n,
+                                                          int cpw, int rec_stride, int link_chunk, float* __restrict__ J) {
     extern __shared__ __align__(16) float smem[];
     float* tw = smem;
     block_copy_words(tw, tree_words, tree_nwords);
-    unsigned* anc = reinterpret_cast<unsigned*>(smem + tree_nwords);          // [MAXL] q columns on the path root -> body
-    int* jbody = reinterpret_cast<int*>(anc + MAXL);                          // [32] body driven by q column j
+    unsigned* anc = reinterpret_cast<unsigned*>(smem + tree_nwords);          // [TRK_MAX_LINKS] q columns on the path root -> body
+    int* jbody = reinterpret_cast<int*>(anc + TRK_MAX_LINKS);                 // [32] body driven by q column j
     int* jprism = jbody + 32;                                                  // [32] 1 = prismatic
     float* stage = reinterpret_cast<float*>(jprism + 32);
     __syncthreads();
@@ -230,73 +230,92 @@ __global__ void __launch_bounds__(kBlock) k_link_jacobian(const float* __restric
         }
     }
     __syncthreads();
-    float* wst = stage + (size_t)warp * 32 * rec_stride;
+    // per warp: two output tiles | cpw records (p, quat per body; masked axis per q column) | cpw x n_live pose slots
     const int row = 7 * D, per_cfg = L * row;
-    const float invD = 1.f / (float)D;
-    for (long long base = ((long long)blockIdx.x * nwarps + warp) * 32; base < n; base += (long long)gridDim.x * nwarps * 32) {
-        {   // phase 1
-            const long long cfg = base + lane;
-            float W[MAXL][12];
-            unsigned long long pass;
-            fk_generic<MAXL>(hdr, recs, q + (cfg < n ? cfg : n - 1) * D, W, pass);
+    const int tile_words = (link_chunk * row + 4 + 3) & ~3;                   // + 4: room for the alignment phase
+    const int warp_words = 2 * tile_words + cpw * rec_stride + cpw * 12 * live.n_live;
+    float* tile = stage + (size_t)warp * warp_words;
+    float* wst = tile + 2 * tile_words;
+    float* wlive = wst + cpw * rec_stride;
+    int buf = 0;
+    const float invD = 1.f / (float)D, invL = 1.f / (float)L;
+    for (long long base = ((long long)blockIdx.x * nwarps + warp) * cpw; base < n; base += (long long)gridDim.x * nwarps * cpw) {
+        const int ncfg = (int)((n - base) < cpw ? (n - base) : cpw);
+        if (lane < ncfg) {   // phase 1: one lane per configuration
             float* rec = wst + lane * rec_stride;
-            for (int i = 0; i < L; ++i) {
-                const LinkRec& r = recs[i];
-                const int b = r.body;
-                const float* w = W[b];
-                float qt[4];
-                quat_of_rotation(w, qt);
-                rec[b * 7 + 0] = w[9]; rec[b * 7 + 1] = w[10]; rec[b * 7 + 2] = w[11];
-                rec[b * 7 + 3] = qt[0]; rec[b * 7 + 4] = qt[1]; rec[b * 7 + 5] = qt[2]; rec[b * 7 + 6] = qt[3];
-                if (r.qidx >= 0) {
-                    const float mk = (pass >> b) & 1ull ? 1.f : 0.f;
-                    float ax, ay, az;
-                    if ((r.flags & F_KIND_MASK) == TRK_KIND_REVOLUTE) {
-                        const int k = (r.flags >> F_AXIS_SHIFT) & 3;
-                        ax = r.s * w[k]; ay = r.s * w[3 + k]; az = r.s * w[6 + k];
-                    } else {
-                        const float* wp = W[r.parent];
-                        ax = wp[0] * r.ax[0] + wp[1] * r.ax[1] + wp[2] * r.ax[2];
-                        ay = wp[3] * r.ax[0] + wp[4] * r.ax[1] + wp[5] * r.ax[2];
-                        az = wp[6] * r.ax[0] + wp[7] * r.ax[1] + wp[8] * r.ax[2];
-                    }
-                    float* a = rec + L * 7 + r.qidx * 3;
-                    a[0] = mk * ax; a[1] = mk * ay; a[2] = mk * az;
-                }
-            }
+            float* axes = rec + L * 7;
+            fk_live(hdr, recs, live, q + (base + lane) * D, wlive + lane, cpw,
+                    [&](int, const LinkRec& r, const float* w, const float* wp, bool pass) {
+                        float qt[4];
+                        quat_of_rotation(w, qt);
+                        float* o = rec + r.body * 7;
+                        o[0] = w[9]; o[1] = w[10]; o[2] = w[11]; o[3] = qt[0]; o[4] = qt[1]; o[5] = qt[2]; o[6] = qt[3];
+                        if (r.qidx >= 0) {
+                            const float mk = pass ? 1.f : 0.f;
+                            float ax, ay, az;
+                            if ((r.flags & F_KIND_MASK) == TRK_KIND_REVOLUTE) {
+                                const int k = (r.flags >> F_AXIS_SHIFT) & 3;
+                                ax = r.s * w[k]; ay = r.s * w[3 + k]; az = r.s * w[6 + k];
+                            } else {
+                                ax = wp[0] * r.ax[0] + wp[1] * r.ax[1] + wp[2] * r.ax[2];
+                                ay = wp[3] * r.ax[0] + wp[4] * r.ax[1] + wp[5] * r.ax[2];
+                                az = wp[6] * r.ax[0] + wp[7] * r.ax[1] + wp[8] * r.ax[2];
+                            }
+                            float* a = axes + r.qidx * 3;
+                            a[0] = mk * ax; a[1] = mk * ay; a[2] = mk * az;
+                        }
+                    });
         }
         __syncwarp();
-        const int ncfg = (int)((n - base) < 32 ? (n - base) : 32);
-        for (int c = 0; c < ncfg; ++c) {   // phase 2
-            const float* rec = wst + c * rec_stride;
-            const float* axes = rec + L * 7;
-            float* out = J + (base + c) * (long long)per_cfg;
-            for (int l = 0; l < L; ++l) {
-                const unsigned al = anc[l];
-                const float px = rec[l * 7], py = rec[l * 7 + 1], pz = rec[l * 7 + 2];
-                const float qw = rec[l * 7 + 3], qx = rec[l * 7 + 4], qy = rec[l * 7 + 5], qz = rec[l * 7 + 6];
-                for (int e = lane; e < row; e += 32) {
-                    const int r = __float2int_rz(((float)e + 0.5f) * invD);
-                    const int j = e - r * D;
-                    float val = 0.f;
-                    if ((al >> j) & 1u) {
-                        const float ax = axes[j * 3], ay = axes[j * 3 + 1], az = axes[j * 3 + 2];
-                        if (jprism[j]) {
-                            val = r == 0 ? ax : (r == 1 ? ay : (r == 2 ? az : 0.f));
-                        } else if (r < 3) {
-                            const float* pj = rec + jbody[j] * 7;
-                            const float dx = px - pj[0], dy = py - pj[1], dz = pz - pj[2];
-                            val = r == 0 ? ay * dz - az * dy : (r == 1 ? az * dx - ax * dz : ax * dy - ay * dx);
-                        } else if (r == 3) {
-                            val = -0.5f * (ax * qx + ay * qy + az * qz);
-                        } else {
-                            const float cx = ay * qz - az * qy, cy = az * qx - ax * qz, cz = ax * qy - ay * qx;
-                            val = 0.5f * (r == 4 ? qw * ax + cx : (r == 5 ? qw * ay + cy : qw * az + cz));
-                        }
-                    }
-                    __stcs(out + l * row + e, val);
-                }
+        // phase 2: the warp's output is one contiguous run of ncfg * L link blocks (row = 7 * D floats each); handle
+        // `link_chunk` blocks per pass, whatever configuration they belong to
+        const int n_inst = ncfg * L;
+        const long long out0 = base * (long long)per_cfg;
+        for (int u0 = 0; u0 < n_inst; u0 += link_chunk, buf ^= 1) {
+            const int nu = min(link_chunk, n_inst - u0);
+            const long long f0 = out0 + (long long)u0 * row;
+            const int ph = (int)(f0 & 3);                        // same 16-byte phase in shared and global memory
+            float* tl = tile + buf * tile_words + ph;
+            // 2a: lane <- (link block, q column); its seven values go to the tile at their output offsets.  Branch-free
+            // (non-ancestor columns are computed and zeroed) so that four columns per lane are in flight at once.
+            const int ncol = nu * D;
+#pragma unroll 4
+            for (int t = lane; t < ncol; t += 32) {
+                const int ll = __float2int_rz(((float)t + 0.5f) * invD);
+                const int j = t - ll * D, u = u0 + ll;
+                const int c = __float2int_rz(((float)u + 0.5f) * invL);
+                const int l = u - c * L;
+                const float* rec = wst + c * rec_stride;
+                const float* a = rec + L * 7 + j * 3;
+                const float* pl = rec + l * 7;
+                const float* pj = rec + jbody[j] * 7;
+                const bool on = ((anc[l] >> j) & 1u) != 0, pris = jprism[j] != 0;
+                const bool rev = on && !pris, pr = on && pris;     // selects, not products: NaN poses must not leak into zero columns
+                const float ax = a[0], ay = a[1], az = a[2];
+                const float dx = pl[0] - pj[0], dy = pl[1] - pj[1], dz = pl[2] - pj[2];
+                const float qw = pl[3], qx = pl[4], qy = pl[5], qz = pl[6];
+                float* o = tl + ll * row + j;
+                o[0]     = rev ? ay * dz - az * dy : (pr ? ax : 0.f);
+                o[D]     = rev ? az * dx - ax * dz : (pr ? ay : 0.f);
+                o[2 * D] = rev ? ax * dy - ay * dx : (pr ? az : 0.f);
+                o[3 * D] = rev ? -0.5f * (ax * qx + ay * qy + az * qz) : 0.f;
+                o[4 * D] = rev ? 0.5f * (qw * ax + (ay * qz - az * qy)) : 0.f;
+                o[5 * D] = rev ? 0.5f * (qw * ay + (az * qx - ax * qz)) : 0.f;
+                o[6 * D] = rev ? 0.5f * (qw * az + (ax * qy - ay * qx)) : 0.f;
             }
+            __syncwarp();
+            // 2b: contiguous copy, 16-byte stores between a scalar head and tail.  The other tile buffer is filled by
+            // the next pass, so the barrier above is the only one per pass.
+            const int nf = nu * row;
+            const int head = min((4 - ph) & 3, nf);
+            const int nbody = (nf - head) >> 2;
+            const int tail0 = head + 4 * nbody;
+            if (lane < head) __stcs(J + f0 + lane, tl[lane]);
+            float4* d4 = reinterpret_cast<float4*>(J + f0 + head);
+            const float4* s4 = reinterpret_cast<const float4*>(tl + head);
+#pragma unroll 4
+            for (int e = lane; e < nbody; e += 32) __stcs(d4 + e, s4[e]);
+            if (lane < nf - tail0) __stcs(J + f0 + tail0 + lane, tl[tail0 + lane]);
         }
         __syncwarp();
     }
@@ -400,7 +419,30 @@ struct trk_model {
     int family;                 // trk::StaticFamily id, 0 = generic
     int32_t parent[TRK_MAX_LINKS];
     int32_t qidx[TRK_MAX_LINKS];
+    LiveSlots live;             // shared-memory pose slots of the runtime-tree kernels
 };
+
+// Parents-first walk: a body's pose slot is released once its last child has been composed (the child already holds
+// the parent pose in registers, so it may take over the very slot), leaves need none.
+static void assign_live_slots(const int32_t* topo, const int32_t* parent, int L, LiveSlots& ls) {
+    int pos_of[TRK_MAX_LINKS], last_child[TRK_MAX_LINKS], slot_of[TRK_MAX_LINKS];
+    bool busy[TRK_MAX_LINKS] = {false};
+    for (int i = 0; i < L; ++i) { pos_of[topo[i]] = i; last_child[i] = -1; }
+    for (int i = 0; i < L; ++i) { const int p = parent[topo[i]]; if (p >= 0) last_child[pos_of[p]] = i; }
+    ls.n_live = 0;
+    for (int i = 0; i < L; ++i) {
+        const int p = parent[topo[i]];
+        ls.par[i] = (int8_t)(p >= 0 ? slot_of[pos_of[p]] : -1);
+        if (p >= 0 && last_child[pos_of[p]] == i) busy[slot_of[pos_of[p]]] = false;
+        ls.own[i] = -1; slot_of[i] = -1;
+        if (last_child[i] >= 0) {
+            int s = 0;
+            while (busy[s]) ++s;
+            busy[s] = true; slot_of[i] = s; ls.own[i] = (int8_t)s;
+            if (s + 1 > ls.n_live) ls.n_live = s + 1;
+        }
+    }
+}
 
 struct trk_cost {
     int device;
@@ -543,6 +585,7 @@ int trk_model_create(const trk_model_desc* d, int device, trk_model** out) {
     m->maxl_bucket = L <= 16 ? 16 : (L <= 32 ? 32 : 64);
     memcpy(m->parent, d->parent, L * sizeof(int32_t));
     memcpy(m->qidx, d->q_index, L * sizeof(int32_t));
+    assign_live_slots(d->topo, d->parent, L, m->live);
     cudaError_t e = cudaDeviceGetAttribute(&m->n_sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) { delete m; return cuda_fail(e, "cudaDeviceGetAttribute"); }
     e = cudaMalloc(&m->d_words, nwords * sizeof(float));
@@ -895,29 +938,29 @@ int trk_link_jacobian(const trk_model* m, const float* q, int64_t n, float* J, v
     if (m->D < 1) return fail(TRK_E_RANGE, "the model has no movable joint");
     if (n == 0) return TRK_OK;
     TRK_CHECK_PTR(q, "q"); TRK_CHECK_PTR(J, "J");
+    TRK_CHECK_ALIGN16(J, "J");
     DeviceGuard guard(m->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int rec_stride = (m->L * 7 + m->D * 3) | 1;                       // odd: lanes hit distinct banks in phase 1
-    const size_t fixed = (size_t)m->nwords * 4 + (size_t)(m->maxl_bucket + 64) * 4;
-    const size_t per_warp = (size_t)32 * rec_stride * 4;
-    int warps = kWarps;
-    while (warps > 1 && fixed + warps * per_warp > 100 * 1024) --warps;     // two blocks per SM where possible
+    int link_chunk = 512 / (7 * m->D);                                       // link blocks per output tile (~2 KB)
+    link_chunk = link_chunk < 1 ? 1 : link_chunk;
+    const size_t tile_words = ((size_t)link_chunk * 7 * m->D + 4 + 3) & ~(size_t)3;
+    // configurations per warp pass: shared memory per warp decides how many warps an SM holds, and the kernel is
+    // latency-bound, so trade phase-1 lane use for residency (TRK_B200_JAC_BUDGET: bytes per warp, default 24 KB)
+    static const long budget = [] { const char* v = getenv("TRK_B200_JAC_BUDGET"); long b = v ? atol(v) : 0; return b > 0 ? b : 24576L; }();
+    const size_t per_cfg_words = (size_t)rec_stride + 12 * (size_t)m->live.n_live;
+    int cpw = 32;
+    while (cpw > 4 && (2 * tile_words + cpw * per_cfg_words) * 4 > (size_t)budget) cpw >>= 1;
+    const size_t per_warp = (2 * tile_words + cpw * per_cfg_words) * 4;
+    const size_t fixed = (size_t)m->nwords * 4 + (size_t)(TRK_MAX_LINKS + 64) * 4;
+    const int warps = kWarps;
     const size_t smem = fixed + warps * per_warp;
-    long long tiles = (n + 32LL * warps - 1) / (32LL * warps);
-    const long long cap = (long long)m->n_sms * 8;
+    long long tiles = (n + (long long)cpw * warps - 1) / ((long long)cpw * warps);
+    const long long cap = (long long)m->n_sms * 16;
     const int grid = (int)(tiles < cap ? tiles : cap);
-    cudaError_t e = cudaSuccess;
-#define LAUNCH_JAC(MAXL)                                                                                  \
-    do {                                                                                                  \
-        e = allow_smem(k_link_jacobian<MAXL>, smem);                                                      \
-        if (e == cudaSuccess) k_link_jacobian<MAXL><<<grid, warps * 32, smem, st>>>(m->d_words, m->nwords, q, n, rec_stride, J); \
-    } while (0)
-    switch (m->maxl_bucket) {
-        case 16: LAUNCH_JAC(16); break;
-        case 32: LAUNCH_JAC(32); break;
-        default: LAUNCH_JAC(64); break;
-    }
-#undef LAUNCH_JAC
+    cudaError_t e = allow_smem(k_link_jacobian, smem);
+    if (e == cudaSuccess)
+        k_link_jacobian<<<grid, warps * 32, smem, st>>>(m->d_words, m->nwords, m->live, q, n, cpw, rec_stride, link_chunk, J);
     if (e == cudaSuccess) e = cudaGetLastError();
     return e == cudaSuccess ? TRK_OK : cuda_fail(e, "link_jacobian launch");
 }
