@@ -1,0 +1,117 @@
+"""The runtime-tree ("generic") kernel family - what serves any URDF outside the compiled-in set and every tree with
+attached points - exercised on all shipped robots by switching the compiled-in families off
+(TRK_B200_FORCE_GENERIC, read by trk_model_create)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROBOT_NAMES, get_desc, load_golden, planning_cost_from_golden, rel_err, stretch_cost_from_golden
+from oracle import c_oracle as co
+from oracle import restatement as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def generic_models():
+    from torch_robotics_b200._lib import DeviceModel
+    os.environ["TRK_B200_FORCE_GENERIC"] = "1"
+    try:
+        models = {r: DeviceModel(get_desc(r), DEV) for r in ROBOT_NAMES}
+    finally:
+        del os.environ["TRK_B200_FORCE_GENERIC"]
+    for m in models.values():
+        assert m.kernel_family == "generic"
+    return models
+
+
+def t(a):
+    return torch.as_tensor(np.ascontiguousarray(a), device=DEV)
+
+
+@pytest.mark.parametrize("robot", ROBOT_NAMES)
+def test_fk_forward_backward_vs_golden(generic_models, robot):
+    g, d, m = load_golden(f"fk_{robot}"), get_desc(robot), generic_models[robot]
+    sel = [d.link_names.index(n) for n in g["out_link_names"]]
+    sel_arg = None if sel == list(range(d.n_links)) else sel
+    H = m.fk_forward(t(g["q"]), sel_arg).cpu().numpy()
+    assert rel_err(H, g["H"]) < 1e-5
+    grad = m.fk_backward(t(g["q"]), t(g["G"]), sel_arg).cpu().numpy()
+    assert rel_err(grad, g["grad_q"]) < 1e-4
+
+
+@pytest.mark.parametrize("robot", ROBOT_NAMES)
+@pytest.mark.parametrize("n", [1, 33, 4099])
+def test_fk_vs_oracle_ragged_and_subselection(generic_models, robot, n):
+    d, m = get_desc(robot), generic_models[robot]
+    rng = np.random.default_rng(n)
+    q = rng.uniform(-3.5, 3.5, (n, d.n_dofs)).astype(np.float32)
+    H = m.fk_forward(t(q)).cpu().numpy()
+    assert rel_err(H, co.fk_forward(co.Tree(d), q)) < 1e-5
+    sel = [int(v) for v in rng.permutation(d.n_links)[: max(1, d.n_links // 2)]]
+    Hs = m.fk_forward(t(q), sel).cpu().numpy()
+    assert np.array_equal(Hs, H[:, sel])
+    G = rng.standard_normal(Hs.shape).astype(np.float32)
+    grad = m.fk_backward(t(q), t(G), sel).cpu().numpy()
+    assert rel_err(grad, co.fk_backward(co.Tree(d), q, G, sel)) < 1e-4
+    # clamped joints: exactly zero gradient
+    _, mask = orc.joint_angles(d, q, np.float32)
+    for b in range(d.n_links):
+        if d.q_index[b] >= 0:
+            assert np.all(grad[mask[:, b] == 0, d.q_index[b]] == 0)
+
+
+@pytest.mark.parametrize("case", ["panda_spheres3d", "panda_two_objects", "panda_boxes"])
+def test_objective_vs_golden_and_static_family(generic_models, case):
+    from torch_robotics_b200._lib import DeviceCost, DeviceModel
+    g, d = load_golden(f"planning_{case}"), get_desc("panda")
+    cost = planning_cost_from_golden(g)
+    q = t(g["q"].reshape(-1, 7))
+    r = DeviceCost(generic_models["panda"], cost).objective(q, want_terms=True, want_occupancy=True, want_argmin=True)
+    terms = r["terms"].cpu().numpy()
+    for k, name in enumerate(("self", "obj", "ws", "ee")):
+        assert rel_err(terms[:, k], g[f"cost_{name}"].reshape(-1)) < 1e-5
+    # decisions are shared with the compiled-in family bit for bit (same positions would be needed for the costs)
+    s = DeviceCost(DeviceModel(d, DEV), cost).objective(q, want_terms=True, want_occupancy=True, want_argmin=True)
+    assert np.mean(r["occupancy"].cpu().numpy() != s["occupancy"].cpu().numpy()) < 0.01
+    assert np.mean(r["argmin"].cpu().numpy() != s["argmin"].cpu().numpy()) < 0.01
+    assert rel_err(r["total"].cpu().numpy(), s["total"].cpu().numpy()) < 1e-5
+    assert rel_err(r["grad_q"].cpu().numpy(), s["grad_q"].cpu().numpy()) < 1e-4
+    fwd = DeviceCost(generic_models["panda"], cost).objective(q, want_grad=False, want_terms=False)
+    assert torch.equal(fwd["total"], r["total"]) and fwd["grad_q"] is None
+
+
+def test_objective_vs_oracle_at_scale(generic_models):
+    from torch_robotics_b200._lib import DeviceCost
+    for robot, cost in (("panda", planning_cost_from_golden(load_golden("planning_panda_spheres3d"))),
+                        ("stretch", stretch_cost_from_golden(load_golden("objective_stretch")))):
+        d, m = get_desc(robot), generic_models[robot]
+        rng = np.random.default_rng(3)
+        lo = np.where(d.has_lim[d.controlled] > 0, d.lo[d.controlled], -np.pi).astype(np.float32)
+        hi = np.where(d.has_lim[d.controlled] > 0, d.hi[d.controlled], np.pi).astype(np.float32)
+        q = (lo + rng.random((100_003, d.n_dofs), dtype=np.float32) * (hi - lo) * 1.1 - 0.05 * (hi - lo)).astype(np.float32)
+        r = DeviceCost(m, cost).objective(t(q), want_terms=True, want_occupancy=True, want_argmin=True)
+        o = co.objective(co.Tree(d), co.Cost(cost), q)
+        assert rel_err(r["total"].cpu().numpy(), o["total"]) < 1e-5
+        gd = np.abs(r["grad_q"].cpu().numpy() - o["grad_q"]).max(axis=1) / np.abs(o["grad_q"]).max()
+        assert (gd >= 1e-4).sum() <= 30 and gd[gd < 1e-4].max() < 1e-4
+        assert np.mean(r["occupancy"].cpu().numpy() != o["occ"]) < 1e-4
+        assert np.mean(r["argmin"].cpu().numpy() != o["argmin"]) < 1e-4
+
+
+def test_ee_target_per_configuration_and_margin_override(generic_models):
+    from torch_robotics_b200._lib import DeviceCost
+    g, d, m = load_golden("planning_panda_spheres3d"), get_desc("panda"), generic_models["panda"]
+    cost = planning_cost_from_golden(g)
+    q = g["q"].reshape(-1, 7)
+    rng = np.random.default_rng(9)
+    tgt = np.tile(g["H_target"].reshape(1, 4, 4), (q.shape[0], 1, 1)).astype(np.float32)
+    tgt[:, :3, 3] += rng.normal(0, 0.2, (q.shape[0], 3)).astype(np.float32)
+    r = DeviceCost(m, cost).objective(t(q), ee_target_cfg=t(tgt), want_occupancy=True, margin_override=0.0)
+    o = co.objective(co.Tree(d), co.Cost(cost), q, ee_target_cfg=tgt, margin_override=0.0)
+    assert rel_err(r["total"].cpu().numpy(), o["total"]) < 1e-5
+    assert rel_err(r["grad_q"].cpu().numpy(), o["grad_q"]) < 1e-4
+    assert np.array_equal(r["occupancy"].cpu().numpy(), o["occ"])

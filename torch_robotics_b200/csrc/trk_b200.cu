@@ -29,84 +29,97 @@ constexpr int kWarps = kBlock / 32;
 // ------------------------------------------------------------------------------------------
 // generic kernels
 // ------------------------------------------------------------------------------------------
-template <int MAXL>
+// Shared memory of the runtime-tree kernels: tree words | [cost words] | per warp { stage (2 KB) | live pose slots
+// (n_live x 12 x 32) | joint columns (D x 12 x 32, reverse mode only) | pair-position slots (n_pslots x 3 x 32) }.
+__host__ __device__ __forceinline__ int generic_warp_words(int stage_words, int n_live, int n_joint_cols, int n_pslots) {
+    return stage_words + (n_live * 12 + n_joint_cols * 12 + n_pslots * 3) * 32;
+}
+
 __global__ void __launch_bounds__(kBlock) k_fk_forward_generic(const float* __restrict__ tree_words, int tree_nwords,
-                                                               const float* __restrict__ q, long long n, SlotMap slots,
-                                                               int n_sel, float* __restrict__ H) {
+                                                               const __grid_constant__ TreePlan plan, const float* __restrict__ q, long long n,
+                                                               const __grid_constant__ SlotMap slots, int n_sel, float* __restrict__ H) {
     extern __shared__ __align__(16) float smem[];
     float* tw = smem;
-    float4* stage = reinterpret_cast<float4*>(smem + tree_nwords) + (threadIdx.x >> 5) * 128;
     block_copy_words(tw, tree_words, tree_nwords);
     __syncthreads();
     const TreeHeader* hdr = reinterpret_cast<const TreeHeader*>(tw);
     const LinkRec* recs = reinterpret_cast<const LinkRec*>(tw + 16);
-    const int lane = threadIdx.x & 31, D = hdr->D, L = hdr->L;
-    for (long long base = (long long)blockIdx.x * kBlock; base < n; base += (long long)gridDim.x * kBlock) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nthreads = blockDim.x, D = hdr->D;
+    float* wbase = smem + tree_nwords + (size_t)warp * generic_warp_words(512, plan.n_live, 0, 0);
+    float4* stage = reinterpret_cast<float4*>(wbase);
+    float* wl = wbase + 512 + lane;
+    for (long long base = (long long)blockIdx.x * nthreads; base < n; base += (long long)gridDim.x * nthreads) {
         const long long cfg = base + threadIdx.x;
         const long long warp_cfg0 = base + (threadIdx.x & ~31);
         if (warp_cfg0 >= n) continue;   // warp-uniform
-        float W[MAXL][12];
-        unsigned long long pass;
-        fk_generic<MAXL>(hdr, recs, q + (cfg < n ? cfg : n - 1) * D, W, pass);
-        for (int i = 0; i < L; ++i) {
-            const int b = recs[i].body;
-            const int s = slots.slot[b];
-            if (s < 0) continue;
-            const float* w = W[b];
-            warp_store_link(stage, lane, make_float4(w[0], w[1], w[2], w[9]), make_float4(w[3], w[4], w[5], w[10]),
-                            make_float4(w[6], w[7], w[8], w[11]), warp_cfg0, n, n_sel, s, H);
-        }
+        fk_live(hdr, recs, plan, q + (cfg < n ? cfg : n - 1) * D, wl, 32,
+                [&](int, const LinkRec& r, const float* w, const float*, bool) {
+                    const int s = slots.slot[r.body];
+                    if (s >= 0)
+                        warp_store_link(stage, lane, make_float4(w[0], w[1], w[2], w[9]), make_float4(w[3], w[4], w[5], w[10]),
+                                        make_float4(w[6], w[7], w[8], w[11]), warp_cfg0, n, n_sel, s, H);
+                });
     }
 }
 
-template <int MAXL>
 __global__ void __launch_bounds__(kBlock) k_fk_backward_generic(const float* __restrict__ tree_words, int tree_nwords,
-                                                                const float* __restrict__ q, long long n, SlotMap slots,
-                                                                int n_sel, const float* __restrict__ G,
+                                                                const __grid_constant__ TreePlan plan, const float* __restrict__ q, long long n,
+                                                                const __grid_constant__ SlotMap slots, int n_sel, const float* __restrict__ G,
                                                                 float* __restrict__ grad_q) {
     extern __shared__ __align__(16) float smem[];
     float* tw = smem;
-    float4* stage = reinterpret_cast<float4*>(smem + tree_nwords) + (threadIdx.x >> 5) * 128;
     block_copy_words(tw, tree_words, tree_nwords);
     __syncthreads();
     const TreeHeader* hdr = reinterpret_cast<const TreeHeader*>(tw);
     const LinkRec* recs = reinterpret_cast<const LinkRec*>(tw + 16);
-    const int lane = threadIdx.x & 31, D = hdr->D, L = hdr->L;
-    for (long long base = (long long)blockIdx.x * kBlock; base < n; base += (long long)gridDim.x * kBlock) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nthreads = blockDim.x, D = hdr->D;
+    float* wbase = smem + tree_nwords + (size_t)warp * generic_warp_words(1024, plan.n_live, D, 0);
+    float4* stage = reinterpret_cast<float4*>(wbase);      // two 2-KB buffers: the next body's G streams in while this one is used
+    float* wl = wbase + 1024 + lane;
+    float* JS = wbase + 1024 + plan.n_live * 12 * 32 + lane;
+    const int L = hdr->L;
+    for (long long base = (long long)blockIdx.x * nthreads; base < n; base += (long long)gridDim.x * nthreads) {
         const long long cfg = base + threadIdx.x;
         const long long warp_cfg0 = base + (threadIdx.x & ~31);
         if (warp_cfg0 >= n) continue;
-        float W[MAXL][12], F[MAXL][3], T[MAXL][3];
-        unsigned long long pass;
-        fk_generic<MAXL>(hdr, recs, q + (cfg < n ? cfg : n - 1) * D, W, pass);
-        for (int i = 0; i < L; ++i) {
-            const int b = recs[i].body;
-            const int s = slots.slot[b];
-            if (s < 0) {
-                F[b][0] = F[b][1] = F[b][2] = 0.f;
-                T[b][0] = T[b][1] = T[b][2] = 0.f;
-                continue;
-            }
-            float4 m0, m1, m2;
-            warp_load_link(stage, lane, warp_cfg0, n, n_sel, s, G, m0, m1, m2);
-            const float gR[9] = {m0.x, m0.y, m0.z, m1.x, m1.y, m1.z, m2.x, m2.y, m2.z};
-            const float gx = m0.w, gy = m1.w, gz = m2.w;
-            const float* w = W[b];
-            float ax, ay, az;
-            axial_gR_Rt(gR, w, ax, ay, az);
-            F[b][0] = gx; F[b][1] = gy; F[b][2] = gz;
-            T[b][0] = w[10] * gz - w[11] * gy + ax;
-            T[b][1] = w[11] * gx - w[9] * gz + ay;
-            T[b][2] = w[9] * gy - w[10] * gx + az;
+        unsigned pass_mask = 0u;
+        {
+            const int s0 = slots.slot[recs[0].body];
+            if (s0 >= 0) warp_prefetch_link(stage, lane, warp_cfg0, n, n_sel, s0, G);
+            cp_async_commit();
         }
-        if (cfg < n) tree_backward_generic<MAXL>(hdr, recs, W, F, T, pass, grad_q + cfg * D);
+        fk_live(hdr, recs, plan, q + (cfg < n ? cfg : n - 1) * D, wl, 32,
+                [&](int i, const LinkRec& r, const float* w, const float* wp, bool pass) {
+                    if (i + 1 < L) {
+                        const int sn = slots.slot[recs[i + 1].body];
+                        if (sn >= 0) warp_prefetch_link(stage + ((i + 1) & 1) * 128, lane, warp_cfg0, n, n_sel, sn, G);
+                    }
+                    cp_async_commit();
+                    if (r.qidx >= 0) {
+                        joint_store_axis(JS, r, w, wp);
+                        if (pass) pass_mask |= 1u << r.qidx;
+                    }
+                    const int s = slots.slot[r.body], c = plan.jm[r.body];
+                    if (s < 0 || c < 0) return;     // not selected, or no joint above: no gradient (warp-uniform)
+                    cp_async_wait<1>();
+                    __syncwarp();
+                    const float4* st = stage + (i & 1) * 128;
+                    const float4 m0 = st[stage_idx(lane, 0)], m1 = st[stage_idx(lane, 1)], m2 = st[stage_idx(lane, 2)];
+                    __syncwarp();
+                    const float gR[9] = {m0.x, m0.y, m0.z, m1.x, m1.y, m1.z, m2.x, m2.y, m2.z};
+                    float ax, ay, az;
+                    axial_gR_Rt(gR, w, ax, ay, az);
+                    joint_fold(JS, c, w[9], w[10], w[11], m0.w, m1.w, m2.w, ax, ay, az);
+                });
+        cp_async_wait<0>();
+        if (cfg < n) joint_reverse_sweep(JS, plan, D, pass_mask, grad_q + cfg * D);
     }
 }
 
-template <int MAXL, bool WANT_GRAD>
+template <bool WANT_GRAD>
 __global__ void __launch_bounds__(kBlock) k_objective_generic(const float* __restrict__ tree_words, int tree_nwords,
                                                               const float* __restrict__ cost_words, int cost_nwords,
-                                                              const float* __restrict__ q, long long n,
+                                                              const __grid_constant__ TreePlan plan, const float* __restrict__ q, long long n,
                                                               const float* __restrict__ ee_target_cfg, float margin_override,
                                                               int use_override, float* __restrict__ cost_total,
                                                               float* __restrict__ cost_terms, float* __restrict__ grad_q,
@@ -121,62 +134,88 @@ __global__ void __launch_bounds__(kBlock) k_objective_generic(const float* __res
     const LinkRec* recs = reinterpret_cast<const LinkRec*>(tw + 16);
     const CostView cv(cw);
     const CostHeader* h = cv.h;
-    const int D = hdr->D, L = hdr->L;
-    for (long long cfg = (long long)blockIdx.x * kBlock + threadIdx.x; cfg < n; cfg += (long long)gridDim.x * kBlock) {
-        float W[MAXL][12], F[MAXL][3];
-        unsigned long long pass;
-        fk_generic<MAXL>(hdr, recs, q + cfg * D, W, pass);
-        if (WANT_GRAD)
-            for (int b = 0; b < L; ++b) F[b][0] = F[b][1] = F[b][2] = 0.f;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nthreads = blockDim.x, D = hdr->D;
+    const int njc = WANT_GRAD ? D : 0;
+    float* wbase = smem + tree_nwords + ((cost_nwords + 3) & ~3) + (size_t)warp * generic_warp_words(0, plan.n_live, njc, h->n_pslots);
+    float* wl = wbase + lane;
+    float* JS = wbase + plan.n_live * 12 * 32 + lane;
+    float* PS = wbase + (plan.n_live + njc) * 12 * 32 + lane;           // pair-position slots [slot * 3 + k][lane]
+    const int P = h->P, S = h->S;
+    for (long long cfg = (long long)blockIdx.x * nthreads + threadIdx.x; cfg < n; cfg += (long long)gridDim.x * nthreads) {
         float terms[4] = {0.f, 0.f, 0.f, 0.f};
-        unsigned occ;
-        collision_terms<WANT_GRAD, true>(
-            cv, cv.pt_link, cv.pair_i, cv.pair_j, [&](int b, float& x, float& y, float& z) { x = W[b][9]; y = W[b][10]; z = W[b][11]; },
-            [&](int b, float gx, float gy, float gz) { F[b][0] += gx; F[b][1] += gy; F[b][2] += gz; }, margin_override,
-            use_override != 0, terms, occ, argmin ? argmin + cfg * (long long)(h->nObj * h->S) : nullptr);
-        float gR[9], gp[3];
-        if (h->ee_enabled) {
-            float Rt[9], pt[3];
-            if (ee_target_cfg) {
-                const float* Ht = ee_target_cfg + cfg * 16;
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    Rt[i * 3 + 0] = __ldg(Ht + i * 4 + 0); Rt[i * 3 + 1] = __ldg(Ht + i * 4 + 1);
-                    Rt[i * 3 + 2] = __ldg(Ht + i * 4 + 2); pt[i] = __ldg(Ht + i * 4 + 3);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 9; ++i) Rt[i] = h->ee_R[i];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) pt[i] = h->ee_t[i];
+        unsigned occ = 0u, pass_mask = 0u;
+        int* argmin_row = argmin ? argmin + cfg * (long long)(h->nObj * S) : nullptr;
+        // forward: every body is seen once with its pose in registers; its collision points are evaluated on the spot
+        // and their forces go straight to the accumulator of the joint above
+        fk_live(hdr, recs, plan, q + cfg * D, wl, 32, [&](int, const LinkRec& r, const float* w, const float* wp, bool pass) {
+            const int b = r.body;
+            if (WANT_GRAD && r.qidx >= 0) {
+                joint_store_axis(JS, r, w, wp);
+                if (pass) pass_mask |= 1u << r.qidx;
             }
-            const float* w = W[h->ee_link];
-            terms[3] = ee_term<WANT_GRAD>(h, w, w + 9, Rt, pt, gR, gp);
+            const float x = w[9], y = w[10], z = w[11];
+            const int ps = cv.pslot_of_body[b];
+            if (ps >= 0) { PS[ps * 96] = x; PS[ps * 96 + 32] = y; PS[ps * 96 + 64] = z; }
+            const int c = plan.jm[b];
+#pragma unroll 1
+            for (int k = cv.bp_start[b]; k < cv.bp_start[b + 1]; ++k) {
+                const int s = cv.bp_list[k];
+                float gx = 0.f, gy = 0.f, gz = 0.f;
+                if (h->nObj > 0) {
+                    const float m = cv.pt_mobj[s];
+                    terms[1] = __fadd_rn(terms[1], object_point_term<WANT_GRAD, true>(cv, x, y, z, m, use_override ? margin_override : m,
+                                                                                      occ, argmin_row, s, gx, gy, gz));
+                }
+                if (h->ws_enabled) {
+                    const float m = cv.pt_mws[s];
+                    terms[2] = __fadd_rn(terms[2], ws_point_term<WANT_GRAD, true>(h, x, y, z, m, use_override ? margin_override : m, occ,
+                                                                                  gx, gy, gz));
+                }
+                if (WANT_GRAD && c >= 0) joint_fold(JS, c, x, y, z, gx, gy, gz, 0.f, 0.f, 0.f);
+            }
+            if (h->ee_enabled && b == h->ee_link) {
+                float Rt[9], pt[3], gR[9], gp[3];
+                if (ee_target_cfg) {
+                    const float* Ht = ee_target_cfg + cfg * 16;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        Rt[i * 3 + 0] = __ldg(Ht + i * 4 + 0); Rt[i * 3 + 1] = __ldg(Ht + i * 4 + 1);
+                        Rt[i * 3 + 2] = __ldg(Ht + i * 4 + 2); pt[i] = __ldg(Ht + i * 4 + 3);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) Rt[i] = h->ee_R[i];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) pt[i] = h->ee_t[i];
+                }
+                terms[3] = ee_term<WANT_GRAD>(h, w, w + 9, Rt, pt, gR, gp);
+                if (WANT_GRAD && c >= 0) {
+                    float ax, ay, az;
+                    axial_gR_Rt(gR, w, ax, ay, az);
+                    joint_fold(JS, c, x, y, z, gp[0], gp[1], gp[2], ax, ay, az);
+                }
+            }
+        });
+        // self-collision pairs need both bodies: positions come from the pair slots
+#pragma unroll 1
+        for (int p = 0; p < P; ++p) {
+            const float* a = PS + cv.pair_pi[p] * 96;
+            const float* bq = PS + cv.pair_pj[p] * 96;
+            const float xi = a[0], yi = a[32], zi = a[64], xj = bq[0], yj = bq[32], zj = bq[64];
+            const float m = cv.pair_m[p];
+            float ux, uy, uz;
+            terms[0] = __fadd_rn(terms[0], pair_term<WANT_GRAD, true>(h, xi, yi, zi, xj, yj, zj, m, use_override ? margin_override : m,
+                                                                      occ, ux, uy, uz));
+            if (WANT_GRAD) {
+                const int ci = plan.jm[cv.pair_i[p]], cj = plan.jm[cv.pair_j[p]];
+                if (ci >= 0) joint_fold(JS, ci, xi, yi, zi, -ux, -uy, -uz, 0.f, 0.f, 0.f);
+                if (cj >= 0) joint_fold(JS, cj, xj, yj, zj, ux, uy, uz, 0.f, 0.f, 0.f);
+            }
         }
         if (cost_total) cost_total[cfg] = weighted_total(h, terms);
         if (cost_terms) reinterpret_cast<float4*>(cost_terms)[cfg] = make_float4(terms[0], terms[1], terms[2], terms[3]);
         if (occupancy) occupancy[cfg] = (uint8_t)occ;
-        if (WANT_GRAD) {
-            float T[MAXL][3];
-            for (int b = 0; b < L; ++b) {
-                const float* w = W[b];
-                const float fx = F[b][0], fy = F[b][1], fz = F[b][2];
-                T[b][0] = w[10] * fz - w[11] * fy;
-                T[b][1] = w[11] * fx - w[9] * fz;
-                T[b][2] = w[9] * fy - w[10] * fx;
-            }
-            if (h->ee_enabled) {
-                const int e = h->ee_link;
-                const float* w = W[e];
-                float ax, ay, az;
-                axial_gR_Rt(gR, w, ax, ay, az);
-                F[e][0] += gp[0]; F[e][1] += gp[1]; F[e][2] += gp[2];
-                T[e][0] += w[10] * gp[2] - w[11] * gp[1] + ax;
-                T[e][1] += w[11] * gp[0] - w[9] * gp[2] + ay;
-                T[e][2] += w[9] * gp[1] - w[10] * gp[0] + az;
-            }
-            tree_backward_generic<MAXL>(hdr, recs, W, F, T, pass, grad_q + cfg * D);
-        }
+        if (WANT_GRAD) joint_reverse_sweep(JS, plan, D, pass_mask, grad_q + cfg * D);
     }
 }
 
@@ -209,7 +248,7 @@ __device__ __forceinline__ void quat_of_rotation(const float* R, float* qo) {
 }
 
 __global__ void __launch_bounds__(kBlock) k_link_jacobian(const float* __restrict__ tree_words, int tree_nwords,
-                                                          const LiveSlots live, const float* __restrict__ q, long long n,
+                                                          const __grid_constant__ TreePlan live, const float* __restrict__ q, long long n,
                                                           int cpw, int rec_stride, int link_chunk, float* __restrict__ J) {
     extern __shared__ __align__(16) float smem[];
     float* tw = smem;
@@ -419,12 +458,24 @@ struct trk_model {
     int family;                 // trk::StaticFamily id, 0 = generic
     int32_t parent[TRK_MAX_LINKS];
     int32_t qidx[TRK_MAX_LINKS];
-    LiveSlots live;             // shared-memory pose slots of the runtime-tree kernels
+    TreePlan live;              // live pose slots + joint tables of the runtime-tree kernels
 };
 
 // Parents-first walk: a body's pose slot is released once its last child has been composed (the child already holds
 // the parent pose in registers, so it may take over the very slot), leaves need none.
-static void assign_live_slots(const int32_t* topo, const int32_t* parent, int L, LiveSlots& ls) {
+static void build_tree_plan(const int32_t* topo, const int32_t* parent, const int32_t* qidx, const int32_t* kind, int L, TreePlan& ls) {
+    memset(&ls, 0, sizeof(ls));
+    int nj = 0;
+    for (int i = 0; i < L; ++i) {   // joint tables (parents first)
+        const int b = topo[i], p = parent[b];
+        const int up = p >= 0 ? ls.jm[p] : -1;
+        ls.jm[b] = (int8_t)(qidx[b] >= 0 ? qidx[b] : up);
+        if (qidx[b] >= 0) {
+            ls.pjoint[qidx[b]] = (int8_t)up;
+            ls.jorder[nj++] = (int8_t)qidx[b];
+            if (kind[b] == TRK_KIND_PRISMATIC) ls.prism_mask |= 1u << qidx[b];
+        }
+    }
     int pos_of[TRK_MAX_LINKS], last_child[TRK_MAX_LINKS], slot_of[TRK_MAX_LINKS];
     bool busy[TRK_MAX_LINKS] = {false};
     for (int i = 0; i < L; ++i) { pos_of[topo[i]] = i; last_child[i] = -1; }
@@ -450,6 +501,7 @@ struct trk_cost {
     int S, nObj, K, P;
     int ee_enabled;
     int n_slots;                // bodies referenced by the tables
+    int n_pslots;               // bodies referenced by self-collision pairs
     int cm_match;               // cost table equals the compile-time collision model of the model's family
     float* d_words;
     int nwords;
@@ -479,6 +531,21 @@ static int grid_for(const trk_model* m, long long n, int blocks_per_sm) {
     long long need = (n + kBlock - 1) / kBlock;
     long long cap = (long long)m->n_sms * blocks_per_sm;
     return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+// Block size and dynamic shared memory of a runtime-tree kernel: per-warp words as generic_warp_words() lays them out;
+// four warps per block unless that would leave fewer than two blocks per SM.
+static int align4(int x) { return (x + 3) & ~3; }
+struct GenericLaunch { int warps, grid; size_t smem; };
+static GenericLaunch generic_launch(const trk_model* m, long long n, size_t fixed_words, int stage_words, int n_joint_cols, int n_pslots) {
+    const size_t per_warp = (size_t)generic_warp_words(stage_words, m->live.n_live, n_joint_cols, n_pslots) * 4;
+    GenericLaunch g;
+    g.warps = kWarps;
+    while (g.warps > 1 && fixed_words * 4 + g.warps * per_warp > 100 * 1024) --g.warps;
+    g.smem = fixed_words * 4 + g.warps * per_warp;
+    const long long need = (n + g.warps * 32 - 1) / (g.warps * 32), cap = (long long)m->n_sms * 16;
+    g.grid = (int)(need < cap ? (need > 0 ? need : 1) : cap);
+    return g;
 }
 
 static int build_slots(const trk_model* m, const int32_t* link_sel, int32_t n_sel, SlotMap& sm, int& n_out) {
@@ -585,7 +652,7 @@ int trk_model_create(const trk_model_desc* d, int device, trk_model** out) {
     m->maxl_bucket = L <= 16 ? 16 : (L <= 32 ? 32 : 64);
     memcpy(m->parent, d->parent, L * sizeof(int32_t));
     memcpy(m->qidx, d->q_index, L * sizeof(int32_t));
-    assign_live_slots(d->topo, d->parent, L, m->live);
+    build_tree_plan(d->topo, d->parent, d->q_index, d->kind, L, m->live);
     cudaError_t e = cudaDeviceGetAttribute(&m->n_sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) { delete m; return cuda_fail(e, "cudaDeviceGetAttribute"); }
     e = cudaMalloc(&m->d_words, nwords * sizeof(float));
@@ -593,6 +660,7 @@ int trk_model_create(const trk_model_desc* d, int device, trk_model** out) {
     e = cudaMemcpy(m->d_words, words.data(), nwords * sizeof(float), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(m->d_words); delete m; return cuda_fail(e, "cudaMemcpy(tree)"); }
     m->family = trk::match_static_family(words.data(), nwords);
+    if (getenv("TRK_B200_FORCE_GENERIC")) m->family = 0;   // diagnostic switch: serve a compiled-in robot with the runtime-tree kernels
     *out = m;
     return TRK_OK;
 }
@@ -622,14 +690,11 @@ int trk_fk_forward(const trk_model* m, const float* q, int64_t n, const int32_t*
         cudaError_t e = trk::launch_static_fk_forward(m->family, m->n_sms, q, n, sm, n_out, H, st);
         return e == cudaSuccess ? TRK_OK : cuda_fail(e, "fk_forward(static)");
     }
-    const size_t smem = (size_t)m->nwords * 4 + kWarps * 2048;
-    const int grid = grid_for(m, n, 16);
-    switch (m->maxl_bucket) {
-        case 16: k_fk_forward_generic<16><<<grid, kBlock, smem, st>>>(m->d_words, m->nwords, q, n, sm, n_out, H); break;
-        case 32: k_fk_forward_generic<32><<<grid, kBlock, smem, st>>>(m->d_words, m->nwords, q, n, sm, n_out, H); break;
-        default: k_fk_forward_generic<64><<<grid, kBlock, smem, st>>>(m->d_words, m->nwords, q, n, sm, n_out, H); break;
-    }
-    cudaError_t e = cudaGetLastError();
+    const GenericLaunch gl = generic_launch(m, n, m->nwords, 512, 0, 0);
+    cudaError_t e = allow_smem(k_fk_forward_generic, gl.smem);
+    if (e != cudaSuccess) return cuda_fail(e, "fk_forward smem");
+    k_fk_forward_generic<<<gl.grid, gl.warps * 32, gl.smem, st>>>(m->d_words, m->nwords, m->live, q, n, sm, n_out, H);
+    e = cudaGetLastError();
     return e == cudaSuccess ? TRK_OK : cuda_fail(e, "fk_forward launch");
 }
 
@@ -649,18 +714,15 @@ int trk_fk_backward(const trk_model* m, const float* q, int64_t n, const int32_t
         cudaError_t e = trk::launch_static_fk_backward(m->family, m->n_sms, q, n, sm, n_out, G, grad_q, st);
         return e == cudaSuccess ? TRK_OK : cuda_fail(e, "fk_backward(static)");
     }
-    const size_t smem = (size_t)m->nwords * 4 + kWarps * 2048;
-    const int grid = grid_for(m, n, 16);
-    switch (m->maxl_bucket) {
-        case 16: k_fk_backward_generic<16><<<grid, kBlock, smem, st>>>(m->d_words, m->nwords, q, n, sm, n_out, G, grad_q); break;
-        case 32: k_fk_backward_generic<32><<<grid, kBlock, smem, st>>>(m->d_words, m->nwords, q, n, sm, n_out, G, grad_q); break;
-        default: k_fk_backward_generic<64><<<grid, kBlock, smem, st>>>(m->d_words, m->nwords, q, n, sm, n_out, G, grad_q); break;
-    }
-    cudaError_t e = cudaGetLastError();
+    if (m->D == 0) return TRK_OK;     // no movable joint: grad_q has no columns
+    const GenericLaunch gl = generic_launch(m, n, m->nwords, 1024, m->D, 0);
+    cudaError_t e = allow_smem(k_fk_backward_generic, gl.smem);
+    if (e != cudaSuccess) return cuda_fail(e, "fk_backward smem");
+    k_fk_backward_generic<<<gl.grid, gl.warps * 32, gl.smem, st>>>(m->d_words, m->nwords, m->live, q, n, sm, n_out, G, grad_q);
+    e = cudaGetLastError();
     return e == cudaSuccess ? TRK_OK : cuda_fail(e, "fk_backward launch");
 }
 
-static int align4(int x) { return (x + 3) & ~3; }
 
 int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) {
     TRK_CHECK_PTR(m, "model"); TRK_CHECK_PTR(d, "desc"); TRK_CHECK_PTR(out, "out");
@@ -722,7 +784,8 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
     const int o_pt_link = take(S), o_mobj = take(S), o_mws = take(S), o_ostart = take(nObj + 1), o_oid = take(nObj),
               o_oR = take(nObj * 9), o_opos = take(nObj * 3), o_sph = take(K * 4), o_pi = take(P), o_pj = take(P), o_pm = take(P), o_ormax = take(nObj), o_oc2 = take(nObj), o_sphq = take(KQ * 4), o_oqs = take(nObj + 1), o_otol = take(nObj),
               o_sob = take(m->L), o_pts = take(S), o_psi = take(P), o_psj = take(P),
-              o_obs = take(nObj + 1), o_box = take(KB * 8);
+              o_obs = take(nObj + 1), o_box = take(KB * 8),
+              o_psb = take(m->L), o_ppi = take(P), o_ppj = take(P), o_bps = take(m->L + 1), o_bpl = take(S);
     const int nwords = off;
     trk_cost* c = new (std::nothrow) trk_cost();
     if (!c) return fail(TRK_E_RANGE, "out of host memory");
@@ -809,6 +872,21 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
             }
             h->grid_data = reinterpret_cast<const float4*>(d->grid_data);
         }
+        {   // pair-position slots and the body -> points lists of the runtime-tree objective kernel
+            int n_ps = 0;
+            for (int b = 0; b < m->L; ++b) iw[o_psb + b] = -1;
+            auto pslot = [&](int b) { if (iw[o_psb + b] < 0) iw[o_psb + b] = n_ps++; return iw[o_psb + b]; };
+            for (int p = 0; p < P; ++p) { iw[o_ppi + p] = pslot(d->pair_i[p]); iw[o_ppj + p] = pslot(d->pair_j[p]); }
+            int pos = 0;
+            for (int b = 0; b < m->L; ++b) {
+                iw[o_bps + b] = pos;
+                for (int s2 = 0; s2 < S; ++s2) if (d->pt_link[s2] == b) iw[o_bpl + pos++] = s2;
+            }
+            iw[o_bps + m->L] = pos;
+            h->n_pslots = n_ps; h->off_pslot_of_body = o_psb; h->off_pair_pi = o_ppi; h->off_pair_pj = o_ppj;
+            h->off_bp_start = o_bps; h->off_bp_list = o_bpl;
+            c->n_pslots = n_ps;
+        }
         h->n_slots = n_slots; h->off_slot_of_body = o_sob; h->off_pt_slot = o_pts; h->off_pair_si = o_psi; h->off_pair_sj = o_psj;
         c->n_slots = n_slots;
     }
@@ -877,24 +955,17 @@ int trk_objective(const trk_model* m, const trk_cost* c, const float* q, int64_t
                                                      occupancy, argmin, st);
         return e == cudaSuccess ? TRK_OK : cuda_fail(e, "objective(static)");
     }
-    const size_t smem = (size_t)(m->nwords + c->nwords) * 4;
-    const int grid = grid_for(m, n, 16);
-#define LAUNCH_OBJ(MAXL)                                                                                                \
-    do {                                                                                                                \
-        if (grad_q)                                                                                                     \
-            k_objective_generic<MAXL, true><<<grid, kBlock, smem, st>>>(m->d_words, m->nwords, c->d_words, c->nwords, q, n, \
-                ee_target_cfg, margin_override, use_override, cost_total, cost_terms, grad_q, occupancy, argmin);       \
-        else                                                                                                            \
-            k_objective_generic<MAXL, false><<<grid, kBlock, smem, st>>>(m->d_words, m->nwords, c->d_words, c->nwords, q, n, \
-                ee_target_cfg, margin_override, use_override, cost_total, cost_terms, grad_q, occupancy, argmin);       \
-    } while (0)
-    switch (m->maxl_bucket) {
-        case 16: LAUNCH_OBJ(16); break;
-        case 32: LAUNCH_OBJ(32); break;
-        default: LAUNCH_OBJ(64); break;
-    }
-#undef LAUNCH_OBJ
-    cudaError_t e = cudaGetLastError();
+    const GenericLaunch gl = generic_launch(m, n, (size_t)m->nwords + align4(c->nwords), 0, grad_q ? m->D : 0, c->n_pslots);
+    cudaError_t e = allow_smem(k_objective_generic<true>, gl.smem);
+    if (e == cudaSuccess) e = allow_smem(k_objective_generic<false>, gl.smem);
+    if (e != cudaSuccess) return cuda_fail(e, "objective smem");
+    if (grad_q)
+        k_objective_generic<true><<<gl.grid, gl.warps * 32, gl.smem, st>>>(m->d_words, m->nwords, c->d_words, c->nwords, m->live, q, n,
+            ee_target_cfg, margin_override, use_override, cost_total, cost_terms, grad_q, occupancy, argmin);
+    else
+        k_objective_generic<false><<<gl.grid, gl.warps * 32, gl.smem, st>>>(m->d_words, m->nwords, c->d_words, c->nwords, m->live, q, n,
+            ee_target_cfg, margin_override, use_override, cost_total, cost_terms, grad_q, occupancy, argmin);
+    e = cudaGetLastError();
     return e == cudaSuccess ? TRK_OK : cuda_fail(e, "objective launch");
 }
 
