@@ -272,6 +272,15 @@ def main():
         def bwd():
             L_.check(L_.lib().trk_fk_backward(model.handle, q2.data_ptr(), n2, None, L, Gbuf.data_ptr(), gq.data_ptr(), L_.stream_ptr(dev)), "fk_backward")
         ms_f, ms_b = timed(fwd), timed(bwd)
+        del Hbuf, Gbuf
+        n3 = 1 << 19
+        Jbuf = torch.empty((n3, L, 7, desc.n_dofs), dtype=torch.float32, device=dev)
+
+        def jac():
+            L_.check(L_.lib().trk_link_jacobian(model.handle, q2.data_ptr(), n3, Jbuf.data_ptr(), L_.stream_ptr(dev)), "link_jacobian")
+        ms_j = timed(jac)
+        by_j = n3 * (desc.n_dofs * 4 + L * 7 * desc.n_dofs * 4)
+        del Jbuf
         by_f, by_b = n2 * (desc.n_dofs * 4 + L * 64), n2 * (2 * desc.n_dofs * 4 + L * 64)
         hbm = measured_peaks()["hbm_gbs"]
         extra = {"fk_forward_1M": {"ms": ms_f, "configs_per_s": n2 / ms_f * 1e3, "GBps": by_f / ms_f / 1e6, "hbm_frac": by_f / ms_f / 1e6 / hbm,
@@ -279,8 +288,9 @@ def main():
                  "fk_backward_1M": {"ms": ms_b, "configs_per_s": n2 / ms_b * 1e3, "GBps": by_b / ms_b / 1e6, "hbm_frac": by_b / ms_b / 1e6 / hbm,
                                     "bytes_per_config": by_b / n2},
                  "fk_fwd_bwd_1M_configs_per_s": n2 / (ms_f + ms_b) * 1e3,
+                 "link_jacobian_512k": {"ms": ms_j, "configs_per_s": n3 / ms_j * 1e3, "GBps": by_j / ms_j / 1e6, "hbm_frac": by_j / ms_j / 1e6 / hbm,
+                                        "bytes_per_config": by_j / n3},
                  "note": "1,048,576 configs: H (738 MB) exceeds L2; CUDA events around 10 back-to-back launches, median of 5"}
-        del Hbuf, Gbuf
 
     times = torch.tensor([span_ms, total_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
