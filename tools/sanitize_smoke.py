@@ -39,5 +39,36 @@ g = load_golden("objective_stretch"); d = get_desc("stretch"); m = DeviceModel(d
 DeviceCost(m, stretch_cost_from_golden(g)).objective(torch.as_tensor(g["q"], device=dev))
 g = load_golden("ik_panda"); m = DeviceModel(get_desc("panda"), dev)
 m.ik_adam(torch.as_tensor(g["q0"], device=dev), g["H_target"], 10, g["lower"], g["upper"], n_iters=5, lr=0.2, se3_eps=0.05, want_loss_stats=True)
+# runtime-tree family on the compiled-in robots too (objective with and without gradient, sub-selections)
+os.environ["TRK_B200_FORCE_GENERIC"] = "1"
+for robot, n in (("panda", 517), ("stretch", 131), ("shadow_hand", 65)):
+    d = get_desc(robot); mg2 = DeviceModel(d, dev)
+    assert mg2.kernel_family == "generic"
+    q = torch.as_tensor(rng.uniform(-3, 3, (n, d.n_dofs)).astype(np.float32), device=dev)
+    H = mg2.fk_forward(q); mg2.fk_backward(q, torch.randn_like(H))
+    sel = [int(v) for v in rng.permutation(d.n_links)[:3]]
+    Hs = mg2.fk_forward(q, sel); mg2.fk_backward(q, torch.randn_like(Hs), sel)
+    mg2.link_jacobian(q)
+gq = load_golden("planning_panda_boxes"); mgp = DeviceModel(get_desc("panda"), dev)
+dcg = DeviceCost(mgp, planning_cost_from_golden(gq)); qq = torch.as_tensor(gq["q"].reshape(-1, 7), device=dev)
+dcg.objective(qq, want_terms=True, want_occupancy=True, want_argmin=True); dcg.objective(qq, want_grad=False)
+DeviceCost(DeviceModel(get_desc("stretch"), dev), stretch_cost_from_golden(load_golden("objective_stretch"))).objective(torch.as_tensor(load_golden("objective_stretch")["q"], device=dev))
+del os.environ["TRK_B200_FORCE_GENERIC"]
+# attached collision points (45-sphere Panda model, grasped box) and the voxel SDF (precompute + lookup + standalone query)
+from torch_robotics_b200.environments.env_spheres_3d import EnvSpheres3D
+from torch_robotics_b200.environments.objects import GraspedObjectPandaBox
+from torch_robotics_b200.robots.robot_panda import RobotPanda
+from torch_robotics_b200.tasks.tasks import PlanningTask
+TA = dict(device=dev, dtype=torch.float32)
+env = EnvSpheres3D(precompute_sdf_obj_fixed=True, sdf_cell_size=0.1, tensor_args=TA)
+for robot in (RobotPanda(tensor_args=TA), RobotPanda(sphere_config=True, tensor_args=TA),
+              RobotPanda(grasped_object=GraspedObjectPandaBox(tensor_args=TA), tensor_args=TA)):
+    task = PlanningTask(env=env, robot=robot, tensor_args=TA)
+    qt = (robot.q_min + torch.rand(9, 7, 7, device=dev) * (robot.q_max - robot.q_min)).requires_grad_(True)
+    task.compute_collision_cost(qt).sum().backward()
+    task.compute_collision(qt.detach())
+    robot.diff_panda.compute_analytical_jacobian_all_links(qt.detach().reshape(-1, 7))
+X = (torch.rand(300, 3, device=dev) * 2.4 - 1.2).requires_grad_(True)
+env.grid_map_sdf_obj_fixed(X).sum().backward()
 torch.cuda.synchronize()
 print("sanitize_smoke: all kernel families ran")

@@ -83,18 +83,17 @@ __global__ void __launch_bounds__(kBlock) k_fk_backward_generic(const float* __r
         const long long warp_cfg0 = base + (threadIdx.x & ~31);
         if (warp_cfg0 >= n) continue;
         unsigned pass_mask = 0u;
-        {
-            const int s0 = slots.slot[recs[0].body];
-            if (s0 >= 0) warp_prefetch_link(stage, lane, warp_cfg0, n, n_sel, s0, G);
+        // a body's G is fetched only if it will be consumed (selected and below some joint): every stage buffer that
+        // is written is also waited for before it is written again
+        auto fetch = [&](int pos) {
+            const int bn = recs[pos].body, sn = slots.slot[bn];
+            if (sn >= 0 && plan.jm[bn] >= 0) warp_prefetch_link(stage + (pos & 1) * 128, lane, warp_cfg0, n, n_sel, sn, G);
             cp_async_commit();
-        }
+        };
+        fetch(0);
         fk_live(hdr, recs, plan, q + (cfg < n ? cfg : n - 1) * D, wl, 32,
                 [&](int i, const LinkRec& r, const float* w, const float* wp, bool pass) {
-                    if (i + 1 < L) {
-                        const int sn = slots.slot[recs[i + 1].body];
-                        if (sn >= 0) warp_prefetch_link(stage + ((i + 1) & 1) * 128, lane, warp_cfg0, n, n_sel, sn, G);
-                    }
-                    cp_async_commit();
+                    if (i + 1 < L) fetch(i + 1); else cp_async_commit();
                     if (r.qidx >= 0) {
                         joint_store_axis(JS, r, w, wp);
                         if (pass) pass_mask |= 1u << r.qidx;
