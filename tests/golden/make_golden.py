@@ -262,6 +262,26 @@ def golden_planning_boxes():
     planning_case("panda_boxes", robot, env, task, q, H_target, dict(w_pos=1.0, w_rot=1.0, square=True))
 
 
+def golden_planning_envs():
+    """The reference's other Panda 3-D environments (SURVEY.md section 8 row f2 names them): EnvTableShelf (a posed
+    table + a posed ten-board shelf, rounded boxes), EnvMazeBoxes3D (fourteen rounded pillars) and
+    EnvSpheres3DExtraObjects (fixed + extra sphere objects)."""
+    from torch_robotics.environments.env_table_shelf import EnvTableShelf
+    from torch_robotics.environments.env_maze_boxes_3d import EnvMazeBoxes3D
+    from torch_robotics.environments.env_spheres_3d_extra_objects import EnvSpheres3DExtraObjects
+    gen = torch.Generator().manual_seed(1123)
+    robot = quiet(RobotPanda, tensor_args=TA)
+    H_target = ee_target()
+    for tag, cls in (("table_shelf", EnvTableShelf), ("maze_boxes", EnvMazeBoxes3D), ("spheres3d_extra", EnvSpheres3DExtraObjects)):
+        env = quiet(cls, tensor_args=TA)
+        task = quiet(PlanningTask, env=env, robot=robot, tensor_args=TA)
+        q = (robot.q_min + torch.rand(6, 12, 7, generator=gen) * (robot.q_max - robot.q_min)).contiguous()
+        planning_case(f"panda_{tag}", robot, env, task, q, H_target, dict(w_pos=1.0, w_rot=1.0, square=True))
+        g = dict(np.load(os.path.join(HERE, f"planning_panda_{tag}.npz")))
+        g["env_limits"] = env.limits.numpy()
+        np.savez_compressed(os.path.join(HERE, f"planning_panda_{tag}.npz"), **g)
+
+
 def golden_stretch_objective():
     """Config 5: Stretch has no collision model in the reference; compose the generic field classes
     exactly as SURVEY.md section 8(d) item 5 specifies."""
@@ -535,7 +555,9 @@ def golden_link_jacobians():
 
 
 if __name__ == "__main__":
-    if os.environ.get("GOLDEN_ONLY") == "jacobian":
+    if os.environ.get("GOLDEN_ONLY") == "envs":
+        golden_planning_envs()
+    elif os.environ.get("GOLDEN_ONLY") == "jacobian":
         golden_link_jacobians()
     elif os.environ.get("GOLDEN_ONLY") == "voxel":
         golden_voxel_sdf()
@@ -549,6 +571,7 @@ if __name__ == "__main__":
         golden_fk()
         golden_planning()
         golden_planning_boxes()
+        golden_planning_envs()
         golden_stretch_objective()
         golden_ik()
         golden_trajectories()
