@@ -260,3 +260,21 @@ def test_host_pipeline_matches_device_call(planning):
     pipe.run(q_host, cost_host, grad_host)
     r = dc.objective(q_host.to(DEV))
     assert torch.equal(cost_host, r["total"].cpu()) and torch.equal(grad_host, r["grad_q"].cpu())
+
+
+def test_cost_and_grad_without_autograd_matches_autograd():
+    """PlanningTask.compute_cost_and_grad: one launch, same numbers as compute_collision_cost + backward."""
+    from torch_robotics_b200.environments.env_spheres_3d import EnvSpheres3D
+    from torch_robotics_b200.robots.robot_panda import RobotPanda
+    from torch_robotics_b200.tasks.tasks import PlanningTask
+    TA = dict(device="cuda:0", dtype=torch.float32)
+    robot = RobotPanda(tensor_args=TA)
+    task = PlanningTask(env=EnvSpheres3D(tensor_args=TA), robot=robot, tensor_args=TA)
+    q = (robot.q_min + torch.rand(7, 9, 7, device="cuda:0") * (robot.q_max - robot.q_min)).requires_grad_(True)
+    c = task.compute_collision_cost(q)
+    c.sum().backward()
+    c2, g2 = task.compute_cost_and_grad(q)
+    assert c2.shape == (7, 9) and g2.shape == (7, 9, 7)
+    assert torch.equal(c2, c.detach()) and torch.equal(g2, q.grad)
+    c3, g3 = task.compute_cost_and_grad(q[0])                     # [h, D] -> batch of one
+    assert torch.equal(c3.reshape(-1), c2[0]) and torch.equal(g3.reshape(9, 7), g2[0])

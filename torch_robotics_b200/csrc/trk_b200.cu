@@ -776,8 +776,8 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
         }
     }
 
-    int KQ = 0;   // spheres padded per object to a multiple of four (scan table)
-    for (int o = 0; o < nObj; ++o) KQ += (d->obj_start[o + 1] - d->obj_start[o] + 3) & ~3;
+    int KQ = 0;   // spheres padded per object to a multiple of two (scan table)
+    for (int o = 0; o < nObj; ++o) KQ += (d->obj_start[o + 1] - d->obj_start[o] + 1) & ~1;
     int off = (int)(sizeof(CostHeader) / 4);
     auto take = [&](int nw) { int o = off; off = align4(off + nw); return o; };
     const int o_pt_link = take(S), o_mobj = take(S), o_mws = take(S), o_ostart = take(nObj + 1), o_oid = take(nObj),
@@ -824,7 +824,7 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
                 qw[0] = -2.f * cc[0]; qw[1] = -2.f * cc[1]; qw[2] = -2.f * cc[2]; qw[3] = c2;
             }
             iw[o_oqs + o] = qpos;
-            const int padded = (k1 - k0 + 3) & ~3;
+            const int padded = (k1 - k0 + 1) & ~1;
             for (int k = k1 - k0; k < padded; ++k) {   // dummies that can never be nearest
                 float* qw = w + o_sphq + 4 * (qpos + k);
                 qw[0] = qw[1] = qw[2] = 0.f; qw[3] = 1e30f;
