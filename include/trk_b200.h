@@ -232,8 +232,8 @@ int trk_cost_stage(const trk_model* model, const trk_cost* cost, const float* li
  *   valid_out [n] uint8  result of the last termination test                  (nullable)
  *   valid_count [n_iters] device int32: seeds passing the test at each iteration (zeroed by the call)
  *   loss_sum / loss_sqsum [n_iters] device fp32 sums of the loss and its square (nullable, zeroed by the call)
- * Returns TRK_E_UNSUPPORTED for models served by the runtime-tree family (callers then run the
- * iteration loop over trk_fk_forward / trk_fk_backward, still on the GPU).
+ * Compiled-in robots keep q and the Adam moments in registers; models served by the runtime-tree family keep them
+ * in shared-memory columns (same arithmetic).
  */
 typedef struct trk_ik_params {
     int32_t      ee_link;          /* body whose pose is driven to the target */

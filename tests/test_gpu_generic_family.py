@@ -115,3 +115,38 @@ def test_ee_target_per_configuration_and_margin_override(generic_models):
     assert rel_err(r["total"].cpu().numpy(), o["total"]) < 1e-5
     assert rel_err(r["grad_q"].cpu().numpy(), o["grad_q"]) < 1e-4
     assert np.array_equal(r["occupancy"].cpu().numpy(), o["occ"])
+
+
+def test_fused_ik_matches_golden_and_compiled_in_family(generic_models):
+    """k_ik_adam_generic: iterates equal the reference's Adam loop (golden ik_panda.npz) and the register-resident
+    kernel's; termination masks and per-iteration valid counts are identical."""
+    from torch_robotics_b200._lib import DeviceModel
+    g, d = load_golden("ik_panda"), get_desc("panda")
+    mg, ms = generic_models["panda"], DeviceModel(d, DEV)
+    q0 = t(g["q0"])
+    for iters in (1, 5, 40):
+        kw = dict(n_iters=iters + 1, n_updates=iters, lr=0.2, se3_eps=0.05, want_loss_stats=True)
+        rg = mg.ik_adam(q0, g["H_target"], 10, g["lower"], g["upper"], **kw)
+        rs = ms.ik_adam(q0, g["H_target"], 10, g["lower"], g["upper"], **kw)
+        assert rel_err(rg["q"].cpu().numpy(), g[f"q_ik_{iters}"]) < (1e-4 if iters < 40 else 5e-3)
+        assert rel_err(rg["q"].cpu().numpy(), rs["q"].cpu().numpy()) < (1e-4 if iters < 40 else 5e-3)
+        if iters < 40:
+            assert torch.equal(rg["valid"], rs["valid"]) and torch.equal(rg["valid_count"], rs["valid_count"])
+            assert np.array_equal(torch.nonzero(rg["valid"]).reshape(-1).cpu().numpy(), g[f"idx_valid_{iters}"])
+        assert rel_err(rg["loss_sum"].cpu().numpy(), rs["loss_sum"].cpu().numpy()) < 1e-3
+
+
+def test_fused_ik_converges_on_a_tree_with_prismatic_joints(generic_models):
+    """Stretch (prismatic lift / telescope, branches): reachable targets are reached from perturbed seeds."""
+    d, m = get_desc("stretch"), generic_models["stretch"]
+    ee = d.link_names.index("link_straight_gripper")
+    rng = np.random.default_rng(21)
+    lo = np.where(d.has_lim[d.controlled] > 0, d.lo[d.controlled], -np.pi).astype(np.float32)
+    hi = np.where(d.has_lim[d.controlled] > 0, d.hi[d.controlled], np.pi).astype(np.float32)
+    q_goal = (lo + rng.random((64, d.n_dofs), dtype=np.float32) * (hi - lo) * 0.6 + 0.2 * (hi - lo)).astype(np.float32)
+    Rw, pw = orc.fk_forward(d, q_goal, np.float32)
+    H = orc.homogeneous(Rw, pw, [ee])[:, 0]
+    q0 = np.clip(q_goal + rng.normal(0, 0.1, q_goal.shape).astype(np.float32), lo, hi)
+    r = m.ik_adam(t(q0), t(H), ee, lo, hi, n_iters=300, lr=0.02, se3_eps=0.02)
+    assert r["valid"].float().mean().item() > 0.9
+    assert int(r["valid_count"][-1]) == int(r["valid"].sum())

@@ -224,10 +224,8 @@ class DeviceModel:
     def ik_adam(self, q0: torch.Tensor, H_target, ee_link: int, lower, upper, n_iters: int, n_updates: Optional[int] = None,
                 lr=1e-2, betas=(0.9, 0.999), eps=1e-8, w_se3=1.0, w_joint_limits=300.0, se3_eps=1e-1, want_loss_stats=False):
         """Fused Adam IK (trk_ik_adam).  q0 [S, D] is not modified.  Returns dict(q, err, valid (bool), valid_count
-        [n_iters] int32, loss_sum / loss_sqsum [n_iters] or None).  Raises NotImplementedError for models without a
-        compiled-in kernel family (callers then iterate over fk / fk_backward)."""
-        if self.kernel_family == "generic":
-            raise NotImplementedError("fused IK is available for compiled-in robots only")
+        [n_iters] int32, loss_sum / loss_sqsum [n_iters] or None).  Compiled-in robots run the register-resident kernel,
+        any other tree the runtime-tree one (state in shared-memory columns)."""
         q = require_cuda_f32(q0, "q0").clone()
         S, D = q.shape
         dev = q.device

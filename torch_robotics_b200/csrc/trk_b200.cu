@@ -359,6 +359,134 @@ __global__ void __launch_bounds__(kBlock) k_link_jacobian(const float* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused batched Adam inverse kinematics for the runtime-tree family: the loop of k_ik_adam_static (trk_static.cuh;
+// DifferentiableTree.inverse_kinematics, robot_tree.py:303-442) with q, the Adam moments, the joint axes / origins and
+// the live poses in per-lane shared-memory columns instead of registers.  One thread owns one seed for all iterations.
+// Per-warp words: (n_live * 12 + D * 6 + D * 3) * 32.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_ik_adam_generic(const float* __restrict__ tree_words, int tree_nwords,
+                                                            const __grid_constant__ TreePlan plan, const __grid_constant__ trk::IKParams P,
+                                                            const float* __restrict__ step_size, const float* __restrict__ bc2_sqrt,
+                                                            const float* __restrict__ target_seed, long long n_seeds,
+                                                            float* __restrict__ q_io, float* __restrict__ err_out,
+                                                            uint8_t* __restrict__ valid_out, int* __restrict__ valid_count,
+                                                            float* __restrict__ loss_sum, float* __restrict__ loss_sqsum) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ int s_cnt;
+    __shared__ float s_sum, s_sq;
+    float* tw = smem;
+    block_copy_words(tw, tree_words, tree_nwords);
+    __syncthreads();
+    const TreeHeader* hdr = reinterpret_cast<const TreeHeader*>(tw);
+    const LinkRec* recs = reinterpret_cast<const LinkRec*>(tw + 16);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, D = hdr->D;
+    float* wbase = smem + tree_nwords + (size_t)warp * (plan.n_live * 12 + D * 9) * 32;
+    float* wl = wbase + lane;                                  // live poses
+    float* JA = wbase + plan.n_live * 12 * 32 + lane;          // [c * 6 + k]: axis (3), origin (3) of q column c
+    float* QS = JA + D * 6 * 32;                               // [c * 3 + k]: q, exp_avg, exp_avg_sq
+    const long long seed = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = seed < n_seeds;
+    for (int c = 0; c < D; ++c) { QS[(c * 3) * 32] = live ? q_io[seed * D + c] : 0.f; QS[(c * 3 + 1) * 32] = 0.f; QS[(c * 3 + 2) * 32] = 0.f; }
+    float Rt[9], pt[3];
+    {
+        const float* Ht = (P.per_seed_target && live) ? target_seed + seed * 16 : P.target;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            Rt[i * 3 + 0] = Ht[i * 4 + 0]; Rt[i * 3 + 1] = Ht[i * 4 + 1]; Rt[i * 3 + 2] = Ht[i * 4 + 2]; pt[i] = Ht[i * 4 + 3];
+        }
+    }
+    EEParams ee;
+    ee.ee_w_rot = 1.f; ee.ee_w_pos = 1.f; ee.ee_square = 0; ee.w[3] = P.w_se3;
+    float err = 0.f;
+    bool valid = false;
+#pragma unroll 1
+    for (int it = 0; it < P.n_iters; ++it) {
+        if (threadIdx.x == 0) { s_cnt = 0; s_sum = 0.f; s_sq = 0.f; }
+        __syncthreads();
+        float Wee[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) Wee[k] = 0.f;
+        unsigned pass_mask = 0u;
+        fk_live_q(hdr, recs, plan, [&](int c) { return QS[(c * 3) * 32]; }, wl, 32,
+                  [&](int, const LinkRec& r, const float* w, const float* wp, bool pass) {
+                      if (r.qidx >= 0) {
+                          float ax, ay, az;
+                          if ((r.flags & F_KIND_MASK) == TRK_KIND_REVOLUTE) {
+                              const int k = (r.flags >> F_AXIS_SHIFT) & 3;
+                              ax = r.s * (k == 0 ? w[0] : (k == 1 ? w[1] : w[2]));
+                              ay = r.s * (k == 0 ? w[3] : (k == 1 ? w[4] : w[5]));
+                              az = r.s * (k == 0 ? w[6] : (k == 1 ? w[7] : w[8]));
+                          } else {
+                              ax = wp[0] * r.ax[0] + wp[1] * r.ax[1] + wp[2] * r.ax[2];
+                              ay = wp[3] * r.ax[0] + wp[4] * r.ax[1] + wp[5] * r.ax[2];
+                              az = wp[6] * r.ax[0] + wp[7] * r.ax[1] + wp[8] * r.ax[2];
+                          }
+                          float* j = JA + r.qidx * 6 * 32;
+                          j[0] = ax; j[32] = ay; j[64] = az; j[96] = w[9]; j[128] = w[10]; j[160] = w[11];
+                          if (pass) pass_mask |= 1u << r.qidx;
+                      }
+                      if (r.body == P.ee_link) {
+#pragma unroll
+                          for (int k = 0; k < 12; ++k) Wee[k] = w[k];
+                      }
+                  });
+        float gR[9], gp[3];
+        err = ee_term<true>(&ee, Wee, &Wee[9], Rt, pt, gR, gp);       // SE3_distance, un-squared, weights 1
+        bool in_lim = true;
+        float e_lim = 0.f;
+        for (int c = 0; c < D; ++c) {
+            const float lo = P.lower[c], hi = P.upper[c], qc = QS[(c * 3) * 32];
+            in_lim = in_lim && (qc >= lo) && (qc <= hi);
+            const float dl = lo - qc, dh = hi - qc;
+            e_lim += (qc < lo ? dl * dl : 0.f) + (qc > hi ? dh * dh : 0.f);
+        }
+        valid = in_lim && (err < P.se3_eps);
+        const float loss = P.w_se3 * err + P.w_lim * e_lim;
+        const unsigned ball = __ballot_sync(0xffffffffu, valid && live);
+        float ls = live ? loss : 0.f, lq = live ? loss * loss : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { ls += __shfl_xor_sync(0xffffffffu, ls, o); lq += __shfl_xor_sync(0xffffffffu, lq, o); }
+        if (lane == 0) { atomicAdd(&s_cnt, __popc(ball)); atomicAdd(&s_sum, ls); atomicAdd(&s_sq, lq); }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicAdd(valid_count + it, s_cnt);
+            if (loss_sum) { atomicAdd(loss_sum + it, s_sum); atomicAdd(loss_sqsum + it, s_sq); }
+        }
+        if (it >= P.n_updates) continue;
+        // the only wrench is the EE one: d loss / d q_c = axis_c . (T - p_c x F) for the joints above the EE body
+        float tx, ty, tz;
+        axial_gR_Rt(gR, Wee, tx, ty, tz);
+        const float fx = gp[0], fy = gp[1], fz = gp[2];
+        tx += Wee[10] * fz - Wee[11] * fy; ty += Wee[11] * fx - Wee[9] * fz; tz += Wee[9] * fy - Wee[10] * fx;
+        const float ss = step_size[it], inv_b2s = 1.f / bc2_sqrt[it];
+        const unsigned gmask = P.anc_mask & pass_mask;
+        for (int c = 0; c < D; ++c) {
+            const float* j = JA + c * 6 * 32;
+            const float ax = j[0], ay = j[32], az = j[64], px = j[96], py = j[128], pz = j[160];
+            float g = ((plan.prism_mask >> c) & 1u)
+                          ? ax * fx + ay * fy + az * fz
+                          : ax * (tx - (py * fz - pz * fy)) + ay * (ty - (pz * fx - px * fz)) + az * (tz - (px * fy - py * fx));
+            g = ((gmask >> c) & 1u) ? g : 0.f;
+            const float lo = P.lower[c], hi = P.upper[c];
+            float* s = QS + c * 3 * 32;
+            const float qc = s[0];
+            g += P.w_lim * ((qc < lo ? -2.f * (lo - qc) : 0.f) + (qc > hi ? -2.f * (hi - qc) : 0.f));
+            const float mom = fmaf(1.f - P.beta1, g - s[32], s[32]);                 // exp_avg.lerp_(grad, 1 - beta1)
+            const float var = fmaf((1.f - P.beta2) * g, g, s[64] * P.beta2);          // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+            float rs_unused;
+            const float denom = sqrt_rn_core(var, rs_unused) * inv_b2s + P.eps;
+            s[0] = qc - ss * __fdividef(mom, denom);
+            s[32] = mom; s[64] = var;
+        }
+    }
+    if (live) {
+        for (int c = 0; c < D; ++c) q_io[seed * D + c] = QS[(c * 3) * 32];
+        if (err_out) err_out[seed] = err;
+        if (valid_out) valid_out[seed] = valid ? 1 : 0;
+    }
+}
+
 // cost stage on caller-supplied positions (DistanceField.compute_cost, distance_fields.py:26-55)
 template <int MAXL, bool WANT_GRAD>
 __global__ void __launch_bounds__(kBlock) k_cost_stage(const float* __restrict__ cost_words, int cost_nwords, int L,
@@ -972,7 +1100,7 @@ int trk_ik_adam(const trk_model* m, const trk_ik_params* p, const float* step_si
                 const float* target_seed, int64_t n, float* q_io, float* err_out, uint8_t* valid_out, int32_t* valid_count,
                 float* loss_sum, float* loss_sqsum, void* stream) {
     TRK_CHECK_PTR(m, "model"); TRK_CHECK_PTR(p, "params");
-    if (!m->family) return fail(TRK_E_UNSUPPORTED, "fused IK needs a compiled-in robot (model is served by the runtime-tree family)");
+
     if (n < 0) return fail(TRK_E_RANGE, "n=%lld", (long long)n);
     if (p->n_iters < 1 || p->n_updates < 0 || p->n_updates > p->n_iters) return fail(TRK_E_RANGE, "n_iters=%d n_updates=%d", p->n_iters, p->n_updates);
     if (p->ee_link < 0 || p->ee_link >= m->L) return fail(TRK_E_RANGE, "ee_link=%d", p->ee_link);
@@ -997,8 +1125,22 @@ int trk_ik_adam(const trk_model* m, const trk_ik_params* p, const float* step_si
     if (e == cudaSuccess && loss_sqsum) e = cudaMemsetAsync(loss_sqsum, 0, sizeof(float) * p->n_iters, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(ik statistics)");
     if (loss_sum && !loss_sqsum) return fail(TRK_E_NULL, "loss_sqsum is required with loss_sum");
-    e = trk::launch_static_ik(m->family, P, step_size, bc2_sqrt, target_seed, n, q_io, err_out, valid_out, valid_count, loss_sum,
-                              loss_sqsum, st);
+    if (m->family) {
+        e = trk::launch_static_ik(m->family, P, step_size, bc2_sqrt, target_seed, n, q_io, err_out, valid_out, valid_count, loss_sum,
+                                  loss_sqsum, st);
+    } else {
+        const size_t per_warp = (size_t)(m->live.n_live * 12 + m->D * 9) * 32 * 4;
+        int warps = kWarps;
+        while (warps > 1 && (size_t)m->nwords * 4 + warps * per_warp > 100 * 1024) --warps;
+        const size_t smem = (size_t)m->nwords * 4 + warps * per_warp;
+        const long long blocks = (n + warps * 32 - 1) / (warps * 32);
+        e = allow_smem(k_ik_adam_generic, smem);
+        if (e == cudaSuccess) {
+            k_ik_adam_generic<<<(unsigned)blocks, warps * 32, smem, st>>>(m->d_words, m->nwords, m->live, P, step_size, bc2_sqrt, target_seed, n,
+                                                                          q_io, err_out, valid_out, valid_count, loss_sum, loss_sqsum);
+            e = cudaGetLastError();
+        }
+    }
     return e == cudaSuccess ? TRK_OK : cuda_fail(e, "ik_adam launch");
 }
 

@@ -167,7 +167,7 @@ class DifferentiableTree(torch.nn.Module):
             q0 = torch.clamp(q0, lower, upper)
             assert q0.shape == (batch_size, self._n_dofs)
         model = self.device_model(device)
-        if model.kernel_family != "generic" and not debug and max_iters >= 1:
+        if not debug and max_iters >= 1:      # debug=True keeps the step-by-step torch loop (prints per-iteration state)
             return self._inverse_kinematics_fused(model, q0, H_target, link_name, batch_size, max_iters, lr, se3_eps,
                                                   lower, upper, print_freq)
         q = q0.clone().requires_grad_(True)
