@@ -11,6 +11,7 @@
 // trk_model_create() selects a family by comparing the model's table image with each robot's
 // `words` image; anything else is served by the runtime-tree family in trk_b200.cu.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -318,7 +319,10 @@ __global__ void __launch_bounds__(kSBlock) k_fk_forward_static(const float* __re
 template <class R>
 struct FkTma {
     static constexpr int L = R::L;
-    static constexpr int kChunk = L < 11 ? L : 11;                  // links per bulk store
+#ifndef TRK_TMA_CHUNK
+#define TRK_TMA_CHUNK 11
+#endif
+    static constexpr int kChunk = L < TRK_TMA_CHUNK ? L : TRK_TMA_CHUNK;   // links per bulk store
     static constexpr int kRowBytes = kChunk * 64 + 16;              // +16: rows land on distinct bank groups
     static constexpr int kWarpBytes = 32 * kRowBytes;
     static constexpr size_t smem_bytes = (size_t)(kSBlock / 32) * kWarpBytes;
@@ -374,6 +378,71 @@ __global__ void __launch_bounds__(kSBlock) k_fk_forward_static_tma(const float* 
         });
     }
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// The same with ONE tensor store per warp and chunk of links.  The per-lane bulk stores above are issued from a
+// lane-serialised loop (UBLKCP takes uniform operands): ~320 of the ~860 warp instructions of a tile.  Here H is
+// described to the TMA engine as a 3-D tensor [N][L][16 floats]; a warp's 32 x kChunk link matrices form one dense
+// box in shared memory (64-byte swizzle: the 16-byte chunk index is XORed with address bits 7-8, which makes the
+// lane-strided float4 writes conflict-free without padding) and an elected lane issues a single
+// cp.async.bulk.tensor.3d store; rows beyond N and links beyond L are clipped by the hardware.
+template <class R>
+__global__ void __launch_bounds__(kSBlock) k_fk_forward_static_tmap(const __grid_constant__ CUtensorMap tmap,
+                                                                    const float* __restrict__ q, long long n) {
+    extern __shared__ __align__(1024) unsigned char smem_tmap[];
+    using T = FkTma<R>;
+    constexpr int L = R::L, D = R::D, kChunk = T::kChunk;
+    constexpr unsigned kTileBytes = 32u * kChunk * 64u;            // a multiple of 2048
+    const int lane = threadIdx.x & 31;
+    unsigned tile_s = (unsigned)__cvta_generic_to_shared(smem_tmap);
+    tile_s = ((tile_s + 1023u) & ~1023u) + (threadIdx.x >> 5) * kTileBytes;
+    const unsigned row_off = (unsigned)lane * kChunk * 64u;
+    const long long stride = (long long)gridDim.x * kSBlock;
+    long long base = (long long)blockIdx.x * kSBlock;
+    float qn[D > 0 ? D : 1];
+    {
+        const long long cfg = base + threadIdx.x;
+        const float* qrow = q + (cfg < n ? cfg : n - 1) * D;
+        sfor<D>([&](auto c) { qn[c] = (base < n) ? __ldg(qrow + c) : 0.f; });
+    }
+    for (; base < n; base += stride) {
+        const long long warp_cfg0 = base + (threadIdx.x & ~31);
+        float qc[D > 0 ? D : 1];
+        sfor<D>([&](auto c) { qc[c] = qn[c]; });
+        {
+            const long long nb = base + stride, ncfg = nb + threadIdx.x;
+            const float* qrow = q + (ncfg < n ? ncfg : n - 1) * D;
+            if (nb < n) sfor<D>([&](auto c) { qn[c] = __ldg(qrow + c); });
+        }
+        if (warp_cfg0 >= n) continue;   // warp-uniform; lanes past n compute a clamped row that the store clips
+        float W[L][12];
+        unsigned pass;
+        STree<R>::forward([&](int c) { return qc[c]; }, W, pass, [&](auto ic, const float (&)[12], const float (&w)[12]) {
+            constexpr int i = decltype(ic)::value, j = i % kChunk, c0 = i - j;
+            if constexpr (j == 0) {   // the previous tensor store must have finished READING the tile
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+            }
+            const unsigned off = row_off + j * 64u;
+            const unsigned sw = ((off >> 7) & 3u) << 4;
+            const unsigned a = tile_s + off;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + (0u ^ sw)), "f"(w[0]), "f"(w[1]), "f"(w[2]), "f"(w[9]) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + (16u ^ sw)), "f"(w[3]), "f"(w[4]), "f"(w[5]), "f"(w[10]) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + (32u ^ sw)), "f"(w[6]), "f"(w[7]), "f"(w[8]), "f"(w[11]) : "memory");
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a + (48u ^ sw)), "f"(0.f), "f"(0.f), "f"(0.f), "f"(1.f) : "memory");
+            if constexpr (j == kChunk - 1 || i == L - 1) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                                 ::"l"(reinterpret_cast<unsigned long long>(&tmap)), "r"(0), "r"(c0), "r"((int)warp_cfg0),
+                                   "r"(tile_s) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        });
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 template <class R>
@@ -887,6 +956,27 @@ inline int persistent_grid(K kernel, int n_sms, size_t smem, long long n) {
     return (int)(need < cap ? (need > 0 ? need : 1) : cap);
 }
 
+// H [N][L][4][4] fp32 as a 3-D tensor for cp.async.bulk.tensor stores: box = 32 configurations x chunk links x 16 floats,
+// 64-byte swizzle.  cuTensorMapEncodeTiled is taken from the driver at run time (no link-time dependency on libcuda).
+inline bool encode_fk_tensor_map(CUtensorMap* map, float* H, int L, long long n, int chunk) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeFn>(p);
+    }();
+    if (!fn) return false;
+    const cuuint64_t dims[3] = {16, (cuuint64_t)L, (cuuint64_t)n};
+    const cuuint64_t strides[2] = {64, (cuuint64_t)L * 64};
+    const cuuint32_t box[3] = {16, (cuuint32_t)chunk, 32};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, H, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <class R>
 cudaError_t launch_fk_forward_t(int n_sms, const float* q, long long n, const SlotMap& sm, int n_sel, float* H,
                                        cudaStream_t st) {
@@ -895,6 +985,20 @@ cudaError_t launch_fk_forward_t(int n_sms, const float* q, long long n, const Sl
                                                                                  // does not track async-proxy writes)
         bool identity = (n_sel == R::L) && !no_tma;
         for (int b = 0; identity && b < R::L; ++b) identity = (sm.slot[b] == b);
+        static const bool row_mode = std::getenv("TRK_B200_TMA_ROWS") != nullptr;   // A/B switch: per-lane bulk stores
+        if (identity && !row_mode && n < 0x7fffffffLL) {   // one tensor store per warp and chunk of links
+            CUtensorMap tmap;
+            if (encode_fk_tensor_map(&tmap, H, R::L, n, FkTma<R>::kChunk)) {
+                auto kt = k_fk_forward_static_tmap<R>;
+                constexpr size_t smem = (size_t)(kSBlock / 32) * 32 * FkTma<R>::kChunk * 64 + 1024;
+                if (smem > 48 * 1024) {
+                    cudaError_t e = cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e != cudaSuccess) return e;
+                }
+                kt<<<persistent_grid(kt, n_sms, smem, n), kSBlock, smem, st>>>(tmap, q, n);
+                return cudaGetLastError();
+            }
+        }
         if (identity) {   // all links in body order: TMA bulk-store variant
             auto kt = k_fk_forward_static_tma<R>;
             constexpr size_t smem = FkTma<R>::smem_bytes;
