@@ -314,6 +314,9 @@ __global__ void __launch_bounds__(kBlock) k_link_jacobian(const float* __restric
             const long long f0 = out0 + (long long)u0 * row;
             const int ph = (int)(f0 & 3);                        // same 16-byte phase in shared and global memory
             float* tl = tile + buf * tile_words + ph;
+            // this buffer left with the bulk store issued two passes ago: it must have been read before it is refilled
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
             // 2a: lane <- (link block, q column); its seven values go to the tile at their output offsets.  Branch-free
             // (non-ancestor columns are computed and zeroed) so that four columns per lane are in flight at once.
             const int ncol = nu * D;
@@ -341,22 +344,26 @@ __global__ void __launch_bounds__(kBlock) k_link_jacobian(const float* __restric
                 o[5 * D] = rev ? 0.5f * (qw * ay + (az * qx - ax * qz)) : 0.f;
                 o[6 * D] = rev ? 0.5f * (qw * az + (ax * qy - ay * qx)) : 0.f;
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            // 2b: contiguous copy, 16-byte stores between a scalar head and tail.  The other tile buffer is filled by
-            // the next pass, so the barrier above is the only one per pass.
+            // 2b: the tile is a contiguous span of J: its 16-byte aligned body leaves with ONE bulk store
+            // (cp.async.bulk.global.shared::cta) issued by lane 0, a scalar head and tail cover the misaligned ends.
             const int nf = nu * row;
             const int head = min((4 - ph) & 3, nf);
             const int nbody = (nf - head) >> 2;
             const int tail0 = head + 4 * nbody;
             if (lane < head) __stcs(J + f0 + lane, tl[lane]);
-            float4* d4 = reinterpret_cast<float4*>(J + f0 + head);
-            const float4* s4 = reinterpret_cast<const float4*>(tl + head);
-#pragma unroll 4
-            for (int e = lane; e < nbody; e += 32) __stcs(d4 + e, s4[e]);
+            if (lane == 0) {
+                if (nbody > 0)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                 ::"l"(J + f0 + head), "r"((unsigned)__cvta_generic_to_shared(tl + head)), "r"(nbody * 16) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
             if (lane < nf - tail0) __stcs(J + f0 + tail0 + lane, tl[tail0 + lane]);
         }
         __syncwarp();
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------
