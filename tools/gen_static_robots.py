@@ -127,6 +127,19 @@ def emit_panda_collision():
     return "\n".join(out)
 
 
+def emit_stretch_collision():
+    """Compile-time collision model of BASELINE config 5 (the reference has no Stretch
+    collision model): collision points at the origins of the 14 movable links + link_straight_gripper, no self pairs."""
+    d = compile_urdf(os.path.join(DATA, dict(ROBOTS)["stretch"]), "stretch")
+    pts = list(d.controlled) + [d.link_names.index("link_straight_gripper")]
+    return "\n".join(["struct StretchCollision {   // config 5: 15 object / workspace collision points, no self-collision pairs",
+                      f"    static constexpr int S = {len(pts)}, P = 0;",
+                      f"    static constexpr int pt_link[S] = {{{', '.join(map(str, pts))}}};",
+                      "    static constexpr int pair_i[1] = {0};",
+                      "    static constexpr int pair_j[1] = {0};",
+                      "};"])
+
+
 def main():
     parts = ["// GENERATED by tools/gen_static_robots.py - do not edit.",
              "// constexpr kinematic tables of the shipped robots (parents-first order).",
@@ -137,7 +150,7 @@ def main():
         cname, text = emit_robot(name, d)
         names.append(cname)
         parts += [text, ""]
-    parts += [emit_panda_collision(), ""]
+    parts += [emit_panda_collision(), "", emit_stretch_collision(), ""]
     parts += ["}  // namespace robots", "",
               "#define TRK_FOR_EACH_STATIC_ROBOT(X) " + " ".join(f"X(robots::{n})" for n in names), "",
               "}  // namespace trk", ""]

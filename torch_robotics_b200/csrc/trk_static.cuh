@@ -505,7 +505,27 @@ __global__ void __launch_bounds__(kSBlock) k_fk_backward_static(const float* __r
     }
 }
 
-template <class R, bool WANT_GRAD, bool CLAMP>
+// Compile-time numbering of the bodies a collision model CM references, in the order trk_cost_create assigns the
+// dense slots (pairs first, i then j, then collision points; first appearance wins).  With it the table-driven
+// objective kernel below contains slot code only for those bodies (Stretch: 15 of 44) instead of a run-time lookup
+// and a branch per body in both sweeps.
+template <class CM, int L>
+struct CMSlots {
+    __host__ __device__ static constexpr int slot(int b) {
+        int seen[L] = {};
+        for (int i = 0; i < L; ++i) seen[i] = -1;
+        int n = 0;
+        for (int p = 0; p < CM::P; ++p) {
+            if (seen[CM::pair_i[p]] < 0) seen[CM::pair_i[p]] = n++;
+            if (seen[CM::pair_j[p]] < 0) seen[CM::pair_j[p]] = n++;
+        }
+        for (int s2 = 0; s2 < CM::S; ++s2)
+            if (seen[CM::pt_link[s2]] < 0) seen[CM::pt_link[s2]] = n++;
+        return seen[b];
+    }
+};
+
+template <class R, bool WANT_GRAD, bool CLAMP, class CM = void>
 __global__ void __launch_bounds__(kSBlock, 4) k_objective_static(const float* __restrict__ cost_words, int cost_nwords, int n_slots,
                                                               const float* __restrict__ q, long long n,
                                                               const float* __restrict__ ee_target_cfg, float margin_override,
@@ -547,8 +567,7 @@ __global__ void __launch_bounds__(kSBlock, 4) k_objective_static(const float* __
         unsigned pass;
         STree<R>::forward([&](int c) { return __ldg(qrow + c); }, W, pass, [&](auto ic, const float (&wp)[12], const float (&w)[12]) {
             constexpr int i = decltype(ic)::value, b = R::body[i];
-            const int sl = cv.slot_of_body[b];
-            if (sl >= 0) {
+            auto park = [&](int sl) {
                 spos[(sl * 3 + 0) * kSBlock + tid] = w[9];
                 spos[(sl * 3 + 1) * kSBlock + tid] = w[10];
                 spos[(sl * 3 + 2) * kSBlock + tid] = w[11];
@@ -557,6 +576,13 @@ __global__ void __launch_bounds__(kSBlock, 4) k_objective_static(const float* __
                     sgrd[(sl * 3 + 1) * kSBlock + tid] = 0.f;
                     sgrd[(sl * 3 + 2) * kSBlock + tid] = 0.f;
                 }
+            };
+            if constexpr (!std::is_void<CM>::value) {
+                constexpr int sl = CMSlots<CM, L>::slot(b);
+                if constexpr (sl >= 0) park(sl);
+            } else {
+                const int sl = cv.slot_of_body[b];
+                if (sl >= 0) park(sl);
             }
             if (WANT_GRAD) {
                 constexpr int qi = R::qidx[i];
@@ -597,10 +623,9 @@ __global__ void __launch_bounds__(kSBlock, 4) k_objective_static(const float* __
             STree<R>::backward(JA, [&](auto bc, float (&f)[3], float (&t)[3], float (&pos)[3]) {
                 constexpr int b = decltype(bc)::value;
                 constexpr int qb = R::qidx[STree<R>::topo_index_of(b)];
-                const int sl = cv.slot_of_body[b];
                 sfor<3>([&](auto rc) { f[rc] = 0.f; t[rc] = 0.f; pos[rc] = 0.f; });
                 if constexpr (qb >= 0) sfor<3>([&](auto rc) { pos[rc] = PJ[qb][rc]; });
-                if (sl >= 0) {
+                auto fetch = [&](int sl) {
                     sfor<3>([&](auto rc) {
                         pos[rc] = spos[(sl * 3 + rc) * kSBlock + tid];
                         f[rc] = sgrd[(sl * 3 + rc) * kSBlock + tid];
@@ -608,6 +633,13 @@ __global__ void __launch_bounds__(kSBlock, 4) k_objective_static(const float* __
                     t[0] = pos[1] * f[2] - pos[2] * f[1];
                     t[1] = pos[2] * f[0] - pos[0] * f[2];
                     t[2] = pos[0] * f[1] - pos[1] * f[0];
+                };
+                if constexpr (!std::is_void<CM>::value) {
+                    constexpr int sl = CMSlots<CM, L>::slot(b);
+                    if constexpr (sl >= 0) fetch(sl);
+                } else {
+                    const int sl = cv.slot_of_body[b];
+                    if (sl >= 0) fetch(sl);
                 }
                 if (b == e) sfor<3>([&](auto rc) { f[rc] += eF[rc]; t[rc] += eT[rc]; });
             }, pass, [&](int c, float g) { grow[c] = g; });
@@ -901,8 +933,11 @@ cudaError_t launch_ik_t(const IKParams& P, const float* step_size, const float* 
 }
 
 // which compile-time collision model (if any) belongs to a compiled-in robot
-template <class R> struct CollisionModelOf { using type = void; };
-template <> struct CollisionModelOf<robots::Panda> { using type = robots::PandaCollision; };
+// in_registers: body positions / gradients of the model fit in registers (k_objective_cm); otherwise the model only
+// fixes the shared-memory slot numbering of k_objective_static at compile time
+template <class R> struct CollisionModelOf { using type = void; static constexpr bool in_registers = false; };
+template <> struct CollisionModelOf<robots::Panda> { using type = robots::PandaCollision; static constexpr bool in_registers = true; };
+template <> struct CollisionModelOf<robots::Stretch> { using type = robots::StretchCollision; static constexpr bool in_registers = false; };
 
 // does a runtime cost table list exactly CM's points and pairs?
 template <class CM>
@@ -1023,12 +1058,12 @@ cudaError_t launch_fk_backward_t(int n_sms, const float* q, long long n, const S
     return cudaGetLastError();
 }
 
-template <class R, bool WANT_GRAD, bool CLAMP>
+template <class R, bool WANT_GRAD, bool CLAMP, class CM = void>
 inline cudaError_t launch_objective_k(int n_sms, const float* cost_words, int cost_nwords, int n_slots, const float* q, long long n,
                                       const float* ee_target_cfg, float margin_override, int use_override, float* cost_total,
                                       float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin, cudaStream_t st) {
     const size_t smem = ((size_t)cost_nwords + (size_t)6 * n_slots * kSBlock) * sizeof(float);
-    auto k = k_objective_static<R, WANT_GRAD, CLAMP>;
+    auto k = k_objective_static<R, WANT_GRAD, CLAMP, CM>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1057,14 +1092,19 @@ cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwor
 #define TRK_OBJ_ARGS n_sms, cost_words, cost_nwords, q, n, ee_target_cfg, margin_override, use_override, cost_total, cost_terms, \
                      grad_q, occupancy, argmin, st
     using CM = typename CollisionModelOf<R>::type;
-    if constexpr (!std::is_void<CM>::value) {
-        if (cm_match) {
-            if (grad_q) return clamp_any ? launch_objective_cm_k<R, CM, true, true>(TRK_OBJ_ARGS) : launch_objective_cm_k<R, CM, true, false>(TRK_OBJ_ARGS);
-            return clamp_any ? launch_objective_cm_k<R, CM, false, true>(TRK_OBJ_ARGS) : launch_objective_cm_k<R, CM, false, false>(TRK_OBJ_ARGS);
-        }
-    }
 #define TRK_OBJ_ARGS_S n_sms, cost_words, cost_nwords, n_slots, q, n, ee_target_cfg, margin_override, use_override, cost_total, cost_terms, \
                        grad_q, occupancy, argmin, st
+    if constexpr (!std::is_void<CM>::value) {
+        if (cm_match) {
+            if constexpr (CollisionModelOf<R>::in_registers) {
+                if (grad_q) return clamp_any ? launch_objective_cm_k<R, CM, true, true>(TRK_OBJ_ARGS) : launch_objective_cm_k<R, CM, true, false>(TRK_OBJ_ARGS);
+                return clamp_any ? launch_objective_cm_k<R, CM, false, true>(TRK_OBJ_ARGS) : launch_objective_cm_k<R, CM, false, false>(TRK_OBJ_ARGS);
+            } else {
+                if (grad_q) return clamp_any ? launch_objective_k<R, true, true, CM>(TRK_OBJ_ARGS_S) : launch_objective_k<R, true, false, CM>(TRK_OBJ_ARGS_S);
+                return clamp_any ? launch_objective_k<R, false, true, CM>(TRK_OBJ_ARGS_S) : launch_objective_k<R, false, false, CM>(TRK_OBJ_ARGS_S);
+            }
+        }
+    }
     if (grad_q) return clamp_any ? launch_objective_k<R, true, true>(TRK_OBJ_ARGS_S) : launch_objective_k<R, true, false>(TRK_OBJ_ARGS_S);
     return clamp_any ? launch_objective_k<R, false, true>(TRK_OBJ_ARGS_S) : launch_objective_k<R, false, false>(TRK_OBJ_ARGS_S);
 #undef TRK_OBJ_ARGS_S
