@@ -159,6 +159,52 @@ def workload_config(world):
             "l2": "q+cost+grad = 251 MB per step > 126 MB L2 (inputs larger than L2, no flush needed)"}
 
 
+
+def other_baseline_configs(dev, timed):
+    """BASELINE configs 4 and 5 on one GPU: fused Adam IK (Panda, 1M seeds x 500 iterations) and the Stretch objective
+    (44 links, 15 collision points, 2,097,152 configurations), each against its FP32 bound."""
+    import torch
+    from torch_robotics_b200._lib import DeviceCost, DeviceModel
+    from torch_robotics_b200.descriptor import build_cost_descriptor, compile_urdf
+    from torch_robotics_b200.environments.env_spheres_3d import SPHERE_CENTERS, SPHERE_RADIUS
+    from torch_robotics_b200.workloads import ik_example_target
+    fp32_peak = 148 * 128 * 2 * measured_peaks()["sm_max_mhz"] * 1e6
+    out = {}
+    # config 4
+    desc, _ = panda_objective_descriptors()
+    model = DeviceModel(desc, dev)
+    S, iters = 1_000_000, 500
+    lim = np.array([[desc.lo[b], desc.hi[b]] for b in desc.controlled], np.float32)
+    lo, hi = lim[:, 0] + np.float32(np.pi / 64), lim[:, 1] - np.float32(np.pi / 64)
+    q0 = torch.as_tensor((lo + np.random.default_rng(7).random((S, desc.n_dofs), dtype=np.float32) * (hi - lo)).astype(np.float32), device=dev)
+    Ht = ik_example_target().reshape(4, 4)
+    ee = desc.link_names.index("ee_link")
+    run = lambda: model.ik_adam(q0, Ht, ee, lo, hi, n_iters=iters, lr=0.2, se3_eps=0.05)
+    ms = timed(run, reps=3, inner=1)
+    res = run()
+    out["ik_adam_1M_seeds_500_iters"] = {"ms": ms, "seed_iters_per_s": S * iters / ms * 1e3,
+                                         "fp32_frac": S * iters / ms * 1e3 * 1200 / fp32_peak, "flop_per_seed_iter": 1200,
+                                         "valid_fraction": float(res["valid"].float().mean().item())}
+    # config 5
+    urdf = os.path.join(ROOT, "torch_robotics_b200", "data", "urdf", "robots", "habitat_stretch", "urdf", "hab_stretch.urdf")
+    ds = compile_urdf(urdf, "stretch")
+    ms_model = DeviceModel(ds, dev)
+    pts = list(ds.controlled) + [ds.link_names.index("link_straight_gripper")]
+    cost = build_cost_descriptor(pt_link=pts, pt_radius=[0.05] * len(pts), cutoff_obj=0.01,
+                                 objects=[(np.array(SPHERE_CENTERS, np.float32), np.full(10, SPHERE_RADIUS, np.float32), None, None)],
+                                 ws_min=[-1, -1, -1], ws_max=[1, 1, 1], ee_link=ds.link_names.index("link_straight_gripper"), ee_target=Ht)
+    dcs = DeviceCost(ms_model, cost)
+    n5 = 1 << 21
+    has = ds.has_lim[ds.controlled] > 0
+    lo5 = np.where(has, ds.lo[ds.controlled], -np.pi).astype(np.float32)
+    hi5 = np.where(has, ds.hi[ds.controlled], np.pi).astype(np.float32)
+    q5 = torch.as_tensor((lo5 + np.random.default_rng(5).random((n5, ds.n_dofs), dtype=np.float32) * (hi5 - lo5)).astype(np.float32), device=dev)
+    tot, grad = torch.empty(n5, device=dev), torch.empty_like(q5)
+    ms5 = timed(lambda: dcs.objective(q5, want_terms=False, out_total=tot, out_grad=grad))
+    out["stretch_objective_2M"] = {"ms": ms5, "configs_per_s": n5 / ms5 * 1e3, "fp32_frac": n5 / ms5 * 1e3 * 5880 / fp32_peak,
+                                   "flop_per_config": 5880, "kernel_family": ms_model.kernel_family}
+    return out
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -291,6 +337,7 @@ def main():
                  "link_jacobian_512k": {"ms": ms_j, "configs_per_s": n3 / ms_j * 1e3, "GBps": by_j / ms_j / 1e6, "hbm_frac": by_j / ms_j / 1e6 / hbm,
                                         "bytes_per_config": by_j / n3},
                  "note": "1,048,576 configs: H (738 MB) exceeds L2; CUDA events around 10 back-to-back launches, median of 5"}
+        extra.update(other_baseline_configs(dev, timed))
 
     times = torch.tensor([span_ms, total_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
