@@ -30,3 +30,7 @@ def test_invalid_arguments_return_status_not_crash():
     md.n_links = 1000
     assert L.trk_model_create(ctypes.byref(md), 0, ctypes.byref(out)) == -2
     assert L.trk_fk_forward(None, None, 0, None, 0, None, None) == -1
+    assert L.trk_link_jacobian(None, None, 0, None, None) == -1
+    assert b"model" in L.trk_last_error()
+    assert L.trk_cost_create(None, None, ctypes.byref(out)) == -1
+    assert L.trk_objective_host(None, None, None, 0, 8, None, None) == -1

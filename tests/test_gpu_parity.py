@@ -261,3 +261,34 @@ def test_box_obstacles_bit_exact_vs_oracle_at_scale(models):
     gp = np.zeros_like(pw)
     np.add.at(gp, (slice(None), cost.pt_link), ro["gx"])
     assert rel_err(r["grad_pos"].cpu().numpy(), gp) < 1e-5
+
+
+def test_new_entry_points_validate_arguments(models):
+    """Argument errors of the later-added entry points surface as RuntimeError with the library's message."""
+    import ctypes
+    from torch_robotics_b200 import _lib
+    from torch_robotics_b200._lib import DeviceCost
+    from torch_robotics_b200.descriptor import VoxelSDF, build_cost_descriptor
+    m = models["panda"]
+    L = _lib.lib()
+    q = torch.zeros(4, 7, device=DEV)
+    J = torch.empty(4 * 11 * 7 * 7 + 1, device=DEV)
+    assert L.trk_link_jacobian(m.handle, q.data_ptr(), 4, J.data_ptr() + 4, None) == -3            # misaligned output
+    assert b"16-byte" in L.trk_last_error()
+    assert L.trk_link_jacobian(m.handle, q.data_ptr(), -1, J.data_ptr(), None) == -2
+    assert m.link_jacobian(torch.empty(0, 7, device=DEV)).shape == (0, 11, 7, 7)
+    with pytest.raises(RuntimeError):
+        m.link_jacobian(torch.zeros(4, 6, device=DEV))
+    # voxel SDF: the grid object must own no primitives, have the identity pose and a positive extent
+    grid = np.zeros((2, 2, 2, 4), np.float32)
+    good = build_cost_descriptor(pt_link=[2], pt_radius=[0.1], objects=[VoxelSDF((2, 2, 2), np.zeros(3), np.ones(3), grid)])
+    DeviceCost(m, good)
+    bad = build_cost_descriptor(pt_link=[2], pt_radius=[0.1], objects=[VoxelSDF((2, 2, 2), np.zeros(3), np.array([1.0, 0.0, 1.0]), grid)])
+    with pytest.raises(RuntimeError, match="extent"):
+        DeviceCost(m, bad)
+    wrong_shape = build_cost_descriptor(pt_link=[2], pt_radius=[0.1], objects=[VoxelSDF((3, 2, 2), np.zeros(3), np.ones(3), grid)])
+    with pytest.raises(RuntimeError, match="voxel SDF data"):
+        DeviceCost(m, wrong_shape)
+    # objective / IK on an empty batch
+    r = DeviceCost(m, good).objective(torch.empty(0, 7, device=DEV))
+    assert r["total"].shape == (0,) and r["grad_q"].shape == (0, 7)

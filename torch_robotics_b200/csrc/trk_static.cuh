@@ -677,6 +677,7 @@ __global__ void __launch_bounds__(kSBlock, TRK_CM_MINBLOCKS) k_objective_cm(cons
     constexpr int L = R::L, D = R::D;
     float* cw = smem;
     float* spt = smem + cost_nwords;                  // [3 * CM::S][kSBlock] collision-point positions / gradients
+    unsigned* spre = reinterpret_cast<unsigned*>(spt + 3 * CM::S * kSBlock);   // [CM::S][kSBlock] joint-scan verdicts
     block_copy_words(cw, cost_words, cost_nwords);
     __syncthreads();
     const CostView cv(cw);
@@ -747,11 +748,27 @@ __global__ void __launch_bounds__(kSBlock, TRK_CM_MINBLOCKS) k_objective_cm(cons
             constexpr int s = decltype(sc)::value, b = CM::pt_link[s];
             sfor<3>([&](auto rc) { spt[(s * 3 + rc) * kSBlock + tid] = P[b][rc]; });
         });
+        // one equal-radius identity-pose sphere object (EnvSpheres3D and most scenes): scan it for all points at once
+        const bool joint_scan = !CLAMP && single_uniform_identity_object(cv);
+        if (joint_scan) {
+            float X[CM::S][3];
+            unsigned pre[CM::S];
+            sfor<CM::S>([&](auto sc) {
+                constexpr int s = decltype(sc)::value, b = CM::pt_link[s];
+                sfor<3>([&](auto rc) { X[s][rc] = P[b][rc]; });
+            });
+            scan_points_uniform<CM::S>(cv, X, pre);
+            sfor<CM::S>([&](auto sc) { spre[decltype(sc)::value * kSBlock + tid] = pre[decltype(sc)::value]; });
+        }
 #pragma unroll 1
         for (int s = 0; s < CM::S; ++s) {
             const float x = spt[(s * 3 + 0) * kSBlock + tid], y = spt[(s * 3 + 1) * kSBlock + tid], z = spt[(s * 3 + 2) * kSBlock + tid];
             float gx = 0.f, gy = 0.f, gz = 0.f;
-            if (h->nObj > 0) {
+            if (joint_scan) {
+                const float m = cv.pt_mobj[s];
+                c_obj = __fadd_rn(c_obj, object_point_term_pre<WANT_GRAD>(cv, x, y, z, m, use_override ? margin_override : m, occ, amrow, s,
+                                                                          gx, gy, gz, spre[s * kSBlock + tid]));
+            } else if (h->nObj > 0) {
                 const float m = cv.pt_mobj[s];
                 c_obj = __fadd_rn(c_obj, object_point_term<WANT_GRAD, CLAMP>(cv, x, y, z, m, use_override ? margin_override : m, occ,
                                                                              amrow, s, gx, gy, gz));
@@ -1077,7 +1094,7 @@ template <class R, class CM, bool WANT_GRAD, bool CLAMP>
 inline cudaError_t launch_objective_cm_k(int n_sms, const float* cost_words, int cost_nwords, const float* q, long long n,
                                          const float* ee_target_cfg, float margin_override, int use_override, float* cost_total,
                                          float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin, cudaStream_t st) {
-    const size_t smem = ((size_t)cost_nwords + (size_t)3 * CM::S * kSBlock) * sizeof(float);
+    const size_t smem = ((size_t)cost_nwords + (size_t)4 * CM::S * kSBlock) * sizeof(float);
     auto k = k_objective_cm<R, CM, WANT_GRAD, CLAMP>;
     k<<<persistent_grid(k, n_sms, smem, n), kSBlock, smem, st>>>(cost_words, cost_nwords, q, n, ee_target_cfg, margin_override,
                                                                  use_override, cost_total, cost_terms, grad_q, occupancy, argmin);
