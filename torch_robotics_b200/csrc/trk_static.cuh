@@ -677,7 +677,6 @@ __global__ void __launch_bounds__(kSBlock, TRK_CM_MINBLOCKS) k_objective_cm(cons
     constexpr int L = R::L, D = R::D;
     float* cw = smem;
     float* spt = smem + cost_nwords;                  // [3 * CM::S][kSBlock] collision-point positions / gradients
-    unsigned* spre = reinterpret_cast<unsigned*>(spt + 3 * CM::S * kSBlock);   // [CM::S][kSBlock] joint-scan verdicts
     block_copy_words(cw, cost_words, cost_nwords);
     __syncthreads();
     const CostView cv(cw);
@@ -742,13 +741,9 @@ __global__ void __launch_bounds__(kSBlock, TRK_CM_MINBLOCKS) k_objective_cm(cons
             }
         });
         int* amrow = argmin ? argmin + cfg * (long long)(h->nObj * h->S) : nullptr;
-        // collision points: positions parked in a [3S][thread] shared column so that the (large) point code
-        // exists once and runs as a loop; gradients come back the same way
-        sfor<CM::S>([&](auto sc) {
-            constexpr int s = decltype(sc)::value, b = CM::pt_link[s];
-            sfor<3>([&](auto rc) { spt[(s * 3 + rc) * kSBlock + tid] = P[b][rc]; });
-        });
-        // one equal-radius identity-pose sphere object (EnvSpheres3D and most scenes): scan it for all points at once
+        // one equal-radius identity-pose sphere object (EnvSpheres3D and most scenes): scan it for all points at once,
+        // then finish every point from registers (static indices: the points' exact evaluations and workspace terms are
+        // independent chains the scheduler can interleave); any other scene takes the table-driven loop below
         const bool joint_scan = !CLAMP && single_uniform_identity_object(cv);
         if (joint_scan) {
             float X[CM::S][3];
@@ -758,34 +753,49 @@ __global__ void __launch_bounds__(kSBlock, TRK_CM_MINBLOCKS) k_objective_cm(cons
                 sfor<3>([&](auto rc) { X[s][rc] = P[b][rc]; });
             });
             scan_points_uniform<CM::S>(cv, X, pre);
-            sfor<CM::S>([&](auto sc) { spre[decltype(sc)::value * kSBlock + tid] = pre[decltype(sc)::value]; });
-        }
-#pragma unroll 1
-        for (int s = 0; s < CM::S; ++s) {
-            const float x = spt[(s * 3 + 0) * kSBlock + tid], y = spt[(s * 3 + 1) * kSBlock + tid], z = spt[(s * 3 + 2) * kSBlock + tid];
-            float gx = 0.f, gy = 0.f, gz = 0.f;
-            if (joint_scan) {
-                const float m = cv.pt_mobj[s];
-                c_obj = __fadd_rn(c_obj, object_point_term_pre<WANT_GRAD>(cv, x, y, z, m, use_override ? margin_override : m, occ, amrow, s,
-                                                                          gx, gy, gz, spre[s * kSBlock + tid]));
-            } else if (h->nObj > 0) {
-                const float m = cv.pt_mobj[s];
-                c_obj = __fadd_rn(c_obj, object_point_term<WANT_GRAD, CLAMP>(cv, x, y, z, m, use_override ? margin_override : m, occ,
-                                                                             amrow, s, gx, gy, gz));
-            }
-            if (h->ws_enabled) {
-                const float m = cv.pt_mws[s];
-                c_ws = __fadd_rn(c_ws, ws_point_term<WANT_GRAD, CLAMP>(h, x, y, z, m, use_override ? margin_override : m, occ, gx, gy, gz));
-            }
-            if (WANT_GRAD) {
-                spt[(s * 3 + 0) * kSBlock + tid] = gx; spt[(s * 3 + 1) * kSBlock + tid] = gy; spt[(s * 3 + 2) * kSBlock + tid] = gz;
-            }
-        }
-        if (WANT_GRAD)
             sfor<CM::S>([&](auto sc) {
                 constexpr int s = decltype(sc)::value, b = CM::pt_link[s];
-                sfor<3>([&](auto rc) { G[b][rc] += spt[(s * 3 + rc) * kSBlock + tid]; });
+                float gx = 0.f, gy = 0.f, gz = 0.f;
+                const float mo = cv.pt_mobj[s];
+                c_obj = __fadd_rn(c_obj, object_point_term_pre<WANT_GRAD>(cv, X[s][0], X[s][1], X[s][2], mo, use_override ? margin_override : mo,
+                                                                          occ, amrow, s, gx, gy, gz, pre[s]));
+                if (h->ws_enabled) {
+                    const float mw = cv.pt_mws[s];
+                    c_ws = __fadd_rn(c_ws, ws_point_term<WANT_GRAD, CLAMP>(h, X[s][0], X[s][1], X[s][2], mw, use_override ? margin_override : mw,
+                                                                           occ, gx, gy, gz));
+                }
+                if (WANT_GRAD) { G[b][0] += gx; G[b][1] += gy; G[b][2] += gz; }
             });
+        } else {
+            // collision points: positions parked in a [3S][thread] shared column so that the (large) general point code
+            // exists once and runs as a loop; gradients come back the same way
+            sfor<CM::S>([&](auto sc) {
+                constexpr int s = decltype(sc)::value, b = CM::pt_link[s];
+                sfor<3>([&](auto rc) { spt[(s * 3 + rc) * kSBlock + tid] = P[b][rc]; });
+            });
+#pragma unroll 1
+            for (int s = 0; s < CM::S; ++s) {
+                const float x = spt[(s * 3 + 0) * kSBlock + tid], y = spt[(s * 3 + 1) * kSBlock + tid], z = spt[(s * 3 + 2) * kSBlock + tid];
+                float gx = 0.f, gy = 0.f, gz = 0.f;
+                if (h->nObj > 0) {
+                    const float m = cv.pt_mobj[s];
+                    c_obj = __fadd_rn(c_obj, object_point_term<WANT_GRAD, CLAMP>(cv, x, y, z, m, use_override ? margin_override : m, occ,
+                                                                                 amrow, s, gx, gy, gz));
+                }
+                if (h->ws_enabled) {
+                    const float m = cv.pt_mws[s];
+                    c_ws = __fadd_rn(c_ws, ws_point_term<WANT_GRAD, CLAMP>(h, x, y, z, m, use_override ? margin_override : m, occ, gx, gy, gz));
+                }
+                if (WANT_GRAD) {
+                    spt[(s * 3 + 0) * kSBlock + tid] = gx; spt[(s * 3 + 1) * kSBlock + tid] = gy; spt[(s * 3 + 2) * kSBlock + tid] = gz;
+                }
+            }
+            if (WANT_GRAD)
+                sfor<CM::S>([&](auto sc) {
+                    constexpr int s = decltype(sc)::value, b = CM::pt_link[s];
+                    sfor<3>([&](auto rc) { G[b][rc] += spt[(s * 3 + rc) * kSBlock + tid]; });
+                });
+        }
         terms[0] = c_self; terms[1] = c_obj; terms[2] = c_ws;
         if (cost_total) cost_total[cfg] = weighted_total(h, terms);
         if (cost_terms) reinterpret_cast<float4*>(cost_terms)[cfg] = make_float4(terms[0], terms[1], terms[2], terms[3]);
@@ -1094,7 +1104,7 @@ template <class R, class CM, bool WANT_GRAD, bool CLAMP>
 inline cudaError_t launch_objective_cm_k(int n_sms, const float* cost_words, int cost_nwords, const float* q, long long n,
                                          const float* ee_target_cfg, float margin_override, int use_override, float* cost_total,
                                          float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin, cudaStream_t st) {
-    const size_t smem = ((size_t)cost_nwords + (size_t)4 * CM::S * kSBlock) * sizeof(float);
+    const size_t smem = ((size_t)cost_nwords + (size_t)3 * CM::S * kSBlock) * sizeof(float);
     auto k = k_objective_cm<R, CM, WANT_GRAD, CLAMP>;
     k<<<persistent_grid(k, n_sms, smem, n), kSBlock, smem, st>>>(cost_words, cost_nwords, q, n, ee_target_cfg, margin_override,
                                                                  use_override, cost_total, cost_terms, grad_q, occupancy, argmin);
