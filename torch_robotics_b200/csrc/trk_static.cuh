@@ -606,6 +606,36 @@ __global__ void __launch_bounds__(kSBlock, 4) k_objective_static(const float* __
             }
         }
         unsigned occ;
+        bool joint_done = false;
+        if constexpr (!std::is_void<CM>::value && !CLAMP) {
+            // compile-time collision model with no self pairs + one equal-radius identity-pose sphere object: the points
+            // are scanned jointly in groups of five (one sphere-table load serves five points, five chains in flight)
+            if constexpr (CM::P == 0) {
+                if (single_uniform_identity_object(cv)) {
+                    occ = 0u;
+                    float c_obj = 0.f, c_ws = 0.f;
+                    int* amrow = argmin ? argmin + cfg * (long long)(h->nObj * h->S) : nullptr;
+                    constexpr int kGroup = 5;
+                    sfor<(CM::S + kGroup - 1) / kGroup>([&](auto gc) {
+                        constexpr int s0 = decltype(gc)::value * kGroup, np = (CM::S - s0) < kGroup ? (CM::S - s0) : kGroup;
+                        joint_points_terms<WANT_GRAD, CLAMP, s0, np>(
+                            cv,
+                            [&](int p, float& x, float& y, float& z) {
+                                const int sl = cv.pt_slot[s0 + p];
+                                x = spos[(sl * 3 + 0) * kSBlock + tid]; y = spos[(sl * 3 + 1) * kSBlock + tid]; z = spos[(sl * 3 + 2) * kSBlock + tid];
+                            },
+                            [&](int p, float gx, float gy, float gz) {
+                                const int sl = cv.pt_slot[s0 + p];
+                                sgrd[(sl * 3 + 0) * kSBlock + tid] += gx; sgrd[(sl * 3 + 1) * kSBlock + tid] += gy; sgrd[(sl * 3 + 2) * kSBlock + tid] += gz;
+                            },
+                            margin_override, use_override != 0, c_obj, c_ws, occ, amrow);
+                    });
+                    terms[0] = 0.f; terms[1] = c_obj; terms[2] = c_ws;
+                    joint_done = true;
+                }
+            }
+        }
+        if (!joint_done)
         collision_terms<WANT_GRAD, CLAMP>(
             cv, cv.pt_slot, cv.pair_si, cv.pair_sj,
             [&](int b, float& x, float& y, float& z) {
