@@ -233,6 +233,8 @@ def main():
     from torch_robotics_b200.distributed import bind_to_gpu_numa_node
     numa_bound = bind_to_gpu_numa_node(local_rank) if world > 1 else False
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own version / debug banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     desc, cost = panda_objective_descriptors()
