@@ -796,6 +796,23 @@ __global__ void __launch_bounds__(kSBlock, TRK_CM_MINBLOCKS) k_objective_cm(cons
                 }
                 if (WANT_GRAD) { G[b][0] += gx; G[b][1] += gy; G[b][2] += gz; }
             });
+        } else if (!CLAMP && all_uniform_identity_objects(cv)) {
+            // several equal-radius identity-pose sphere objects: one joint scan per object
+            joint_points_terms_multi<WANT_GRAD, CLAMP, 0, CM::S>(
+                cv,
+                [&](int p, float& x, float& y, float& z) {
+                    sfor<CM::S>([&](auto sc) {
+                        constexpr int s = decltype(sc)::value, b = CM::pt_link[s];
+                        if (p == s) { x = P[b][0]; y = P[b][1]; z = P[b][2]; }
+                    });
+                },
+                [&](int p, float gx, float gy, float gz) {
+                    sfor<CM::S>([&](auto sc) {
+                        constexpr int s = decltype(sc)::value, b = CM::pt_link[s];
+                        if (p == s) { G[b][0] += gx; G[b][1] += gy; G[b][2] += gz; }
+                    });
+                },
+                margin_override, use_override != 0, c_obj, c_ws, occ, amrow);
         } else if (CLAMP && single_grid_object(cv)) {
             // the scene is one voxel SDF: all cell gathers in flight at once, points finished from registers
             joint_grid_points_terms<WANT_GRAD, 0, CM::S>(
