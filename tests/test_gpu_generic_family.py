@@ -150,3 +150,45 @@ def test_fused_ik_converges_on_a_tree_with_prismatic_joints(generic_models):
     r = m.ik_adam(t(q0), t(H), ee, lo, hi, n_iters=300, lr=0.02, se3_eps=0.02)
     assert r["valid"].float().mean().item() > 0.9
     assert int(r["valid_count"][-1]) == int(r["valid"].sum())
+
+
+def test_base_pose_is_a_rigid_motion_of_the_scene():
+    """A robot with a base pose B (served by the runtime-tree kernels: the compiled-in tables have the identity root)
+    sees obstacles O and an EE target T exactly as the identity-base robot sees B^-1 O and B^-1 T: same costs, same
+    gradients; link poses and Jacobians are those of the identity-base robot moved by B."""
+    from torch_robotics_b200._lib import DeviceCost, DeviceModel
+    from torch_robotics_b200.descriptor import build_cost_descriptor, quat_wxyz_to_matrix
+    import copy
+    d0 = get_desc("panda")
+    quat = np.array([0.8, 0.2, -0.4, 0.4], np.float32)
+    quat /= np.linalg.norm(quat)
+    Rb, tb = quat_wxyz_to_matrix(quat).astype(np.float64), np.array([0.3, -0.2, 0.15])
+    d1 = copy.deepcopy(d0)
+    d1.base_R, d1.base_t = Rb.astype(np.float32), tb.astype(np.float32)
+    m0, m1 = DeviceModel(d0, DEV), DeviceModel(d1, DEV)
+    assert m0.kernel_family == "panda" and m1.kernel_family == "generic"
+    rng = np.random.default_rng(17)
+    q = rng.uniform(-2.0, 2.0, (3001, 7)).astype(np.float32)
+    H0, H1 = m0.fk_forward(t(q)).cpu().numpy().astype(np.float64), m1.fk_forward(t(q)).cpu().numpy()
+    B = np.eye(4)
+    B[:3, :3], B[:3, 3] = Rb, tb
+    assert rel_err(H1, B @ H0) < 1e-5
+    # objective: world-frame spheres / EE target for the moved robot, pulled back by B^-1 for the identity-base robot
+    centers_w = rng.uniform(-0.6, 0.6, (7, 3))
+    radii = np.full(7, 0.12, np.float32)
+    Tw = np.eye(4)
+    Tw[:3, :3], Tw[:3, 3] = quat_wxyz_to_matrix(np.array([0.6, -0.3, 0.1, 0.7], np.float32) / np.float32(0.9746794)), [0.4, 0.1, 0.5]
+    Binv = np.linalg.inv(B)
+    pairs = [(9, 0), (9, 1), (4, 1), (6, 2)]
+    common = dict(pt_link=[2, 3, 5, 7, 9], pt_radius=[0.125, 0.125, 0.13, 0.1, 0.08], cutoff_obj=0.01, self_pairs=pairs,
+                  self_margin=[0.05], ee_link=10)
+    c1 = build_cost_descriptor(objects=[(centers_w.astype(np.float32), radii, None, None)], ee_target=Tw.astype(np.float32), **common)
+    c0 = build_cost_descriptor(objects=[((centers_w @ Binv[:3, :3].T + Binv[:3, 3]).astype(np.float32), radii, None, None)],
+                               ee_target=(Binv @ Tw).astype(np.float32), **common)
+    r1 = DeviceCost(m1, c1).objective(t(q), want_terms=True)
+    r0 = DeviceCost(m0, c0).objective(t(q), want_terms=True)
+    assert rel_err(r1["terms"].cpu().numpy(), r0["terms"].cpu().numpy()) < 2e-5
+    assert rel_err(r1["grad_q"].cpu().numpy(), r0["grad_q"].cpu().numpy()) < 1e-4
+    # Jacobians: positions rotate with B
+    J0, J1 = m0.link_jacobian(t(q[:200])).cpu().numpy().astype(np.float64), m1.link_jacobian(t(q[:200])).cpu().numpy()
+    assert rel_err(J1[:, :, 0:3, :], np.einsum("ij,nljd->nlid", Rb, J0[:, :, 0:3, :])) < 1e-5
