@@ -292,3 +292,35 @@ def test_new_entry_points_validate_arguments(models):
     # objective / IK on an empty batch
     r = DeviceCost(m, good).objective(torch.empty(0, 7, device=DEV))
     assert r["total"].shape == (0,) and r["grad_q"].shape == (0, 7)
+
+
+@pytest.mark.parametrize("robot,n_pts", [("panda", 7), ("ur10", 3), ("shadow_hand", 11), ("stretch", 9)])
+def test_table_driven_static_objective_joint_scan_vs_oracle(models, robot, n_pts):
+    """Compiled-in robots with collision points / pairs that are NOT a compile-time collision model go through the
+    table-driven k_objective_static; with one equal-radius sphere object its points are scanned jointly in run-time
+    groups of five (ragged last group).  Costs, gradients, masks and arg-min against the C oracle."""
+    from oracle import c_oracle as co
+    from torch_robotics_b200._lib import DeviceCost
+    from torch_robotics_b200.descriptor import build_cost_descriptor
+    d, m = get_desc(robot), models[robot]
+    assert m.kernel_family != "generic"
+    rng = np.random.default_rng(n_pts)
+    pts = [int(v) for v in rng.permutation(np.arange(1, d.n_links))[:n_pts]]
+    pairs = [(pts[0], 0), (pts[-1], pts[1])] if n_pts > 2 else []
+    centers = rng.uniform(-0.6, 0.6, (9, 3)).astype(np.float32)
+    cost = build_cost_descriptor(pt_link=pts, pt_radius=rng.uniform(0.03, 0.1, n_pts).astype(np.float32), cutoff_obj=0.02,
+                                 objects=[(centers, np.full(9, 0.1, np.float32), None, None)], ws_min=[-0.8, -0.8, -0.2], ws_max=[0.8, 0.8, 1.2],
+                                 self_pairs=pairs, self_margin=[0.04], ee_link=d.n_links - 1, ee_target=np.eye(4, dtype=np.float32))
+    lo = np.where(d.has_lim[d.controlled] > 0, d.lo[d.controlled], -np.pi).astype(np.float32)
+    hi = np.where(d.has_lim[d.controlled] > 0, d.hi[d.controlled], np.pi).astype(np.float32)
+    q = (lo + rng.random((30_011, d.n_dofs), dtype=np.float32) * (hi - lo)).astype(np.float32)
+    r = DeviceCost(m, cost).objective(t(q), want_terms=True, want_occupancy=True, want_argmin=True)
+    o = co.objective(co.Tree(d), co.Cost(cost), q)
+    assert rel_err(r["terms"].cpu().numpy(), o["terms"]) < POSE_TOL
+    gd = np.abs(r["grad_q"].cpu().numpy() - o["grad_q"]).max(axis=1) / np.abs(o["grad_q"]).max()
+    assert (gd >= GRAD_TOL).sum() <= 10 and gd[gd < GRAD_TOL].max() < GRAD_TOL
+    assert np.mean(r["occupancy"].cpu().numpy() != o["occ"]) < 1e-3
+    assert np.mean(r["argmin"].cpu().numpy() != o["argmin"]) < 1e-3
+    fwd = DeviceCost(m, cost).objective(t(q), want_grad=False, want_terms=False, want_occupancy=True, margin_override=0.0)
+    o0 = co.objective(co.Tree(d), co.Cost(cost), q, margin_override=0.0)
+    assert np.mean(fwd["occupancy"].cpu().numpy() != o0["occ"]) < 1e-3 and torch.equal(fwd["total"], r["total"])

@@ -635,6 +635,32 @@ __global__ void __launch_bounds__(kSBlock, 4) k_objective_static(const float* __
                 }
             }
         }
+        if constexpr (std::is_void<CM>::value && !CLAMP) {
+            // table-driven model, one equal-radius identity-pose sphere object: self pairs from the tables, then the
+            // collision points in groups of five through the joint scan
+            if (single_uniform_identity_object(cv)) {
+                auto slot_pos = [&](int sl, float& x, float& y, float& z) {
+                    x = spos[(sl * 3 + 0) * kSBlock + tid]; y = spos[(sl * 3 + 1) * kSBlock + tid]; z = spos[(sl * 3 + 2) * kSBlock + tid];
+                };
+                auto slot_acc = [&](int sl, float gx, float gy, float gz) {
+                    sgrd[(sl * 3 + 0) * kSBlock + tid] += gx; sgrd[(sl * 3 + 1) * kSBlock + tid] += gy; sgrd[(sl * 3 + 2) * kSBlock + tid] += gz;
+                };
+                occ = 0u;
+                terms[0] = self_pairs_term<WANT_GRAD, CLAMP>(cv, cv.pair_si, cv.pair_sj, slot_pos, slot_acc, margin_override, use_override != 0, occ);
+                float c_obj = 0.f, c_ws = 0.f;
+                int* amrow = argmin ? argmin + cfg * (long long)(h->nObj * h->S) : nullptr;
+                const int S = h->S;
+#pragma unroll 1
+                for (int s0 = 0; s0 < S; s0 += 5)
+                    joint_points_terms_rt<WANT_GRAD, CLAMP, 5>(
+                        cv, s0, (S - s0) < 5 ? (S - s0) : 5,
+                        [&](int s, float& x, float& y, float& z) { slot_pos(cv.pt_slot[s], x, y, z); },
+                        [&](int s, float gx, float gy, float gz) { slot_acc(cv.pt_slot[s], gx, gy, gz); },
+                        margin_override, use_override != 0, c_obj, c_ws, occ, amrow);
+                terms[1] = c_obj; terms[2] = c_ws;
+                joint_done = true;
+            }
+        }
         if (!joint_done)
         collision_terms<WANT_GRAD, CLAMP>(
             cv, cv.pt_slot, cv.pair_si, cv.pair_sj,
