@@ -120,9 +120,13 @@ __global__ void __launch_bounds__(kBlock) k_objective_generic(const float* __res
                                                               const float* __restrict__ cost_words, int cost_nwords,
                                                               const __grid_constant__ TreePlan plan, const float* __restrict__ q, long long n,
                                                               const float* __restrict__ ee_target_cfg, float margin_override,
-                                                              int use_override, float* __restrict__ cost_total,
+                                                              int use_override, int joint, float* __restrict__ cost_total,
                                                               float* __restrict__ cost_terms, float* __restrict__ grad_q,
                                                               uint8_t* __restrict__ occupancy, int* __restrict__ argmin) {
+    // joint != 0: the scene is one equal-radius identity-pose sphere object without relu (decided on the host): every
+    // referenced body's position is parked in a slot during the sweep and the collision points are evaluated afterwards
+    // through the joint scan in groups of five; otherwise a point is evaluated while its body's pose is in registers
+    // and only the bodies of self-collision pairs are parked.
     extern __shared__ __align__(16) float smem[];
     float* tw = smem;
     float* cw = smem + tree_nwords;
@@ -135,11 +139,19 @@ __global__ void __launch_bounds__(kBlock) k_objective_generic(const float* __res
     const CostHeader* h = cv.h;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nthreads = blockDim.x, D = hdr->D;
     const int njc = WANT_GRAD ? D : 0;
-    float* wbase = smem + tree_nwords + ((cost_nwords + 3) & ~3) + (size_t)warp * generic_warp_words(0, plan.n_live, njc, h->n_pslots);
+    const int n_pos = joint ? h->n_slots : h->n_pslots;
+    int* slot_jm = reinterpret_cast<int*>(smem + tree_nwords + ((cost_nwords + 3) & ~3));   // [TRK_MAX_LINKS] joint column above a slot's body
+    if (threadIdx.x == 0)
+        for (int b = 0; b < hdr->L; ++b) {
+            const int sl = joint ? cv.slot_of_body[b] : cv.pslot_of_body[b];
+            if (sl >= 0) slot_jm[sl] = plan.jm[b];
+        }
+    __syncthreads();
+    float* wbase = smem + tree_nwords + ((cost_nwords + 3) & ~3) + TRK_MAX_LINKS + (size_t)warp * generic_warp_words(0, plan.n_live, njc, n_pos);
     float* wl = wbase + lane;
     float* JS = wbase + plan.n_live * 12 * 32 + lane;
     float* PS = wbase + (plan.n_live + njc) * 12 * 32 + lane;           // pair-position slots [slot * 3 + k][lane]
-    const int P = h->P, S = h->S;
+    const int S = h->S;
     for (long long cfg = (long long)blockIdx.x * nthreads + threadIdx.x; cfg < n; cfg += (long long)gridDim.x * nthreads) {
         float terms[4] = {0.f, 0.f, 0.f, 0.f};
         unsigned occ = 0u, pass_mask = 0u;
@@ -153,24 +165,26 @@ __global__ void __launch_bounds__(kBlock) k_objective_generic(const float* __res
                 if (pass) pass_mask |= 1u << r.qidx;
             }
             const float x = w[9], y = w[10], z = w[11];
-            const int ps = cv.pslot_of_body[b];
+            const int ps = joint ? cv.slot_of_body[b] : cv.pslot_of_body[b];
             if (ps >= 0) { PS[ps * 96] = x; PS[ps * 96 + 32] = y; PS[ps * 96 + 64] = z; }
             const int c = plan.jm[b];
+            if (!joint) {
 #pragma unroll 1
-            for (int k = cv.bp_start[b]; k < cv.bp_start[b + 1]; ++k) {
-                const int s = cv.bp_list[k];
-                float gx = 0.f, gy = 0.f, gz = 0.f;
-                if (h->nObj > 0) {
-                    const float m = cv.pt_mobj[s];
-                    terms[1] = __fadd_rn(terms[1], object_point_term<WANT_GRAD, true>(cv, x, y, z, m, use_override ? margin_override : m,
-                                                                                      occ, argmin_row, s, gx, gy, gz));
+                for (int k = cv.bp_start[b]; k < cv.bp_start[b + 1]; ++k) {
+                    const int s = cv.bp_list[k];
+                    float gx = 0.f, gy = 0.f, gz = 0.f;
+                    if (h->nObj > 0) {
+                        const float m = cv.pt_mobj[s];
+                        terms[1] = __fadd_rn(terms[1], object_point_term<WANT_GRAD, true>(cv, x, y, z, m, use_override ? margin_override : m,
+                                                                                          occ, argmin_row, s, gx, gy, gz));
+                    }
+                    if (h->ws_enabled) {
+                        const float m = cv.pt_mws[s];
+                        terms[2] = __fadd_rn(terms[2], ws_point_term<WANT_GRAD, true>(h, x, y, z, m, use_override ? margin_override : m, occ,
+                                                                                      gx, gy, gz));
+                    }
+                    if (WANT_GRAD && c >= 0) joint_fold(JS, c, x, y, z, gx, gy, gz, 0.f, 0.f, 0.f);
                 }
-                if (h->ws_enabled) {
-                    const float m = cv.pt_mws[s];
-                    terms[2] = __fadd_rn(terms[2], ws_point_term<WANT_GRAD, true>(h, x, y, z, m, use_override ? margin_override : m, occ,
-                                                                                  gx, gy, gz));
-                }
-                if (WANT_GRAD && c >= 0) joint_fold(JS, c, x, y, z, gx, gy, gz, 0.f, 0.f, 0.f);
             }
             if (h->ee_enabled && b == h->ee_link) {
                 float Rt[9], pt[3], gR[9], gp[3];
@@ -195,21 +209,22 @@ __global__ void __launch_bounds__(kBlock) k_objective_generic(const float* __res
                 }
             }
         });
-        // self-collision pairs need both bodies: positions come from the pair slots
+        // self-collision pairs need both bodies: positions come from the slots; forces go to the joint above each body
+        auto slot_pos = [&](int sl, float& x, float& y, float& z) { x = PS[sl * 96]; y = PS[sl * 96 + 32]; z = PS[sl * 96 + 64]; };
+        auto slot_acc = [&](int sl, float gx, float gy, float gz) {
+            const int c = slot_jm[sl];
+            if (c >= 0) joint_fold(JS, c, PS[sl * 96], PS[sl * 96 + 32], PS[sl * 96 + 64], gx, gy, gz, 0.f, 0.f, 0.f);
+        };
+        terms[0] = self_pairs_term<WANT_GRAD, true>(cv, joint ? cv.pair_si : cv.pair_pi, joint ? cv.pair_sj : cv.pair_pj, slot_pos, slot_acc,
+                                                    margin_override, use_override != 0, occ);
+        if (joint) {
 #pragma unroll 1
-        for (int p = 0; p < P; ++p) {
-            const float* a = PS + cv.pair_pi[p] * 96;
-            const float* bq = PS + cv.pair_pj[p] * 96;
-            const float xi = a[0], yi = a[32], zi = a[64], xj = bq[0], yj = bq[32], zj = bq[64];
-            const float m = cv.pair_m[p];
-            float ux, uy, uz;
-            terms[0] = __fadd_rn(terms[0], pair_term<WANT_GRAD, true>(h, xi, yi, zi, xj, yj, zj, m, use_override ? margin_override : m,
-                                                                      occ, ux, uy, uz));
-            if (WANT_GRAD) {
-                const int ci = plan.jm[cv.pair_i[p]], cj = plan.jm[cv.pair_j[p]];
-                if (ci >= 0) joint_fold(JS, ci, xi, yi, zi, -ux, -uy, -uz, 0.f, 0.f, 0.f);
-                if (cj >= 0) joint_fold(JS, cj, xj, yj, zj, ux, uy, uz, 0.f, 0.f, 0.f);
-            }
+            for (int s0 = 0; s0 < S; s0 += 5)
+                joint_points_terms_rt<WANT_GRAD, true, 5>(
+                    cv, s0, (S - s0) < 5 ? (S - s0) : 5,
+                    [&](int s, float& x, float& y, float& z) { slot_pos(cv.pt_slot[s], x, y, z); },
+                    [&](int s, float gx, float gy, float gz) { slot_acc(cv.pt_slot[s], gx, gy, gz); },
+                    margin_override, use_override != 0, terms[1], terms[2], occ, argmin_row);
         }
         if (cost_total) cost_total[cfg] = weighted_total(h, terms);
         if (cost_terms) reinterpret_cast<float4*>(cost_terms)[cfg] = make_float4(terms[0], terms[1], terms[2], terms[3]);
@@ -597,7 +612,8 @@ struct trk_model {
 
 // Parents-first walk: a body's pose slot is released once its last child has been composed (the child already holds
 // the parent pose in registers, so it may take over the very slot), leaves need none.
-static void build_tree_plan(const int32_t* topo, const int32_t* parent, const int32_t* qidx, const int32_t* kind, int L, TreePlan& ls) {
+static void build_tree_plan(const int32_t* topo, const int32_t* parent, const int32_t* qidx, const int32_t* kind, const float* R_fixed, int L,
+                            TreePlan& ls) {
     memset(&ls, 0, sizeof(ls));
     int nj = 0;
     for (int i = 0; i < L; ++i) {   // joint tables (parents first)
@@ -620,6 +636,13 @@ static void build_tree_plan(const int32_t* topo, const int32_t* parent, const in
         ls.par[i] = (int8_t)(p >= 0 ? slot_of[pos_of[p]] : -1);
         if (p >= 0 && last_child[pos_of[p]] == i) busy[slot_of[pos_of[p]]] = false;
         ls.own[i] = -1; slot_of[i] = -1;
+        {
+            const int b = topo[i];
+            const float* Rf = R_fixed + 9 * b;
+            const bool ident = Rf[0] == 1.f && Rf[4] == 1.f && Rf[8] == 1.f && Rf[1] == 0.f && Rf[2] == 0.f && Rf[3] == 0.f && Rf[5] == 0.f &&
+                               Rf[6] == 0.f && Rf[7] == 0.f;
+            if (p >= 0 && last_child[i] < 0 && kind[b] == TRK_KIND_FIXED && ident) ls.point_mask |= 1ull << i;
+        }
         if (last_child[i] >= 0) {
             int s = 0;
             while (busy[s]) ++s;
@@ -786,7 +809,7 @@ int trk_model_create(const trk_model_desc* d, int device, trk_model** out) {
     m->maxl_bucket = L <= 16 ? 16 : (L <= 32 ? 32 : 64);
     memcpy(m->parent, d->parent, L * sizeof(int32_t));
     memcpy(m->qidx, d->q_index, L * sizeof(int32_t));
-    build_tree_plan(d->topo, d->parent, d->q_index, d->kind, L, m->live);
+    build_tree_plan(d->topo, d->parent, d->q_index, d->kind, d->R_fixed, L, m->live);
     cudaError_t e = cudaDeviceGetAttribute(&m->n_sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) { delete m; return cuda_fail(e, "cudaDeviceGetAttribute"); }
     e = cudaMalloc(&m->d_words, nwords * sizeof(float));
@@ -1089,16 +1112,23 @@ int trk_objective(const trk_model* m, const trk_cost* c, const float* q, int64_t
                                                      occupancy, argmin, st);
         return e == cudaSuccess ? TRK_OK : cuda_fail(e, "objective(static)");
     }
-    const GenericLaunch gl = generic_launch(m, n, (size_t)m->nwords + align4(c->nwords), 0, grad_q ? m->D : 0, c->n_pslots);
+    // one equal-radius identity-pose sphere object, no relu on the object term: collision points take the joint scan
+    const CostHeader* gh = reinterpret_cast<const CostHeader*>(c->h_words.data());
+    const int* giw = reinterpret_cast<const int*>(c->h_words.data());
+    const int joint = gh->nObj == 1 && gh->KB == 0 && !gh->clamp_obj && gh->S > 0 &&
+                      (giw[gh->off_obj_ident] & (OBJ_IDENTITY | OBJ_UNIFORM_RADIUS | OBJ_GRID)) == (OBJ_IDENTITY | OBJ_UNIFORM_RADIUS) &&
+                      giw[gh->off_obj_start + 1] > giw[gh->off_obj_start];
+    const GenericLaunch gl = generic_launch(m, n, (size_t)m->nwords + align4(c->nwords) + TRK_MAX_LINKS, 0, grad_q ? m->D : 0,
+                                            joint ? c->n_slots : c->n_pslots);
     cudaError_t e = allow_smem(k_objective_generic<true>, gl.smem);
     if (e == cudaSuccess) e = allow_smem(k_objective_generic<false>, gl.smem);
     if (e != cudaSuccess) return cuda_fail(e, "objective smem");
     if (grad_q)
         k_objective_generic<true><<<gl.grid, gl.warps * 32, gl.smem, st>>>(m->d_words, m->nwords, c->d_words, c->nwords, m->live, q, n,
-            ee_target_cfg, margin_override, use_override, cost_total, cost_terms, grad_q, occupancy, argmin);
+            ee_target_cfg, margin_override, use_override, joint, cost_total, cost_terms, grad_q, occupancy, argmin);
     else
         k_objective_generic<false><<<gl.grid, gl.warps * 32, gl.smem, st>>>(m->d_words, m->nwords, c->d_words, c->nwords, m->live, q, n,
-            ee_target_cfg, margin_override, use_override, cost_total, cost_terms, grad_q, occupancy, argmin);
+            ee_target_cfg, margin_override, use_override, joint, cost_total, cost_terms, grad_q, occupancy, argmin);
     e = cudaGetLastError();
     return e == cudaSuccess ? TRK_OK : cuda_fail(e, "objective launch");
 }
