@@ -722,7 +722,9 @@ struct CMInfo {
 #ifndef TRK_CM_MINBLOCKS
 #define TRK_CM_MINBLOCKS 4
 #endif
-template <class R, class CM, bool WANT_GRAD, bool CLAMP>
+// EE: processing position of the end-effector body when it is known at compile time (the host passes it when the cost
+// tables name the robot's last body, e.g. Panda's ee_link), -1 = chosen at run time (a compare + predicated copies per body)
+template <class R, class CM, bool WANT_GRAD, bool CLAMP, int EE = -1>
 __global__ void __launch_bounds__(kSBlock, TRK_CM_MINBLOCKS) k_objective_cm(const float* __restrict__ cost_words, int cost_nwords,
                                                              const float* __restrict__ q, long long n,
                                                              const float* __restrict__ ee_target_cfg, float margin_override,
@@ -742,7 +744,7 @@ __global__ void __launch_bounds__(kSBlock, TRK_CM_MINBLOCKS) k_objective_cm(cons
         const float* qrow = q + cfg * D;
         float terms[4] = {0.f, 0.f, 0.f, 0.f};
         float Rt[9], pt[3];
-        const int e = h->ee_enabled ? h->ee_link : -1;
+        const int e = EE >= 0 ? R::body[EE] : (h->ee_enabled ? h->ee_link : -1);
         if (e >= 0) {
             if (ee_target_cfg) {
                 const float* Ht = ee_target_cfg + cfg * 16;
@@ -769,7 +771,11 @@ __global__ void __launch_bounds__(kSBlock, TRK_CM_MINBLOCKS) k_objective_cm(cons
                 constexpr int qi = R::qidx[i];
                 if constexpr (qi >= 0) STree<R>::template joint_axis<i>(wp, w, JA[qi]);
             }
-            if (b == e) sfor<12>([&](auto kc) { Wee[kc] = w[kc]; });   // the EE body is chosen at run time: keep a copy
+            if constexpr (EE >= 0) {
+                if constexpr (i == EE) sfor<12>([&](auto kc) { Wee[kc] = w[kc]; });
+            } else {
+                if (b == e) sfor<12>([&](auto kc) { Wee[kc] = w[kc]; });   // the EE body is chosen at run time: keep a copy
+            }
         });
         if (e >= 0) {
             float gR[9], gp[3];
@@ -903,7 +909,11 @@ __global__ void __launch_bounds__(kSBlock, TRK_CM_MINBLOCKS) k_objective_cm(cons
                 } else {
                     sfor<3>([&](auto rc) { f[rc] = 0.f; t[rc] = 0.f; });
                 }
-                if (b == e) sfor<3>([&](auto rc) { f[rc] += eF[rc]; t[rc] += eT[rc]; });
+                if constexpr (EE >= 0) {
+                    if constexpr (b == R::body[EE]) sfor<3>([&](auto rc) { f[rc] += eF[rc]; t[rc] += eT[rc]; });
+                } else {
+                    if (b == e) sfor<3>([&](auto rc) { f[rc] += eF[rc]; t[rc] += eT[rc]; });
+                }
             }, pass, [&](int c, float g) { grow[c] = g; });
         }
     }
@@ -1190,12 +1200,12 @@ inline cudaError_t launch_objective_k(int n_sms, const float* cost_words, int co
     return cudaGetLastError();
 }
 
-template <class R, class CM, bool WANT_GRAD, bool CLAMP>
+template <class R, class CM, bool WANT_GRAD, bool CLAMP, int EE = -1>
 inline cudaError_t launch_objective_cm_k(int n_sms, const float* cost_words, int cost_nwords, const float* q, long long n,
                                          const float* ee_target_cfg, float margin_override, int use_override, float* cost_total,
                                          float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin, cudaStream_t st) {
     const size_t smem = ((size_t)cost_nwords + (size_t)3 * CM::S * kSBlock) * sizeof(float);
-    auto k = k_objective_cm<R, CM, WANT_GRAD, CLAMP>;
+    auto k = k_objective_cm<R, CM, WANT_GRAD, CLAMP, EE>;
     k<<<persistent_grid(k, n_sms, smem, n), kSBlock, smem, st>>>(cost_words, cost_nwords, q, n, ee_target_cfg, margin_override,
                                                                  use_override, cost_total, cost_terms, grad_q, occupancy, argmin);
     return cudaGetLastError();
@@ -1214,6 +1224,10 @@ cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwor
     if constexpr (!std::is_void<CM>::value) {
         if (cm_match) {
             if constexpr (CollisionModelOf<R>::in_registers) {
+                if (cm_match == 2 && !clamp_any) {   // EE = the robot's last body: compile-time end-effector
+                    if (grad_q) return launch_objective_cm_k<R, CM, true, false, R::L - 1>(TRK_OBJ_ARGS);
+                    return launch_objective_cm_k<R, CM, false, false, R::L - 1>(TRK_OBJ_ARGS);
+                }
                 if (grad_q) return clamp_any ? launch_objective_cm_k<R, CM, true, true>(TRK_OBJ_ARGS) : launch_objective_cm_k<R, CM, true, false>(TRK_OBJ_ARGS);
                 return clamp_any ? launch_objective_cm_k<R, CM, false, true>(TRK_OBJ_ARGS) : launch_objective_cm_k<R, CM, false, false>(TRK_OBJ_ARGS);
             } else {
@@ -1279,14 +1293,19 @@ inline cudaError_t launch_static_fk_backward(int family, int n_sms, const float*
     return cudaErrorInvalidValue;
 }
 
-// 1 when `family` has a compile-time collision model and the (host copy of the) cost table matches it
+// > 0 when `family` has a compile-time collision model and the (host copy of the) cost table matches it;
+// 2 when, in addition, the end-effector term is enabled on the robot's last body
 inline int static_cm_match(int family, const float* host_cost_words) {
     int id = 0;
 #define X(Rb)                                                                          \
     ++id;                                                                              \
     if (family == id) {                                                                \
         using CM = typename CollisionModelOf<Rb>::type;                                \
-        if constexpr (!std::is_void<CM>::value) return cost_matches_cm<CM>(host_cost_words) ? 1 : 0; \
+        if constexpr (!std::is_void<CM>::value) {                                      \
+            if (!cost_matches_cm<CM>(host_cost_words)) return 0;                       \
+            const CostHeader* hh = reinterpret_cast<const CostHeader*>(host_cost_words); \
+            return (hh->ee_enabled && hh->ee_link == Rb::body[Rb::L - 1]) ? 2 : 1;     \
+        }                                                                              \
         return 0;                                                                      \
     }
     TRK_FOR_EACH_STATIC_ROBOT(X)
