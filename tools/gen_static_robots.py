@@ -123,6 +123,7 @@ def emit_panda_collision():
            f"    static constexpr int pt_link[S] = {{{', '.join(map(str, pts))}}};",
            f"    static constexpr int pair_i[P] = {{{', '.join(str(a) for a, _ in pairs)}}};",
            f"    static constexpr int pair_j[P] = {{{', '.join(str(b) for _, b in pairs)}}};",
+           f"    static constexpr int ee_body = {idx['ee_link']};   // end-effector body of the planning objective (RobotPanda.link_name_ee)",
            "};"]
     return "\n".join(out)
 
@@ -137,6 +138,7 @@ def emit_stretch_collision():
                       f"    static constexpr int pt_link[S] = {{{', '.join(map(str, pts))}}};",
                       "    static constexpr int pair_i[1] = {0};",
                       "    static constexpr int pair_j[1] = {0};",
+                      f"    static constexpr int ee_body = {d.link_names.index('link_straight_gripper')};",
                       "};"])
 
 

@@ -525,7 +525,7 @@ struct CMSlots {
     }
 };
 
-template <class R, bool WANT_GRAD, bool CLAMP, class CM = void>
+template <class R, bool WANT_GRAD, bool CLAMP, class CM = void, int EE = -1>
 __global__ void __launch_bounds__(kSBlock, 4) k_objective_static(const float* __restrict__ cost_words, int cost_nwords, int n_slots,
                                                               const float* __restrict__ q, long long n,
                                                               const float* __restrict__ ee_target_cfg, float margin_override,
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(kSBlock, 4) k_objective_static(const float* __
         const float* qrow = q + cfg * D;
         float terms[4] = {0.f, 0.f, 0.f, 0.f};
         float Rt[9], pt[3];
-        const int e = h->ee_enabled ? h->ee_link : -1;
+        const int e = EE >= 0 ? R::body[EE] : (h->ee_enabled ? h->ee_link : -1);
         if (e >= 0) {
             if (ee_target_cfg) {
                 const float* Ht = ee_target_cfg + cfg * 16;
@@ -591,7 +591,11 @@ __global__ void __launch_bounds__(kSBlock, 4) k_objective_static(const float* __
                     PJ[qi][0] = w[9]; PJ[qi][1] = w[10]; PJ[qi][2] = w[11];
                 }
             }
-            if (b == e) sfor<12>([&](auto kc) { Wee[kc] = w[kc]; });   // the EE body is chosen at run time: keep a copy
+            if constexpr (EE >= 0) {
+                if constexpr (i == EE) sfor<12>([&](auto kc) { Wee[kc] = w[kc]; });
+            } else {
+                if (b == e) sfor<12>([&](auto kc) { Wee[kc] = w[kc]; });   // the EE body is chosen at run time: keep a copy
+            }
         });
         if (e >= 0) {
             float gR[9], gp[3];
@@ -697,7 +701,11 @@ __global__ void __launch_bounds__(kSBlock, 4) k_objective_static(const float* __
                     const int sl = cv.slot_of_body[b];
                     if (sl >= 0) fetch(sl);
                 }
-                if (b == e) sfor<3>([&](auto rc) { f[rc] += eF[rc]; t[rc] += eT[rc]; });
+                if constexpr (EE >= 0) {
+                    if constexpr (b == R::body[EE]) sfor<3>([&](auto rc) { f[rc] += eF[rc]; t[rc] += eT[rc]; });
+                } else {
+                    if (b == e) sfor<3>([&](auto rc) { f[rc] += eF[rc]; t[rc] += eT[rc]; });
+                }
             }, pass, [&](int c, float g) { grow[c] = g; });
         }
     }
@@ -723,7 +731,8 @@ struct CMInfo {
 #define TRK_CM_MINBLOCKS 4
 #endif
 // EE: processing position of the end-effector body when it is known at compile time (the host passes it when the cost
-// tables name the robot's last body, e.g. Panda's ee_link), -1 = chosen at run time (a compare + predicated copies per body)
+// tables name the collision model's own EE body, e.g. Panda's ee_link), -1 = chosen at run time (a compare + predicated
+// copies per body)
 template <class R, class CM, bool WANT_GRAD, bool CLAMP, int EE = -1>
 __global__ void __launch_bounds__(kSBlock, TRK_CM_MINBLOCKS) k_objective_cm(const float* __restrict__ cost_words, int cost_nwords,
                                                              const float* __restrict__ q, long long n,
@@ -1185,12 +1194,12 @@ cudaError_t launch_fk_backward_t(int n_sms, const float* q, long long n, const S
     return cudaGetLastError();
 }
 
-template <class R, bool WANT_GRAD, bool CLAMP, class CM = void>
+template <class R, bool WANT_GRAD, bool CLAMP, class CM = void, int EE = -1>
 inline cudaError_t launch_objective_k(int n_sms, const float* cost_words, int cost_nwords, int n_slots, const float* q, long long n,
                                       const float* ee_target_cfg, float margin_override, int use_override, float* cost_total,
                                       float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin, cudaStream_t st) {
     const size_t smem = ((size_t)cost_nwords + (size_t)6 * n_slots * kSBlock) * sizeof(float);
-    auto k = k_objective_static<R, WANT_GRAD, CLAMP, CM>;
+    auto k = k_objective_static<R, WANT_GRAD, CLAMP, CM, EE>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -1224,13 +1233,19 @@ cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwor
     if constexpr (!std::is_void<CM>::value) {
         if (cm_match) {
             if constexpr (CollisionModelOf<R>::in_registers) {
-                if (cm_match == 2 && !clamp_any) {   // EE = the robot's last body: compile-time end-effector
-                    if (grad_q) return launch_objective_cm_k<R, CM, true, false, R::L - 1>(TRK_OBJ_ARGS);
-                    return launch_objective_cm_k<R, CM, false, false, R::L - 1>(TRK_OBJ_ARGS);
+                if (cm_match == 2 && !clamp_any) {   // the end-effector is the model's own EE body: known at compile time
+                    constexpr int kEE = STree<R>::topo_index_of(CM::ee_body);
+                    if (grad_q) return launch_objective_cm_k<R, CM, true, false, kEE>(TRK_OBJ_ARGS);
+                    return launch_objective_cm_k<R, CM, false, false, kEE>(TRK_OBJ_ARGS);
                 }
                 if (grad_q) return clamp_any ? launch_objective_cm_k<R, CM, true, true>(TRK_OBJ_ARGS) : launch_objective_cm_k<R, CM, true, false>(TRK_OBJ_ARGS);
                 return clamp_any ? launch_objective_cm_k<R, CM, false, true>(TRK_OBJ_ARGS) : launch_objective_cm_k<R, CM, false, false>(TRK_OBJ_ARGS);
             } else {
+                if (cm_match == 2 && !clamp_any) {
+                    constexpr int kEE = STree<R>::topo_index_of(CM::ee_body);
+                    if (grad_q) return launch_objective_k<R, true, false, CM, kEE>(TRK_OBJ_ARGS_S);
+                    return launch_objective_k<R, false, false, CM, kEE>(TRK_OBJ_ARGS_S);
+                }
                 if (grad_q) return clamp_any ? launch_objective_k<R, true, true, CM>(TRK_OBJ_ARGS_S) : launch_objective_k<R, true, false, CM>(TRK_OBJ_ARGS_S);
                 return clamp_any ? launch_objective_k<R, false, true, CM>(TRK_OBJ_ARGS_S) : launch_objective_k<R, false, false, CM>(TRK_OBJ_ARGS_S);
             }
@@ -1293,20 +1308,26 @@ inline cudaError_t launch_static_fk_backward(int family, int n_sms, const float*
     return cudaErrorInvalidValue;
 }
 
+template <class CM>
+inline int cm_match_value(const float* host_cost_words) {
+    if constexpr (std::is_void<CM>::value) {
+        return 0;
+    } else {
+        if (!cost_matches_cm<CM>(host_cost_words)) return 0;
+        const CostHeader* hh = reinterpret_cast<const CostHeader*>(host_cost_words);
+        return (hh->ee_enabled && hh->ee_link == CM::ee_body) ? 2 : 1;
+    }
+}
+
 // > 0 when `family` has a compile-time collision model and the (host copy of the) cost table matches it;
-// 2 when, in addition, the end-effector term is enabled on the robot's last body
+// 2 when, in addition, the end-effector term is enabled on the model's own EE body (CM::ee_body)
 inline int static_cm_match(int family, const float* host_cost_words) {
     int id = 0;
 #define X(Rb)                                                                          \
     ++id;                                                                              \
     if (family == id) {                                                                \
         using CM = typename CollisionModelOf<Rb>::type;                                \
-        if constexpr (!std::is_void<CM>::value) {                                      \
-            if (!cost_matches_cm<CM>(host_cost_words)) return 0;                       \
-            const CostHeader* hh = reinterpret_cast<const CostHeader*>(host_cost_words); \
-            return (hh->ee_enabled && hh->ee_link == Rb::body[Rb::L - 1]) ? 2 : 1;     \
-        }                                                                              \
-        return 0;                                                                      \
+        return cm_match_value<CM>(host_cost_words);                                   \
     }
     TRK_FOR_EACH_STATIC_ROBOT(X)
 #undef X
