@@ -948,7 +948,8 @@ struct IKParams {
     float target[16];
 };
 
-template <class R>
+// EE: processing position of the end-effector body when it is the robot's last body (the usual choice), -1 = run time
+template <class R, int EE = -1>
 __global__ void __launch_bounds__(kSBlock) k_ik_adam_static(IKParams P, const float* __restrict__ step_size, const float* __restrict__ bc2_sqrt,
                                                             const float* __restrict__ target_seed, long long n_seeds,
                                                             float* __restrict__ q_io, float* __restrict__ err_out,
@@ -988,7 +989,11 @@ __global__ void __launch_bounds__(kSBlock) k_ik_adam_static(IKParams P, const fl
                 STree<R>::template joint_axis<i>(wp, w, JA[qi]);
                 PJ[qi][0] = w[9]; PJ[qi][1] = w[10]; PJ[qi][2] = w[11];
             }
-            if (b == P.ee_link) sfor<12>([&](auto kc) { Wee[kc] = w[kc]; });
+            if constexpr (EE >= 0) {
+                if constexpr (i == EE) sfor<12>([&](auto kc) { Wee[kc] = w[kc]; });
+            } else {
+                if (b == P.ee_link) sfor<12>([&](auto kc) { Wee[kc] = w[kc]; });
+            }
         });
         float gR[9], gp[3];
         err = ee_term<true>(&ee, Wee, &Wee[9], Rt, pt, gR, gp);       // SE3_distance, un-squared, weights 1
@@ -1063,8 +1068,12 @@ cudaError_t launch_ik_t(const IKParams& P, const float* step_size, const float* 
                                long long n_seeds, float* q_io, float* err_out, uint8_t* valid_out, int* valid_count,
                                float* loss_sum, float* loss_sqsum, cudaStream_t st) {
     const long long blocks = (n_seeds + kSBlock - 1) / kSBlock;
-    k_ik_adam_static<R><<<(unsigned)blocks, kSBlock, 0, st>>>(P, step_size, bc2_sqrt, target_seed, n_seeds, q_io, err_out, valid_out,
-                                                             valid_count, loss_sum, loss_sqsum);
+    if (P.ee_link == R::body[R::L - 1])
+        k_ik_adam_static<R, R::L - 1><<<(unsigned)blocks, kSBlock, 0, st>>>(P, step_size, bc2_sqrt, target_seed, n_seeds, q_io, err_out,
+                                                                          valid_out, valid_count, loss_sum, loss_sqsum);
+    else
+        k_ik_adam_static<R><<<(unsigned)blocks, kSBlock, 0, st>>>(P, step_size, bc2_sqrt, target_seed, n_seeds, q_io, err_out, valid_out,
+                                                                 valid_count, loss_sum, loss_sqsum);
     return cudaGetLastError();
 }
 
