@@ -235,6 +235,8 @@ def main():
     if world > 1:
         # stdout carries exactly one JSON line: NCCL's own version / debug banner goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # this level printf()s the banner straight to stdout
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     desc, cost = panda_objective_descriptors()
