@@ -733,7 +733,9 @@ struct CMInfo {
 // EE: processing position of the end-effector body when it is known at compile time (the host passes it when the cost
 // tables name the collision model's own EE body, e.g. Panda's ee_link), -1 = chosen at run time (a compare + predicated
 // copies per body)
-template <class R, class CM, bool WANT_GRAD, bool CLAMP, int EE = -1>
+// HOT: the host has checked that the scene is one equal-radius identity-pose sphere object, so only the joint-scan path
+// is compiled in (a smaller instruction footprint for the common case)
+template <class R, class CM, bool WANT_GRAD, bool CLAMP, int EE = -1, bool HOT = false>
 __global__ void __launch_bounds__(kSBlock, TRK_CM_MINBLOCKS) k_objective_cm(const float* __restrict__ cost_words, int cost_nwords,
                                                              const float* __restrict__ q, long long n,
                                                              const float* __restrict__ ee_target_cfg, float margin_override,
@@ -815,7 +817,7 @@ __global__ void __launch_bounds__(kSBlock, TRK_CM_MINBLOCKS) k_objective_cm(cons
         // one equal-radius identity-pose sphere object (EnvSpheres3D and most scenes): scan it for all points at once,
         // then finish every point from registers (static indices: the points' exact evaluations and workspace terms are
         // independent chains the scheduler can interleave); any other scene takes the table-driven loop below
-        const bool joint_scan = !CLAMP && single_uniform_identity_object(cv);
+        const bool joint_scan = HOT || (!CLAMP && single_uniform_identity_object(cv));
         if (joint_scan) {
             float X[CM::S][3];
             unsigned pre[CM::S];
@@ -837,6 +839,8 @@ __global__ void __launch_bounds__(kSBlock, TRK_CM_MINBLOCKS) k_objective_cm(cons
                 }
                 if (WANT_GRAD) { G[b][0] += gx; G[b][1] += gy; G[b][2] += gz; }
             });
+        } else if constexpr (HOT) {
+            // unreachable: the host only selects this instantiation for the joint-scan scene
         } else if (!CLAMP && all_uniform_identity_objects(cv)) {
             // several equal-radius identity-pose sphere objects: one joint scan per object
             joint_points_terms_multi<WANT_GRAD, CLAMP, 0, CM::S>(
@@ -1218,12 +1222,12 @@ inline cudaError_t launch_objective_k(int n_sms, const float* cost_words, int co
     return cudaGetLastError();
 }
 
-template <class R, class CM, bool WANT_GRAD, bool CLAMP, int EE = -1>
+template <class R, class CM, bool WANT_GRAD, bool CLAMP, int EE = -1, bool HOT = false>
 inline cudaError_t launch_objective_cm_k(int n_sms, const float* cost_words, int cost_nwords, const float* q, long long n,
                                          const float* ee_target_cfg, float margin_override, int use_override, float* cost_total,
                                          float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin, cudaStream_t st) {
     const size_t smem = ((size_t)cost_nwords + (size_t)3 * CM::S * kSBlock) * sizeof(float);
-    auto k = k_objective_cm<R, CM, WANT_GRAD, CLAMP, EE>;
+    auto k = k_objective_cm<R, CM, WANT_GRAD, CLAMP, EE, HOT>;
     k<<<persistent_grid(k, n_sms, smem, n), kSBlock, smem, st>>>(cost_words, cost_nwords, q, n, ee_target_cfg, margin_override,
                                                                  use_override, cost_total, cost_terms, grad_q, occupancy, argmin);
     return cudaGetLastError();
@@ -1242,15 +1246,16 @@ cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwor
     if constexpr (!std::is_void<CM>::value) {
         if (cm_match) {
             if constexpr (CollisionModelOf<R>::in_registers) {
-                if (cm_match == 2 && !clamp_any) {   // the end-effector is the model's own EE body: known at compile time
+                if ((cm_match & 2) && !clamp_any) {   // the end-effector is the model's own EE body: known at compile time
                     constexpr int kEE = STree<R>::topo_index_of(CM::ee_body);
+                    if ((cm_match & 4) && grad_q) return launch_objective_cm_k<R, CM, true, false, kEE, true>(TRK_OBJ_ARGS);   // + joint-scan scene
                     if (grad_q) return launch_objective_cm_k<R, CM, true, false, kEE>(TRK_OBJ_ARGS);
                     return launch_objective_cm_k<R, CM, false, false, kEE>(TRK_OBJ_ARGS);
                 }
                 if (grad_q) return clamp_any ? launch_objective_cm_k<R, CM, true, true>(TRK_OBJ_ARGS) : launch_objective_cm_k<R, CM, true, false>(TRK_OBJ_ARGS);
                 return clamp_any ? launch_objective_cm_k<R, CM, false, true>(TRK_OBJ_ARGS) : launch_objective_cm_k<R, CM, false, false>(TRK_OBJ_ARGS);
             } else {
-                if (cm_match == 2 && !clamp_any) {
+                if ((cm_match & 2) && !clamp_any) {
                     constexpr int kEE = STree<R>::topo_index_of(CM::ee_body);
                     if (grad_q) return launch_objective_k<R, true, false, CM, kEE>(TRK_OBJ_ARGS_S);
                     return launch_objective_k<R, false, false, CM, kEE>(TRK_OBJ_ARGS_S);
@@ -1324,12 +1329,17 @@ inline int cm_match_value(const float* host_cost_words) {
     } else {
         if (!cost_matches_cm<CM>(host_cost_words)) return 0;
         const CostHeader* hh = reinterpret_cast<const CostHeader*>(host_cost_words);
-        return (hh->ee_enabled && hh->ee_link == CM::ee_body) ? 2 : 1;
+        const int* iw = reinterpret_cast<const int*>(host_cost_words);
+        const int need = OBJ_IDENTITY | OBJ_UNIFORM_RADIUS;
+        const bool joint_scene = hh->nObj == 1 && hh->KB == 0 && (iw[hh->off_obj_ident] & (need | OBJ_GRID)) == need &&
+                                 iw[hh->off_obj_start + 1] > iw[hh->off_obj_start];
+        return 1 | ((hh->ee_enabled && hh->ee_link == CM::ee_body) ? 2 : 0) | (joint_scene ? 4 : 0);
     }
 }
 
 // > 0 when `family` has a compile-time collision model and the (host copy of the) cost table matches it;
-// 2 when, in addition, the end-effector term is enabled on the model's own EE body (CM::ee_body)
+// bit 1: the end-effector term is enabled on the model's own EE body (CM::ee_body); bit 2: the scene is one equal-radius
+// identity-pose sphere object (the joint-scan scene)
 inline int static_cm_match(int family, const float* host_cost_words) {
     int id = 0;
 #define X(Rb)                                                                          \
