@@ -730,13 +730,16 @@ struct CMInfo {
 #ifndef TRK_CM_MINBLOCKS
 #define TRK_CM_MINBLOCKS 4
 #endif
+#ifndef TRK_CM_HOT_MINBLOCKS
+#define TRK_CM_HOT_MINBLOCKS 4
+#endif
 // EE: processing position of the end-effector body when it is known at compile time (the host passes it when the cost
 // tables name the collision model's own EE body, e.g. Panda's ee_link), -1 = chosen at run time (a compare + predicated
 // copies per body)
 // HOT: the host has checked that the scene is one equal-radius identity-pose sphere object, so only the joint-scan path
 // is compiled in (a smaller instruction footprint for the common case)
 template <class R, class CM, bool WANT_GRAD, bool CLAMP, int EE = -1, bool HOT = false>
-__global__ void __launch_bounds__(kSBlock, TRK_CM_MINBLOCKS) k_objective_cm(const float* __restrict__ cost_words, int cost_nwords,
+__global__ void __launch_bounds__(kSBlock, HOT ? TRK_CM_HOT_MINBLOCKS : TRK_CM_MINBLOCKS) k_objective_cm(const float* __restrict__ cost_words, int cost_nwords,
                                                              const float* __restrict__ q, long long n,
                                                              const float* __restrict__ ee_target_cfg, float margin_override,
                                                              int use_override, float* __restrict__ cost_total,
