@@ -18,11 +18,15 @@ DEV = "cuda:0"
 @pytest.fixture(scope="module")
 def generic_models():
     from torch_robotics_b200._lib import DeviceModel
+    before = os.environ.get("TRK_B200_FORCE_GENERIC")
     os.environ["TRK_B200_FORCE_GENERIC"] = "1"
     try:
         models = {r: DeviceModel(get_desc(r), DEV) for r in ROBOT_NAMES}
     finally:
-        del os.environ["TRK_B200_FORCE_GENERIC"]
+        if before is None:
+            del os.environ["TRK_B200_FORCE_GENERIC"]
+        else:
+            os.environ["TRK_B200_FORCE_GENERIC"] = before      # the whole suite may be run with the switch set
     for m in models.values():
         assert m.kernel_family == "generic"
     return models
