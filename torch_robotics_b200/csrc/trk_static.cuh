@@ -717,6 +717,13 @@ __global__ void __launch_bounds__(kSBlock, 4) k_objective_static(const float* __
 // shared-memory columns, no table-driven body indexing.  Margins, obstacle spheres, workspace box, EE
 // target and weights remain runtime data.  Used when the cost tables handed to trk_cost_create list
 // exactly CM's points and pairs (RobotPanda's model); any other table takes k_objective_static.
+// Collision-point section, by scene (decided per launch, warp-uniform):
+//   one equal-radius identity-pose sphere object  -> joint scan of all points + finish from registers (the headline path)
+//   several such objects                          -> one joint scan per object, per-point maximum in registers
+//   one voxel SDF (general-tables variant)        -> all cell gathers issued back to back
+//   anything else (boxes, posed objects, relu)    -> the points loop through a small shared-memory column so that the
+//                                                    large general point code exists once
+// Template switches: EE (end-effector position known at compile time), HOT (only the first path is compiled in).
 // ------------------------------------------------------------------------------------------
 template <class CM, int L>
 struct CMInfo {
