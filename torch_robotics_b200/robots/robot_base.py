@@ -4,7 +4,6 @@ object-collision points and their radii, and which body pairs are checked agains
 from __future__ import annotations
 
 import abc
-import itertools
 from abc import ABC
 from math import ceil
 
@@ -12,6 +11,12 @@ import torch
 
 from ..torch_planning_objectives.fields.distance_fields import CollisionSelfField
 from ..torch_utils.torch_utils import to_numpy, to_torch
+
+
+def _points_per_link(requested: int, n_links: int) -> int:
+    """Interpolated points per link: the requested total rounded up to a multiple of the link count (robot_base.py:57-64)."""
+    assert requested >= n_links
+    return ceil(requested / n_links)
 
 
 class RobotBase(ABC):
@@ -33,88 +38,110 @@ class RobotBase(ABC):
         robot_base.py sets up, checked against the reference's SDF primitives in tests/golden."""
         if grasped_object is not None and grasped_object_point_idxs is None:
             raise NotImplementedError("this robot does not attach grasped-object points to its kinematic tree")
-        self.name = name
-        self.tensor_args = tensor_args
-        self.dt = dt
         assert q_limits is not None, "q_limits cannot be None"
+        self.name, self.tensor_args, self.dt = name, tensor_args, dt
+        self._init_configuration_space(q_limits)
+        self.grasped_object = grasped_object
+        self.grasped_object_point_idxs = [] if grasped_object is None else [int(i) for i in grasped_object_point_idxs]
+        assert len(self.grasped_object_point_idxs) == (0 if grasped_object is None else grasped_object.n_base_points_for_collision)
+        self.margin_for_grasped_object_collision_checking = margin_for_grasped_object_collision_checking
+        self.self_collision_margin_robot = self_collision_margin_robot
+        self._init_object_collision_model(link_names_for_object_collision_checking, link_margins_for_object_collision_checking,
+                                          link_idxs_for_object_collision_checking,
+                                          num_interpolated_points_for_object_collision_checking)
+        self.df_collision_self = None
+        if link_names_for_self_collision_checking is not None:
+            self._init_self_collision_model(link_names_for_self_collision_checking, link_names_pairs_for_self_collision_checking,
+                                            link_idxs_for_self_collision_checking,
+                                            link_names_for_self_collision_checking_with_grasped_object,
+                                            self_collision_margin_grasped_object,
+                                            num_interpolated_points_for_self_collision_checking)
+
+    # ---------------------------------------------------------------------------------- construction helpers
+    def _init_configuration_space(self, q_limits):
         self.q_limits = q_limits
         self.q_min, self.q_max = q_limits[0], q_limits[1]
         self.q_min_np, self.q_max_np = to_numpy(self.q_min), to_numpy(self.q_max)
-        self.q_distribution = torch.distributions.uniform.Uniform(self.q_min, self.q_max)
         self.q_dim = len(self.q_min)
-        self.grasped_object = grasped_object
-        n_grasped = 0 if grasped_object is None else grasped_object.n_base_points_for_collision
-        grasped_idxs = [] if grasped_object is None else [int(i) for i in grasped_object_point_idxs]
-        assert len(grasped_idxs) == n_grasped
-        self.grasped_object_point_idxs = grasped_idxs
-        self.margin_for_grasped_object_collision_checking = margin_for_grasped_object_collision_checking
+        self.q_distribution = torch.distributions.uniform.Uniform(self.q_min, self.q_max)
 
-        # ---- object-collision points: one per listed link (points_per_link == 1 in every shipped robot)
-        n_links_obj = len(link_names_for_object_collision_checking)
-        assert num_interpolated_points_for_object_collision_checking >= n_links_obj
-        per_link = ceil(num_interpolated_points_for_object_collision_checking / n_links_obj)
+    def _init_object_collision_model(self, names, radii, body_idxs, n_points_requested):
+        """Collision points against obstacles / workspace: one sphere per listed link origin (every shipped robot has
+        exactly one point per link), then the grasped object's points with their own small margin."""
+        per_link = _points_per_link(n_points_requested, len(names))
         self.points_per_link_object_collision_checking = per_link
-        self.num_interpolated_points_for_object_collision_checking = per_link * n_links_obj
-        self.self_collision_margin_robot = self_collision_margin_robot
-        self.link_names_for_object_collision_checking = link_names_for_object_collision_checking
-        self.n_links_for_object_collision_checking = n_links_obj
-        self.link_margins_for_object_collision_checking = link_margins_for_object_collision_checking
-        self.link_margins_for_object_collision_checking_robot_tensor = torch.tensor(
-            link_margins_for_object_collision_checking, **tensor_args).repeat_interleave(per_link)
-        self.link_margins_for_object_collision_checking_tensor = self.link_margins_for_object_collision_checking_robot_tensor
-        if n_grasped:
-            self.link_margins_for_object_collision_checking_tensor = torch.cat(
-                (self.link_margins_for_object_collision_checking_tensor,
-                 torch.ones(n_grasped, **tensor_args) * margin_for_grasped_object_collision_checking))
-        self.link_idxs_for_object_collision_checking = link_idxs_for_object_collision_checking
+        self.num_interpolated_points_for_object_collision_checking = per_link * len(names)
+        self.link_names_for_object_collision_checking = names
+        self.n_links_for_object_collision_checking = len(names)
+        self.link_margins_for_object_collision_checking = radii
+        self.link_idxs_for_object_collision_checking = body_idxs
+        robot_radii = torch.tensor(radii, **self.tensor_args).repeat_interleave(per_link)
+        self.link_margins_for_object_collision_checking_robot_tensor = robot_radii
+        n_grasped = len(self.grasped_object_point_idxs)
+        grasp_radii = torch.full((n_grasped,), 1.0, **self.tensor_args) * self.margin_for_grasped_object_collision_checking
+        self.link_margins_for_object_collision_checking_tensor = torch.cat((robot_radii, grasp_radii)) if n_grasped else robot_radii
         # columns of fk_map_collision() the object / workspace fields read: the links, then the grasped points
-        self.point_idxs_for_object_collision_checking = list(link_idxs_for_object_collision_checking) + grasped_idxs
+        self.point_idxs_for_object_collision_checking = list(body_idxs) + self.grasped_object_point_idxs
 
-        # ---- self-collision pairs (robot_base.py:87-141)
-        if link_names_for_self_collision_checking is None:
-            self.df_collision_self = None
-            return
-        n_links_self = len(link_names_for_self_collision_checking)
-        assert num_interpolated_points_for_self_collision_checking >= n_links_self
-        p = ceil(num_interpolated_points_for_self_collision_checking / n_links_self)
+    def _init_self_collision_model(self, names, pairs_by_name, body_idxs, names_vs_grasped, margin_grasped, n_points_requested):
+        """Self-collision pairs as (row, row) indices into the list [links..., grasped points...] (robot_base.py:87-141),
+        with one margin per pair."""
+        p = _points_per_link(n_points_requested, len(names))
         self.points_per_link_self_collision_checking = p
-        self.link_names_for_self_collision_checking = link_names_for_self_collision_checking
-        self.link_names_pairs_for_self_collision_checking = link_names_pairs_for_self_collision_checking
-        self.link_idxs_for_self_collision_checking = link_idxs_for_self_collision_checking
-        self.link_names_for_self_collision_checking_with_grasped_object = link_names_for_self_collision_checking_with_grasped_object
-        self.self_collision_margin_grasped_object = self_collision_margin_grasped_object
-        pair_idxs = []
-        for i, link_1 in enumerate(link_names_for_self_collision_checking):
-            for link_2 in link_names_pairs_for_self_collision_checking.get(link_1, []):
-                j = link_names_for_self_collision_checking.index(link_2)
-                pair_idxs.extend((i * p + m, j * p + n) for m, n in itertools.product(range(p), range(p)))
-        margin_list = [self_collision_margin_robot] * len(pair_idxs)
-        rows = list(link_idxs_for_self_collision_checking)
-        if n_grasped:
-            last_row = n_links_self * p
-            for link_1 in link_names_for_self_collision_checking_with_grasped_object:
-                j = link_names_for_self_collision_checking.index(link_1)
-                extra = [(last_row + m, j * p + n) for m, n in itertools.product(range(n_grasped), range(p))]
-                pair_idxs.extend(extra)
-                margin_list.extend([self_collision_margin_grasped_object] * len(extra))
-            rows = rows + grasped_idxs
-        margins = to_torch(margin_list, **tensor_args)
-        self.df_collision_self = CollisionSelfField(
-            self, link_idxs_for_collision_checking=rows,
-            idxs_links_distance_matrix=pair_idxs, num_interpolated_points=p * n_links_self,
-            cutoff_margin=margins, tensor_args=tensor_args)
+        self.link_names_for_self_collision_checking = names
+        self.link_names_pairs_for_self_collision_checking = pairs_by_name
+        self.link_idxs_for_self_collision_checking = body_idxs
+        self.link_names_for_self_collision_checking_with_grasped_object = names_vs_grasped
+        self.self_collision_margin_grasped_object = margin_grasped
+        row_of = {n: k for k, n in enumerate(names)}
 
+        def block(rows_a, rows_b):
+            return [(a, b) for a in rows_a for b in rows_b]
+
+        pair_rows, pair_margins = [], []
+        for first in names:
+            for second in pairs_by_name.get(first, []):
+                new = block(range(row_of[first] * p, (row_of[first] + 1) * p), range(row_of[second] * p, (row_of[second] + 1) * p))
+                pair_rows += new
+                pair_margins += [self.self_collision_margin_robot] * len(new)
+        rows = list(body_idxs)
+        n_grasped = len(self.grasped_object_point_idxs)
+        if n_grasped:
+            first_grasp_row = len(names) * p
+            for link in names_vs_grasped:
+                new = block(range(first_grasp_row, first_grasp_row + n_grasped), range(row_of[link] * p, (row_of[link] + 1) * p))
+                pair_rows += new
+                pair_margins += [margin_grasped] * len(new)
+            rows += self.grasped_object_point_idxs
+        self.df_collision_self = CollisionSelfField(
+            self, link_idxs_for_collision_checking=rows, idxs_links_distance_matrix=pair_rows,
+            num_interpolated_points=p * len(names), cutoff_margin=to_torch(pair_margins, **self.tensor_args),
+            tensor_args=self.tensor_args)
+
+    # ---------------------------------------------------------------------------------- state helpers
     def random_q(self, n_samples=10):
         return self.q_distribution.sample((n_samples,))
 
     def get_position(self, x):
-        return x[..., :self.q_dim]
+        return self._state_block(x, 0)
+
+    def _state_block(self, x, k):
+        return x[..., k * self.q_dim:(k + 1) * self.q_dim]
 
     def get_velocity(self, x):
-        return x[..., self.q_dim:2 * self.q_dim]
+        """Velocity block of the state; a position-only trajectory is differentiated (central differences, self.dt)."""
+        v = self._state_block(x, 1)
+        if x.nelement() != 0 and v.nelement() == 0:
+            from ..trajectory.utils import finite_difference_vector
+            return finite_difference_vector(x, dt=self.dt, method="central")
+        return v
 
     def get_acceleration(self, x):
-        return x[..., 2 * self.q_dim:3 * self.q_dim]
+        a = self._state_block(x, 2)
+        if x.nelement() != 0 and a.nelement() == 0:
+            from ..trajectory.utils import finite_difference_vector
+            return finite_difference_vector(self.get_velocity(x), dt=self.dt, method="central")
+        return a
 
     def distance_q(self, q1, q2):
         return torch.linalg.norm(q1 - q2, dim=-1)

@@ -6,9 +6,10 @@ import torch
 
 
 def fix_random_seed(seed):
-    random.seed(seed)
-    np.random.seed(seed)
-    torch.manual_seed(seed)
+    """Seed python, numpy and torch (CPU and CUDA generators); cuDNN autotuning off so that runs repeat."""
+    seed = int(seed)
+    for seeder in (random.seed, np.random.seed, torch.manual_seed):
+        seeder(seed)
     if torch.cuda.is_available():
-        torch.cuda.manual_seed(seed)
+        torch.cuda.manual_seed_all(seed)
     torch.backends.cudnn.benchmark = False

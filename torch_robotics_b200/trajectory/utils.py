@@ -15,3 +15,18 @@ def interpolate_traj_via_points(trajs, num_interpolation=10):
     a, b = trajs[..., :-1, None, :], trajs[..., 1:, None, :]
     out = a * alpha + b * (1 - alpha)
     return out.reshape(trajs.shape[:-2] + (-1, D))
+
+
+def finite_difference_vector(x, dt=1., method="forward"):
+    """Time derivative of a trajectory x [..., H, D] by finite differences along the horizon; border rows that have no
+    neighbour on the needed side stay zero (reference: trajectory/utils.py:53-64)."""
+    out = torch.zeros_like(x)
+    if method == "forward":
+        out[..., :-1, :] = (x[..., 1:, :] - x[..., :-1, :]) / dt
+    elif method == "backward":
+        out[..., 1:, :] = (x[..., 1:, :] - x[..., :-1, :]) / dt
+    elif method == "central":
+        out[..., 1:-1, :] = (x[..., 2:, :] - x[..., :-2, :]) / (2 * dt)
+    else:
+        raise NotImplementedError(method)
+    return out
