@@ -493,6 +493,26 @@ def golden_attached_points():
     _point_model_case("panda_sphere_model", q, pos_fn, list(range(len(names), len(names) + len(spheres))), radii, env, 0.01,
                       extra=dict(sphere_links=np.array([l for l, _ in spheres]), sphere_offsets=offs.numpy()))
 
+    # (3) the Tiago sphere model (data/configs/tiago/tiago_sphere_config.yaml: [x, y, z, radius, group] per link) on the
+    # branching dual-arm holonomic-base robot: sphere centres and their Jacobian-free gradient path through a 19-link tree
+    cfg = yaml.safe_load(open("/root/reference/torch_robotics/data/configs/tiago/tiago_sphere_config.yaml"))
+    model = quiet(ROBOTS["tiago_dual_holo"])
+    tnames = model.get_link_names()
+    tsph = [(l, s) for l, lst in cfg.items() if isinstance(lst, list) and l in tnames for s in lst]
+    toffs = torch.tensor([s[:3] for _, s in tsph], **TA)
+    tradii = torch.tensor([s[3] for _, s in tsph], **TA)
+
+    def tiago_pos(qq):
+        shp = qq.shape
+        frames = model.compute_forward_kinematics_all_links(qq.reshape(-1, shp[-1]), return_dict=True)
+        link_pos = torch.stack([frames[n].translation for n in tnames], dim=-2)
+        pts = torch.stack([frames[l].transform_point(toffs[i:i + 1]).reshape(-1, 3) for i, (l, _) in enumerate(tsph)], dim=-2)
+        return torch.cat((link_pos, pts), dim=-2).reshape(*shp[:-1], len(tnames) + len(tsph), 3)
+
+    qt = sample_q(model, 64, gen).reshape(8, 8, -1).contiguous()
+    _point_model_case("tiago_sphere_model", qt, tiago_pos, list(range(len(tnames), len(tnames) + len(tsph))), tradii, env, 0.01,
+                      extra=dict(sphere_links=np.array([l for l, _ in tsph]), sphere_offsets=toffs.numpy()))
+
 
 def golden_voxel_sdf():
     """EnvBase(precompute_sdf_obj_fixed=True) replaces the fixed objects by a GridMapSDF

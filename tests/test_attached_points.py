@@ -152,3 +152,52 @@ def test_gpu_bit_exact_masks_vs_oracle(case):
     assert rel_err(out["total"].cpu().numpy(), o["total"]) < 1e-5
     gd = np.abs(out["grad_q"].cpu().numpy() - o["grad_q"]).max(axis=1) / np.abs(o["grad_q"]).max()
     assert (gd >= 1e-4).sum() <= 30 and gd[gd < 1e-4].max() < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------- Tiago sphere model
+def tiago_with_spheres():
+    """tiago_dual_holo (19 links, two arms) + the 14 spheres of data/configs/tiago, attached as points."""
+    import os
+    from conftest import get_desc
+    from torch_robotics_b200.descriptor import attach_points, build_cost_descriptor, load_sphere_config
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spheres = load_sphere_config(os.path.join(root, "torch_robotics_b200", "data", "configs", "tiago", "tiago_sphere_config.json"))
+    d, ids = attach_points(get_desc("tiago_dual_holo"), [(s[0], s[1]) for s in spheres])
+    return d, ids, spheres, build_cost_descriptor
+
+
+def tiago_cost(g, ids, spheres, build):
+    return build(pt_link=ids, pt_radius=np.array([s[2] for s in spheres], np.float32), cutoff_obj=float(g["cutoff"]),
+                 objects=[(g["centers"], g["radii"], None, None)], ws_min=g["ws_min"], ws_max=g["ws_max"])
+
+
+def test_tiago_sphere_model_oracle_matches_reference():
+    g = load_golden("points_tiago_sphere_model")
+    d, ids, spheres, build = tiago_with_spheres()
+    assert ids == list(g["pt_cols"]) and [s[0] for s in spheres] == list(g["sphere_links"])
+    assert np.array_equal(d.trans[ids], g["sphere_offsets"]) and np.array_equal(np.array([s[2] for s in spheres], np.float32), g["pt_radius"])
+    cost = tiago_cost(g, ids, spheres, build)
+    q = g["q"].reshape(-1, d.n_dofs)
+    for o in (orc.objective(d, cost, q, dtype=np.float32), co.objective(co.Tree(d), co.Cost(cost), q)):
+        if "pw" in o:
+            assert rel_err(o["pw"], g["link_pos"].reshape(q.shape[0], -1, 3)) < 1e-5
+        assert rel_err(o["terms"][:, 1], g["cost_obj"].reshape(-1)) < 1e-5
+        assert rel_err(o["terms"][:, 2], g["cost_ws"].reshape(-1)) < 1e-5
+        assert rel_err(o["grad_q"], g["grad_total"].reshape(-1, d.n_dofs)) < 1e-4
+        assert np.mean(((o["occ"] >> 1) & 1) != g["occ_obj"].reshape(-1)) < 0.02
+
+
+@pytest.mark.gpu
+def test_gpu_tiago_sphere_model_matches_reference():
+    from torch_robotics_b200._lib import DeviceCost, DeviceModel
+    g = load_golden("points_tiago_sphere_model")
+    d, ids, spheres, build = tiago_with_spheres()
+    m = DeviceModel(d, "cuda:0")
+    assert m.kernel_family == "generic"
+    q = torch.as_tensor(g["q"].reshape(-1, d.n_dofs), device="cuda:0")
+    H = m.fk_forward(q)
+    assert rel_err(H[:, :, :3, 3].cpu().numpy(), g["link_pos"].reshape(q.shape[0], -1, 3)) < 1e-5
+    r = DeviceCost(m, tiago_cost(g, ids, spheres, build)).objective(q, want_terms=True, want_occupancy=True)
+    assert rel_err(r["terms"][:, 1].cpu().numpy(), g["cost_obj"].reshape(-1)) < 1e-5
+    assert rel_err(r["terms"][:, 2].cpu().numpy(), g["cost_ws"].reshape(-1)) < 1e-5
+    assert rel_err(r["grad_q"].cpu().numpy(), g["grad_total"].reshape(-1, d.n_dofs)) < 1e-4
