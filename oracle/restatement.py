@@ -12,6 +12,9 @@ What is restated (all citations relative to /root/reference/torch_robotics):
                                                    :194-215, :283-291, :307-332; environments/primitives.py:108-112,:387-405
   * EE SE(3) distance                              geometrics/utils.py:130-154,:209-224; distance_fields.py:347-356
   * IK loss / termination / Adam loop              models/robot_tree.py:303-442
+  * boxes / rounded boxes, posed objects           environments/primitives.py:198-334, :387-405
+  * voxel SDF lookup with surrogate gradient       environments/grid_map_sdf.py:96-112
+  * link Jacobians (position + quaternion)         models/robot_tree.py:250-265, geometrics/quaternion.py:135-166
   * reverse mode: the reference relies on autograd; the analytic form restated here is the one
     SURVEY.md section 8(a) derives (per-link wrench accumulated leaf->root).
 
