@@ -1107,7 +1107,7 @@ int trk_objective(const trk_model* m, const trk_cost* c, const float* q, int64_t
     if (m->family && trk::static_objective_supported(m->family)) {
         const CostHeader* hh = reinterpret_cast<const CostHeader*>(c->h_words.data());
         const int clamp_any = hh->clamp_self | hh->clamp_obj | hh->clamp_ws | (hh->KB > 0 ? 1 : 0) | (hh->grid_obj >= 0 ? 1 : 0);   // general-tables variant
-        cudaError_t e = trk::launch_static_objective(m->family, m->n_sms, c->d_words, c->nwords, c->n_slots, clamp_any, c->cm_match, q, n, ee_target_cfg,
+        cudaError_t e = trk::launch_static_objective(m->family, m->n_sms, c->h_words.data(), c->d_words, c->nwords, c->n_slots, clamp_any, c->cm_match, q, n, ee_target_cfg,
                                                      margin_override, use_override, cost_total, cost_terms, grad_q,
                                                      occupancy, argmin, st);
         return e == cudaSuccess ? TRK_OK : cuda_fail(e, "objective(static)");

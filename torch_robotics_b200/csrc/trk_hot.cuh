@@ -1,0 +1,737 @@
+// Headline kernel of the compiled-in family: fused objective (FK + self pairs + sphere scene + workspace box + EE SE(3)
+// term + reverse mode) for a robot whose collision model is known at compile time, in the common planning scene
+// (ONE equal-radius identity-pose sphere object, workspace box on, EE term on the model's own EE body, no relu).
+//
+// The kernel is issue-bound (one warp instruction per clock per SM sub-partition whatever the pipe,
+// profiles/r01_microbench_fp32.md), so everything here is about instructions per configuration and about keeping the
+// straight-line body inside the 32 KB instruction cache level:
+//   * fixed bodies are never composed: at compile time every fixed chain is folded into one constant transform relative
+//     to its nearest movable ancestor (HTree::origin); a fixed body costs three FMAs for its position, and only when the
+//     collision model or the EE term needs it;
+//   * joint clamp = max.NaN / min.NaN (torch.clamp semantics incl. NaN) + one compare for the gradient mask;
+//   * sin/cos: two-constant Cody-Waite with a magic-number round (no conversion instructions, no large-argument path)
+//     for joints whose limits bound the argument;
+//   * every uniform scalar (margins, weights, box, EE target) is a kernel parameter, i.e. a constant-bank operand of the
+//     arithmetic instruction itself: no table loads, no `use_override` selects (the host resolves the margins);
+//   * sphere scan: two spheres per packed fma.rn.f32x2 (FFMA2: one issue slot for two FMAs; IEEE per lane, so keys
+//     and decisions are bit-identical to the scalar scan);
+//   * reverse mode: one running wrench per open branch, first writes are assignments (no zero-initialised accumulators),
+//     cross products fused into the accumulation, bodies whose position cannot depend on any joint receive no force.
+// Decision arithmetic (distances that feed `<`, arg-min, arg-max) is the canonical sequence of trk_device.cuh.
+#pragma once
+
+#include "trk_device.cuh"
+
+namespace trk {
+
+#ifndef TRK_HOT_MINBLOCKS
+#define TRK_HOT_MINBLOCKS 4
+#endif
+#ifndef TRK_HOT_QSTAGE      // 0: direct loads, 1: next configuration's q prefetched into registers, 2: cp.async block tile + barrier,
+                            // 3: cp.async per-warp tile (no block barrier)
+#define TRK_HOT_QSTAGE 1
+#endif
+
+constexpr int kHotMaxPairs = 16, kHotMaxPoints = 8;
+
+struct HotParams {
+    float m_pair[kHotMaxPairs], mo_pair[kHotMaxPairs];   // self pairs: cost margin / occupancy margin
+    float m_obj[kHotMaxPoints], mo_obj[kHotMaxPoints];   // collision points vs the sphere object
+    float m_ws[kHotMaxPoints], mo_ws[kHotMaxPoints];     // collision points vs the workspace box
+    float w[4];
+    float ws_min[3], ws_max[3];
+    float ee_R[9], ee_t[3];
+    float ee_w_pos, ee_w_rot;
+    int   ee_square;
+    float tol, c2max;          // gap test of the scan
+    unsigned lowmask;          // index bits packed into the scan keys
+    int   n_pairs2;            // padded spheres / 2
+    int   n_sph;
+    int   off_sphq, off_sph;   // word offsets into the cost buffer
+    // collision points whose position is a compile-time constant (HTree::pos_is_const): evaluated once on the host with
+    // the same arithmetic (hot_params_from_cost)
+    float c_obj_const, c_ws_const;
+    unsigned occ_const;
+    int   widx_const[kHotMaxPoints];
+};
+
+__device__ __forceinline__ float fmax_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float fmin_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+
+// sin/cos for |x| <= 64 (k = round(x 2/pi) < 2^6: the products k*c1, k*c2 need no third constant): same kernels and
+// the same quadrant logic as trk_sincos; the round is a magic-number add, so no FRND / F2I.
+__device__ __forceinline__ void trk_sincos_small(float x, float& s, float& c) {
+    const float km = fmaf(x, 0.63661977236758134308f, 12582912.f);
+    const int k = __float_as_int(km);
+    const float kf = km - 12582912.f;
+    float r = fmaf(kf, -0x1.921fb6p+0f, x);
+    r = fmaf(kf, 0x1.777a5cp-25f, r);
+    const float r2 = r * r;
+    float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+    sp = fmaf(sp, r2, -1.6666654611e-1f);
+    sp = fmaf(sp * r2, r, r);
+    float cp = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    cp = fmaf(cp, r2, 4.166664568298827e-2f);
+    cp = fmaf(cp, r2, -0.5f);
+    cp = fmaf(cp, r2, 1.0f);
+    const float ss = (k & 1) ? cp : sp, cc = (k & 1) ? sp : cp;
+    s = __int_as_float(__float_as_int(ss) ^ ((k << 30) & 0x80000000));
+    c = __int_as_float(__float_as_int(cc) ^ (((k << 30) ^ (k << 31)) & 0x80000000));
+}
+
+// sqrt_rn_core with the zero guard folded into a clamp of the reciprocal-root estimate: rs <= 2^60 (the estimate of any
+// s >= 2^-100 is below 2^51), so s == 0 gives g = 0 * 2^60 = 0 without a select, and direction vectors v * (w * rs)
+// vanish with v instead of becoming 0 * inf.  Same result as sqrt_rn_core for s == 0 and 2^-100 <= s < 2^126.
+__device__ __forceinline__ float sqrt_rn_clamped(float s, float& rs) {
+    rs = fminf(mufu_rsq(s), 0x1p60f);
+    float g = __fmul_rn(s, rs);
+    const float hh = __fmul_rn(rs, 0.5f);
+    const float r = __fmaf_rn(-g, g, s);
+    return __fmaf_rn(r, hh, g);
+}
+__device__ __forceinline__ float norm3_clamped(float vx, float vy, float vz, float& rs) {
+    float s = __fmul_rn(vx, vx);
+    s = __fmaf_rn(vy, vy, s);
+    s = __fmaf_rn(vz, vz, s);
+    return sqrt_rn_clamped(s, rs);
+}
+
+// acc (+)= w * c for an immediate c; unit coefficients are taken first by the callers so that the remaining terms fuse
+__device__ __forceinline__ void hterm(float& acc, bool& started, float w, float c) {
+    if (c == 0.f) return;
+    if (!started) {
+        started = true;
+        acc = (c == 1.f) ? w : ((c == -1.f) ? -w : w * c);
+        return;
+    }
+    acc = (c == 1.f) ? acc + w : ((c == -1.f) ? acc - w : fmaf(w, c, acc));
+}
+// sum_k w[k] * c[k] (+ init when has_init): +-1 coefficients first (they are moves / adds), then the rest as FMAs
+__device__ __forceinline__ float hdot3(float w0, float w1, float w2, float c0, float c1, float c2, bool has_init, float init) {
+    float acc = init;
+    bool st = has_init;
+    if (c0 == 1.f || c0 == -1.f) hterm(acc, st, w0, c0);
+    if (c1 == 1.f || c1 == -1.f) hterm(acc, st, w1, c1);
+    if (c2 == 1.f || c2 == -1.f) hterm(acc, st, w2, c2);
+    if (!(c0 == 1.f || c0 == -1.f)) hterm(acc, st, w0, c0);
+    if (!(c1 == 1.f || c1 == -1.f)) hterm(acc, st, w1, c1);
+    if (!(c2 == 1.f || c2 == -1.f)) hterm(acc, st, w2, c2);
+    return st ? acc : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// compile-time view of a robot's tables with the fixed chains folded away
+// ------------------------------------------------------------------------------------------
+struct HXf { float R[9]; float t[3]; };
+
+template <class R>
+struct HTree {
+    static constexpr int L = R::L, D = R::D;
+    __host__ __device__ static constexpr int tix(int body) {
+        for (int i = 0; i < L; ++i) if (R::body[i] == body) return i;
+        return 0;
+    }
+    __host__ __device__ static constexpr int pix(int i) { return R::parent[i] < 0 ? -1 : tix(R::parent[i]); }   // topo index of the parent
+    __host__ __device__ static constexpr bool movable(int i) { return R::qidx[i] >= 0 && R::kind[i] != TRK_KIND_FIXED; }
+    __host__ __device__ static constexpr bool revolute(int i) { return movable(i) && R::kind[i] == TRK_KIND_REVOLUTE; }
+    // nearest movable-or-root ancestor-or-self
+    __host__ __device__ static constexpr int anchor(int i) {
+        int a = i;
+        while (pix(a) >= 0 && !movable(a)) a = pix(a);
+        return a;
+    }
+    __host__ __device__ static constexpr int ap(int i) { return anchor(pix(i)); }   // i is not the root
+    __host__ __device__ static constexpr HXf identity() { return HXf{{1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f}, {0.f, 0.f, 0.f}}; }
+    // pose of body j in the frame of anchor(j): identity for movable bodies and the root, the folded chain otherwise
+    __host__ __device__ static constexpr HXf rel(int j) {
+        if (pix(j) < 0 || movable(j)) return identity();
+        return origin(j);
+    }
+    // joint-origin frame of body i (before the joint motion) in the frame of ap(i): rel(parent) o (Rf_i, t_i)
+    __host__ __device__ static constexpr HXf origin(int i) {
+        const HXf p = rel(pix(i));
+        HXf o = identity();
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) {
+                float acc = 0.f;
+                for (int k = 0; k < 3; ++k) acc += p.R[r * 3 + k] * R::Rf[i][k * 3 + c];
+                o.R[r * 3 + c] = acc;
+            }
+            float acc = p.t[r];
+            for (int k = 0; k < 3; ++k) acc += p.R[r * 3 + k] * R::t[i][k];
+            o.t[r] = acc;
+        }
+        return o;
+    }
+    // prismatic axis in the frame of ap(i) (the reference adds axis * q to the joint-origin translation in the PARENT's
+    // frame, rigid_body.py:176)
+    __host__ __device__ static constexpr float paxis(int i, int r) {
+        const HXf p = rel(pix(i));
+        return p.R[r * 3 + 0] * R::ax[i][0] + p.R[r * 3 + 1] * R::ax[i][1] + p.R[r * 3 + 2] * R::ax[i][2];
+    }
+    __host__ __device__ static constexpr bool origin_t_zero(int i) {
+        const HXf o = origin(i);
+        return o.t[0] == 0.f && o.t[1] == 0.f && o.t[2] == 0.f;
+    }
+    // the origin of body b coincides structurally with the origin of movable body j (an ancestor-or-self anchor): every
+    // translation on the way is exactly zero and no prismatic joint moves it
+    __host__ __device__ static constexpr bool coincident(int b, int j) {
+        int a = b;
+        while (a != j) {
+            if (!origin_t_zero(a)) return false;
+            if (movable(a) && !revolute(a)) return false;
+            a = ap(a);
+            if (pix(a) < 0 && a != j) return false;
+        }
+        return true;
+    }
+    // a force applied at the origin of body b moves no joint: every movable ancestor-or-self is revolute about an axis
+    // through that origin (or there is none)
+    __host__ __device__ static constexpr bool force_is_useless(int b) {
+        int j = anchor(b);
+        while (pix(j) >= 0) {
+            if (!revolute(j) || !coincident(b, j)) return false;
+            j = ap(j);
+        }
+        return true;
+    }
+
+    // the world position of body b does not depend on q (same criterion), and its value
+    __host__ __device__ static constexpr bool pos_is_const(int b) { return force_is_useless(b); }
+    __host__ __device__ static constexpr HXf const_pose(int b) {      // .t = the constant position; valid when pos_is_const(b)
+        const int a = anchor(b);
+        if (pix(a) < 0) return rel(b);
+        int top = a;
+        while (pix(ap(top)) >= 0) top = ap(top);
+        return origin(top);
+    }
+
+    // pose of movable body I from the pose of its anchor-parent.  ROOTP: the anchor-parent is the root (identity pose).
+    template <int I, bool SMALL>
+    static __device__ __forceinline__ void compose(const float (&Wp)[12], float theta, float (&Wc)[12]) {
+        constexpr HXf O = origin(I);
+        constexpr bool rootp = pix(ap(I)) < 0;
+        float A[9];
+        sfor<3>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            sfor<3>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                if constexpr (rootp) A[r * 3 + c] = O.R[r * 3 + c];
+                else A[r * 3 + c] = hdot3(Wp[r * 3 + 0], Wp[r * 3 + 1], Wp[r * 3 + 2], O.R[0 + c], O.R[3 + c], O.R[6 + c], false, 0.f);
+            });
+            if constexpr (R::kind[I] == TRK_KIND_PRISMATIC) {
+                constexpr float a0 = paxis(I, 0), a1 = paxis(I, 1), a2 = paxis(I, 2);
+                const float t0 = (a0 != 0.f) ? fmaf(a0, theta, O.t[0]) : O.t[0];
+                const float t1 = (a1 != 0.f) ? fmaf(a1, theta, O.t[1]) : O.t[1];
+                const float t2 = (a2 != 0.f) ? fmaf(a2, theta, O.t[2]) : O.t[2];
+                if constexpr (rootp) Wc[9 + r] = (r == 0) ? t0 : ((r == 1) ? t1 : t2);
+                else Wc[9 + r] = fmaf(Wp[r * 3 + 2], t2, fmaf(Wp[r * 3 + 1], t1, fmaf(Wp[r * 3 + 0], t0, Wp[9 + r])));
+            } else {
+                if constexpr (rootp) Wc[9 + r] = O.t[r];
+                else Wc[9 + r] = hdot3(Wp[r * 3 + 0], Wp[r * 3 + 1], Wp[r * 3 + 2], O.t[0], O.t[1], O.t[2], true, Wp[9 + r]);
+            }
+        });
+        if constexpr (R::kind[I] == TRK_KIND_REVOLUTE && R::axis_s[I] != 0.f) {
+            float sn, cs;
+            if constexpr (SMALL) trk_sincos_small(theta, sn, cs); else trk_sincos(theta, sn, cs);
+            if constexpr (R::axis_s[I] < 0.f) sn = -sn;
+            constexpr int k = R::axis_k[I], ci = (k + 1) % 3, cj = (k + 2) % 3;
+            sfor<3>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                if constexpr (rootp) {
+                    constexpr float a = O.R[r * 3 + ci], b = O.R[r * 3 + cj];
+                    Wc[r * 3 + ci] = hdot3(cs, sn, 0.f, a, b, 0.f, false, 0.f);
+                    Wc[r * 3 + cj] = hdot3(cs, sn, 0.f, b, -a, 0.f, false, 0.f);
+                } else {
+                    const float a = A[r * 3 + ci], b = A[r * 3 + cj];
+                    Wc[r * 3 + ci] = fmaf(cs, a, sn * b);
+                    Wc[r * 3 + cj] = fmaf(cs, b, -(sn * a));
+                }
+                Wc[r * 3 + k] = A[r * 3 + k];
+            });
+        } else {
+            sfor<9>([&](auto ic) { Wc[ic] = A[ic]; });
+        }
+    }
+
+    // position of fixed body I from the pose of its anchor
+    template <int I>
+    static __device__ __forceinline__ void fixed_position(const float (&Wa)[12], float (&p)[3]) {
+        constexpr HXf O = origin(I);
+        constexpr bool rootp = pix(ap(I)) < 0;
+        sfor<3>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            if constexpr (rootp) p[r] = O.t[r];
+            else p[r] = hdot3(Wa[r * 3 + 0], Wa[r * 3 + 1], Wa[r * 3 + 2], O.t[0], O.t[1], O.t[2], true, Wa[9 + r]);
+        });
+    }
+    // rotation of fixed body I from the pose of its anchor
+    template <int I>
+    static __device__ __forceinline__ void fixed_rotation(const float (&Wa)[12], float (&Rb)[9]) {
+        constexpr HXf O = origin(I);
+        constexpr bool rootp = pix(ap(I)) < 0;
+        sfor<9>([&](auto ec) {
+            constexpr int e = decltype(ec)::value, r = e / 3, c = e % 3;
+            if constexpr (rootp) Rb[e] = O.R[e];
+            else Rb[e] = hdot3(Wa[r * 3 + 0], Wa[r * 3 + 1], Wa[r * 3 + 2], O.R[0 + c], O.R[3 + c], O.R[6 + c], false, 0.f);
+        });
+    }
+    // world joint axis of movable body I
+    template <int I>
+    static __device__ __forceinline__ void joint_axis(const float (&Wp)[12], const float (&Wb)[12], float (&ja)[3]) {
+        if constexpr (R::kind[I] == TRK_KIND_REVOLUTE) {
+            constexpr int k = R::axis_k[I];
+            constexpr float sgn = R::axis_s[I];
+            ja[0] = sgn * Wb[0 + k]; ja[1] = sgn * Wb[3 + k]; ja[2] = sgn * Wb[6 + k];
+        } else {
+            constexpr bool rootp = pix(ap(I)) < 0;
+            constexpr float a0 = paxis(I, 0), a1 = paxis(I, 1), a2 = paxis(I, 2);
+            sfor<3>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                if constexpr (rootp) ja[r] = (r == 0) ? a0 : ((r == 1) ? a1 : a2);
+                else ja[r] = hdot3(Wp[r * 3 + 0], Wp[r * 3 + 1], Wp[r * 3 + 2], a0, a1, a2, false, 0.f);
+            });
+        }
+    }
+    // |theta| of joint I is bounded by its limits (the clamp), so the short sin/cos applies
+    __host__ __device__ static constexpr bool small_angle(int i) {
+        return R::has_lim[i] != 0 && R::lo[i] >= -64.f && R::hi[i] <= 64.f;
+    }
+};
+
+// which bodies of the collision model CM (and the EE body, topo index EE) carry positions / forces
+template <class R, class CM, int EE>
+struct HotPlan {
+    using T = HTree<R>;
+    static constexpr int L = R::L;
+    __host__ __device__ static constexpr bool in_cm(int i) {
+        const int b = R::body[i];
+        for (int s = 0; s < CM::S; ++s) if (CM::pt_link[s] == b) return true;
+        for (int p = 0; p < CM::P; ++p) if (CM::pair_i[p] == b || CM::pair_j[p] == b) return true;
+        return false;
+    }
+    __host__ __device__ static constexpr bool pos_needed(int i) { return in_cm(i) || i == EE; }
+    __host__ __device__ static constexpr bool has_force(int i) { return in_cm(i) && !T::force_is_useless(i); }
+    // collision points whose position moves with the joints ("dynamic"), in table order
+    __host__ __device__ static constexpr bool point_is_const(int s) { return T::pos_is_const(T::tix(CM::pt_link[s])); }
+    __host__ __device__ static constexpr int n_dyn_points() {
+        int nd = 0;
+        for (int s = 0; s < CM::S; ++s) if (!point_is_const(s)) ++nd;
+        return nd;
+    }
+    __host__ __device__ static constexpr int dyn_point(int k) {       // k-th dynamic point -> point index
+        int nd = 0;
+        for (int s = 0; s < CM::S; ++s) if (!point_is_const(s)) { if (nd == k) return s; ++nd; }
+        return 0;
+    }
+    __host__ __device__ static constexpr int dyn_rank(int s) {        // point index -> rank among the dynamic points, -1 = constant
+        if (point_is_const(s)) return -1;
+        int nd = 0;
+        for (int s2 = 0; s2 < s; ++s2) if (!point_is_const(s2)) ++nd;
+        return nd;
+    }
+    // the constant points as data (for the host: it evaluates them once per launch)
+    struct ConstPoints { bool is_const[kHotMaxPoints]; float pos[kHotMaxPoints][3]; };
+    __host__ __device__ static constexpr ConstPoints make_const_points() {
+        ConstPoints c{};
+        for (int s = 0; s < CM::S; ++s) {
+            c.is_const[s] = point_is_const(s);
+            const HXf pose = T::const_pose(T::tix(CM::pt_link[s]));
+            for (int r = 0; r < 3; ++r) c.pos[s][r] = c.is_const[s] ? pose.t[r] : 0.f;
+        }
+        return c;
+    }
+    static constexpr ConstPoints kConstPoints = make_const_points();
+    // movable body m: some body anchored at m carries a force (or the EE wrench)
+    __host__ __device__ static constexpr bool own_wrench(int m) {
+        for (int b = 0; b < L; ++b) if (T::anchor(b) == m && (has_force(b) || b == EE)) return true;
+        return false;
+    }
+    __host__ __device__ static constexpr bool subtree_wrench(int m) {
+        if (own_wrench(m)) return true;
+        for (int c = m + 1; c < L; ++c) if (T::movable(c) && T::ap(c) == m && subtree_wrench(c)) return true;
+        return false;
+    }
+    // accumulator of movable body m already written when body b (anchored at m) adds its force: a child pushed, the EE
+    // wrench came first, or a body with a larger topo index did
+    __host__ __device__ static constexpr bool started_before_body(int m, int b) {
+        for (int c = m + 1; c < L; ++c) if (T::movable(c) && T::ap(c) == m && subtree_wrench(c)) return true;
+        if (T::anchor(EE) == m && b != EE) return true;
+        for (int b2 = b + 1; b2 < L; ++b2) if (b2 != EE && T::anchor(b2) == m && has_force(b2)) return true;
+        return false;
+    }
+    // accumulator of pa already written when movable child c pushes into it
+    __host__ __device__ static constexpr bool started_before_child(int pa, int c) {
+        for (int c2 = c + 1; c2 < L; ++c2) if (T::movable(c2) && T::ap(c2) == pa && subtree_wrench(c2)) return true;
+        return false;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+template <class R, class CM, int EE, bool PER_CFG_TARGET, bool WANT_GRAD>
+__global__ void __launch_bounds__(kSBlock, TRK_HOT_MINBLOCKS)
+k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ cost_words, const float* __restrict__ q, long long n,
+                const float* __restrict__ ee_target_cfg, float* __restrict__ cost_total, float* __restrict__ cost_terms,
+                float* __restrict__ grad_q, uint8_t* __restrict__ occupancy, int* __restrict__ argmin) {
+    using T = HTree<R>;
+    using Plan = HotPlan<R, CM, EE>;
+    constexpr int L = R::L, D = R::D, S = CM::S, P = CM::P;
+    static_assert(S <= kHotMaxPoints && P <= kHotMaxPairs, "collision model too large for HotParams");
+    extern __shared__ __align__(16) float hsm[];
+    // [n_pairs2 * 8] scan table, two spheres interleaved: (ax, bx, ay, by) (az, bz, aw, bw) | [n_sph * 4] (c, r) | q tiles
+    float4* tq = reinterpret_cast<float4*>(hsm);
+    float4* tsph = tq + 2 * hp.n_pairs2;
+    const int tid = threadIdx.x;
+    {
+        const float* sphq = cost_words + hp.off_sphq;
+        for (int i = tid; i < hp.n_pairs2 * 8; i += kSBlock) {
+            const int k = i >> 2, comp = i & 3;
+            hsm[(k >> 1) * 8 + comp * 2 + (k & 1)] = __ldg(sphq + i);
+        }
+        const float4* sph = reinterpret_cast<const float4*>(cost_words + hp.off_sph);
+        for (int i = tid; i < hp.n_sph; i += kSBlock) tsph[i] = __ldg(sph + i);
+    }
+#if TRK_HOT_QSTAGE >= 2
+    // q staging: a group of kStage threads (the block, or one warp: no block barrier) copies the group's kStage x D
+    // joint values with cp.async into its own double buffer while the previous tile is being evaluated
+    constexpr int kStage = (TRK_HOT_QSTAGE == 2) ? kSBlock : 32;
+    constexpr int kTileWords = kStage * D, kTileChunks = (kTileWords + 3) / 4;
+    static_assert((kTileWords * 4) % 16 == 0, "a staged tile must be a whole number of 16-byte chunks");
+    const int gt = tid % kStage;
+    float* qs = reinterpret_cast<float*>(tsph + hp.n_sph) + (tid / kStage) * 2 * kTileWords;      // [group][2][kStage * D]
+    auto stage_sync = [&]() { if (TRK_HOT_QSTAGE == 2) __syncthreads(); else __syncwarp(); };
+    // a full tile is kTileChunks 16-byte chunks; the last (partial) tile zero-fills what lies beyond n
+    auto prefetch_tile = [&](long long tile, int buf) {
+        const long long cfg0 = tile * kSBlock + (tid / kStage) * kStage;      // first configuration of the group's tile
+        const float* src0 = q + cfg0 * D;
+        const unsigned dst0 = (unsigned)__cvta_generic_to_shared(qs) + (unsigned)(buf * kTileWords * 4);
+        if (cfg0 + kStage <= n) {
+#pragma unroll
+            for (int c0 = 0; c0 < kTileChunks; c0 += kStage) {
+                const int c = c0 + gt;
+                if (c0 + kStage <= kTileChunks || c < kTileChunks)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + 16u * c), "l"(src0 + 4 * c) : "memory");
+            }
+        } else {
+            const long long left_words = (n - cfg0) * D;
+            for (int c = gt; c < kTileChunks; c += kStage) {
+                const long long left = (left_words - 4 * c) * 4;
+                const int bytes = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst0 + 16u * c), "l"(bytes > 0 ? src0 + 4 * c : q), "r"(bytes) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#endif
+    const long long n_tiles = (n + kSBlock - 1) / kSBlock;
+    long long tile = blockIdx.x;
+#if TRK_HOT_QSTAGE >= 2
+    int buf = 0;
+    if (tile < n_tiles) prefetch_tile(tile, 0);
+#elif TRK_HOT_QSTAGE == 1
+    float qn[D];
+    {
+        const long long c0 = tile * kSBlock + tid;
+        const float* qrow = q + (c0 < n ? c0 : n - 1) * D;
+        sfor<D>([&](auto c) { qn[c] = __ldg(qrow + c); });
+    }
+#endif
+    __syncthreads();
+    for (; tile < n_tiles; tile += gridDim.x) {
+        const long long cfg = tile * kSBlock + tid;
+        const bool live = cfg < n;
+        float qv[D];
+#if TRK_HOT_QSTAGE >= 2
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        stage_sync();
+        sfor<D>([&](auto c) { qv[c] = qs[buf * kTileWords + gt * D + c]; });
+        if (tile + gridDim.x < n_tiles) prefetch_tile(tile + gridDim.x, buf ^ 1);
+        buf ^= 1;
+#elif TRK_HOT_QSTAGE == 1
+        sfor<D>([&](auto c) { qv[c] = qn[c]; });
+        {
+            const long long c1 = cfg + (long long)gridDim.x * kSBlock;
+            const float* qrow = q + (c1 < n ? c1 : n - 1) * D;
+            sfor<D>([&](auto c) { qn[c] = __ldg(qrow + c); });
+        }
+#else
+        {
+            const float* qrow = q + (live ? cfg : n - 1) * D;
+            sfor<D>([&](auto c) { qv[c] = __ldg(qrow + c); });
+        }
+#endif
+        // ---------------- forward kinematics (movable bodies only; fixed bodies on demand) ----------------
+        float W[L][12], Pb[L][3], JA[D > 0 ? D : 1][3], Ree[9];
+        unsigned pass = 0u;
+        sfor<L>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            if constexpr (T::pix(i) < 0) {
+                sfor<3>([&](auto rc) { Pb[i][rc] = 0.f; });
+                if constexpr (i == EE) sfor<9>([&](auto e) { Ree[e] = (e == 0 || e == 4 || e == 8) ? 1.f : 0.f; });
+            } else if constexpr (T::movable(i)) {
+                constexpr int qi = R::qidx[i];
+                const float qraw = qv[qi];
+                float theta = qraw;
+                if constexpr (R::has_lim[i] != 0) {
+                    constexpr float lo = R::lo[i], hi = R::hi[i];
+                    theta = fmin_nan(fmax_nan(qraw, lo), hi);                  // torch.clamp: NaN propagates
+                    if (theta == qraw) pass |= (1u << qi);                     // gradient passes inside [lo, hi], bounds included
+                } else {
+                    pass |= (1u << qi);
+                }
+                constexpr int a = T::ap(i);
+                T::template compose<i, T::small_angle(i)>(W[a], theta, W[i]);
+                sfor<3>([&](auto rc) { Pb[i][rc] = W[i][9 + rc]; });
+                T::template joint_axis<i>(W[a], W[i], JA[qi]);
+                if constexpr (i == EE) sfor<9>([&](auto e) { Ree[e] = W[i][e]; });
+            } else {
+                constexpr int a = T::anchor(i);
+                if constexpr (Plan::pos_needed(i)) T::template fixed_position<i>(W[a], Pb[i]);
+                if constexpr (i == EE) T::template fixed_rotation<i>(W[a], Ree);
+            }
+        });
+        // ---------------- EE SE(3) term (geometrics/utils.py:130-154; distance_fields.py:347-356) ----------------
+        float Rt[9], pt[3];
+        if constexpr (PER_CFG_TARGET) {
+            const float* Ht = ee_target_cfg + (live ? cfg : 0) * 16;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                const float4 row = __ldg(reinterpret_cast<const float4*>(Ht) + i);
+                Rt[i * 3 + 0] = row.x; Rt[i * 3 + 1] = row.y; Rt[i * 3 + 2] = row.z; pt[i] = row.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) Rt[i] = hp.ee_R[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) pt[i] = hp.ee_t[i];
+        }
+        float c_ee, eF[3], eT[3];
+        {
+            float dg[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                dg[i] = __fmaf_rn(Ree[i * 3 + 2], Rt[i * 3 + 2], __fmaf_rn(Ree[i * 3 + 1], Rt[i * 3 + 1], __fmul_rn(Ree[i * 3 + 0], Rt[i * 3 + 0])));
+            const float tr = __fadd_rn(__fadd_rn(dg[0], dg[1]), dg[2]);
+            const float phi = __fmul_rn(__fsub_rn(tr, 1.f), 0.5f);
+            float Dd = __fmul_rn(hp.ee_w_rot, __fsub_rn(1.f, phi));
+            const float vx = __fsub_rn(Pb[EE][0], pt[0]), vy = __fsub_rn(Pb[EE][1], pt[1]), vz = __fsub_rn(Pb[EE][2], pt[2]);
+            float rs;
+            const float dist = norm3_clamped(vx, vy, vz, rs);
+            Dd = __fadd_rn(Dd, __fmul_rn(hp.ee_w_pos, dist));
+            c_ee = hp.ee_square ? __fmul_rn(Dd, Dd) : Dd;
+            if constexpr (WANT_GRAD) {
+            const float scale = hp.w[3] * (hp.ee_square ? 2.f * Dd : 1.f);
+            const float kr = scale * (-0.5f * hp.ee_w_rot);
+            const float kp = scale * hp.ee_w_pos * rs;
+            eF[0] = kp * vx; eF[1] = kp * vy; eF[2] = kp * vz;
+            // torque about the world origin: p x F + kr * axial(Rt Ree^T)
+            const float m21 = Rt[6] * Ree[3] + Rt[7] * Ree[4] + Rt[8] * Ree[5];
+            const float m12 = Rt[3] * Ree[6] + Rt[4] * Ree[7] + Rt[5] * Ree[8];
+            const float m02 = Rt[0] * Ree[6] + Rt[1] * Ree[7] + Rt[2] * Ree[8];
+            const float m20 = Rt[6] * Ree[0] + Rt[7] * Ree[1] + Rt[8] * Ree[2];
+            const float m10 = Rt[3] * Ree[0] + Rt[4] * Ree[1] + Rt[5] * Ree[2];
+            const float m01 = Rt[0] * Ree[3] + Rt[1] * Ree[4] + Rt[2] * Ree[5];
+            eT[0] = fmaf(kr, m21 - m12, fmaf(Pb[EE][1], eF[2], -(Pb[EE][2] * eF[1])));
+            eT[1] = fmaf(kr, m02 - m20, fmaf(Pb[EE][2], eF[0], -(Pb[EE][0] * eF[2])));
+            eT[2] = fmaf(kr, m10 - m01, fmaf(Pb[EE][0], eF[1], -(Pb[EE][1] * eF[0])));
+            }
+        }
+        // ---------------- self-collision pairs (distance_fields.py:194-215) ----------------
+        float G[L][3];
+        bool gst[L];
+        sfor<L>([&](auto ic) { gst[ic] = false; });
+        auto add_force = [&](auto bc, float fx, float fy, float fz) {   // G[b] += f with a compile-time "first write"
+            constexpr int b = decltype(bc)::value;
+            if (gst[b]) { G[b][0] += fx; G[b][1] += fy; G[b][2] += fz; }
+            else { G[b][0] = fx; G[b][1] = fy; G[b][2] = fz; gst[b] = true; }
+        };
+        bool occ_self = false, occ_obj = false, occ_ws = false;
+        float c_self = 0.f;
+        sfor<P>([&](auto pc) {
+            constexpr int p = decltype(pc)::value, bi = T::tix(CM::pair_i[p]), bj = T::tix(CM::pair_j[p]);
+            const float vx = __fsub_rn(Pb[bi][0], Pb[bj][0]), vy = __fsub_rn(Pb[bi][1], Pb[bj][1]), vz = __fsub_rn(Pb[bi][2], Pb[bj][2]);
+            float rs;
+            const float dist = norm3_clamped(vx, vy, vz, rs);
+            occ_self = occ_self || (dist < hp.mo_pair[p]);
+            c_self = __fadd_rn(c_self, -__fsub_rn(dist, hp.m_pair[p]));
+            if constexpr (WANT_GRAD) {
+                const float inv = hp.w[0] * rs;      // d(-dist)/d x_i = -v / dist (zero when the origins coincide: v = 0)
+                if constexpr (Plan::has_force(bi)) add_force(IC<bi>{}, -(vx * inv), -(vy * inv), -(vz * inv));
+                if constexpr (Plan::has_force(bj)) add_force(IC<bj>{}, vx * inv, vy * inv, vz * inv);
+            }
+        });
+        // ---------------- sphere object: joint scan of the moving collision points, two spheres per FFMA2 ----------------
+        // (points whose position is a compile-time constant were evaluated on the host: HotParams::*_const)
+        constexpr int ND = Plan::n_dyn_points();
+        float m1[ND > 0 ? ND : 1], m2[ND > 0 ? ND : 1];
+        {
+            float2 X2[ND > 0 ? ND : 1][3];
+            sfor<ND>([&](auto kc) {
+                constexpr int b = T::tix(CM::pt_link[Plan::dyn_point(decltype(kc)::value)]);
+                sfor<3>([&](auto rc) { X2[kc][rc] = make_float2(Pb[b][rc], Pb[b][rc]); });
+            });
+            const float kInf = __int_as_float(0x7f800000);
+#pragma unroll
+            for (int k = 0; k < ND; ++k) { m1[k] = kInf; m2[k] = kInf; }
+            const unsigned keep = ~hp.lowmask;
+            unsigned idx = 0u;
+            float4 t0 = tq[0], t1 = tq[1];
+#pragma unroll 1
+            for (int j = 0; j < hp.n_pairs2; ++j, idx += 2u) {
+                const float2 cx = make_float2(t0.x, t0.y), cy = make_float2(t0.z, t0.w), cz = make_float2(t1.x, t1.y), cw = make_float2(t1.z, t1.w);
+                const int jn = (j + 1 < hp.n_pairs2) ? j + 1 : j;      // next pair's table entry is in flight during this one
+                t0 = tq[2 * jn]; t1 = tq[2 * jn + 1];
+#pragma unroll
+                for (int k = 0; k < ND; ++k) {
+                    const float2 k2 = __ffma2_rn(X2[k][0], cx, __ffma2_rn(X2[k][1], cy, __ffma2_rn(X2[k][2], cz, cw)));
+                    const float pa = __uint_as_float((__float_as_uint(k2.x) & keep) | idx);
+                    const float pb = __uint_as_float((__float_as_uint(k2.y) & keep) | (idx + 1u));
+                    const float lo = fminf(pa, pb), hi = fmaxf(pa, pb);
+                    m2[k] = fmin3(fmaxf(m1[k], lo), m2[k], hi);
+                    m1[k] = fminf(m1[k], lo);
+                }
+            }
+        }
+        int widx[ND > 0 ? ND : 1];
+        bool all_certain = true;
+        sfor<ND>([&](auto kc) {
+            constexpr int k = decltype(kc)::value, b = T::tix(CM::pt_link[Plan::dyn_point(k)]);
+            const float xx = __fmaf_rn(Pb[b][2], Pb[b][2], __fmaf_rn(Pb[b][1], Pb[b][1], __fmul_rn(Pb[b][0], Pb[b][0])));
+            all_certain = all_certain && ((m2[k] - m1[k]) > hp.tol * (xx + hp.c2max));
+            widx[k] = (int)(__float_as_uint(m1[k]) & hp.lowmask);
+        });
+        if (!all_certain) {   // near tie (or NaN) on some point: exact scan of the uncertain points, first index wins (rare)
+            sfor<ND>([&](auto kc) {
+                constexpr int k = decltype(kc)::value, b = T::tix(CM::pt_link[Plan::dyn_point(k)]);
+                const float xx = __fmaf_rn(Pb[b][2], Pb[b][2], __fmaf_rn(Pb[b][1], Pb[b][1], __fmul_rn(Pb[b][0], Pb[b][0])));
+                if (!((m2[k] - m1[k]) > hp.tol * (xx + hp.c2max))) {
+                    float best = __int_as_float(0x7f800000);
+                    int bidx = 0;
+#pragma unroll 1
+                    for (int kk = 0; kk < hp.n_sph; ++kk) {
+                        const float4 c = tsph[kk];
+                        const float sd = __fsub_rn(norm3_rn(__fsub_rn(Pb[b][0], c.x), __fsub_rn(Pb[b][1], c.y), __fsub_rn(Pb[b][2], c.z)), c.w);
+                        if (sd < best) { best = sd; bidx = kk; }
+                    }
+                    widx[k] = bidx;
+                }
+            });
+        }
+        // ---------------- moving collision points: exact evaluation of the winner + workspace box ----------------
+        float c_obj = hp.c_obj_const, c_ws = hp.c_ws_const;
+        sfor<ND>([&](auto kc) {
+            constexpr int k = decltype(kc)::value, s = Plan::dyn_point(k), b = T::tix(CM::pt_link[s]);
+            const float x = Pb[b][0], y = Pb[b][1], z = Pb[b][2];
+            const float4 c = tsph[widx[k]];
+            const float vx = __fsub_rn(x, c.x), vy = __fsub_rn(y, c.y), vz = __fsub_rn(z, c.z);
+            float rs;
+            const float best = __fsub_rn(norm3_clamped(vx, vy, vz, rs), c.w);
+            occ_obj = occ_obj || (best < hp.mo_obj[s]);
+            c_obj = __fadd_rn(c_obj, -__fsub_rn(best, hp.m_obj[s]));
+            // workspace box (distance_fields.py:319-332): the six half-space distances in the reference's order
+            // [x - min (3), max - x (3)]; value = margin - smallest distance (= the reference's max of margin - d_i: rounding
+            // is monotone); the gradient goes to the first index that attains the smallest distance
+            const float e0 = __fsub_rn(x, hp.ws_min[0]), e1 = __fsub_rn(y, hp.ws_min[1]), e2 = __fsub_rn(z, hp.ws_min[2]);
+            const float f0 = __fsub_rn(hp.ws_max[0], x), f1 = __fsub_rn(hp.ws_max[1], y), f2 = __fsub_rn(hp.ws_max[2], z);
+            const float emin = fmin3(e0, e1, e2), fmn = fmin3(f0, f1, f2);
+            const float dmin = fminf(emin, fmn);
+            occ_ws = occ_ws || (dmin < hp.mo_ws[s]);
+            c_ws = __fadd_rn(c_ws, -__fsub_rn(dmin, hp.m_ws[s]));
+            if constexpr (WANT_GRAD) {
+                const float w1 = hp.w[1] * rs;
+                float gx = -(w1 * vx), gy = -(w1 * vy), gz = -(w1 * vz);
+                const bool upper = fmn < emin;                       // ties go to the lower index: the x - min side
+                float g = upper ? hp.w[2] : -hp.w[2];
+                g = (dmin != 0.f) ? g : 0.f;                         // sign(d) |d| has zero gradient at d == 0
+                const float a0 = upper ? f0 : e0, a1 = upper ? f1 : e1;
+                const bool p0 = a0 == dmin, p1 = a1 == dmin;
+                gx += p0 ? g : 0.f;
+                gy += (!p0 && p1) ? g : 0.f;
+                gz += (!p0 && !p1) ? g : 0.f;
+                if constexpr (Plan::has_force(b)) add_force(IC<b>{}, gx, gy, gz);
+            }
+        });
+        // ---------------- outputs ----------------
+        if (live) {
+            const float total = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(hp.w[0], c_self), __fmul_rn(hp.w[1], c_obj)), __fmul_rn(hp.w[2], c_ws)),
+                                          __fmul_rn(hp.w[3], c_ee));
+            if (cost_total) cost_total[cfg] = total;
+            if (cost_terms) reinterpret_cast<float4*>(cost_terms)[cfg] = make_float4(c_self, c_obj, c_ws, c_ee);
+            if (occupancy) occupancy[cfg] = (uint8_t)(hp.occ_const | (occ_self ? TRK_OCC_SELF : 0u) | (occ_obj ? TRK_OCC_OBJECT : 0u) | (occ_ws ? TRK_OCC_WS : 0u));
+            if (argmin) {
+                int* row = argmin + cfg * S;
+                sfor<S>([&](auto sc) {
+                    constexpr int s = decltype(sc)::value, rk = Plan::dyn_rank(s);
+                    if constexpr (rk >= 0) row[s] = widx[rk];
+                    else row[s] = hp.widx_const[s];
+                });
+            }
+        }
+        // ---------------- reverse mode: leaf -> root over the movable bodies ----------------
+        if constexpr (WANT_GRAD) {
+        float F[L][3], Tq[L][3], gq[D > 0 ? D : 1];
+        sfor<D>([&](auto c) { gq[c] = 0.f; });
+        sfor<L>([&](auto ic) {
+            constexpr int i = L - 1 - decltype(ic)::value;
+            if constexpr (T::pix(i) >= 0 && T::movable(i) && Plan::subtree_wrench(i)) {
+                // forces of the bodies anchored here (the EE wrench first, then bodies by decreasing topo index)
+                if constexpr (T::anchor(EE) == i) {
+                    constexpr bool st = Plan::started_before_body(i, EE);
+                    sfor<3>([&](auto rc) {
+                        F[i][rc] = st ? F[i][rc] + eF[rc] : eF[rc];
+                        Tq[i][rc] = st ? Tq[i][rc] + eT[rc] : eT[rc];
+                    });
+                }
+                sfor<L>([&](auto bc) {
+                    constexpr int b = L - 1 - decltype(bc)::value;
+                    if constexpr (b != EE && T::anchor(b) == i && Plan::has_force(b)) {
+                        constexpr bool st = Plan::started_before_body(i, b);
+                        const float px = Pb[b][0], py = Pb[b][1], pz = Pb[b][2], fx = G[b][0], fy = G[b][1], fz = G[b][2];
+                        if constexpr (st) {
+                            F[i][0] += fx; F[i][1] += fy; F[i][2] += fz;
+                            Tq[i][0] = fmaf(py, fz, fmaf(-pz, fy, Tq[i][0]));
+                            Tq[i][1] = fmaf(pz, fx, fmaf(-px, fz, Tq[i][1]));
+                            Tq[i][2] = fmaf(px, fy, fmaf(-py, fx, Tq[i][2]));
+                        } else {
+                            F[i][0] = fx; F[i][1] = fy; F[i][2] = fz;
+                            Tq[i][0] = fmaf(py, fz, -(pz * fy));
+                            Tq[i][1] = fmaf(pz, fx, -(px * fz));
+                            Tq[i][2] = fmaf(px, fy, -(py * fx));
+                        }
+                    }
+                });
+                // project on the joint axis: revolute a . (T - p x F), prismatic a . F; torch.clamp's mask
+                constexpr int qi = R::qidx[i];
+                float g;
+                if constexpr (R::kind[i] == TRK_KIND_REVOLUTE) {
+                    const float px = Pb[i][0], py = Pb[i][1], pz = Pb[i][2];
+                    const float mx = fmaf(pz, F[i][1], fmaf(-py, F[i][2], Tq[i][0]));
+                    const float my = fmaf(px, F[i][2], fmaf(-pz, F[i][0], Tq[i][1]));
+                    const float mz = fmaf(py, F[i][0], fmaf(-px, F[i][1], Tq[i][2]));
+                    g = fmaf(JA[qi][2], mz, fmaf(JA[qi][1], my, JA[qi][0] * mx));
+                } else {
+                    g = fmaf(JA[qi][2], F[i][2], fmaf(JA[qi][1], F[i][1], JA[qi][0] * F[i][0]));
+                }
+                gq[qi] = ((pass >> qi) & 1u) ? g : 0.f;
+                // hand the branch's wrench to the anchor-parent
+                constexpr int pa = T::ap(i);
+                if constexpr (T::pix(pa) >= 0) {
+                    constexpr bool st = Plan::started_before_child(pa, i);
+                    sfor<3>([&](auto rc) {
+                        F[pa][rc] = st ? F[pa][rc] + F[i][rc] : F[i][rc];
+                        Tq[pa][rc] = st ? Tq[pa][rc] + Tq[i][rc] : Tq[i][rc];
+                    });
+                }
+            }
+        });
+        if (live) {
+            float* grow = grad_q + cfg * D;
+            sfor<D>([&](auto c) { grow[c] = gq[c]; });
+        }
+        }
+    }
+}
+
+}  // namespace trk

@@ -14,6 +14,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -942,6 +944,10 @@ __global__ void __launch_bounds__(kSBlock, HOT ? TRK_CM_HOT_MINBLOCKS : TRK_CM_M
     }
 }
 
+}  // namespace trk
+#include "trk_hot.cuh"
+namespace trk {
+
 // ------------------------------------------------------------------------------------------
 // Fused batched Adam inverse kinematics (DifferentiableTree.inverse_kinematics, robot_tree.py:303-442):
 // one thread owns one seed and keeps q, the Adam moments and the gradient in registers for all iterations.
@@ -1243,8 +1249,83 @@ inline cudaError_t launch_objective_cm_k(int n_sms, const float* cost_words, int
     return cudaGetLastError();
 }
 
+
+// Host side of k_objective_hot: the uniform scalars of the cost table become kernel parameters (margins already resolved
+// against `margin_override`), the sphere tables stay in the device cost buffer.
+template <class R, class CM, int EE>
+inline void hot_params_from_cost(const float* hw, float margin_override, int use_override, HotParams& hp) {
+    const CostHeader* h = reinterpret_cast<const CostHeader*>(hw);
+    const int* iw = reinterpret_cast<const int*>(hw);
+    std::memset(&hp, 0, sizeof(hp));
+    for (int p = 0; p < CM::P; ++p) {
+        hp.m_pair[p] = hw[h->off_pair_m + p];
+        hp.mo_pair[p] = use_override ? margin_override : hp.m_pair[p];
+    }
+    for (int s2 = 0; s2 < CM::S; ++s2) {
+        hp.m_obj[s2] = hw[h->off_pt_mobj + s2]; hp.mo_obj[s2] = use_override ? margin_override : hp.m_obj[s2];
+        hp.m_ws[s2] = hw[h->off_pt_mws + s2];   hp.mo_ws[s2] = use_override ? margin_override : hp.m_ws[s2];
+    }
+    for (int i = 0; i < 4; ++i) hp.w[i] = h->w[i];
+    for (int i = 0; i < 3; ++i) { hp.ws_min[i] = h->ws_min[i]; hp.ws_max[i] = h->ws_max[i]; hp.ee_t[i] = h->ee_t[i]; }
+    for (int i = 0; i < 9; ++i) hp.ee_R[i] = h->ee_R[i];
+    hp.ee_w_pos = h->ee_w_pos; hp.ee_w_rot = h->ee_w_rot; hp.ee_square = h->ee_square;
+    hp.tol = hw[h->off_obj_tol]; hp.c2max = hw[h->off_obj_c2max];
+    hp.lowmask = (1u << (iw[h->off_obj_ident] >> OBJ_BITS_SHIFT)) - 1u;
+    hp.n_pairs2 = (iw[h->off_obj_qstart + 1] - iw[h->off_obj_qstart]) / 2;
+    hp.n_sph = iw[h->off_obj_start + 1] - iw[h->off_obj_start];
+    hp.off_sphq = h->off_sphq + 4 * iw[h->off_obj_qstart];
+    hp.off_sph = h->off_sph + 4 * iw[h->off_obj_start];
+    // collision points at a constant position: the device arithmetic (trk_device.cuh: norm3_rn, first index wins,
+    // margin - sdf, max over the six half-spaces) restated with correctly rounded host operations
+    constexpr auto cp = HotPlan<R, CM, EE>::kConstPoints;
+    const float* sph = hw + hp.off_sph;
+    for (int s2 = 0; s2 < CM::S; ++s2) {
+        if (!cp.is_const[s2]) continue;
+        const float x = cp.pos[s2][0], y = cp.pos[s2][1], z = cp.pos[s2][2];
+        float best = INFINITY;
+        int bidx = 0;
+        for (int k = 0; k < hp.n_sph; ++k) {
+            const float vx = x - sph[4 * k], vy = y - sph[4 * k + 1], vz = z - sph[4 * k + 2];
+            const float sd = sqrtf(fmaf(vz, vz, fmaf(vy, vy, vx * vx))) - sph[4 * k + 3];
+            if (sd < best) { best = sd; bidx = k; }
+        }
+        hp.widx_const[s2] = bidx;
+        if (best < hp.mo_obj[s2]) hp.occ_const |= TRK_OCC_OBJECT;
+        hp.c_obj_const = hp.c_obj_const + -(best - hp.m_obj[s2]);
+        const float d[6] = {x - hp.ws_min[0], y - hp.ws_min[1], z - hp.ws_min[2], hp.ws_max[0] - x, hp.ws_max[1] - y, hp.ws_max[2] - z};
+        float dmin = d[0];
+        for (int i = 1; i < 6; ++i) dmin = fminf(dmin, d[i]);
+        if (dmin < hp.mo_ws[s2]) hp.occ_const |= TRK_OCC_WS;
+        hp.c_ws_const = hp.c_ws_const + -(dmin - hp.m_ws[s2]);
+    }
+}
+
+template <class R, class CM, int EE>
+inline cudaError_t launch_objective_hot(int n_sms, const float* host_words, const float* cost_words, const float* q, long long n,
+                                        const float* ee_target_cfg, float margin_override, int use_override, float* cost_total,
+                                        float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin, cudaStream_t st) {
+    HotParams hp;
+    hot_params_from_cost<R, CM, EE>(host_words, margin_override, use_override, hp);
+    const size_t smem = ((size_t)hp.n_pairs2 * 8 + (size_t)hp.n_sph * 4 + (TRK_HOT_QSTAGE >= 2 ? 2 * kSBlock * R::D : 0)) * sizeof(float);
+    auto launch = [&](auto k) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        k<<<persistent_grid(k, n_sms, smem, n), kSBlock, smem, st>>>(hp, cost_words, q, n, ee_target_cfg, cost_total, cost_terms, grad_q,
+                                                                     occupancy, argmin);
+        return cudaGetLastError();
+    };
+    if (grad_q) {
+        if (ee_target_cfg) return launch(k_objective_hot<R, CM, EE, true, true>);
+        return launch(k_objective_hot<R, CM, EE, false, true>);
+    }
+    if (ee_target_cfg) return launch(k_objective_hot<R, CM, EE, true, false>);
+    return launch(k_objective_hot<R, CM, EE, false, false>);
+}
+
 template <class R>
-cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwords, int n_slots, int clamp_any, int cm_match, const float* q,
+cudaError_t launch_objective_t(int n_sms, const float* host_words, const float* cost_words, int cost_nwords, int n_slots, int clamp_any, int cm_match, const float* q,
                                       long long n, const float* ee_target_cfg, float margin_override, int use_override,
                                       float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin,
                                       cudaStream_t st) {
@@ -1258,6 +1339,14 @@ cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwor
             if constexpr (CollisionModelOf<R>::in_registers) {
                 if ((cm_match & 2) && !clamp_any) {   // the end-effector is the model's own EE body: known at compile time
                     constexpr int kEE = STree<R>::topo_index_of(CM::ee_body);
+                    if constexpr (CM::S <= kHotMaxPoints && CM::P <= kHotMaxPairs) {
+                        // + joint-scan scene, workspace box and both EE weights on, 16-byte aligned q: the headline kernel
+                        static const bool no_hot = std::getenv("TRK_B200_NO_HOT") != nullptr;   // A/B switch
+                        if ((cm_match & 12) == 12 && !no_hot && (reinterpret_cast<uintptr_t>(q) & 15u) == 0 &&
+                            (!ee_target_cfg || (reinterpret_cast<uintptr_t>(ee_target_cfg) & 15u) == 0))
+                            return launch_objective_hot<R, CM, kEE>(n_sms, host_words, cost_words, q, n, ee_target_cfg, margin_override, use_override,
+                                                                    cost_total, cost_terms, grad_q, occupancy, argmin, st);
+                    }
                     if ((cm_match & 4) && grad_q) return launch_objective_cm_k<R, CM, true, false, kEE, true>(TRK_OBJ_ARGS);   // + joint-scan scene
                     if (grad_q) return launch_objective_cm_k<R, CM, true, false, kEE>(TRK_OBJ_ARGS);
                     return launch_objective_cm_k<R, CM, false, false, kEE>(TRK_OBJ_ARGS);
@@ -1289,7 +1378,7 @@ cudaError_t launch_objective_t(int n_sms, const float* cost_words, int cost_nwor
 #define TRK_LAUNCHER_SIGNATURES(KW, Rb)                                                                                                   \
     KW template cudaError_t launch_fk_forward_t<Rb>(int, const float*, long long, const SlotMap&, int, float*, cudaStream_t);           \
     KW template cudaError_t launch_fk_backward_t<Rb>(int, const float*, long long, const SlotMap&, int, const float*, float*, cudaStream_t); \
-    KW template cudaError_t launch_objective_t<Rb>(int, const float*, int, int, int, int, const float*, long long, const float*, float, int, \
+    KW template cudaError_t launch_objective_t<Rb>(int, const float*, const float*, int, int, int, int, const float*, long long, const float*, float, int, \
                                                    float*, float*, float*, uint8_t*, int*, cudaStream_t);                               \
     KW template cudaError_t launch_ik_t<Rb>(const IKParams&, const float*, const float*, const float*, long long, float*, float*,        \
                                             uint8_t*, int*, float*, float*, cudaStream_t);
@@ -1343,13 +1432,15 @@ inline int cm_match_value(const float* host_cost_words) {
         const int need = OBJ_IDENTITY | OBJ_UNIFORM_RADIUS;
         const bool joint_scene = hh->nObj == 1 && hh->KB == 0 && (iw[hh->off_obj_ident] & (need | OBJ_GRID)) == need &&
                                  iw[hh->off_obj_start + 1] > iw[hh->off_obj_start];
-        return 1 | ((hh->ee_enabled && hh->ee_link == CM::ee_body) ? 2 : 0) | (joint_scene ? 4 : 0);
+        const bool hot_terms = hh->ws_enabled && hh->ee_w_pos > 0.f && hh->ee_w_rot > 0.f;
+        return 1 | ((hh->ee_enabled && hh->ee_link == CM::ee_body) ? 2 : 0) | (joint_scene ? 4 : 0) | (hot_terms ? 8 : 0);
     }
 }
 
 // > 0 when `family` has a compile-time collision model and the (host copy of the) cost table matches it;
 // bit 1: the end-effector term is enabled on the model's own EE body (CM::ee_body); bit 2: the scene is one equal-radius
-// identity-pose sphere object (the joint-scan scene)
+// identity-pose sphere object (the joint-scan scene); bit 3: workspace box on and both EE weights positive (what
+// k_objective_hot assumes on top of bits 1 and 2)
 inline int static_cm_match(int family, const float* host_cost_words) {
     int id = 0;
 #define X(Rb)                                                                          \
@@ -1363,7 +1454,7 @@ inline int static_cm_match(int family, const float* host_cost_words) {
     return 0;
 }
 
-inline cudaError_t launch_static_objective(int family, int n_sms, const float* cost_words, int cost_nwords, int n_slots, int clamp_any, int cm_match,
+inline cudaError_t launch_static_objective(int family, int n_sms, const float* host_words, const float* cost_words, int cost_nwords, int n_slots, int clamp_any, int cm_match,
                                            const float* q, long long n, const float* ee_target_cfg, float margin_override, int use_override,
                                            float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin,
                                            cudaStream_t st) {
@@ -1371,7 +1462,7 @@ inline cudaError_t launch_static_objective(int family, int n_sms, const float* c
 #define X(Rb) \
     ++id;     \
     if (family == id)  \
-        return launch_objective_t<Rb>(n_sms, cost_words, cost_nwords, n_slots, clamp_any, cm_match, q, n, ee_target_cfg, margin_override, use_override, \
+        return launch_objective_t<Rb>(n_sms, host_words, cost_words, cost_nwords, n_slots, clamp_any, cm_match, q, n, ee_target_cfg, margin_override, use_override, \
                                       cost_total, cost_terms, grad_q, occupancy, argmin, st);
     TRK_FOR_EACH_STATIC_ROBOT(X)
 #undef X
