@@ -165,6 +165,7 @@ class DeviceModel:
         check(lib().trk_model_create(C.byref(md), idx, C.byref(h)), "trk_model_create")
         self.handle = h
         self.n_links, self.n_dofs = desc.n_links, desc.n_dofs
+        self._ik_schedules = {}
 
     @property
     def kernel_family(self) -> str:
@@ -230,9 +231,18 @@ class DeviceModel:
         S, D = q.shape
         dev = q.device
         n_updates = n_iters if n_updates is None else n_updates
-        t = np.arange(1, n_iters + 1, dtype=np.float64)
-        step_size = torch.as_tensor((lr / (1.0 - betas[0] ** t)).astype(np.float32), device=dev)
-        bc2 = torch.as_tensor(np.sqrt(1.0 - betas[1] ** t).astype(np.float32), device=dev)
+        # Adam's per-iteration bias corrections: device-resident, cached per schedule (two small uploads otherwise
+        # cost more than the kernel for a few thousand seeds)
+        key = (int(n_iters), float(lr), float(betas[0]), float(betas[1]), str(dev))
+        sched = self._ik_schedules.get(key)
+        if sched is None:
+            t = np.arange(1, n_iters + 1, dtype=np.float64)
+            sched = (torch.as_tensor((lr / (1.0 - betas[0] ** t)).astype(np.float32), device=dev),
+                     torch.as_tensor(np.sqrt(1.0 - betas[1] ** t).astype(np.float32), device=dev))
+            if len(self._ik_schedules) > 16:
+                self._ik_schedules.clear()
+            self._ik_schedules[key] = sched
+        step_size, bc2 = sched
         lo = _c32(lower.detach().cpu().numpy() if torch.is_tensor(lower) else lower, np.float32).reshape(-1)
         hi = _c32(upper.detach().cpu().numpy() if torch.is_tensor(upper) else upper, np.float32).reshape(-1)
         if lo.shape[0] != D or hi.shape[0] != D:

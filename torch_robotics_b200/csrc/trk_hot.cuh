@@ -32,7 +32,7 @@ namespace trk {
 #define TRK_HOT_QSTAGE 1
 #endif
 
-constexpr int kHotMaxPairs = 16, kHotMaxPoints = 8;
+constexpr int kHotMaxPairs = 16, kHotMaxPoints = 16;
 
 struct HotParams {
     float m_pair[kHotMaxPairs], mo_pair[kHotMaxPairs];   // self pairs: cost margin / occupancy margin
@@ -196,6 +196,15 @@ struct HTree {
         return true;
     }
 
+    // movable body j is an ancestor-or-self anchor of body b (its joint moves b)
+    __host__ __device__ static constexpr bool is_anchor_above(int j, int b) {
+        int a = anchor(b);
+        while (true) {
+            if (a == j) return true;
+            if (pix(a) < 0) return false;
+            a = ap(a);
+        }
+    }
     // the world position of body b does not depend on q (same criterion), and its value
     __host__ __device__ static constexpr bool pos_is_const(int b) { return force_is_useless(b); }
     __host__ __device__ static constexpr HXf const_pose(int b) {      // .t = the constant position; valid when pos_is_const(b)
@@ -352,12 +361,17 @@ struct HotPlan {
         for (int c = m + 1; c < L; ++c) if (T::movable(c) && T::ap(c) == m && subtree_wrench(c)) return true;
         return false;
     }
-    // accumulator of movable body m already written when body b (anchored at m) adds its force: a child pushed, the EE
-    // wrench came first, or a body with a larger topo index did
-    __host__ __device__ static constexpr bool started_before_body(int m, int b) {
+    // accumulator of movable body m already written when the EE wrench (anchored at m) arrives: a child pushed
+    __host__ __device__ static constexpr bool started_before_ee(int m) {
         for (int c = m + 1; c < L; ++c) if (T::movable(c) && T::ap(c) == m && subtree_wrench(c)) return true;
-        if (T::anchor(EE) == m && b != EE) return true;
-        for (int b2 = b + 1; b2 < L; ++b2) if (b2 != EE && T::anchor(b2) == m && has_force(b2)) return true;
+        return false;
+    }
+    // ... when body b (anchored at m) adds its force: a child pushed, the EE wrench came first, or a body with a larger
+    // topo index did (the EE body itself may also carry a collision point)
+    __host__ __device__ static constexpr bool started_before_body(int m, int b) {
+        if (started_before_ee(m)) return true;
+        if (T::anchor(EE) == m) return true;
+        for (int b2 = b + 1; b2 < L; ++b2) if (T::anchor(b2) == m && has_force(b2)) return true;
         return false;
     }
     // accumulator of pa already written when movable child c pushes into it
@@ -678,7 +692,7 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
             if constexpr (T::pix(i) >= 0 && T::movable(i) && Plan::subtree_wrench(i)) {
                 // forces of the bodies anchored here (the EE wrench first, then bodies by decreasing topo index)
                 if constexpr (T::anchor(EE) == i) {
-                    constexpr bool st = Plan::started_before_body(i, EE);
+                    constexpr bool st = Plan::started_before_ee(i);
                     sfor<3>([&](auto rc) {
                         F[i][rc] = st ? F[i][rc] + eF[rc] : eF[rc];
                         Tq[i][rc] = st ? Tq[i][rc] + eT[rc] : eT[rc];
@@ -686,7 +700,7 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
                 }
                 sfor<L>([&](auto bc) {
                     constexpr int b = L - 1 - decltype(bc)::value;
-                    if constexpr (b != EE && T::anchor(b) == i && Plan::has_force(b)) {
+                    if constexpr (T::anchor(b) == i && Plan::has_force(b)) {
                         constexpr bool st = Plan::started_before_body(i, b);
                         const float px = Pb[b][0], py = Pb[b][1], pz = Pb[b][2], fx = G[b][0], fy = G[b][1], fz = G[b][2];
                         if constexpr (st) {

@@ -1083,12 +1083,166 @@ __global__ void __launch_bounds__(kSBlock) k_ik_adam_static(IKParams P, const fl
     }
 }
 
+
+// The same with the end-effector body (topo index EE) at compile time and the folded tree of trk_hot.cuh: only the movable
+// ancestors of the EE body are composed, fixed chains cost three FMAs, the joints off the EE chain never enter the loop body.
+template <class R, int EE>
+__global__ void __launch_bounds__(kSBlock) k_ik_adam_hot(IKParams P, const float* __restrict__ step_size, const float* __restrict__ bc2_sqrt,
+                                                         const float* __restrict__ target_seed, long long n_seeds,
+                                                         float* __restrict__ q_io, float* __restrict__ err_out,
+                                                         uint8_t* __restrict__ valid_out, int* __restrict__ valid_count,
+                                                         float* __restrict__ loss_sum, float* __restrict__ loss_sqsum) {
+    using T = HTree<R>;
+    constexpr int L = R::L, D = R::D;
+    __shared__ int s_cnt;
+    __shared__ float s_sum, s_sq;
+    const long long seed = (long long)blockIdx.x * kSBlock + threadIdx.x;
+    const bool live = seed < n_seeds;
+    const int lane = threadIdx.x & 31;
+    float qv[D], mom[D], var[D];
+    sfor<D>([&](auto c) { qv[c] = live ? q_io[seed * D + c] : 0.f; mom[c] = 0.f; var[c] = 0.f; });
+    float Rt[9], pt[3];
+    {
+        const float* Ht = (P.per_seed_target && live) ? target_seed + seed * 16 : P.target;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            Rt[i * 3 + 0] = Ht[i * 4 + 0]; Rt[i * 3 + 1] = Ht[i * 4 + 1]; Rt[i * 3 + 2] = Ht[i * 4 + 2]; pt[i] = Ht[i * 4 + 3];
+        }
+    }
+    float err = 0.f;
+    bool valid = false;
+#pragma unroll 1
+    for (int it = 0; it < P.n_iters; ++it) {
+        if (threadIdx.x == 0) { s_cnt = 0; s_sum = 0.f; s_sq = 0.f; }
+        __syncthreads();
+        float W[L][12], JA[D][3], Ree[9], pee[3];
+        unsigned pass = 0u;
+        sfor<L>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            if constexpr (T::pix(i) >= 0 && T::movable(i) && T::is_anchor_above(i, EE)) {
+                constexpr int qi = R::qidx[i];
+                const float qraw = qv[qi];
+                float theta = qraw;
+                if constexpr (R::has_lim[i] != 0) {
+                    constexpr float lo = R::lo[i], hi = R::hi[i];
+                    theta = fmin_nan(fmax_nan(qraw, lo), hi);
+                    if (theta == qraw) pass |= (1u << qi);
+                } else {
+                    pass |= (1u << qi);
+                }
+                constexpr int a = T::ap(i);
+                T::template compose<i, T::small_angle(i)>(W[a], theta, W[i]);
+                T::template joint_axis<i>(W[a], W[i], JA[qi]);
+            }
+        });
+        if constexpr (T::pix(EE) < 0) {
+            sfor<9>([&](auto e) { Ree[e] = (e == 0 || e == 4 || e == 8) ? 1.f : 0.f; });
+            sfor<3>([&](auto rc) { pee[rc] = 0.f; });
+        } else if constexpr (T::movable(EE)) {
+            sfor<9>([&](auto e) { Ree[e] = W[EE][e]; });
+            sfor<3>([&](auto rc) { pee[rc] = W[EE][9 + rc]; });
+        } else {
+            T::template fixed_rotation<EE>(W[T::anchor(EE)], Ree);
+            T::template fixed_position<EE>(W[T::anchor(EE)], pee);
+        }
+        // SE3_distance, un-squared, weights 1 (ee_term of trk_device.cuh) and its wrench about the world origin
+        float eF[3], eT[3];
+        {
+            float dg[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                dg[i] = __fmaf_rn(Ree[i * 3 + 2], Rt[i * 3 + 2], __fmaf_rn(Ree[i * 3 + 1], Rt[i * 3 + 1], __fmul_rn(Ree[i * 3 + 0], Rt[i * 3 + 0])));
+            const float tr = __fadd_rn(__fadd_rn(dg[0], dg[1]), dg[2]);
+            const float phi = __fmul_rn(__fsub_rn(tr, 1.f), 0.5f);
+            const float vx = __fsub_rn(pee[0], pt[0]), vy = __fsub_rn(pee[1], pt[1]), vz = __fsub_rn(pee[2], pt[2]);
+            float rs;
+            const float dist = norm3_clamped(vx, vy, vz, rs);
+            err = __fadd_rn(__fsub_rn(1.f, phi), dist);
+            const float kr = -0.5f * P.w_se3, kp = P.w_se3 * rs;
+            eF[0] = kp * vx; eF[1] = kp * vy; eF[2] = kp * vz;
+            const float m21 = Rt[6] * Ree[3] + Rt[7] * Ree[4] + Rt[8] * Ree[5];
+            const float m12 = Rt[3] * Ree[6] + Rt[4] * Ree[7] + Rt[5] * Ree[8];
+            const float m02 = Rt[0] * Ree[6] + Rt[1] * Ree[7] + Rt[2] * Ree[8];
+            const float m20 = Rt[6] * Ree[0] + Rt[7] * Ree[1] + Rt[8] * Ree[2];
+            const float m10 = Rt[3] * Ree[0] + Rt[4] * Ree[1] + Rt[5] * Ree[2];
+            const float m01 = Rt[0] * Ree[3] + Rt[1] * Ree[4] + Rt[2] * Ree[5];
+            eT[0] = fmaf(kr, m21 - m12, fmaf(pee[1], eF[2], -(pee[2] * eF[1])));
+            eT[1] = fmaf(kr, m02 - m20, fmaf(pee[2], eF[0], -(pee[0] * eF[2])));
+            eT[2] = fmaf(kr, m10 - m01, fmaf(pee[0], eF[1], -(pee[1] * eF[0])));
+        }
+        bool in_lim = true;
+        float e_lim = 0.f;
+        sfor<D>([&](auto c) {
+            const float lo = P.lower[c], hi = P.upper[c];
+            in_lim = in_lim && (qv[c] >= lo) && (qv[c] <= hi);
+            const float dl = lo - qv[c], dh = hi - qv[c];
+            e_lim += (qv[c] < lo ? dl * dl : 0.f) + (qv[c] > hi ? dh * dh : 0.f);
+        });
+        valid = in_lim && (err < P.se3_eps);
+        const float loss = P.w_se3 * err + P.w_lim * e_lim;
+        const unsigned ball = __ballot_sync(0xffffffffu, valid && live);
+        if (loss_sum) {      // loss statistics are optional (print_freq of the reference loop)
+            float ls = live ? loss : 0.f, lq = live ? loss * loss : 0.f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { ls += __shfl_xor_sync(0xffffffffu, ls, o); lq += __shfl_xor_sync(0xffffffffu, lq, o); }
+            if (lane == 0) { atomicAdd(&s_sum, ls); atomicAdd(&s_sq, lq); }
+        }
+        if (lane == 0) atomicAdd(&s_cnt, __popc(ball));
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicAdd(valid_count + it, s_cnt);
+            if (loss_sum) { atomicAdd(loss_sum + it, s_sum); atomicAdd(loss_sqsum + it, s_sq); }
+        }
+        if (it >= P.n_updates) continue;
+        // d loss / d q_j = a_j . (T - p_j x F) for the joints above the EE body, 0 elsewhere; torch.clamp's mask of FK
+        float grad[D];
+        sfor<D>([&](auto c) { grad[c] = 0.f; });
+        sfor<L>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            if constexpr (T::pix(i) >= 0 && T::movable(i) && T::is_anchor_above(i, EE)) {
+                constexpr int qi = R::qidx[i];
+                float g;
+                if constexpr (R::kind[i] == TRK_KIND_REVOLUTE) {
+                    const float px = W[i][9], py = W[i][10], pz = W[i][11];
+                    const float mx = fmaf(pz, eF[1], fmaf(-py, eF[2], eT[0]));
+                    const float my = fmaf(px, eF[2], fmaf(-pz, eF[0], eT[1]));
+                    const float mz = fmaf(py, eF[0], fmaf(-px, eF[1], eT[2]));
+                    g = fmaf(JA[qi][2], mz, fmaf(JA[qi][1], my, JA[qi][0] * mx));
+                } else {
+                    g = fmaf(JA[qi][2], eF[2], fmaf(JA[qi][1], eF[1], JA[qi][0] * eF[0]));
+                }
+                grad[qi] = ((pass >> qi) & 1u) ? g : 0.f;
+            }
+        });
+        const float ss = step_size[it], inv_b2s = 1.f / bc2_sqrt[it];
+        sfor<D>([&](auto c) {
+            const float lo = P.lower[c], hi = P.upper[c];
+            float g = grad[c];
+            g += P.w_lim * ((qv[c] < lo ? -2.f * (lo - qv[c]) : 0.f) + (qv[c] > hi ? -2.f * (hi - qv[c]) : 0.f));
+            mom[c] = fmaf(1.f - P.beta1, g - mom[c], mom[c]);                 // exp_avg.lerp_(grad, 1 - beta1)
+            var[c] = fmaf((1.f - P.beta2) * g, g, var[c] * P.beta2);          // exp_avg_sq.mul_(beta2).addcmul_(g, g, 1 - beta2)
+            float rs_unused;
+            const float denom = sqrt_rn_core(var[c], rs_unused) * inv_b2s + P.eps;   // sqrt(v) / sqrt(1 - beta2^t) + eps
+            qv[c] = qv[c] - ss * __fdividef(mom[c], denom);                        // param.addcdiv_(exp_avg, denom, -step_size)
+        });
+    }
+    if (live) {
+        sfor<D>([&](auto c) { q_io[seed * D + c] = qv[c]; });
+        if (err_out) err_out[seed] = err;
+        if (valid_out) valid_out[seed] = valid ? 1 : 0;
+    }
+}
+
 template <class R>
 cudaError_t launch_ik_t(const IKParams& P, const float* step_size, const float* bc2_sqrt, const float* target_seed,
                                long long n_seeds, float* q_io, float* err_out, uint8_t* valid_out, int* valid_count,
                                float* loss_sum, float* loss_sqsum, cudaStream_t st) {
     const long long blocks = (n_seeds + kSBlock - 1) / kSBlock;
-    if (P.ee_link == R::body[R::L - 1])
+    static const bool no_hot = std::getenv("TRK_B200_NO_HOT") != nullptr;   // A/B switch
+    if (P.ee_link == R::body[R::L - 1] && !no_hot)
+        k_ik_adam_hot<R, R::L - 1><<<(unsigned)blocks, kSBlock, 0, st>>>(P, step_size, bc2_sqrt, target_seed, n_seeds, q_io, err_out,
+                                                                       valid_out, valid_count, loss_sum, loss_sqsum);
+    else if (P.ee_link == R::body[R::L - 1])
         k_ik_adam_static<R, R::L - 1><<<(unsigned)blocks, kSBlock, 0, st>>>(P, step_size, bc2_sqrt, target_seed, n_seeds, q_io, err_out,
                                                                           valid_out, valid_count, loss_sum, loss_sqsum);
     else
@@ -1336,17 +1490,20 @@ cudaError_t launch_objective_t(int n_sms, const float* host_words, const float* 
                        grad_q, occupancy, argmin, st
     if constexpr (!std::is_void<CM>::value) {
         if (cm_match) {
+            if constexpr (CM::S <= kHotMaxPoints && CM::P <= kHotMaxPairs) {
+                // model's own EE body + joint-scan scene + workspace box and both EE weights on + no relu + 16-byte aligned q:
+                // the headline kernel (trk_hot.cuh)
+                static const bool no_hot = std::getenv("TRK_B200_NO_HOT") != nullptr;   // A/B switch
+                if ((cm_match & 14) == 14 && !clamp_any && !no_hot && (reinterpret_cast<uintptr_t>(q) & 15u) == 0 &&
+                    (!ee_target_cfg || (reinterpret_cast<uintptr_t>(ee_target_cfg) & 15u) == 0)) {
+                    constexpr int kEE = STree<R>::topo_index_of(CM::ee_body);
+                    return launch_objective_hot<R, CM, kEE>(n_sms, host_words, cost_words, q, n, ee_target_cfg, margin_override, use_override,
+                                                            cost_total, cost_terms, grad_q, occupancy, argmin, st);
+                }
+            }
             if constexpr (CollisionModelOf<R>::in_registers) {
                 if ((cm_match & 2) && !clamp_any) {   // the end-effector is the model's own EE body: known at compile time
                     constexpr int kEE = STree<R>::topo_index_of(CM::ee_body);
-                    if constexpr (CM::S <= kHotMaxPoints && CM::P <= kHotMaxPairs) {
-                        // + joint-scan scene, workspace box and both EE weights on, 16-byte aligned q: the headline kernel
-                        static const bool no_hot = std::getenv("TRK_B200_NO_HOT") != nullptr;   // A/B switch
-                        if ((cm_match & 12) == 12 && !no_hot && (reinterpret_cast<uintptr_t>(q) & 15u) == 0 &&
-                            (!ee_target_cfg || (reinterpret_cast<uintptr_t>(ee_target_cfg) & 15u) == 0))
-                            return launch_objective_hot<R, CM, kEE>(n_sms, host_words, cost_words, q, n, ee_target_cfg, margin_override, use_override,
-                                                                    cost_total, cost_terms, grad_q, occupancy, argmin, st);
-                    }
                     if ((cm_match & 4) && grad_q) return launch_objective_cm_k<R, CM, true, false, kEE, true>(TRK_OBJ_ARGS);   // + joint-scan scene
                     if (grad_q) return launch_objective_cm_k<R, CM, true, false, kEE>(TRK_OBJ_ARGS);
                     return launch_objective_cm_k<R, CM, false, false, kEE>(TRK_OBJ_ARGS);
