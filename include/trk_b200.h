@@ -260,6 +260,17 @@ int trk_ik_adam(const trk_model* model, const trk_ik_params* params, const float
 int trk_link_jacobian(const trk_model* model, const float* q, int64_t n, float* J, void* stream);
 
 /*
+ * Replaces DifferentiableTree.compute_forward_kinematics_and_geometric_jacobian (robot_tree.py:218-248) for one link:
+ * q [N, D] -> pose12 [N, 12] (world rotation of `link` row-major, then its position), lin [N, 3, D], ang [N, 3, D] with
+ *   lin[:, c] = z_c x (p_link - p_c), ang[:, c] = z_c   for the q columns set in `col_mask`, zero elsewhere,
+ * z_c / p_c = axis column / position of the body q column c drives (joint limits clamped as in trk_fk_forward).  The
+ * reference includes a column when the joint's index in the URDF is not larger than the index of the joint above `link`
+ * (robot_tree.py:237-240); the caller passes that selection as the mask.
+ */
+int trk_geometric_jacobian(const trk_model* model, const float* q, int64_t n, int32_t link, uint32_t col_mask, float* pose12,
+                           float* lin, float* ang, void* stream);
+
+/*
  * Self-test of the branch-free correctly-rounded square root used for every distance that feeds a
  * comparison (trk_device.cuh: sqrt_rn_core): y_core[i] from that routine, y_ref[i] from sqrt.rn.f32.
  * The two must be bit-identical for x == 0 and 2^-100 <= x < 2^126.  All pointers are device memory.

@@ -358,6 +358,30 @@ def golden_ik():
 
 
 
+def golden_ik_500():
+    """BASELINE config 4's settings (examples/inverse_kinematics.py:37-42: 500 iterations, lr 0.2, se3_eps 0.05) on 64
+    explicit seeds.  Adam's normalised steps make the iterates chaotic over hundreds of iterations: two fp32
+    implementations of the same loop drift apart (the numpy restatement vs this reference run: median 0.06 rad, three of 64
+    validity flags differ), so the fixture also records the per-seed SE(3) error for the tests' boundary analysis."""
+    gen = torch.Generator().manual_seed(77)
+    model = quiet(R.DifferentiableFrankaPanda, gripper=False)
+    H_target = ee_target()
+    lower, upper, _, _ = model.get_joint_limit_array()
+    eps = torch.pi / 64
+    lo = torch.tensor(lower + eps, **TA)
+    hi = torch.tensor(upper - eps, **TA)
+    S = 64
+    q0 = (lo + torch.rand(S, 7, generator=gen) * (hi - lo)).contiguous()
+    q_ik, idx = quiet(model.inverse_kinematics, H_target, link_name="ee_link", batch_size=S, max_iters=500, lr=2e-1, se3_eps=5e-2,
+                      q0=q0.clone(), q0_noise=0.0, eps_joint_lim=eps, print_freq=-1)
+    H = model.compute_forward_kinematics_all_links(q_ik.detach(), link_list=["ee_link"]).squeeze(1)
+    err = SE3_distance(H, H_target).detach().numpy().reshape(-1)
+    np.savez_compressed(os.path.join(HERE, "ik_panda_500.npz"), q0=q0.numpy(), q_ik_500=q_ik.detach().numpy(),
+                        idx_valid_500=idx.numpy().astype(np.int64), err_500=err.astype(np.float32), lower=lo.numpy(), upper=hi.numpy(),
+                        H_target=H_target.numpy().reshape(4, 4))
+    print("ik 500: valid", len(idx), "of", S)
+
+
 def golden_trajectories():
     """Trajectory collision classification (tasks.py:234-328) on Panda + EnvSpheres3D: interpolation between
     waypoints, zero-margin collision flags, free / colliding index lists, joint-limit filter, statistics."""
@@ -574,11 +598,39 @@ def golden_link_jacobians():
     np.savez_compressed(os.path.join(HERE, "link_jacobians.npz"), **out)
 
 
+def golden_geometric_jacobian():
+    """compute_forward_kinematics_and_geometric_jacobian (robot_tree.py:218-248) for links of the Panda (chain, z axes), the
+    UR10 (y and z axes) and the dual-arm Tiago (branches: the reference's joint-index rule admits joints that are not
+    ancestors of the link).  These robots have only positive-axis, limited revolute joints: for them the stateful pose
+    propagation the reference uses here (update_kinematic_state) gives the same poses as its stateless FK.  (It does not for
+    negative axes - rigid_body.py:101-106 picks z_rot and drops the sign - nor for continuous joints, which it clamps.)"""
+    gen = torch.Generator().manual_seed(99)
+    out = {}
+    for name, links in (("panda", ["ee_link", "panda_link4"]), ("ur10", ["ee_link", "forearm_link"]),
+                        ("tiago_dual_holo", ["arm_right_7_link", "arm_left_4_link"])):
+        model = quiet(ROBOTS[name])
+        names = model.get_link_names()
+        links = [ln if ln in names else names[-1] for ln in links]
+        q = sample_q(model, 24, gen)
+        out[f"{name}_q"] = q.numpy()
+        out[f"{name}_links"] = np.array(links)
+        # stateless FK first: the stateful call below overwrites body.pose, which the stateless recursion starts from
+        Hs_all = {ln: model.compute_forward_kinematics_all_links(q, link_list=[ln])[:, 0].clone() for ln in links}
+        for ln in links:
+            pos, rot, lin, ang = model.compute_forward_kinematics_and_geometric_jacobian(q, torch.zeros_like(q), ln)
+            assert torch.allclose(Hs_all[ln][:, :3, 3], pos, atol=1e-6), (name, ln)      # stateful == stateless for these robots
+            out[f"{name}_{ln}_pos"], out[f"{name}_{ln}_rot"] = pos.detach().numpy(), rot.detach().numpy()
+            out[f"{name}_{ln}_lin"], out[f"{name}_{ln}_ang"] = lin.detach().numpy(), ang.detach().numpy()
+            print("geometric jacobian", name, ln, tuple(lin.shape), float(lin.abs().max()))
+    np.savez_compressed(os.path.join(HERE, "geometric_jacobian.npz"), **out)
+
+
 if __name__ == "__main__":
     if os.environ.get("GOLDEN_ONLY") == "envs":
         golden_planning_envs()
     elif os.environ.get("GOLDEN_ONLY") == "jacobian":
         golden_link_jacobians()
+        golden_geometric_jacobian()
     elif os.environ.get("GOLDEN_ONLY") == "voxel":
         golden_voxel_sdf()
     elif os.environ.get("GOLDEN_ONLY") == "points":
@@ -587,6 +639,10 @@ if __name__ == "__main__":
         golden_trajectories()
     elif os.environ.get("GOLDEN_ONLY") == "boxes":
         golden_planning_boxes()
+    elif os.environ.get("GOLDEN_ONLY") == "ik500":
+        golden_ik_500()
+    elif os.environ.get("GOLDEN_ONLY") == "geometric_jacobian":
+        golden_geometric_jacobian()
     else:
         golden_fk()
         golden_planning()
@@ -594,7 +650,9 @@ if __name__ == "__main__":
         golden_planning_envs()
         golden_stretch_objective()
         golden_ik()
+        golden_ik_500()
         golden_trajectories()
         golden_attached_points()
         golden_voxel_sdf()
         golden_link_jacobians()
+        golden_geometric_jacobian()

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import get_desc, load_golden, planning_cost_from_golden, rel_err, stretch_cost_from_golden
+from conftest import assert_differences_are_near_ties, get_desc, load_golden, planning_cost_from_golden, rel_err, stretch_cost_from_golden
 from oracle import c_oracle as co
 
 pytestmark = pytest.mark.gpu
@@ -89,12 +89,11 @@ def test_config3_planning_objective_4096x64():
     gd = np.abs(r["grad_q"].cpu().numpy() - o["grad_q"]).max(axis=1) / np.abs(o["grad_q"]).max()
     flipped = gd >= 1e-4
     print(f"config 3: gradient rows on a decision boundary: {int(flipped.sum())} of {len(gd)}")
-    assert flipped.sum() <= 30 and gd[~flipped].max() < 1e-4
-    n_am = int((r["argmin"].cpu().numpy() != o["argmin"]).sum())
-    n_occ = int((r["occupancy"].cpu().numpy() != o["occ"]).sum())
-    print(f"config 3: arg-min differences {n_am} of {o['argmin'].size}, occupancy differences {n_occ} of {o['occ'].size} "
-          "(end-to-end; both sides differ by an ulp in sin/cos)")
-    assert n_am <= 30 and n_occ <= 30
+    assert gd[~flipped].max() < 1e-4
+    # every difference is proven to be a near-tie: within a few ulp of a decision boundary on the oracle's own positions
+    n_diff = assert_differences_are_near_ties(d, cost, q, r["argmin"].cpu().numpy(), o["argmin"], r["occupancy"].cpu().numpy(), o["occ"],
+                                              np.flatnonzero(flipped), "config 3")
+    assert n_diff <= 30
     # the (b, h) shaped public entry point gives the same numbers
     from torch_robotics_b200 import ops
     c = ops.objective(dc, t(q))
@@ -116,7 +115,9 @@ def test_config5_stretch_objective_2M():
     o = co.objective(co.Tree(d), co.Cost(cost), q[sub])
     assert rel_err(r["total"][sub].cpu().numpy(), o["total"]) < 1e-5
     gd = np.abs(r["grad_q"][sub].cpu().numpy() - o["grad_q"]).max(axis=1) / np.abs(o["grad_q"]).max()
-    assert (gd >= 1e-4).sum() <= 30 and gd[gd < 1e-4].max() < 1e-4
+    assert gd[gd < 1e-4].max() < 1e-4
+    n_diff = assert_differences_are_near_ties(d, cost, q[sub], None, None, None, None, np.flatnonzero(gd >= 1e-4), "config 5")
+    assert n_diff <= 30
     r2 = dc.objective(t(q[sub]), want_grad=True, want_terms=False)
     assert torch.equal(r2["total"], r["total"][sub]) and torch.equal(r2["grad_q"], r["grad_q"][sub])
 

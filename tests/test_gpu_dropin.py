@@ -84,9 +84,11 @@ def test_planning_task_cost_and_collision(planning):
     coll = task.compute_collision(q.detach())
     assert coll.dtype == torch.bool and np.array_equal(coll.cpu().numpy(), g["occ_all_default"])
     assert np.array_equal(task.compute_collision(q.detach(), margin=0.0).cpu().numpy(), g["occ_all_zero"])
-    # 2-D and 1-D inputs follow the reference's shape rules (tasks.py:145-155)
+    # 2-D and 1-D inputs follow the reference's shape rules: the distance-field branch (tasks.py:199-230) returns what the
+    # fields return, and they always answer [batch, horizon] (distance_fields.py:26-58) -> [b, 1] and [1, 1]
     assert task.compute_collision_cost(q.detach()[0]).shape == (16, 1)
-    assert task.compute_collision_cost(q.detach()[0, 0]).shape == (1,)
+    assert task.compute_collision_cost(q.detach()[0, 0]).shape == (1, 1)
+    assert task.compute_collision(q.detach()[0, 0]).shape == (1, 1)
 
 
 def test_individual_fields_match_reference(planning):
@@ -149,8 +151,26 @@ def test_inverse_kinematics_matches_reference_iterates():
         q_ik, idx = panda.inverse_kinematics(Ht, link_name="ee_link", batch_size=24, max_iters=iters, lr=2e-1, se3_eps=5e-2,
                                              q0=t(g["q0"]).clone(), q0_noise=0.0, eps_joint_lim=torch.pi / 64, print_freq=-1)
         assert rel_err(q_ik.detach().cpu().numpy(), g[f"q_ik_{iters}"]) < (1e-4 if iters < 40 else 5e-3)
+        ref_idx = g[f"idx_valid_{iters}"]
         if iters < 40:
-            assert np.array_equal(idx.cpu().numpy(), g[f"idx_valid_{iters}"])
+            assert np.array_equal(idx.cpu().numpy(), ref_idx)
+        else:
+            # 40 Adam iterations amplify fp32 differences to ~1e-3 rad: a seed's validity may differ from the reference's
+            # only if the REFERENCE's own final iterate sits on the termination boundary (SE(3) error within the drift of
+            # se3_eps, or a joint within the drift of a limit) - checked per differing seed with the oracle on the golden q
+            from conftest import get_desc
+            from oracle import restatement as orc
+            diff = np.setxor1d(idx.cpu().numpy(), ref_idx)
+            d = get_desc("panda")
+            for s_ in diff:
+                qg = g[f"q_ik_{iters}"][s_:s_ + 1]
+                Rw, pw = orc.fk_forward(d, qg, np.float64)
+                err = float(orc.ee_term(type("C", (), dict(ee_w_pos=1.0, ee_w_rot=1.0, ee_square=0, weights=np.ones(4)))(), Rw[:, 10], pw[:, 10],
+                                        g["H_target"], dtype=np.float64)["dist"][0])
+                lim_gap = float(np.minimum(np.abs(qg - g["lower"]), np.abs(qg - g["upper"])).min())
+                assert abs(err - 5e-2) < 2e-2 or lim_gap < 2e-2, f"seed {s_}: validity differs away from the termination boundary"
+            print(f"IK 40 iterations: {len(diff)} validity differences, all on the termination boundary")
+            assert len(diff) <= 2
 
 
 def test_fused_ik_kernel_vs_oracle_and_torch_loop():
@@ -278,3 +298,88 @@ def test_cost_and_grad_without_autograd_matches_autograd():
     assert torch.equal(c2, c.detach()) and torch.equal(g2, q.grad)
     c3, g3 = task.compute_cost_and_grad(q[0])                     # [h, D] -> batch of one
     assert torch.equal(c3.reshape(-1), c2[0]) and torch.equal(g3.reshape(9, 7), g2[0])
+
+
+def test_fused_tables_follow_base_pose_and_moving_obstacles():
+    """The cached device tables of PlanningTask / the fields are keyed on the tree's model generation and on the
+    obstacles' pose revision: a base-pose update or a moved obstacle must never be answered from stale tables."""
+    from torch_robotics_b200.environments.env_base import EnvBase
+    from torch_robotics_b200.environments.primitives import MultiSphereField, ObjectField
+    from torch_robotics_b200.robots.robot_panda import RobotPanda
+    from torch_robotics_b200.tasks.tasks import PlanningTask
+    g = load_golden("planning_panda_spheres3d")
+    q = t(g["q"])
+
+    def make(pos):
+        spheres = MultiSphereField(np.array([[0.3, 0.2, 0.5], [-0.3, 0.3, 0.6]]), np.array([0.15, 0.15]), tensor_args=TA)
+        obj = ObjectField([spheres], "moving")
+        obj.set_position_orientation(pos=pos)
+        env = EnvBase(limits=torch.tensor([[-1., -1., -1.], [1., 1., 1.]], **TA), obj_fixed_list=[obj], tensor_args=TA)
+        robot = RobotPanda(tensor_args=TA)
+        return robot, obj, PlanningTask(env=env, robot=robot, tensor_args=TA)
+
+    robot, obj, task = make([0.0, 0.0, 0.0])
+    c_a = task.compute_collision_cost(q)
+    pos_field = task.df_collision_objects.compute_cost(q, robot.fk_map_collision(q), field_type="sdf")
+    for p in ([0.1, 0.0, 0.0], [0.0, 0.2, -0.1], [0.05, -0.1, 0.1]):      # A -> B -> C -> D: every move must be seen
+        obj.set_position_orientation(pos=p)
+        c_new = task.compute_collision_cost(q)
+        _, _, fresh = make(p)
+        assert torch.equal(c_new, fresh.compute_collision_cost(q)), p
+        f_new = task.df_collision_objects.compute_cost(q, robot.fk_map_collision(q), field_type="sdf")
+        assert not torch.equal(f_new, pos_field)
+    assert not torch.equal(c_new, c_a)
+    # base pose: FK and the fused objective must move together
+    obj.set_position_orientation(pos=[0.0, 0.0, 0.0])
+    c0 = task.compute_collision_cost(q)
+    robot.diff_panda.update_base_pose(torch.tensor([0.2, -0.1, 0.05, 1.0, 0.0, 0.0, 0.0]))
+    c1 = task.compute_collision_cost(q)
+    assert not torch.equal(c0, c1)
+    pos = robot.fk_map_collision(q)
+    parts = sum(f.compute_cost(q, pos, field_type="sdf") for f in task.get_collision_fields())
+    assert rel_err(c1.cpu().numpy(), parts.cpu().numpy()) < 1e-5      # fused tables == per-field tables on the moved robot
+
+
+def test_inverse_kinematics_500_iterations_config4_settings():
+    """BASELINE config 4's settings (500 Adam iterations, lr 0.2, se3_eps 0.05) on the 64 explicit seeds of the reference run
+    in tests/golden/ik_panda_500.npz.  Adam's normalised steps are chaotic over hundreds of iterations: the numpy fp32
+    restatement of the very same loop drifts from the reference run by 0.06 rad (median) and flips 3 of 64 validity flags
+    (tests/golden/make_golden.py:golden_ik_500), so iterates are compared statistically and decisions exactly:
+      * idx_valid must be EXACTLY the reference's termination test (robot_tree.py:419-442) applied to the kernel's own
+        iterate (oracle, float64), except seeds whose error is within 1e-5 of se3_eps;
+      * the kernel's drift from the reference run is no larger than the restatement's own drift (x2);
+      * the number of valid seeds agrees with the reference's within the restatement's own disagreement (x2)."""
+    from conftest import get_desc
+    from oracle import restatement as orc
+    from torch_robotics_b200.torch_kinematics_tree.models.robots import DifferentiableFrankaPanda
+    g, d = load_golden("ik_panda_500"), get_desc("panda")
+    panda = DifferentiableFrankaPanda(gripper=False, device=DEV)
+    q_ik, idx = panda.inverse_kinematics(t(g["H_target"]), link_name="ee_link", batch_size=64, max_iters=500, lr=2e-1, se3_eps=5e-2,
+                                         q0=t(g["q0"]).clone(), q0_noise=0.0, eps_joint_lim=torch.pi / 64, print_freq=-1)
+    qk = q_ik.detach().cpu().numpy()
+    idx = idx.cpu().numpy()
+    # (1) decisions: exact on the kernel's own iterate.  The loop returns the flags of its LAST termination test, taken before the
+    # final Adam step (robot_tree.py:347-354, :384), so the iterate they belong to is the one after 499 updates
+    lo, hi = g["lower"], g["upper"]
+    pre = panda.device_model(DEV).ik_adam(t(g["q0"]), g["H_target"], 10, lo, hi, n_iters=500, n_updates=499, lr=0.2, se3_eps=0.05)
+    assert np.array_equal(torch.nonzero(pre["valid"]).reshape(-1).cpu().numpy(), idx)
+    q_pre = pre["q"].cpu().numpy()
+    Rw, pw = orc.fk_forward(d, q_pre, np.float64)
+    cost = type("C", (), dict(ee_w_pos=1.0, ee_w_rot=1.0, ee_square=0, weights=np.ones(4)))()
+    err = np.asarray(orc.ee_term(cost, Rw[:, 10], pw[:, 10], g["H_target"], dtype=np.float64)["dist"]).reshape(-1)
+    inside = np.all((q_pre >= lo) & (q_pre <= hi), axis=1)
+    expect = np.flatnonzero(inside & (err < 5e-2))
+    for s_ in np.setxor1d(idx, expect):
+        assert abs(err[s_] - 5e-2) < 1e-5, f"seed {s_}: idx_valid disagrees with the termination test on its iterate (err {err[s_]:.6f})"
+    # (2) drift vs the reference run, against the restatement's own drift
+    qo, idxo = orc.ik_adam(d, 10, g["q0"], g["H_target"], g["lower"], g["upper"], 500, 0.2, 0.05)
+    drift_k = np.abs(qk - g["q_ik_500"]).max(axis=1)
+    drift_o = np.abs(qo - g["q_ik_500"]).max(axis=1)
+    print(f"IK 500 iterations: median / max drift from the reference run: kernel {np.median(drift_k):.3f} / {drift_k.max():.3f} rad, "
+          f"numpy restatement {np.median(drift_o):.3f} / {drift_o.max():.3f} rad; valid seeds: kernel {len(idx)}, reference "
+          f"{len(g['idx_valid_500'])}, restatement {len(idxo)}")
+    assert np.median(drift_k) <= 2.0 * max(np.median(drift_o), 1e-3)
+    # (3) validity: the same seeds within what chaos allows (the restatement itself flips 3 of 64 against the reference run), and the
+    # same NUMBER of valid seeds within the binomial spread of 64 draws at p ~ 0.75 (sigma = 3.5)
+    assert len(np.setxor1d(idx, g["idx_valid_500"])) <= 12
+    assert abs(len(idx) - len(g["idx_valid_500"])) <= 6

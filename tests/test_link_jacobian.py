@@ -96,3 +96,32 @@ def test_gpu_link_list_and_attached_points():
     Jp = full.device_model("cuda:0").link_jacobian(q).cpu().numpy()
     Jo = orc.link_jacobian(full._desc, q.cpu().numpy(), np.float32)
     assert rel_err(Jp[:, ids[0], :3], Jo[:, ids[0], :3]) < 1e-5
+
+
+@pytest.mark.gpu
+def test_geometric_jacobian_matches_reference():
+    """compute_forward_kinematics_and_geometric_jacobian (robot_tree.py:218-248) against the reference's own output:
+    position, wxyz quaternion, linear and angular Jacobian of a link - Panda (chain), UR10 (y / z axes), dual-arm Tiago
+    (branches: the reference's joint-index rule admits joints that are not ancestors of the link)."""
+    import torch
+    from torch_robotics_b200.torch_kinematics_tree.models import robots as R
+    g = load_golden("geometric_jacobian")
+    for name, cls in (("panda", R.DifferentiableFrankaPanda), ("ur10", R.DifferentiableUR10), ("tiago_dual_holo", R.DifferentiableTiagoDualHolo)):
+        tree = cls(device="cuda:0")
+        q = torch.as_tensor(g[f"{name}_q"], device="cuda:0")
+        links = [str(x) for x in g[f"{name}_links"]]
+        for ln in links:
+            pos, rot, lin, ang = tree.compute_forward_kinematics_and_geometric_jacobian(q, torch.zeros_like(q), ln)
+            assert lin.shape == (q.shape[0], 3, tree._n_dofs) and rot.shape == (q.shape[0], 4)
+            assert rel_err(pos.cpu().numpy(), g[f"{name}_{ln}_pos"]) < 1e-5, (name, ln)
+            # a quaternion and its negative are the same rotation; the branch choice can flip on a near-tie of the trace test
+            rq, rg = rot.cpu().numpy(), g[f"{name}_{ln}_rot"]
+            sgn = np.sign(np.sum(rq * rg, axis=1, keepdims=True))
+            assert rel_err(rq * sgn, rg) < 1e-5, (name, ln)
+            assert rel_err(lin.cpu().numpy(), g[f"{name}_{ln}_lin"]) < 1e-5, (name, ln)
+            assert rel_err(ang.cpu().numpy(), g[f"{name}_{ln}_ang"]) < 1e-5, (name, ln)
+            zc_ref = np.all(g[f"{name}_{ln}_ang"] == 0, axis=(0, 1))
+            zc = np.all(ang.cpu().numpy() == 0, axis=(0, 1))
+            assert np.array_equal(zc, zc_ref), f"{name}/{ln}: excluded q columns differ"
+        p2, r2 = tree.compute_forward_kinematics(q, None, links[0], state_less=False)
+        assert rel_err(p2.cpu().numpy(), g[f"{name}_{links[0]}_pos"]) < 1e-5

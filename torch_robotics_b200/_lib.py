@@ -59,7 +59,7 @@ EXPORTS = [
     "trk_abi_version", "trk_last_error", "trk_model_create", "trk_model_destroy", "trk_model_kernel_family",
     "trk_fk_forward", "trk_fk_backward", "trk_cost_create", "trk_cost_destroy", "trk_cost_set_ee_target",
     "trk_cost_set_weights", "trk_objective", "trk_objective_host", "trk_cost_stage", "trk_selftest_sqrt", "trk_ik_adam",
-    "trk_link_jacobian",
+    "trk_link_jacobian", "trk_geometric_jacobian",
 ]
 
 
@@ -95,6 +95,7 @@ def lib() -> C.CDLL:
         L.trk_cost_stage.argtypes = [vp, vp, vp, vp, i64, vp, f32, vp, vp, vp, vp, vp, vp, vp]
         L.trk_selftest_sqrt.argtypes = [vp, i64, vp, vp, vp]
         L.trk_link_jacobian.argtypes = [vp, vp, i64, vp, vp]
+        L.trk_geometric_jacobian.argtypes = [vp, vp, i64, i32, C.c_uint32, vp, vp, vp, vp]
         L.trk_objective_host.argtypes = [vp, vp, vp, i64, i32, vp, vp]
         L.trk_ik_adam.argtypes = [vp, C.POINTER(IKParamsC), vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
         for name in EXPORTS:
@@ -209,6 +210,22 @@ class DeviceModel:
         J = torch.empty((q.shape[0], self.n_links, 7, self.n_dofs), dtype=torch.float32, device=q.device)
         check(lib().trk_link_jacobian(self.handle, q.data_ptr(), q.shape[0], J.data_ptr(), stream_ptr(q.device)), "trk_link_jacobian")
         return J
+
+    def geometric_jacobian(self, q: torch.Tensor, link: int, col_mask: int):
+        """q [N, D] -> (pose [N, 12] = R row-major | p of body `link`, lin [N, 3, D], ang [N, 3, D]) for the q columns in
+        `col_mask` (trk_geometric_jacobian)."""
+        q = require_cuda_f32(q, "q")
+        if q.ndim != 2 or q.shape[1] != self.n_dofs:
+            raise RuntimeError(f"q must be [N, {self.n_dofs}], got {tuple(q.shape)}")
+        if q.device != self.device:
+            raise RuntimeError(f"q is on {q.device} but the model lives on {self.device}")
+        n = q.shape[0]
+        pose = torch.empty((n, 12), dtype=torch.float32, device=q.device)
+        lin = torch.empty((n, 3, self.n_dofs), dtype=torch.float32, device=q.device)
+        ang = torch.empty_like(lin)
+        check(lib().trk_geometric_jacobian(self.handle, q.data_ptr(), n, int(link), int(col_mask) & 0xFFFFFFFF, pose.data_ptr(), lin.data_ptr(),
+                                           ang.data_ptr(), stream_ptr(q.device)), "trk_geometric_jacobian")
+        return pose, lin, ang
 
     def fk_backward(self, q: torch.Tensor, G: torch.Tensor, link_sel=None) -> torch.Tensor:
         q = require_cuda_f32(q, "q")
@@ -388,8 +405,12 @@ class DeviceCost:
         if link_pos.ndim != 3 or link_pos.shape[1:] != (m.n_links, 3):
             raise RuntimeError(f"link_pos must be [N, {m.n_links}, 3], got {tuple(link_pos.shape)}")
         n, dev = link_pos.shape[0], link_pos.device
+        if dev != m.device:
+            raise RuntimeError(f"link_pos is on {dev}, the model on {m.device}")
         if ee_pose is not None:
             ee_pose = require_cuda_f32(ee_pose, "ee_pose")
+            if tuple(ee_pose.shape) != (n, 4, 4) or ee_pose.device != dev:
+                raise RuntimeError(f"ee_pose must be [{n}, 4, 4] on {dev}, got {tuple(ee_pose.shape)} on {ee_pose.device}")
         total = torch.empty(n, dtype=torch.float32, device=dev)
         terms = torch.empty((n, 4), dtype=torch.float32, device=dev)
         gpos = torch.empty_like(link_pos) if want_grad else None
@@ -397,6 +418,8 @@ class DeviceCost:
         occ = torch.empty(n, dtype=torch.uint8, device=dev) if want_occupancy else None
         amin = torch.empty((n, self.cost.n_objects, self.cost.n_points), dtype=torch.int32, device=dev) if want_argmin else None
         tgt = None if ee_target_cfg is None else require_cuda_f32(ee_target_cfg, "ee_target_cfg")
+        if tgt is not None and (tuple(tgt.shape) != (n, 4, 4) or tgt.device != dev):
+            raise RuntimeError(f"ee_target_cfg must be [{n}, 4, 4] on {dev}, got {tuple(tgt.shape)} on {tgt.device}")
         mo = float("nan") if margin_override is None else float(margin_override)
         ptr = lambda t: None if t is None else t.data_ptr()
         check(lib().trk_cost_stage(m.handle, self.handle, link_pos.data_ptr(), ptr(ee_pose), n, ptr(tgt), mo, ptr(total),

@@ -115,6 +115,66 @@ __global__ void __launch_bounds__(kBlock) k_fk_backward_generic(const float* __r
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Geometric Jacobian of one link (compute_forward_kinematics_and_geometric_jacobian, robot_tree.py:218-248):
+//   lin[:, c] = z_c x (p_link - p_c),  ang[:, c] = z_c   for every q column c in `col_mask`, zero elsewhere,
+// z_c = the joint-axis column of the world rotation of the body q column c drives (the reference takes the column of
+// the axis' non-zero component, sign and joint type ignored: rigid_body.py:97-99), p_c that body's world position.
+// One thread per configuration; z_c / p_c wait in per-lane shared-memory columns until the link's position is known.
+// Outputs: pose [N][12] (R row-major | p), lin / ang [N][3][D].
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_geometric_jacobian(const float* __restrict__ tree_words, int tree_nwords,
+                                                               const __grid_constant__ TreePlan live, const float* __restrict__ q, long long n,
+                                                               int link_body, unsigned col_mask, float* __restrict__ pose,
+                                                               float* __restrict__ lin, float* __restrict__ ang) {
+    extern __shared__ __align__(16) float smem[];
+    float* tw = smem;
+    block_copy_words(tw, tree_words, tree_nwords);
+    __syncthreads();
+    const TreeHeader* hdr = reinterpret_cast<const TreeHeader*>(tw);
+    const LinkRec* recs = reinterpret_cast<const LinkRec*>(tw + 16);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, D = hdr->D;
+    float* wbase = smem + tree_nwords + (size_t)warp * (live.n_live * 12 + D * 6) * 32;
+    float* wl = wbase + lane;
+    float* jc = wbase + live.n_live * 12 * 32 + lane;       // [(c * 6 + k) * 32]: k 0-2 axis column, 3-5 position
+    for (long long cfg = (long long)blockIdx.x * blockDim.x + threadIdx.x; cfg < n; cfg += (long long)gridDim.x * blockDim.x) {
+        float pe[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) pe[k] = 0.f;
+        fk_live(hdr, recs, live, q + cfg * D, wl, 32, [&](int, const LinkRec& r, const float* w, const float*, bool) {
+            if (r.qidx >= 0) {
+                int k = (r.flags >> F_AXIS_SHIFT) & 3;
+                if ((r.flags & F_KIND_MASK) == TRK_KIND_PRISMATIC) k = r.ax[0] != 0.f ? 0 : (r.ax[1] != 0.f ? 1 : 2);
+                float* o = jc + r.qidx * 6 * 32;
+                o[0] = k == 0 ? w[0] : (k == 1 ? w[1] : w[2]);
+                o[32] = k == 0 ? w[3] : (k == 1 ? w[4] : w[5]);
+                o[64] = k == 0 ? w[6] : (k == 1 ? w[7] : w[8]);
+                o[96] = w[9]; o[128] = w[10]; o[160] = w[11];
+            }
+            if (r.body == link_body) {
+#pragma unroll
+                for (int k = 0; k < 12; ++k) pe[k] = w[k];
+            }
+        });
+        float* po = pose + cfg * 12;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) po[k] = pe[k];
+        float* lo = lin + cfg * 3 * D;
+        float* ao = ang + cfg * 3 * D;
+        for (int c = 0; c < D; ++c) {
+            float zx = 0.f, zy = 0.f, zz = 0.f, lx = 0.f, ly = 0.f, lz = 0.f;
+            if ((col_mask >> c) & 1u) {
+                const float* o = jc + c * 6 * 32;
+                zx = o[0]; zy = o[32]; zz = o[64];
+                const float dx = pe[9] - o[96], dy = pe[10] - o[128], dz = pe[11] - o[160];
+                lx = zy * dz - zz * dy; ly = zz * dx - zx * dz; lz = zx * dy - zy * dx;
+            }
+            lo[c] = lx; lo[D + c] = ly; lo[2 * D + c] = lz;
+            ao[c] = zx; ao[D + c] = zy; ao[2 * D + c] = zz;
+        }
+    }
+}
+
 template <bool WANT_GRAD>
 __global__ void __launch_bounds__(kBlock) k_objective_generic(const float* __restrict__ tree_words, int tree_nwords,
                                                               const float* __restrict__ cost_words, int cost_nwords,
@@ -1212,6 +1272,29 @@ int trk_link_jacobian(const trk_model* m, const float* q, int64_t n, float* J, v
         k_link_jacobian<<<grid, warps * 32, smem, st>>>(m->d_words, m->nwords, m->live, q, n, cpw, rec_stride, link_chunk, J);
     if (e == cudaSuccess) e = cudaGetLastError();
     return e == cudaSuccess ? TRK_OK : cuda_fail(e, "link_jacobian launch");
+}
+
+int trk_geometric_jacobian(const trk_model* m, const float* q, int64_t n, int32_t link, uint32_t col_mask, float* pose12,
+                           float* lin, float* ang, void* stream) {
+    TRK_CHECK_PTR(m, "model");
+    if (n < 0) return fail(TRK_E_RANGE, "n=%lld", (long long)n);
+    if (link < 0 || link >= m->L) return fail(TRK_E_RANGE, "link=%d outside the model", link);
+    if (m->D < 1) return fail(TRK_E_RANGE, "the model has no movable joint");
+    if (n == 0) return TRK_OK;
+    TRK_CHECK_PTR(q, "q"); TRK_CHECK_PTR(pose12, "pose12"); TRK_CHECK_PTR(lin, "lin"); TRK_CHECK_PTR(ang, "ang");
+    DeviceGuard guard(m->device);
+    const size_t per_warp = (size_t)(m->live.n_live * 12 + m->D * 6) * 32 * 4;
+    int warps = kWarps;
+    while (warps > 1 && (size_t)m->nwords * 4 + warps * per_warp > 100 * 1024) --warps;
+    const size_t smem = (size_t)m->nwords * 4 + warps * per_warp;
+    const long long need = (n + warps * 32 - 1) / (warps * 32), cap = (long long)m->n_sms * 16;
+    cudaError_t e = allow_smem(k_geometric_jacobian, smem);
+    if (e == cudaSuccess) {
+        k_geometric_jacobian<<<(int)(need < cap ? need : cap), warps * 32, smem, (cudaStream_t)stream>>>(m->d_words, m->nwords, m->live, q, n, link,
+                                                                                                  col_mask, pose12, lin, ang);
+        e = cudaGetLastError();
+    }
+    return e == cudaSuccess ? TRK_OK : cuda_fail(e, "geometric_jacobian launch");
 }
 
 int trk_selftest_sqrt(const float* x, int64_t n, float* y_core, float* y_ref, void* stream) {

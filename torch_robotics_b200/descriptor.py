@@ -93,6 +93,7 @@ class TreeDescriptor:
     depth: np.ndarray       # int32 [L]
     limits: List[Optional[Dict[str, float]]]   # per body, as models/utils.py:234-243 stores them
     controlled: List[int] = field(default_factory=list)   # body index per q column
+    urdf_joint_index: List[int] = field(default_factory=list)   # per body: position of its parent joint among the <joint> elements, -1 for the root
     base_R: np.ndarray = field(default_factory=lambda: np.eye(3, dtype=np.float32))
     base_t: np.ndarray = field(default_factory=lambda: np.zeros(3, dtype=np.float32))
 
@@ -147,6 +148,7 @@ def compile_urdf(path: str, name: str = "") -> TreeDescriptor:
     joint_names = ["base_joint"] * L
     joint_types = ["fixed"] * L
     controlled: List[int] = []
+    urdf_joint_index = [-1] * L
 
     if joint_of(link_names[0]) is not None:
         raise ValueError(f"{path}: the first <link> ({link_names[0]}) must be the tree root "
@@ -157,6 +159,7 @@ def compile_urdf(path: str, name: str = "") -> TreeDescriptor:
         if j is None:
             raise ValueError(f"{path}: link {link_names[i]} has no parent joint (multiple roots)")
         jt = j.get("type")
+        urdf_joint_index[i] = joints.index(j)
         joint_names[i] = j.get("name")
         joint_types[i] = jt
         parent[i] = name_to_idx[j.find("parent").get("link")]
@@ -216,7 +219,7 @@ def compile_urdf(path: str, name: str = "") -> TreeDescriptor:
         name=name or root.get("name", ""), link_names=link_names, joint_names=joint_names,
         joint_types=joint_types, parent=parent, kind=kind, axis_k=axis_k, axis_s=axis_s, axis=axis,
         q_index=q_index, R_fixed=R_fixed, trans=trans, lo=lo, hi=hi, has_lim=has_lim,
-        topo=np.asarray(topo, np.int32), depth=depth, limits=limits, controlled=controlled)
+        topo=np.asarray(topo, np.int32), depth=depth, limits=limits, controlled=controlled, urdf_joint_index=urdf_joint_index)
 
 
 def attach_bodies(desc: TreeDescriptor, bodies) -> "tuple[TreeDescriptor, list]":

@@ -101,6 +101,7 @@ class ObjectField(PrimitiveShapeField):
         return f"ObjectField(fields={self.fields})"
 
     def set_position_orientation(self, pos=None, ori=None):
+        self._pose_revision = getattr(self, "_pose_revision", 0) + 1      # cache keys of the fused cost tables see the move
         if pos is not None:
             assert len(pos) == 3
             self.pos = to_torch(pos, **self.tensor_args)

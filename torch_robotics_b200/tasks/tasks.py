@@ -92,13 +92,24 @@ class PlanningTask(Task):
             clamp_obj=f_obj.clamp_sdf, clamp_ws=self.df_collision_ws_boundaries.clamp_sdf, **ee)
 
     def _fused_cost(self, device, ee_field=None, ee_link_name=None) -> DeviceCost:
-        key = (torch.device(device).index, self.df_collision_objects._signature(), id(ee_field), ee_link_name)
-        dc = self._fused.get(key)
-        if dc is None:
+        tree = _tree_of(self.robot)
+        sig, refs = self.df_collision_objects._signature()
+        settings, srefs = [], []
+        for f in (self.df_collision_self, self.df_collision_objects, self.df_collision_ws_boundaries):
+            if f is not None:
+                k, r = f._settings_key()
+                settings.append(k)
+                srefs += list(r)
+        # keyed on content identity AND on the tree's model generation (update_base_pose / attach_* rebuild the device
+        # model); the entry keeps every object whose id is part of the key alive, so ids cannot be recycled under it
+        key = (torch.device(device).index, getattr(tree, "_model_generation", 0), sig, tuple(settings), id(ee_field), ee_link_name)
+        entry = self._fused.get(key)
+        if entry is None:
             if len(self._fused) > 8:
                 self._fused.clear()
-            dc = DeviceCost(_tree_of(self.robot).device_model(device), self.cost_descriptor(ee_field, ee_link_name))
-            self._fused[key] = dc
+            entry = (DeviceCost(tree.device_model(device), self.cost_descriptor(ee_field, ee_link_name)), refs, tuple(srefs), ee_field)
+            self._fused[key] = entry
+        dc = entry[0]
         if ee_field is not None:
             tgt = torch.as_tensor(ee_field.target_H).reshape(4, 4).detach().float().cpu().numpy()
             if (tgt != dc.cost.ee_target).any():
@@ -108,7 +119,7 @@ class PlanningTask(Task):
     @staticmethod
     def _as_bhd(q):
         if q.ndim == 1:
-            return q.reshape(1, 1, -1), (1,)
+            return q.reshape(1, 1, -1), (1, 1)       # the reference's fields always answer [batch, horizon] (distance_fields.py:26-58)
         if q.ndim == 2:
             return q.unsqueeze(1), (q.shape[0], 1)
         if q.ndim == 3:

@@ -68,6 +68,7 @@ class DifferentiableTree(torch.nn.Module):
         self._controlled_joints = list(self._desc.controlled)
         self._name_to_idx_map = self._desc.name_to_idx()
         self._device_models: Dict[int, DeviceModel] = {}
+        self._model_generation = 0      # bumped whenever the device model must be rebuilt: dependants key their caches on it
 
     # ------------------------------------------------------------------------------------ device side
     def device_model(self, device) -> DeviceModel:
@@ -84,6 +85,7 @@ class DifferentiableTree(torch.nn.Module):
         self._bodies = [BodyView(self._desc, i) for i in range(self._desc.n_links)]
         self._name_to_idx_map = self._desc.name_to_idx()
         self._device_models.clear()
+        self._model_generation += 1
 
     def attach_link(self, name, parent, xyz, rpy=(0.0, 0.0, 0.0)):
         """Append a fixed link `name` under `parent` with the given joint origin - the in-memory equivalent of the
@@ -108,6 +110,7 @@ class DifferentiableTree(torch.nn.Module):
         self._desc.base_t = p[:3].copy()
         self._desc.base_R = quat_wxyz_to_matrix(p[3:7])
         self._device_models.clear()
+        self._model_generation += 1
 
     def reset(self):
         pass
@@ -145,9 +148,32 @@ class DifferentiableTree(torch.nn.Module):
         return J if idx == list(range(self._desc.n_links)) else J[:, idx]
 
     def compute_forward_kinematics(self, q, qd=None, link_name=None, state_less=True):
-        if not state_less:
-            raise NotImplementedError("only the stateless FK path is provided")
-        return self.compute_forward_kinematics_all_links(q, link_list=[link_name])
+        """state_less=True: [B, 1, 4, 4] of `link_name`.  Otherwise (position [B, 3], quaternion wxyz [B, 4]) as the
+        reference's stateful call returns them (robot_tree.py:196-216); body velocities are not propagated (qd is unused)."""
+        if state_less:
+            return self.compute_forward_kinematics_all_links(q, link_list=[link_name])
+        H = self.compute_forward_kinematics_all_links(q, link_list=[link_name])[:, 0]
+        return H[:, :3, 3], _quaternion_wxyz_of_frame(H[:, :3, :3])
+
+    def compute_forward_kinematics_and_geometric_jacobian(self, q, qd, link_name):
+        """(ee_pos [B, 3], ee_rot wxyz [B, 4], lin_jac [B, 3, n_dofs], ang_jac [B, 3, n_dofs]) of `link_name`
+        (robot_tree.py:218-248): lin[:, i] = z_i x (p_ee - p_i), ang[:, i] = z_i, one kernel (trk_geometric_jacobian).
+        Like the reference, a joint contributes when its index among the URDF's <joint> elements is not larger than that of
+        the joint above `link_name`, assuming body k hangs from joint k - 1 (:237-240); z_i is the column of the joint axis'
+        non-zero component of the body's world rotation, whatever the axis' sign or the joint type (rigid_body.py:97-99).
+        Poses are those of compute_forward_kinematics_all_links.  The reference propagates them statefully here
+        (update_kinematic_state), which gives the same poses for positive-axis, limited joints (golden: Panda, UR10, Tiago)
+        but rotates negative-axis joints about z without the sign (rigid_body.py:101-106) and clamps continuous joints
+        (:218): those two upstream defects are not reproduced."""
+        assert q.ndim == 2
+        link = self._name_to_idx_map[link_name]
+        link_joint = self._desc.urdf_joint_index[link] if link < len(self._desc.urdf_joint_index) else -1
+        mask = 0
+        for col, body in enumerate(self._controlled_joints):
+            if (body - 1) <= link_joint:
+                mask |= 1 << col
+        pose, lin, ang = self.device_model(q.device).geometric_jacobian(q.detach(), link, mask)
+        return pose[:, 9:12], _quaternion_wxyz_of_frame(pose[:, :9].reshape(-1, 3, 3)), lin, ang
 
     # ------------------------------------------------------------------------------------ IK
     def inverse_kinematics(self, H_target, link_name="ee_link", batch_size=1, max_iters=1000, lr=1e-2, se3_eps=1e-1,
@@ -267,3 +293,31 @@ class DifferentiableTree(torch.nn.Module):
     def print_link_names(self) -> None:
         for n in self.get_link_names():
             print(n)
+
+
+def _quaternion_wxyz_of_frame(R):
+    """Frame.get_quaternion (geometrics/frame.py:87-113, an xyzw quaternion from the homogeneous matrix, un-normalised branch
+    values scaled by 0.5 / sqrt(t)) followed by q_convert_wxyz (quaternion.py:240-242), vectorised over the batch."""
+    m = lambda i, j: R[:, i, j]
+    tr = m(0, 0) + m(1, 1) + m(2, 2) + 1.0              # trace of the 4 x 4 homogeneous matrix
+    # branch 0: trace > 1
+    q0 = torch.stack([m(2, 1) - m(1, 2), m(0, 2) - m(2, 0), m(1, 0) - m(0, 1), tr], dim=-1)
+    t0 = tr
+    # otherwise the largest diagonal element picks (i, j, k)
+    d = torch.stack([m(0, 0), m(1, 1), m(2, 2)], dim=-1)
+    i = torch.zeros_like(tr, dtype=torch.long)
+    i = torch.where(d[:, 1] > d[:, 0], torch.ones_like(i), i)
+    i = torch.where(d[:, 2] > d.gather(1, i[:, None])[:, 0], torch.full_like(i, 2), i)
+    j, k = (i + 1) % 3, (i + 2) % 3
+    ar = torch.arange(R.shape[0], device=R.device)
+    e = lambda a, b: R[ar, a, b]
+    tn = e(i, i) - (e(j, j) + e(k, k)) + 1.0
+    q1 = torch.zeros_like(q0)
+    q1[ar, i] = tn
+    q1[ar, j] = e(i, j) + e(j, i)
+    q1[ar, k] = e(k, i) + e(i, k)
+    q1[:, 3] = e(k, j) - e(j, k)
+    first = tr > 1.0
+    t = torch.where(first, t0, tn)
+    q = torch.where(first[:, None], q0, q1) * (0.5 / torch.sqrt(t))[:, None]
+    return torch.stack([q[:, 3], q[:, 0], q[:, 1], q[:, 2]], dim=-1)

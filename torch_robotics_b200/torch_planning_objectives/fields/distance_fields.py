@@ -89,16 +89,27 @@ class EmbodimentDistanceFieldBase(DistanceField):
         raise NotImplementedError
 
     def _signature(self):
-        return None
+        """(hashable key, objects the key's ids refer to).  The cache entry keeps the objects alive, so an id in the key
+        cannot be recycled by CPython for a different tensor while the entry exists."""
+        return None, ()
+
+    def _settings_key(self):
+        cm = self.cutoff_margin
+        cm_key = (id(cm), cm._version) if torch.is_tensor(cm) else float(cm)
+        return (bool(self.clamp_sdf), cm_key), ((cm,) if torch.is_tensor(cm) else ())
 
     def _device_cost(self, device) -> DeviceCost:
-        key = (torch.device(device).index, self._signature())
-        dc = self._device_costs.get(key)
-        if dc is None:
+        tree = _tree_of(self.robot)
+        sig, refs = self._signature()
+        skey, srefs = self._settings_key()
+        # the tree's generation changes with update_base_pose / attach_*: tables built for an older model are dropped
+        key = (torch.device(device).index, getattr(tree, "_model_generation", 0), sig, skey)
+        entry = self._device_costs.get(key)
+        if entry is None:
             self._device_costs.clear()
-            dc = DeviceCost(_tree_of(self.robot).device_model(device), self._descriptor())
-            self._device_costs[key] = dc
-        return dc
+            entry = (DeviceCost(tree.device_model(device), self._descriptor()), refs, srefs)
+            self._device_costs[key] = entry
+        return entry[0]
 
     def compute_costs_impl(self, q, link_pos, field_type=None, **kwargs):
         # grasped-object points are ordinary columns of link_pos here (bodies attached to the tree, robot_base.py), so
@@ -156,14 +167,20 @@ class CollisionObjectDistanceField(CollisionObjectBase):
         return [] if self.df_obj_list_fn is None else list(self.df_obj_list_fn())
 
     def _signature(self):
-        sig = []
+        sig, refs = [], []
         for obj in self._objects():
             if not hasattr(obj, "fields"):      # GridMapSDF
                 sig.append((id(obj), id(obj.grid)))
+                refs += [obj, obj.grid]
                 continue
-            sig.append((id(obj), obj.pos._version, obj.ori._version, id(obj.pos), id(obj.ori),
-                        tuple((id(f.centers), f.centers._version, getattr(f, 'radii', getattr(f, 'sizes', None))._version) for f in obj.fields)))
-        return tuple(sig)
+            geo = []
+            for f in obj.fields:
+                shape = getattr(f, "radii", getattr(f, "sizes", None))
+                geo.append((id(f.centers), f.centers._version, id(shape), shape._version))
+                refs += [f.centers, shape]
+            sig.append((id(obj), getattr(obj, "_pose_revision", 0), id(obj.pos), obj.pos._version, id(obj.ori), obj.ori._version, tuple(geo)))
+            refs += [obj, obj.pos, obj.ori]
+        return tuple(sig), tuple(refs)
 
     def _descriptor(self):
         links, radius = self._points()
