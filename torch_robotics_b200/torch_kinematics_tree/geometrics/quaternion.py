@@ -27,3 +27,24 @@ def q_to_euler(q):
     pitch = torch.asin(torch.clamp(2.0 * (w * y - z * x), -1.0, 1.0))
     yaw = torch.atan2(2.0 * (w * z + x * y), 1.0 - 2.0 * (y * y + z * z))
     return torch.stack([roll, pitch, yaw], dim=-1)
+
+
+def rotation_matrix_to_q(rot_mat):
+    """Rotation matrices [..., 3, 3] -> unit quaternions (w, x, y, z).  Of the four algebraically equal candidates the one
+    built around the largest of sqrt(1 +- m00 +- m11 +- m22) is returned (its own component is then positive and the
+    division is well conditioned; first candidate on ties) - what the reference computes at geometrics/quaternion.py:135-166."""
+    lead = rot_mat.shape[:-2]
+    m = rot_mat.reshape(lead + (9,))
+    m00, m01, m02, m10, m11, m12, m20, m21, m22 = m.unbind(-1)
+    t = torch.stack([1.0 + m00 + m11 + m22, 1.0 + m00 - m11 - m22, 1.0 - m00 + m11 - m22, 1.0 - m00 - m11 + m22], dim=-1)
+    q_abs = torch.sqrt(torch.clamp(t, min=0.0))
+    pick = q_abs.argmax(dim=-1, keepdim=True)                       # [..., 1]
+    sq = q_abs * q_abs
+    cand = torch.stack([
+        torch.stack([sq[..., 0], m21 - m12, m02 - m20, m10 - m01], dim=-1),
+        torch.stack([m21 - m12, sq[..., 1], m10 + m01, m02 + m20], dim=-1),
+        torch.stack([m02 - m20, m10 + m01, sq[..., 2], m12 + m21], dim=-1),
+        torch.stack([m10 - m01, m20 + m02, m21 + m12, sq[..., 3]], dim=-1)], dim=-2)    # [..., 4 candidates, 4]
+    row = cand.gather(-2, pick[..., None].expand(lead + (1, 4)))[..., 0, :]
+    den = 2.0 * torch.clamp(q_abs.gather(-1, pick), min=0.1)
+    return row / den

@@ -54,3 +54,9 @@ def link_rot_from_link_tensor(link_tensor):
     if link_tensor.shape[-1] == 4:
         return link_tensor[..., :3, :3]
     raise ValueError
+
+
+def link_quat_from_link_tensor(link_tensor):
+    """wxyz quaternions of the links' rotations (reference: geometrics/utils.py:341-344)."""
+    from .quaternion import rotation_matrix_to_q
+    return rotation_matrix_to_q(link_rot_from_link_tensor(link_tensor))

@@ -17,7 +17,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 import torch
 
-from ... import ops
+from ... import compat, ops
 from ..._lib import DeviceModel
 from ...descriptor import TreeDescriptor, attach_bodies, attach_points, compile_urdf, quat_wxyz_to_matrix
 from ...torch_utils.torch_utils import to_torch, torch_intersect_1d
@@ -128,12 +128,18 @@ class DifferentiableTree(torch.nn.Module):
         idx = [self._name_to_idx_map[n] for n in link_list]
         uniq = sorted(set(idx), key=idx.index)
         all_in_order = uniq == list(range(self._desc.n_links))
+        home = q.device
+        if q.device.type != "cuda" and compat.cpu_tensors_accepted():
+            # opt-in compatibility mode (compat.accept_cpu_tensors): the CPU tensor is evaluated on cuda:0 by the same kernels
+            q = q.to(torch.device("cuda", torch.cuda.current_device()))
         H = ops.fk(self.device_model(q.device), q, None if all_in_order else uniq)
         if len(uniq) != len(idx):
             H = H[:, [uniq.index(i) for i in idx]]
+        if H.device != home:
+            H = H.to(home)
         if not return_dict:
             return H
-        return {n: Frame(rot=H[:, k, :3, :3], trans=H[:, k, :3, 3], device=q.device) for k, n in enumerate(link_list)}
+        return {n: Frame(rot=H[:, k, :3, :3], trans=H[:, k, :3, 3], device=home) for k, n in enumerate(link_list)}
 
     def compute_analytical_jacobian_all_links(self, q: torch.Tensor) -> torch.Tensor:
         """q [B, n_dofs] (or [n_dofs]) -> [B, n_links, 7, n_dofs]: d (position xyz, quaternion wxyz) of every link /
