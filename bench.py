@@ -148,8 +148,8 @@ def workload_config(world, configs_per_step=N_TRAJ * HORIZON):
     return {"workload": "panda_fused_objective_fwd_bwd: FK(11 links) + obstacle spheres(5 pts x 10, EnvSpheres3D) + "
                         "self-collision(10 pairs) + ws bounds + EE SE3 cost and grad_q (BASELINE config 3 objective)",
             "configs_per_gpu_per_step": int(configs_per_step), "horizon": HORIZON, "trajectories": int(configs_per_step) // HORIZON,
-            "parallelism": f"batch-sharded x{world}; per step a device sum of the shard's costs + NCCL all-reduce of the scalar "
-                           "on a side stream (overlapped with the next step's kernel)",
+            "parallelism": f"batch-sharded x{world}; per step the kernel's per-block partial sums of the cost are summed (fp64) and the "
+                           "scalar is all-reduced over NCCL on a side stream (overlapped with the next step's kernel)",
             "l2": "q+cost+grad = 251 MB per step > 126 MB L2 (inputs larger than L2, no flush needed)"}
 
 
@@ -336,16 +336,18 @@ def main():
         c1 = [torch.cuda.Event(enable_timing=True) for _ in range(k)]
         last = torch.cuda.Event(enable_timing=True)
         red_done = [None, None]
+        parts = [torch.empty(cost_obj.MAX_BLOCK_SUMS, device=dev), torch.empty(cost_obj.MAX_BLOCK_SUMS, device=dev)]
         for i in range(k):
             totd = tots[i & 1]
             if red_done[i & 1] is not None:
-                main_stream.wait_event(red_done[i & 1])      # step i overwrites the costs step i - 2's reduction read
+                main_stream.wait_event(red_done[i & 1])      # step i overwrites what step i - 2's reduction read
             starts[i].record(main_stream)
-            cost_obj.objective(qd, want_terms=False, out_total=totd, out_grad=gradd)
+            # cost + gradient + the kernel's per-block partial sums of the cost (first stage of the reduction, fused)
+            cost_obj.objective_sum(qd, out_grad=gradd, out_total=totd, out_block_sums=parts[i & 1])
             ends[i].record(main_stream)
             side.wait_event(ends[i])
             with torch.cuda.stream(side):
-                s = totd.sum(dtype=torch.float64).reshape(1)
+                s = parts[i & 1].sum(dtype=torch.float64).reshape(1)
                 c0[i].record(side)
                 if world > 1:
                     dist.all_reduce(s, op=dist.ReduceOp.SUM)
@@ -487,7 +489,7 @@ def main():
                          "peak_source": f"148 SMs x 128 lanes x 2 x sm_max_mhz ({peaks['source']} MEASURED_PEAKS.json)",
                          "hbm": {"achieved": kernel_rate * BYTES_PER_CFG / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                  "frac": kernel_rate * BYTES_PER_CFG / 1e9 / peaks["hbm_gbs"]}},
-            "collective": {"op": "device sum of the shard's costs (fp64) + NCCL all-reduce(SUM) of the scalar, once per step, side stream",
+            "collective": {"op": "fused per-block partial sums (trk_objective_sums) -> fp64 sum of <= 2048 values + NCCL all-reduce(SUM) of the scalar, once per step, side stream",
                            "collective_ms": float(np.median(coll_ms)) if (coll_ms and world > 1) else 0.0,
                            "total_cost_last_step": total_sum},
             "e2e": {"value": world * n / e2e_s, "unit": "configs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -496,7 +498,7 @@ def main():
                     "frac_of_copy_ceiling": copy_s / e2e_s,
                     "api": "C ABI trk_objective_host(pinned q) -> pinned cost, grad_q (8 chunks, H2D / kernel / D2H on three streams); "
                            "copy_only = the same bytes both ways at once without the kernel, all ranks concurrently (the box's ceiling)"},
-            "gpu_launches": args.steps * 2,      # per step: the fused objective kernel + the cost-sum reduction kernel
+            "gpu_launches": args.steps,          # one launch of the fused objective kernel per step (+ a memset and a 2048-value sum of its partials)
             "numa_bound": numa_bound,
             "clocks": {**sampler.result(), "samples_during_headline": clocks_headline["samples"],
                        "note": "sampled at 1 kHz over every timed region of this run (headline, strong, e2e, configs 4 and 5)"},

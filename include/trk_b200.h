@@ -192,6 +192,18 @@ int trk_objective(const trk_model* model, const trk_cost* cost, const float* q, 
                   uint8_t* occupancy, int32_t* argmin, void* stream);
 
 /*
+ * trk_objective with the first stage of the cost reduction fused into the kernel (the caller of PlanningTask sums the
+ * cost over the batch and, across GPUs, all-reduces the scalar: SURVEY.md section 8e).  cost_total (nullable) and grad_q as
+ * above; block_sums [TRK_MAX_BLOCK_SUMS] fp32 DEVICE memory receives one partial sum of the total cost per thread block,
+ * in block order, zero beyond the launch's grid: summing the array (fp64, any fixed order) gives sum(cost_total),
+ * deterministic for a given batch size.  Returns TRK_E_UNSUPPORTED when the model / cost table is not served by the
+ * headline kernel (trk_hot.cuh); sum cost_total instead.
+ */
+#define TRK_MAX_BLOCK_SUMS 2048
+int trk_objective_sums(const trk_model* model, const trk_cost* cost, const float* q, int64_t n, const float* ee_target_cfg,
+                       float margin_override, float* cost_total, float* grad_q, float* block_sums, void* stream);
+
+/*
  * Host-buffer form of trk_objective: q, cost_total and grad_q are HOST pointers (page-locked memory gives
  * asynchronous, overlapped copies; pageable memory works but serialises).  The batch is cut into `n_chunks`
  * pieces that flow through three internal streams - H2D copy, kernel, D2H copy - so both PCIe directions and the

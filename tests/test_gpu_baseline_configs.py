@@ -137,3 +137,32 @@ def test_two_gpus_bit_identical_to_one():
         part = DeviceCost(DeviceModel(d, dev), cost).objective(torch.as_tensor(q[lo:hi], device=dev))
         assert torch.equal(part["total"].cpu(), full["total"][lo:hi].cpu())
         assert torch.equal(part["grad_q"].cpu(), full["grad_q"][lo:hi].cpu())
+
+
+def test_fused_cost_sum_matches_sum_of_costs():
+    """trk_objective_sums: the per-block partial sums the kernel writes add up to sum(cost_total) (fp32 partials: 1e-6
+    relative), the other outputs are bit-identical to trk_objective's, the result is reproducible, and a model that is not
+    served by the headline kernel reports TRK_E_UNSUPPORTED."""
+    from torch_robotics_b200._lib import DeviceCost, DeviceModel
+    g, d = load_golden("planning_panda_spheres3d"), get_desc("panda")
+    cost = planning_cost_from_golden(g)
+    dc = DeviceCost(DeviceModel(d, DEV), cost)
+    for n in (1, 777, 300_001):
+        q = t(uniform_q(d, n, 3))
+        ref = dc.objective(q, want_grad=True, want_terms=False)
+        grad, tot = torch.empty_like(q), torch.empty(n, device=DEV)
+        bs = dc.objective_sum(q, out_grad=grad, out_total=tot)
+        assert torch.equal(tot, ref["total"]) and torch.equal(grad, ref["grad_q"])
+        s, s_ref = float(bs.sum(dtype=torch.float64)), float(ref["total"].sum(dtype=torch.float64))
+        assert abs(s - s_ref) <= 1e-5 * max(1.0, float(ref["total"].abs().sum(dtype=torch.float64)))
+        bs2 = dc.objective_sum(q, out_grad=grad)                       # cost_total is optional; same partials again
+        assert torch.equal(bs, bs2)
+    dk = get_desc("kuka_iiwa")
+    from torch_robotics_b200.descriptor import build_cost_descriptor
+    ck = build_cost_descriptor(pt_link=[3, 5], pt_radius=[0.1, 0.1], cutoff_obj=0.01,
+                               objects=[(np.array([[0.4, 0.0, 0.5]], np.float32), np.array([0.1], np.float32), None, None)],
+                               ws_min=[-1, -1, -1], ws_max=[1, 1, 1])
+    dck = DeviceCost(DeviceModel(dk, DEV), ck)
+    qk = t(uniform_q(dk, 64, 1))
+    with pytest.raises(RuntimeError, match="fused cost reduction"):
+        dck.objective_sum(qk, out_grad=torch.empty_like(qk))

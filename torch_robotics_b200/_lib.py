@@ -59,7 +59,7 @@ EXPORTS = [
     "trk_abi_version", "trk_last_error", "trk_model_create", "trk_model_destroy", "trk_model_kernel_family",
     "trk_fk_forward", "trk_fk_backward", "trk_cost_create", "trk_cost_destroy", "trk_cost_set_ee_target",
     "trk_cost_set_weights", "trk_objective", "trk_objective_host", "trk_cost_stage", "trk_selftest_sqrt", "trk_ik_adam",
-    "trk_link_jacobian", "trk_geometric_jacobian",
+    "trk_link_jacobian", "trk_geometric_jacobian", "trk_objective_sums",
 ]
 
 
@@ -92,6 +92,7 @@ def lib() -> C.CDLL:
         L.trk_cost_set_ee_target.argtypes = [vp, c_float_p, vp]
         L.trk_cost_set_weights.argtypes = [vp, c_float_p, vp]
         L.trk_objective.argtypes = [vp, vp, vp, i64, vp, f32, vp, vp, vp, vp, vp, vp]
+        L.trk_objective_sums.argtypes = [vp, vp, vp, i64, vp, f32, vp, vp, vp, vp]
         L.trk_cost_stage.argtypes = [vp, vp, vp, vp, i64, vp, f32, vp, vp, vp, vp, vp, vp, vp]
         L.trk_selftest_sqrt.argtypes = [vp, i64, vp, vp, vp]
         L.trk_link_jacobian.argtypes = [vp, vp, i64, vp, vp]
@@ -383,6 +384,27 @@ class DeviceCost:
         check(lib().trk_objective(m.handle, self.handle, q.data_ptr(), n, ptr(tgt), mo, ptr(total), ptr(terms), ptr(grad),
                                   ptr(occ), ptr(amin), stream_ptr(dev)), "trk_objective")
         return dict(total=total, terms=terms, grad_q=grad, occupancy=occ, argmin=amin)
+
+    MAX_BLOCK_SUMS = 2048
+
+    def objective_sum(self, q: torch.Tensor, out_grad: torch.Tensor, out_total: Optional[torch.Tensor] = None,
+                      out_block_sums: Optional[torch.Tensor] = None, margin_override: Optional[float] = None) -> torch.Tensor:
+        """Cost + gradient with the first stage of the batch reduction fused into the kernel (trk_objective_sums).  Returns the
+        per-block partial sums [MAX_BLOCK_SUMS] fp32 (zero-padded): `.sum(dtype=torch.float64)` is sum(cost), ready for
+        distributed.total_cost_from_partials.  out_total is optional: planners that only need the scalar skip 4 B / configuration."""
+        m = self.model
+        q = require_cuda_f32(q, "q")
+        n, dev = q.shape[0], q.device
+        if q.ndim != 2 or q.shape[1] != m.n_dofs or dev != m.device:
+            raise RuntimeError(f"q must be [N, {m.n_dofs}] on {m.device}")
+        bs = torch.empty(self.MAX_BLOCK_SUMS, dtype=torch.float32, device=dev) if out_block_sums is None else out_block_sums
+        for name, buf, shape in (("out_total", out_total, (n,)), ("out_grad", out_grad, (n, m.n_dofs)), ("out_block_sums", bs, (self.MAX_BLOCK_SUMS,))):
+            if buf is not None and (tuple(buf.shape) != shape or buf.dtype != torch.float32 or buf.device != dev or not buf.is_contiguous()):
+                raise RuntimeError(f"{name} must be a contiguous float32 tensor of shape {shape} on {dev}")
+        mo = float("nan") if margin_override is None else float(margin_override)
+        check(lib().trk_objective_sums(m.handle, self.handle, q.data_ptr(), n, None, mo, None if out_total is None else out_total.data_ptr(),
+                                       out_grad.data_ptr(), bs.data_ptr(), stream_ptr(dev)), "trk_objective_sums")
+        return bs
 
     def objective_host(self, q_host: torch.Tensor, cost_host: torch.Tensor, grad_host: Optional[torch.Tensor] = None,
                        n_chunks: int = 8) -> None:

@@ -1152,10 +1152,37 @@ int trk_cost_set_weights(trk_cost* c, const float* w4, void* stream) {
     return cost_upload_header(c, stream);
 }
 
+static int objective_impl(const trk_model* m, const trk_cost* c, const float* q, int64_t n, const float* ee_target_cfg,
+                          float margin_override, float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy,
+                          int32_t* argmin, float* block_sums, int* n_block_sums, void* stream);
+
 int trk_objective(const trk_model* m, const trk_cost* c, const float* q, int64_t n, const float* ee_target_cfg,
                   float margin_override, float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy,
                   int32_t* argmin, void* stream) {
+    return objective_impl(m, c, q, n, ee_target_cfg, margin_override, cost_total, cost_terms, grad_q, occupancy, argmin, nullptr, nullptr, stream);
+}
+
+int trk_objective_sums(const trk_model* m, const trk_cost* c, const float* q, int64_t n, const float* ee_target_cfg,
+                       float margin_override, float* cost_total, float* grad_q, float* block_sums, void* stream) {
+    TRK_CHECK_PTR(block_sums, "block_sums");
+    TRK_CHECK_PTR(m, "model");
+    DeviceGuard guard(m->device);
+    cudaError_t e = cudaMemsetAsync(block_sums, 0, sizeof(float) * TRK_MAX_BLOCK_SUMS, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(block_sums)");
+    if (n == 0) return TRK_OK;
+    int n_sums = 0;
+    const int rc = objective_impl(m, c, q, n, ee_target_cfg, margin_override, cost_total, nullptr, grad_q, nullptr, nullptr, block_sums, &n_sums, stream);
+    if (rc != TRK_OK) return rc;
+    if (n_sums <= 0 || n_sums > TRK_MAX_BLOCK_SUMS)
+        return fail(TRK_E_UNSUPPORTED, "this model / cost table is served by a kernel without the fused cost reduction (sum cost_total instead)");
+    return TRK_OK;
+}
+
+static int objective_impl(const trk_model* m, const trk_cost* c, const float* q, int64_t n, const float* ee_target_cfg,
+                          float margin_override, float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy,
+                          int32_t* argmin, float* block_sums, int* n_block_sums, void* stream) {
     TRK_CHECK_PTR(m, "model"); TRK_CHECK_PTR(c, "cost");
+    if (n_block_sums) *n_block_sums = 0;
     if (c->device != m->device || c->L != m->L) return fail(TRK_E_RANGE, "cost tables were built for a different model");
     if (n < 0) return fail(TRK_E_RANGE, "n=%lld", (long long)n);
     if (n == 0) return TRK_OK;
@@ -1169,7 +1196,7 @@ int trk_objective(const trk_model* m, const trk_cost* c, const float* q, int64_t
         const int clamp_any = hh->clamp_self | hh->clamp_obj | hh->clamp_ws | (hh->KB > 0 ? 1 : 0) | (hh->grid_obj >= 0 ? 1 : 0);   // general-tables variant
         cudaError_t e = trk::launch_static_objective(m->family, m->n_sms, c->h_words.data(), c->d_words, c->nwords, c->n_slots, clamp_any, c->cm_match, q, n, ee_target_cfg,
                                                      margin_override, use_override, cost_total, cost_terms, grad_q,
-                                                     occupancy, argmin, st);
+                                                     occupancy, argmin, block_sums, n_block_sums, st);
         return e == cudaSuccess ? TRK_OK : cuda_fail(e, "objective(static)");
     }
     // one equal-radius identity-pose sphere object, no relu on the object term: collision points take the joint scan

@@ -388,7 +388,7 @@ template <class R, class CM, int EE, bool PER_CFG_TARGET, bool WANT_GRAD>
 __global__ void __launch_bounds__(kSBlock, TRK_HOT_MINBLOCKS)
 k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ cost_words, const float* __restrict__ q, long long n,
                 const float* __restrict__ ee_target_cfg, float* __restrict__ cost_total, float* __restrict__ cost_terms,
-                float* __restrict__ grad_q, uint8_t* __restrict__ occupancy, int* __restrict__ argmin) {
+                float* __restrict__ grad_q, uint8_t* __restrict__ occupancy, int* __restrict__ argmin, float* __restrict__ block_sums) {
     using T = HTree<R>;
     using Plan = HotPlan<R, CM, EE>;
     constexpr int L = R::L, D = R::D, S = CM::S, P = CM::P;
@@ -441,6 +441,7 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
 #endif
     const long long n_tiles = (n + kSBlock - 1) / kSBlock;
     long long tile = blockIdx.x;
+    float sum_acc = 0.f;          // this thread's share of sum(total): reduced per block at the end (block_sums)
 #if TRK_HOT_QSTAGE >= 2
     int buf = 0;
     if (tile < n_tiles) prefetch_tile(tile, 0);
@@ -672,6 +673,7 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
             const float total = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(hp.w[0], c_self), __fmul_rn(hp.w[1], c_obj)), __fmul_rn(hp.w[2], c_ws)),
                                           __fmul_rn(hp.w[3], c_ee));
             if (cost_total) cost_total[cfg] = total;
+            sum_acc += total;
             if (cost_terms) reinterpret_cast<float4*>(cost_terms)[cfg] = make_float4(c_self, c_obj, c_ws, c_ee);
             if (occupancy) occupancy[cfg] = (uint8_t)(hp.occ_const | (occ_self ? TRK_OCC_SELF : 0u) | (occ_obj ? TRK_OCC_OBJECT : 0u) | (occ_ws ? TRK_OCC_WS : 0u));
             if (argmin) {
@@ -744,6 +746,21 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
             float* grow = grad_q + cfg * D;
             sfor<D>([&](auto c) { grow[c] = gq[c]; });
         }
+        }
+    }
+    // fused first stage of the cost reduction (distributed.total_cost): one partial sum per block, written (not
+    // accumulated) in block order, so the caller's second stage over gridDim.x values is deterministic
+    if (block_sums) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum_acc += __shfl_xor_sync(0xffffffffu, sum_acc, o);
+        __syncthreads();                                   // the q tiles / tables in shared memory are no longer read
+        if ((tid & 31) == 0) hsm[tid >> 5] = sum_acc;
+        __syncthreads();
+        if (tid == 0) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kSBlock / 32; ++w) s += hsm[w];
+            block_sums[blockIdx.x] = s;
         }
     }
 }

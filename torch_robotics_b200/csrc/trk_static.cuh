@@ -1457,7 +1457,8 @@ inline void hot_params_from_cost(const float* hw, float margin_override, int use
 template <class R, class CM, int EE>
 inline cudaError_t launch_objective_hot(int n_sms, const float* host_words, const float* cost_words, const float* q, long long n,
                                         const float* ee_target_cfg, float margin_override, int use_override, float* cost_total,
-                                        float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin, cudaStream_t st) {
+                                        float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin, float* block_sums, int* n_block_sums,
+                                        cudaStream_t st) {
     HotParams hp;
     hot_params_from_cost<R, CM, EE>(host_words, margin_override, use_override, hp);
     const size_t smem = ((size_t)hp.n_pairs2 * 8 + (size_t)hp.n_sph * 4 + (TRK_HOT_QSTAGE >= 2 ? 2 * kSBlock * R::D : 0)) * sizeof(float);
@@ -1466,8 +1467,9 @@ inline cudaError_t launch_objective_hot(int n_sms, const float* host_words, cons
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        k<<<persistent_grid(k, n_sms, smem, n), kSBlock, smem, st>>>(hp, cost_words, q, n, ee_target_cfg, cost_total, cost_terms, grad_q,
-                                                                     occupancy, argmin);
+        const int grid = persistent_grid(k, n_sms, smem, n);
+        if (n_block_sums) *n_block_sums = grid;
+        k<<<grid, kSBlock, smem, st>>>(hp, cost_words, q, n, ee_target_cfg, cost_total, cost_terms, grad_q, occupancy, argmin, block_sums);
         return cudaGetLastError();
     };
     if (grad_q) {
@@ -1482,7 +1484,8 @@ template <class R>
 cudaError_t launch_objective_t(int n_sms, const float* host_words, const float* cost_words, int cost_nwords, int n_slots, int clamp_any, int cm_match, const float* q,
                                       long long n, const float* ee_target_cfg, float margin_override, int use_override,
                                       float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin,
-                                      cudaStream_t st) {
+                                      float* block_sums, int* n_block_sums, cudaStream_t st) {
+    if (n_block_sums) *n_block_sums = 0;      // stays 0 when the kernel that serves this call has no fused reduction
 #define TRK_OBJ_ARGS n_sms, cost_words, cost_nwords, q, n, ee_target_cfg, margin_override, use_override, cost_total, cost_terms, \
                      grad_q, occupancy, argmin, st
     using CM = typename CollisionModelOf<R>::type;
@@ -1498,7 +1501,7 @@ cudaError_t launch_objective_t(int n_sms, const float* host_words, const float* 
                     (!ee_target_cfg || (reinterpret_cast<uintptr_t>(ee_target_cfg) & 15u) == 0)) {
                     constexpr int kEE = STree<R>::topo_index_of(CM::ee_body);
                     return launch_objective_hot<R, CM, kEE>(n_sms, host_words, cost_words, q, n, ee_target_cfg, margin_override, use_override,
-                                                            cost_total, cost_terms, grad_q, occupancy, argmin, st);
+                                                            cost_total, cost_terms, grad_q, occupancy, argmin, block_sums, n_block_sums, st);
                 }
             }
             if constexpr (CollisionModelOf<R>::in_registers) {
@@ -1536,7 +1539,7 @@ cudaError_t launch_objective_t(int n_sms, const float* host_words, const float* 
     KW template cudaError_t launch_fk_forward_t<Rb>(int, const float*, long long, const SlotMap&, int, float*, cudaStream_t);           \
     KW template cudaError_t launch_fk_backward_t<Rb>(int, const float*, long long, const SlotMap&, int, const float*, float*, cudaStream_t); \
     KW template cudaError_t launch_objective_t<Rb>(int, const float*, const float*, int, int, int, int, const float*, long long, const float*, float, int, \
-                                                   float*, float*, float*, uint8_t*, int*, cudaStream_t);                               \
+                                                   float*, float*, float*, uint8_t*, int*, float*, int*, cudaStream_t);                 \
     KW template cudaError_t launch_ik_t<Rb>(const IKParams&, const float*, const float*, const float*, long long, float*, float*,        \
                                             uint8_t*, int*, float*, float*, cudaStream_t);
 #ifndef TRK_INST_ROBOT   // family dispatch: main translation unit only
@@ -1614,13 +1617,13 @@ inline int static_cm_match(int family, const float* host_cost_words) {
 inline cudaError_t launch_static_objective(int family, int n_sms, const float* host_words, const float* cost_words, int cost_nwords, int n_slots, int clamp_any, int cm_match,
                                            const float* q, long long n, const float* ee_target_cfg, float margin_override, int use_override,
                                            float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin,
-                                           cudaStream_t st) {
+                                           float* block_sums, int* n_block_sums, cudaStream_t st) {
     int id = 0;
 #define X(Rb) \
     ++id;     \
     if (family == id)  \
         return launch_objective_t<Rb>(n_sms, host_words, cost_words, cost_nwords, n_slots, clamp_any, cm_match, q, n, ee_target_cfg, margin_override, use_override, \
-                                      cost_total, cost_terms, grad_q, occupancy, argmin, st);
+                                      cost_total, cost_terms, grad_q, occupancy, argmin, block_sums, n_block_sums, st);
     TRK_FOR_EACH_STATIC_ROBOT(X)
 #undef X
     return cudaErrorInvalidValue;

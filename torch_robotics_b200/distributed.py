@@ -50,6 +50,15 @@ def total_cost(local_cost: torch.Tensor) -> torch.Tensor:
     return s[0]
 
 
+def total_cost_from_partials(block_sums: torch.Tensor) -> torch.Tensor:
+    """The same from the per-block partial sums of DeviceCost.objective_sum (the kernel did the first stage of the reduction):
+    a fixed-order fp64 sum over <= 2048 values + the all-reduce of the scalar."""
+    s = block_sums.sum(dtype=torch.float64).reshape(1)
+    if world()[1] > 1:
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    return s[0]
+
+
 def total_cost_terms(local_terms: torch.Tensor) -> torch.Tensor:
     """Per-term totals [4] (self, object, ws, ee) over all ranks."""
     s = local_terms.double().reshape(-1, local_terms.shape[-1]).sum(0)
