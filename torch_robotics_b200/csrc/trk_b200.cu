@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -302,25 +303,6 @@ __global__ void __launch_bounds__(kBlock) k_objective_generic(const float* __res
 // phase 1, one thread per configuration: FK, quaternions and masked axes into a per-warp shared-memory record;
 // phase 2, the warp writes its 32 configurations' blocks cooperatively, consecutive lanes -> consecutive floats.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void quat_of_rotation(const float* R, float* qo) {
-    const float t[4] = {1.f + R[0] + R[4] + R[8], 1.f + R[0] - R[4] - R[8], 1.f - R[0] + R[4] - R[8], 1.f - R[0] - R[4] + R[8]};
-    float qa[4];
-    int im = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) qa[i] = sqrtf(fmaxf(t[i], 0.f));
-#pragma unroll
-    for (int i = 1; i < 4; ++i) if (qa[i] > qa[im]) im = i;     // first maximum wins (argmax)
-    const float m21 = R[7], m12 = R[5], m02 = R[2], m20 = R[6], m10 = R[3], m01 = R[1];
-    float c[4];
-    if (im == 0)      { c[0] = qa[0] * qa[0]; c[1] = m21 - m12; c[2] = m02 - m20; c[3] = m10 - m01; }
-    else if (im == 1) { c[0] = m21 - m12; c[1] = qa[1] * qa[1]; c[2] = m10 + m01; c[3] = m02 + m20; }
-    else if (im == 2) { c[0] = m02 - m20; c[1] = m10 + m01; c[2] = qa[2] * qa[2]; c[3] = m12 + m21; }
-    else              { c[0] = m10 - m01; c[1] = m20 + m02; c[2] = m21 + m12; c[3] = qa[3] * qa[3]; }
-    const float inv = 1.f / (2.f * fmaxf(qa[im], 0.1f));
-#pragma unroll
-    for (int i = 0; i < 4; ++i) qo[i] = c[i] * inv;
-}
-
 __global__ void __launch_bounds__(kBlock) k_link_jacobian(const float* __restrict__ tree_words, int tree_nwords,
                                                           const __grid_constant__ TreePlan live, const float* __restrict__ q, long long n,
                                                           int cpw, int rec_stride, int link_chunk, float* __restrict__ J) {
@@ -665,6 +647,8 @@ struct trk_model {
     float* d_words;             // device tree buffer
     int nwords;
     int family;                 // trk::StaticFamily id, 0 = generic
+    int ext_family;             // > 0: a compiled-in robot plus attached fixed bodies (trk_ext.cuh serves its objective)
+    std::vector<float> h_words; // host copy of the tree buffer (trk_cost_create folds attached bodies onto their anchors)
     int32_t parent[TRK_MAX_LINKS];
     int32_t qidx[TRK_MAX_LINKS];
     TreePlan live;              // live pose slots + joint tables of the runtime-tree kernels
@@ -723,6 +707,10 @@ struct trk_cost {
     float* d_words;
     int nwords;
     std::vector<float> h_words;  // host mirror, for the setters
+    // attached-body models (trk_ext.cuh): every referenced body as (movable anchor, offset); built when the model is one
+    float* d_ext = nullptr;
+    int ext_nwords = 0, ext_n_ps = 0;
+    bool ext_ok = false;
     // host-buffer pipeline (trk_objective_host): staging buffers, streams and events, created on first use
     float* hp_q = nullptr; float* hp_cost = nullptr; float* hp_grad = nullptr;
     int64_t hp_cap = 0;
@@ -792,6 +780,95 @@ template <typename K>
 static cudaError_t allow_smem(K kernel, size_t bytes) {
     if (bytes <= 48 * 1024) return cudaSuccess;
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// Attached-body model: every body the cost tables reference as (anchor, offset).  Walking up from the body through FIXED
+// joints composes its constant offset in the frame of the first movable body met (anchor 1 + q column) or of the root
+// (anchor 0): pose_body = pose_parent o (Rf, t)  =>  offset_in_parent = Rf offset + t.
+static int build_ext_tables(const trk_model* m, const trk_cost_desc* d, trk_cost* c) {
+    const LinkRec* recs = reinterpret_cast<const LinkRec*>(m->h_words.data() + 16);
+    int rec_of[TRK_MAX_LINKS];
+    for (int i = 0; i < m->L; ++i) rec_of[recs[i].body] = i;
+    auto fold = [&](int body, int& anchor, int& col, float t[3]) {
+        t[0] = t[1] = t[2] = 0.f;
+        int cur = body;
+        while (true) {
+            const LinkRec& r = recs[rec_of[cur]];
+            if (r.qidx >= 0) { anchor = 1 + r.qidx; col = r.qidx; return; }
+            if (r.parent < 0) { anchor = 0; col = -1; return; }
+            const float x = t[0], y = t[1], z = t[2];
+            t[0] = r.Rf[0] * x + r.Rf[1] * y + r.Rf[2] * z + r.t[0];
+            t[1] = r.Rf[3] * x + r.Rf[4] * y + r.Rf[5] * z + r.t[1];
+            t[2] = r.Rf[6] * x + r.Rf[7] * y + r.Rf[8] * z + r.t[2];
+            cur = r.parent;
+        }
+    };
+    const int S = d->n_points, P = d->n_pairs, NA = m->D + 1;
+    struct Pt { int anchor, s; float t[3]; };
+    std::vector<Pt> pts(S);
+    for (int s = 0; s < S; ++s) { int col; pts[s].s = s; fold(d->pt_link[s], pts[s].anchor, col, pts[s].t); }
+    std::stable_sort(pts.begin(), pts.end(), [](const Pt& a, const Pt& b) { return a.anchor < b.anchor; });
+    // pair-position slots: one per distinct pair body, grouped by anchor
+    struct Ps { int anchor, col, body; float t[3]; };
+    std::vector<Ps> ps;
+    std::vector<int> slot_of_body(m->L, -1);
+    for (int p = 0; p < P; ++p)
+        for (int b : {d->pair_i[p], d->pair_j[p]})
+            if (slot_of_body[b] < 0) { Ps e; e.body = b; fold(b, e.anchor, e.col, e.t); slot_of_body[b] = (int)ps.size(); ps.push_back(e); }
+    std::vector<int> order(ps.size());
+    for (size_t i = 0; i < ps.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ps[a].anchor < ps[b].anchor; });
+    std::vector<int> new_slot(ps.size());
+    for (size_t i = 0; i < order.size(); ++i) new_slot[order[i]] = (int)i;
+    const int n_ps = (int)ps.size();
+    int off = (int)(sizeof(trk::ExtHeader) / 4);
+    auto take = [&](int nw) { int o = off; off = align4(off + nw); return o; };
+    const int o_pts = take(NA + 1), o_pt = take(8 * S), o_pss = take(NA + 1), o_ps = take(4 * n_ps), o_psc = take(n_ps), o_pair = take(4 * P);
+    std::vector<float> w(off, 0.f);
+    int* iw = reinterpret_cast<int*>(w.data());
+    trk::ExtHeader* h = reinterpret_cast<trk::ExtHeader*>(w.data());
+    h->n_pts = S; h->n_ps = n_ps; h->n_pairs = P; h->n_anchor = NA;
+    h->off_pt_start = o_pts; h->off_pt = o_pt; h->off_ps_start = o_pss; h->off_ps = o_ps; h->off_ps_col = o_psc; h->off_pair = o_pair;
+    h->total_words = off;
+    {
+        int k = 0;
+        for (int a = 0; a <= NA; ++a) {
+            while (k < S && pts[k].anchor < a) ++k;
+            iw[o_pts + a] = k;
+        }
+        for (int k2 = 0; k2 < S; ++k2) {
+            float* r = w.data() + o_pt + 8 * k2;
+            r[0] = pts[k2].t[0]; r[1] = pts[k2].t[1]; r[2] = pts[k2].t[2];
+            r[3] = d->pt_margin_obj[pts[k2].s]; r[4] = d->pt_margin_ws[pts[k2].s];
+            reinterpret_cast<int*>(r)[5] = pts[k2].s;
+        }
+    }
+    {
+        int k = 0;
+        for (int a = 0; a <= NA; ++a) {
+            while (k < n_ps && ps[order[k]].anchor < a) ++k;
+            iw[o_pss + a] = k;
+        }
+        for (int k2 = 0; k2 < n_ps; ++k2) {
+            const Ps& e = ps[order[k2]];
+            float* r = w.data() + o_ps + 4 * k2;
+            r[0] = e.t[0]; r[1] = e.t[1]; r[2] = e.t[2];
+            iw[o_psc + k2] = e.col;
+        }
+        for (int p = 0; p < P; ++p) {
+            float* r = w.data() + o_pair + 4 * p;
+            reinterpret_cast<int*>(r)[0] = new_slot[slot_of_body[d->pair_i[p]]];
+            reinterpret_cast<int*>(r)[1] = new_slot[slot_of_body[d->pair_j[p]]];
+            r[2] = d->pair_margin[p];
+        }
+    }
+    DeviceGuard guard(m->device);
+    cudaError_t e = cudaMalloc(&c->d_ext, w.size() * sizeof(float));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(ext tables)");
+    e = cudaMemcpy(c->d_ext, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(ext tables)");
+    c->ext_nwords = (int)w.size(); c->ext_n_ps = n_ps; c->ext_ok = true;
+    return TRK_OK;
 }
 
 extern "C" {
@@ -877,7 +954,9 @@ int trk_model_create(const trk_model_desc* d, int device, trk_model** out) {
     e = cudaMemcpy(m->d_words, words.data(), nwords * sizeof(float), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(m->d_words); delete m; return cuda_fail(e, "cudaMemcpy(tree)"); }
     m->family = trk::match_static_family(words.data(), nwords);
-    if (getenv("TRK_B200_FORCE_GENERIC")) m->family = 0;   // diagnostic switch: serve a compiled-in robot with the runtime-tree kernels
+    m->ext_family = m->family ? 0 : trk::match_static_family_prefix(words.data(), nwords);
+    m->h_words = words;
+    if (getenv("TRK_B200_FORCE_GENERIC")) { m->family = 0; m->ext_family = 0; }   // diagnostic switch: runtime-tree kernels only
     *out = m;
     return TRK_OK;
 }
@@ -1114,6 +1193,10 @@ int trk_cost_create(const trk_model* m, const trk_cost_desc* d, trk_cost** out) 
     if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaMalloc(cost)"); }
     e = cudaMemcpy(c->d_words, w, nwords * sizeof(float), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaFree(c->d_words); delete c; return cuda_fail(e, "cudaMemcpy(cost)"); }
+    if (m->ext_family) {
+        const int rc = build_ext_tables(m, d, c);
+        if (rc != TRK_OK) { cudaFree(c->d_words); delete c; return rc; }
+    }
     *out = c;
     return TRK_OK;
 }
@@ -1125,6 +1208,7 @@ void trk_cost_destroy(trk_cost* c) {
     for (int i = 0; i < 3; ++i) if (c->hp_s[i]) cudaStreamDestroy(c->hp_s[i]);
     for (int i = 0; i < c->hp_events; ++i) { cudaEventDestroy(c->hp_in[i]); cudaEventDestroy(c->hp_k[i]); }
     cudaFree(c->d_words);
+    cudaFree(c->d_ext);
     delete c;
 }
 
@@ -1202,6 +1286,22 @@ static int objective_impl(const trk_model* m, const trk_cost* c, const float* q,
     // one equal-radius identity-pose sphere object, no relu on the object term: collision points take the joint scan
     const CostHeader* gh = reinterpret_cast<const CostHeader*>(c->h_words.data());
     const int* giw = reinterpret_cast<const int*>(c->h_words.data());
+    if (m->ext_family && c->ext_ok && !ee_target_cfg) {
+        // a compiled-in robot with attached bodies in the common scene: unrolled FK + points evaluated at their anchors (trk_ext.cuh)
+        static const bool no_hot = getenv("TRK_B200_NO_HOT") != nullptr;   // A/B switch
+        const int need = OBJ_IDENTITY | OBJ_UNIFORM_RADIUS;
+        const bool scene = gh->nObj == 1 && gh->KB == 0 && (giw[gh->off_obj_ident] & (need | OBJ_GRID)) == need &&
+                           giw[gh->off_obj_start + 1] > giw[gh->off_obj_start] && !gh->clamp_self && !gh->clamp_obj && !gh->clamp_ws &&
+                           gh->ws_enabled &&
+                           (!gh->ee_enabled || (gh->ee_w_pos > 0.f && gh->ee_w_rot > 0.f && gh->ee_link == trk::static_family_last_body(m->ext_family)));
+        if (scene && !no_hot) {
+            cudaError_t e = trk::launch_static_objective_ext(m->ext_family, m->n_sms, c->h_words.data(), c->d_words, c->d_ext, c->ext_nwords, c->ext_n_ps,
+                                                             gh->S, q, n, margin_override, use_override, cost_total, cost_terms, grad_q, occupancy, argmin, st);
+            if (e == cudaSuccess) return TRK_OK;
+            if (e != cudaErrorInvalidValue) return cuda_fail(e, "objective(ext)");
+            cudaGetLastError();      // tables too large for the per-thread shared-memory scratch: the runtime-tree kernel serves the call
+        }
+    }
     const int joint = gh->nObj == 1 && gh->KB == 0 && !gh->clamp_obj && gh->S > 0 &&
                       (giw[gh->off_obj_ident] & (OBJ_IDENTITY | OBJ_UNIFORM_RADIUS | OBJ_GRID)) == (OBJ_IDENTITY | OBJ_UNIFORM_RADIUS) &&
                       giw[gh->off_obj_start + 1] > giw[gh->off_obj_start];
@@ -1277,6 +1377,15 @@ int trk_link_jacobian(const trk_model* m, const float* q, int64_t n, float* J, v
     TRK_CHECK_ALIGN16(J, "J");
     DeviceGuard guard(m->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (m->family) {       // compiled-in robots whose tile fits: FK in registers, one bulk store per 32 configurations
+        static const bool no_hot = getenv("TRK_B200_NO_HOT") != nullptr;
+        bool served = false;
+        if (!no_hot) {
+            cudaError_t es = trk::launch_static_link_jacobian(m->family, m->n_sms, q, n, J, st, &served);
+            if (es != cudaSuccess) return cuda_fail(es, "link_jacobian(static) launch");
+            if (served) return TRK_OK;
+        }
+    }
     const int rec_stride = (m->L * 7 + m->D * 3) | 1;                       // odd: lanes hit distinct banks in phase 1
     int link_chunk = 512 / (7 * m->D);                                       // link blocks per output tile (~2 KB)
     link_chunk = link_chunk < 1 ? 1 : link_chunk;

@@ -53,6 +53,10 @@ struct HotParams {
     float c_obj_const, c_ws_const;
     unsigned occ_const;
     int   widx_const[kHotMaxPoints];
+    // k_objective_ext only (its margins live in device tables): the occupancy tests use this margin instead when set
+    int   use_override;
+    float margin_override;
+    int   ee_enabled;          // k_objective_ext: 0 = no EE term (the headline kernel is only selected with one)
 };
 
 __device__ __forceinline__ float fmax_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
@@ -196,6 +200,20 @@ struct HTree {
         return true;
     }
 
+    // movable children in the folded tree (the reverse sweep's "first write is an assignment" bookkeeping)
+    __host__ __device__ static constexpr bool has_movable_child(int i) {
+        for (int c = i + 1; c < L; ++c) if (movable(c) && ap(c) == i) return true;
+        return false;
+    }
+    __host__ __device__ static constexpr bool has_later_movable_sibling(int pa, int i) {
+        for (int c = i + 1; c < L; ++c) if (movable(c) && ap(c) == pa) return true;
+        return false;
+    }
+    // topo index of the body q column c drives
+    __host__ __device__ static constexpr int body_of_column(int c) {
+        for (int i = 0; i < L; ++i) if (R::qidx[i] == c && movable(i)) return i;
+        return 0;
+    }
     // movable body j is an ancestor-or-self anchor of body b (its joint moves b)
     __host__ __device__ static constexpr bool is_anchor_above(int j, int b) {
         int a = anchor(b);
@@ -763,6 +781,145 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
             block_sums[blockIdx.x] = s;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Link Jacobians of a compiled-in robot (compute_analytical_jacobian_all_links, robot_tree.py:250-265; closed form as in
+// k_link_jacobian of trk_b200.cu): J[cfg][link][7][D] = d (position xyz, quaternion wxyz) / d q.
+// Output-bound (L * 7 * D * 4 bytes per configuration).  One warp owns 32 consecutive configurations, whose blocks are ONE
+// contiguous span of J.  A block of four warps owns a 32-configuration tile: lane = configuration; every warp runs the unrolled
+// FK (redundantly: cheaper than exchanging poses), which leaves every
+// joint's world axis and origin in per-lane shared-memory columns, then warp w produces the [7][D] blocks of bodies w, w + 4, ... by a rolled loop
+// over the q columns straight into the tile at its output offsets (row stride L*7*D words: conflict-free when odd, e.g.
+// Panda's 539), and one lane hands the whole tile to the TMA engine with a single linear bulk store.  While a block's tile
+// drains, the other blocks of the SM compute (three tiles fit).  (Unrolling the column loop, or splitting a tile over four
+// warps by body range, made 50-64 KB of straight-line code: 5.4 instruction-fetch stalls per issue, 58-62% of HBM.)
+// ------------------------------------------------------------------------------------------
+template <class R>
+struct JacTile {
+    using T = HTree<R>;
+    static constexpr int L = R::L, D = R::D;
+    static constexpr int kRow = L * 7 * (D > 0 ? D : 1);          // floats per configuration
+    static constexpr int kCols = 6 * (D > 0 ? D : 1);             // per-lane joint columns: axis (3), origin (3) per q column
+    static constexpr size_t smem_bytes = (size_t)32 * (kRow + kCols) * sizeof(float);
+    static constexpr bool fits = smem_bytes <= 75 * 1024;         // three blocks per SM
+    static constexpr int kWarps = 4;                               // warps per tile: all run the FK, each fills every kWarps-th body's block
+    __host__ __device__ static constexpr unsigned anc_mask(int i) {       // q columns that move body i
+        unsigned m = 0u;
+        for (int c = 0; c < D; ++c) if (T::is_anchor_above(T::body_of_column(c), i)) m |= 1u << c;
+        return m;
+    }
+    __host__ __device__ static constexpr unsigned prismatic_mask() {
+        unsigned m = 0u;
+        for (int c = 0; c < D; ++c) if (R::kind[T::body_of_column(c)] == TRK_KIND_PRISMATIC) m |= 1u << c;
+        return m;
+    }
+};
+
+template <class R>
+__global__ void __launch_bounds__(32 * JacTile<R>::kWarps) k_link_jacobian_static(const float* __restrict__ q, long long n, float* __restrict__ J) {
+    using T = HTree<R>;
+    using JT = JacTile<R>;
+    constexpr int L = R::L, D = R::D, kRow = JT::kRow;
+    extern __shared__ __align__(128) float jtile[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned tile_s = (unsigned)__cvta_generic_to_shared(jtile);
+    float* row = jtile + lane * kRow;
+    float* jc = jtile + 32 * kRow + lane;            // joint columns [(c * 6 + k) * 32]: k 0-2 world axis, 3-5 joint origin
+    float qn[D > 0 ? D : 1];                         // next tile's joint values: loaded while the current tile is computed
+    {
+        const long long c0 = (long long)blockIdx.x * 32 + lane;
+        const float* qrow = q + (c0 < n ? c0 : n - 1) * D;
+        sfor<D>([&](auto c) { qn[c] = __ldg(qrow + c); });
+    }
+    for (long long base = (long long)blockIdx.x * 32; base < n; base += (long long)gridDim.x * 32) {
+        float qv[D > 0 ? D : 1];
+        sfor<D>([&](auto c) { qv[c] = qn[c]; });
+        {
+            const long long c1 = base + (long long)gridDim.x * 32 + lane;
+            const float* qrow = q + (c1 < n ? c1 : n - 1) * D;
+            sfor<D>([&](auto c) { qn[c] = __ldg(qrow + c); });
+        }
+        // the previous bulk store must have finished READING the tile (and every warp its joint columns) before they are overwritten
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();
+        float W[L][12];
+        unsigned pass = 0u;
+        // phase 1, every warp: the unrolled FK of the lane's configuration (warp 0 also leaves the joint columns in shared memory)
+        sfor<L>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            if constexpr (T::pix(i) < 0) {
+                sfor<12>([&](auto k) { W[i][k] = (k == 0 || k == 4 || k == 8) ? 1.f : 0.f; });
+            } else if constexpr (T::movable(i)) {
+                constexpr int qi = R::qidx[i];
+                const float qraw = qv[qi];
+                float theta = qraw;
+                if constexpr (R::has_lim[i] != 0) {
+                    constexpr float lo = R::lo[i], hi = R::hi[i];
+                    theta = fmin_nan(fmax_nan(qraw, lo), hi);
+                    if (theta == qraw) pass |= 1u << qi;          // clamped joints: zero columns
+                } else {
+                    pass |= 1u << qi;
+                }
+                constexpr int a = T::ap(i);
+                T::template compose<i, T::small_angle(i)>(W[a], theta, W[i]);
+                float ja[3];
+                T::template joint_axis<i>(W[a], W[i], ja);
+                if (warp == 0) {
+                    float* o = jc + qi * 6 * 32;
+                    o[0] = ja[0]; o[32] = ja[1]; o[64] = ja[2]; o[96] = W[i][9]; o[128] = W[i][10]; o[160] = W[i][11];
+                }
+            } else {
+                constexpr int a = T::anchor(i);
+                float Rb[9], pb[3];
+                T::template fixed_rotation<i>(W[a], Rb);
+                T::template fixed_position<i>(W[a], pb);
+                sfor<9>([&](auto k) { W[i][k] = Rb[k]; });
+                sfor<3>([&](auto k) { W[i][9 + k] = pb[k]; });
+            }
+        });
+        __syncthreads();
+        // phase 2, warp w: the blocks of bodies w, w + kWarps, ...  A body's block is [7][D] at offset body * 7 * D of the row,
+        // filled by a rolled loop over the q columns (unrolled it is 50 KB of straight-line code that stalls on instruction fetch)
+        sfor<L>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            if ((i % JT::kWarps) != warp) return;
+            float qt[4];
+            quat_of_rotation(W[i], qt);
+            const float px = W[i][9], py = W[i][10], pz = W[i][11];
+            const unsigned on_mask = JT::anc_mask(i) & pass;
+            float* o = row + R::body[i] * 7 * D;
+#pragma unroll 1
+            for (int c = 0; c < D; ++c) {
+                const float* j = jc + c * 6 * 32;
+                const float ax = j[0], ay = j[32], az = j[64];
+                const bool on = (on_mask >> c) & 1u, pris = (JT::prismatic_mask() >> c) & 1u;
+                const bool rev = on && !pris, pr = on && pris;      // selects, not products: a NaN pose must not leak into a zero column
+                const float dx = px - j[96], dy = py - j[128], dz = pz - j[160];
+                o[c]         = rev ? ay * dz - az * dy : (pr ? ax : 0.f);
+                o[D + c]     = rev ? az * dx - ax * dz : (pr ? ay : 0.f);
+                o[2 * D + c] = rev ? ax * dy - ay * dx : (pr ? az : 0.f);
+                o[3 * D + c] = rev ? -0.5f * (ax * qt[1] + ay * qt[2] + az * qt[3]) : 0.f;
+                o[4 * D + c] = rev ? 0.5f * (qt[0] * ax + (ay * qt[3] - az * qt[2])) : 0.f;
+                o[5 * D + c] = rev ? 0.5f * (qt[0] * ay + (az * qt[1] - ax * qt[3])) : 0.f;
+                o[6 * D + c] = rev ? 0.5f * (qt[0] * az + (ax * qt[2] - ay * qt[1])) : 0.f;
+            }
+        });
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        const long long left = n - base;
+        const int ncfg = left < 32 ? (int)left : 32;
+        float* dst = J + base * kRow;
+        if ((ncfg * kRow) % 4 == 0) {          // the span is a whole number of 16-byte chunks (always for 32 configurations)
+            if (threadIdx.x == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(tile_s), "r"(ncfg * kRow * 4) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {                                // ragged last tile
+            for (int k = threadIdx.x; k < ncfg * kRow; k += blockDim.x) dst[k] = jtile[k];
+        }
+    }
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 }  // namespace trk

@@ -946,6 +946,7 @@ __global__ void __launch_bounds__(kSBlock, HOT ? TRK_CM_HOT_MINBLOCKS : TRK_CM_M
 
 }  // namespace trk
 #include "trk_hot.cuh"
+#include "trk_ext.cuh"
 namespace trk {
 
 // ------------------------------------------------------------------------------------------
@@ -1233,6 +1234,26 @@ __global__ void __launch_bounds__(kSBlock) k_ik_adam_hot(IKParams P, const float
     }
 }
 
+// link Jacobians of a compiled-in robot: false when the robot's tile does not fit (the caller then uses the runtime-tree kernel)
+template <class R>
+cudaError_t launch_link_jacobian_t(int n_sms, const float* q, long long n, float* J, cudaStream_t st, bool* served) {
+    *served = false;
+    if constexpr (JacTile<R>::fits && R::D > 0) {
+        auto k = k_link_jacobian_static<R>;
+        constexpr size_t smem = JacTile<R>::smem_bytes;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        constexpr int threads = 32 * JacTile<R>::kWarps;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        const long long need = (n + 31) / 32, cap = (long long)n_sms * per_sm;
+        k<<<(int)(need < cap ? need : cap), threads, smem, st>>>(q, n, J);
+        *served = true;
+        return cudaGetLastError();
+    }
+    return cudaSuccess;
+}
+
 template <class R>
 cudaError_t launch_ik_t(const IKParams& P, const float* step_size, const float* bc2_sqrt, const float* target_seed,
                                long long n_seeds, float* q_io, float* err_out, uint8_t* valid_out, int* valid_count,
@@ -1480,6 +1501,79 @@ inline cudaError_t launch_objective_hot(int n_sms, const float* host_words, cons
     return launch(k_objective_hot<R, CM, EE, false, false>);
 }
 
+// ---- attached-body models (trk_ext.cuh) -----------------------------------------------------------------------------
+// the first R::L records of an extended tree equal the compiled-in robot's, the rest are fixed bodies
+template <class R>
+inline bool words_match_prefix(const float* words, int nwords) {
+    if (nwords <= R::n_words) return false;
+    const TreeHeader* hdr = reinterpret_cast<const TreeHeader*>(words);
+    const TreeHeader* h0 = reinterpret_cast<const TreeHeader*>(R::words);
+    if (hdr->D != R::D || hdr->L <= R::L || std::memcmp(hdr->base, h0->base, sizeof(hdr->base)) != 0) return false;
+    if (std::memcmp(words + 16, reinterpret_cast<const float*>(R::words) + 16, sizeof(float) * 24 * R::L) != 0) return false;
+    const LinkRec* recs = reinterpret_cast<const LinkRec*>(words + 16);
+    for (int i = R::L; i < hdr->L; ++i)
+        if ((recs[i].flags & F_KIND_MASK) != TRK_KIND_FIXED || recs[i].qidx >= 0) return false;
+    return true;
+}
+
+inline int match_static_family_prefix(const float* tree_words, int nwords) {
+    int id = 0;
+#define X(Rb) \
+    ++id;     \
+    if (words_match_prefix<Rb>(tree_words, nwords)) return id;
+    TRK_FOR_EACH_STATIC_ROBOT(X)
+#undef X
+    return 0;
+}
+
+// body index of the EE link the extended kernel is compiled for: the base robot's last body
+inline int static_family_last_body(int family) {
+    int id = 0;
+#define X(Rb) \
+    ++id;     \
+    if (family == id) return Rb::body[Rb::L - 1];
+    TRK_FOR_EACH_STATIC_ROBOT(X)
+#undef X
+    return -1;
+}
+
+template <class R>
+cudaError_t launch_objective_ext_t(int n_sms, const float* host_words, const float* cost_words, const float* ext_words, int ext_nwords, int n_ps,
+                                   int n_points, const float* q, long long n, float margin_override, int use_override, float* cost_total,
+                                   float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin, cudaStream_t st) {
+    HotParams hp;
+    const CostHeader* h = reinterpret_cast<const CostHeader*>(host_words);
+    const int* iw = reinterpret_cast<const int*>(host_words);
+    std::memset(&hp, 0, sizeof(hp));
+    for (int i = 0; i < 4; ++i) hp.w[i] = h->w[i];
+    for (int i = 0; i < 3; ++i) { hp.ws_min[i] = h->ws_min[i]; hp.ws_max[i] = h->ws_max[i]; hp.ee_t[i] = h->ee_t[i]; }
+    for (int i = 0; i < 9; ++i) hp.ee_R[i] = h->ee_R[i];
+    hp.ee_w_pos = h->ee_w_pos; hp.ee_w_rot = h->ee_w_rot; hp.ee_square = h->ee_square;
+    hp.tol = host_words[h->off_obj_tol]; hp.c2max = host_words[h->off_obj_c2max];
+    hp.lowmask = (1u << (iw[h->off_obj_ident] >> OBJ_BITS_SHIFT)) - 1u;
+    hp.n_pairs2 = (iw[h->off_obj_qstart + 1] - iw[h->off_obj_qstart]) / 2;
+    hp.n_sph = iw[h->off_obj_start + 1] - iw[h->off_obj_start];
+    hp.off_sphq = h->off_sphq + 4 * iw[h->off_obj_qstart];
+    hp.off_sph = h->off_sph + 4 * iw[h->off_obj_start];
+    hp.use_override = use_override; hp.margin_override = margin_override;
+    hp.ee_enabled = h->ee_enabled;
+    constexpr int kEE = R::L - 1;
+    const size_t table_words = (size_t)hp.n_pairs2 * 8 + (size_t)hp.n_sph * 4 + ((sizeof(HotParams) + 15) / 16) * 4 + ((ext_nwords + 3) & ~3);
+    const size_t smem = (table_words + (size_t)(6 * n_ps + 6 * R::D + 3) * kSBlock) * sizeof(float);
+    auto launch = [&](auto k) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        k<<<persistent_grid(k, n_sms, smem, n), kSBlock, smem, st>>>(hp, cost_words, ext_words, ext_nwords, n_ps, q, n, cost_total, cost_terms, grad_q,
+                                                                     occupancy, argmin, n_points);
+        return cudaGetLastError();
+    };
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (grad_q) return launch(k_objective_ext<R, kEE, true>);
+    return launch(k_objective_ext<R, kEE, false>);
+}
+
 template <class R>
 cudaError_t launch_objective_t(int n_sms, const float* host_words, const float* cost_words, int cost_nwords, int n_slots, int clamp_any, int cm_match, const float* q,
                                       long long n, const float* ee_target_cfg, float margin_override, int use_override,
@@ -1541,7 +1635,10 @@ cudaError_t launch_objective_t(int n_sms, const float* host_words, const float* 
     KW template cudaError_t launch_objective_t<Rb>(int, const float*, const float*, int, int, int, int, const float*, long long, const float*, float, int, \
                                                    float*, float*, float*, uint8_t*, int*, float*, int*, cudaStream_t);                 \
     KW template cudaError_t launch_ik_t<Rb>(const IKParams&, const float*, const float*, const float*, long long, float*, float*,        \
-                                            uint8_t*, int*, float*, float*, cudaStream_t);
+                                            uint8_t*, int*, float*, float*, cudaStream_t);                                                \
+    KW template cudaError_t launch_link_jacobian_t<Rb>(int, const float*, long long, float*, cudaStream_t, bool*);                       \
+    KW template cudaError_t launch_objective_ext_t<Rb>(int, const float*, const float*, const float*, int, int, int, const float*, long long, float, \
+                                                       int, float*, float*, float*, uint8_t*, int*, cudaStream_t);
 #ifndef TRK_INST_ROBOT   // family dispatch: main translation unit only
 #define TRK_DECLARE_EXTERN(Rb) TRK_LAUNCHER_SIGNATURES(extern, Rb)
 TRK_FOR_EACH_STATIC_ROBOT(TRK_DECLARE_EXTERN)
@@ -1557,6 +1654,32 @@ inline cudaError_t launch_static_ik(int family, const IKParams& P, const float* 
     TRK_FOR_EACH_STATIC_ROBOT(X)
 #undef X
     return cudaErrorInvalidValue;
+}
+
+inline cudaError_t launch_static_objective_ext(int family, int n_sms, const float* host_words, const float* cost_words, const float* ext_words,
+                                               int ext_nwords, int n_ps, int n_points, const float* q, long long n, float margin_override,
+                                               int use_override, float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy,
+                                               int* argmin, cudaStream_t st) {
+    int id = 0;
+#define X(Rb) \
+    ++id;     \
+    if (family == id)  \
+        return launch_objective_ext_t<Rb>(n_sms, host_words, cost_words, ext_words, ext_nwords, n_ps, n_points, q, n, margin_override, use_override, \
+                                          cost_total, cost_terms, grad_q, occupancy, argmin, st);
+    TRK_FOR_EACH_STATIC_ROBOT(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+inline cudaError_t launch_static_link_jacobian(int family, int n_sms, const float* q, long long n, float* J, cudaStream_t st, bool* served) {
+    int id = 0;
+    *served = false;
+#define X(Rb) \
+    ++id;     \
+    if (family == id) return launch_link_jacobian_t<Rb>(n_sms, q, n, J, st, served);
+    TRK_FOR_EACH_STATIC_ROBOT(X)
+#undef X
+    return cudaSuccess;
 }
 
 inline cudaError_t launch_static_fk_forward(int family, int n_sms, const float* q, long long n, const SlotMap& sm, int n_sel,
