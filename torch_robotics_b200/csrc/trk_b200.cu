@@ -855,11 +855,17 @@ static int build_ext_tables(const trk_model* m, const trk_cost_desc* d, trk_cost
             r[0] = e.t[0]; r[1] = e.t[1]; r[2] = e.t[2];
             iw[o_psc + k2] = e.col;
         }
-        for (int p = 0; p < P; ++p) {
-            float* r = w.data() + o_pair + 4 * p;
-            reinterpret_cast<int*>(r)[0] = new_slot[slot_of_body[d->pair_i[p]]];
-            reinterpret_cast<int*>(r)[1] = new_slot[slot_of_body[d->pair_j[p]]];
+        std::vector<int> porder(P);
+        for (int p = 0; p < P; ++p) porder[p] = p;
+        std::stable_sort(porder.begin(), porder.end(), [&](int a, int b) { return new_slot[slot_of_body[d->pair_i[a]]] < new_slot[slot_of_body[d->pair_i[b]]]; });
+        for (int k2 = 0; k2 < P; ++k2) {       // sorted by body i's slot (slots are grouped by anchor): runs share the i-side accumulator
+            const int p = porder[k2];
+            float* r = w.data() + o_pair + 4 * k2;
+            const int si = new_slot[slot_of_body[d->pair_i[p]]], sj = new_slot[slot_of_body[d->pair_j[p]]];
+            reinterpret_cast<int*>(r)[0] = si;
+            reinterpret_cast<int*>(r)[1] = sj;
             r[2] = d->pair_margin[p];
+            reinterpret_cast<int*>(r)[3] = (iw[o_psc + si] & 0xff) | ((iw[o_psc + sj] & 0xff) << 8);
         }
     }
     DeviceGuard guard(m->device);

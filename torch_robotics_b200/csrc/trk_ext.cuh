@@ -17,6 +17,10 @@
 
 namespace trk {
 
+#ifndef TRK_EXT_MINBLOCKS
+#define TRK_EXT_MINBLOCKS 4
+#endif
+
 struct ExtHeader {            // device tables built by trk_cost_create for a model with attached bodies
     int n_pts, n_ps, n_pairs, n_anchor;         // collision points, pair-position slots, pairs, movable bodies + 1 (root)
     int off_pt_start, off_pt, off_ps_start, off_ps, off_ps_col, off_pair, total_words, pad;
@@ -25,7 +29,8 @@ struct ExtHeader {            // device tables built by trk_cost_create for a mo
 //   pt_start [n_anchor + 1]   points of anchor a (0 = root, 1 + c = the body q column c drives): pt[pt_start[a] .. pt_start[a+1])
 //   pt       [n_pts][8]       offset xyz, margin (object), margin (ws), point index, 2 pad   (a margin override is a kernel parameter)
 //   ps_start [n_anchor + 1], ps [n_ps][4] offset xyz + pad, ps_col [n_ps] q column of the slot's anchor (-1: root)
-//   pair     [n_pairs][4]     slot i, slot j, margin, pad
+//   pair     [n_pairs][4]     slot i, slot j, margin, q columns of the two anchors (col_i | col_j << 8, 0xff = root: no joint above);
+//                             sorted by slot i, so a run of pairs accumulates the force on body i in registers
 
 struct ExtView {
     const ExtHeader* h;
@@ -41,7 +46,6 @@ struct ExtView {
 // per-thread shared-memory scratch, [slot][thread] layout (stride kSBlock)
 struct ExtScratch {
     float* PS;      // [3 n_ps]  positions of the pair bodies
-    float* PG;      // [3 n_ps]  their position gradients
     float* WS;      // [6 D]     wrench (F, T about the world origin) of the bodies anchored at each movable body
     float* ACC;     // [3]       c_obj, c_ws, occupancy bits
 };
@@ -58,7 +62,6 @@ static __device__ __noinline__ void ext_at_anchor(float r0, float r1, float r2, 
         sc.PS[(3 * k + 0) * kSBlock] = fmaf(r2, tz, fmaf(r1, ty, fmaf(r0, tx, px)));
         sc.PS[(3 * k + 1) * kSBlock] = fmaf(r5, tz, fmaf(r4, ty, fmaf(r3, tx, py)));
         sc.PS[(3 * k + 2) * kSBlock] = fmaf(r8, tz, fmaf(r7, ty, fmaf(r6, tx, pz)));
-        sc.PG[(3 * k + 0) * kSBlock] = 0.f; sc.PG[(3 * k + 1) * kSBlock] = 0.f; sc.PG[(3 * k + 2) * kSBlock] = 0.f;
     }
     // (2) collision points anchored here, five at a time
     float Fx = 0.f, Fy = 0.f, Fz = 0.f, Tx = 0.f, Ty = 0.f, Tz = 0.f, c_obj = 0.f, c_ws = 0.f;
@@ -157,7 +160,7 @@ static __device__ __noinline__ void ext_at_anchor(float r0, float r1, float r2, 
 }
 
 template <class R, int EE, bool WANT_GRAD>
-__global__ void __launch_bounds__(kSBlock) k_objective_ext(const __grid_constant__ HotParams hp_in, const float* __restrict__ cost_words,
+__global__ void __launch_bounds__(kSBlock, TRK_EXT_MINBLOCKS) k_objective_ext(const __grid_constant__ HotParams hp_in, const float* __restrict__ cost_words,
                                                            const float* __restrict__ ext_words_g, int ext_nwords, int n_ps,
                                                            const float* __restrict__ q, long long n, float* __restrict__ cost_total,
                                                            float* __restrict__ cost_terms, float* __restrict__ grad_q,
@@ -187,8 +190,7 @@ __global__ void __launch_bounds__(kSBlock) k_objective_ext(const __grid_constant
     __syncthreads();
     ExtScratch sc;
     sc.PS = scratch + tid;
-    sc.PG = sc.PS + 3 * n_ps * kSBlock;
-    sc.WS = sc.PG + 3 * n_ps * kSBlock;
+    sc.WS = sc.PS + 3 * n_ps * kSBlock;
     sc.ACC = sc.WS + 6 * D * kSBlock;
     const ExtView ev(ew);
     for (long long cfg = (long long)blockIdx.x * kSBlock + tid; cfg < n; cfg += (long long)gridDim.x * kSBlock) {
@@ -265,35 +267,48 @@ __global__ void __launch_bounds__(kSBlock) k_objective_ext(const __grid_constant
         // ---------------- self-collision pairs from the slots (distance_fields.py:194-215) ----------------
         float c_self = 0.f;
         bool occ_self = false;
+        {
+            // A pair's force acts along the line through the two points, so its torque about the world origin is the same at
+            // both ends: body j's anchor receives (+u, +tau), body i's (-u, -tau).  Pairs are sorted by slot i: the wrench on
+            // body i's anchor is kept in registers over a run and flushed when the anchor changes.
+            float aFx = 0.f, aFy = 0.f, aFz = 0.f, aTx = 0.f, aTy = 0.f, aTz = 0.f;
+            int acol = -1;
+            auto flush = [&]() {
+                if (acol >= 0) {
+                    float* w = sc.WS + 6 * acol * kSBlock;
+                    w[0] -= aFx; w[kSBlock] -= aFy; w[2 * kSBlock] -= aFz; w[3 * kSBlock] -= aTx; w[4 * kSBlock] -= aTy; w[5 * kSBlock] -= aTz;
+                }
+                aFx = aFy = aFz = aTx = aTy = aTz = 0.f;
+            };
 #pragma unroll 1
-        for (int p = 0; p < ev.h->n_pairs; ++p) {
-            const float* rec = ev.pair + 4 * p;
-            const int si = __float_as_int(rec[0]), sj = __float_as_int(rec[1]);
-            const float vx = __fsub_rn(sc.PS[(3 * si) * kSBlock], sc.PS[(3 * sj) * kSBlock]);
-            const float vy = __fsub_rn(sc.PS[(3 * si + 1) * kSBlock], sc.PS[(3 * sj + 1) * kSBlock]);
-            const float vz = __fsub_rn(sc.PS[(3 * si + 2) * kSBlock], sc.PS[(3 * sj + 2) * kSBlock]);
-            float rs;
-            const float dist = norm3_clamped(vx, vy, vz, rs);
-            occ_self = occ_self || (dist < (hp->use_override ? hp->margin_override : rec[2]));
-            c_self = __fadd_rn(c_self, -__fsub_rn(dist, rec[2]));
-            if (WANT_GRAD) {
-                const float inv = hp->w[0] * rs;
-                const float ux = vx * inv, uy = vy * inv, uz = vz * inv;
-                sc.PG[(3 * si) * kSBlock] -= ux; sc.PG[(3 * si + 1) * kSBlock] -= uy; sc.PG[(3 * si + 2) * kSBlock] -= uz;
-                sc.PG[(3 * sj) * kSBlock] += ux; sc.PG[(3 * sj + 1) * kSBlock] += uy; sc.PG[(3 * sj + 2) * kSBlock] += uz;
+            for (int p = 0; p < ev.h->n_pairs; ++p) {
+                const float* rec = ev.pair + 4 * p;
+                const int si = __float_as_int(rec[0]), sj = __float_as_int(rec[1]);
+                const float xi = sc.PS[(3 * si) * kSBlock], yi = sc.PS[(3 * si + 1) * kSBlock], zi = sc.PS[(3 * si + 2) * kSBlock];
+                const float vx = __fsub_rn(xi, sc.PS[(3 * sj) * kSBlock]);
+                const float vy = __fsub_rn(yi, sc.PS[(3 * sj + 1) * kSBlock]);
+                const float vz = __fsub_rn(zi, sc.PS[(3 * sj + 2) * kSBlock]);
+                float rs;
+                const float dist = norm3_clamped(vx, vy, vz, rs);
+                occ_self = occ_self || (dist < (hp->use_override ? hp->margin_override : rec[2]));
+                c_self = __fadd_rn(c_self, -__fsub_rn(dist, rec[2]));
+                if (WANT_GRAD) {
+                    const int cols = __float_as_int(rec[3]);
+                    const int ci = (cols & 0xff) == 0xff ? -1 : (cols & 0xff), cj = ((cols >> 8) & 0xff) == 0xff ? -1 : ((cols >> 8) & 0xff);
+                    if (ci != cj) {            // both ends on one anchor: an internal force, no joint sees it
+                        const float inv = hp->w[0] * rs;
+                        const float ux = vx * inv, uy = vy * inv, uz = vz * inv;
+                        const float tx = yi * uz - zi * uy, ty = zi * ux - xi * uz, tz = xi * uy - yi * ux;
+                        if (ci != acol) { flush(); acol = ci; }
+                        aFx += ux; aFy += uy; aFz += uz; aTx += tx; aTy += ty; aTz += tz;
+                        if (cj >= 0) {
+                            float* w = sc.WS + 6 * cj * kSBlock;
+                            w[0] += ux; w[kSBlock] += uy; w[2 * kSBlock] += uz; w[3 * kSBlock] += tx; w[4 * kSBlock] += ty; w[5 * kSBlock] += tz;
+                        }
+                    }
+                }
             }
-        }
-        if (WANT_GRAD) {       // forces on the pair bodies become wrenches of their anchors
-#pragma unroll 1
-            for (int k = 0; k < n_ps; ++k) {
-                const int col = ev.ps_col[k];
-                if (col < 0) continue;
-                const float x = sc.PS[(3 * k) * kSBlock], y = sc.PS[(3 * k + 1) * kSBlock], z = sc.PS[(3 * k + 2) * kSBlock];
-                const float gx = sc.PG[(3 * k) * kSBlock], gy = sc.PG[(3 * k + 1) * kSBlock], gz = sc.PG[(3 * k + 2) * kSBlock];
-                float* w = sc.WS + 6 * col * kSBlock;
-                w[0] += gx; w[kSBlock] += gy; w[2 * kSBlock] += gz;
-                w[3 * kSBlock] += y * gz - z * gy; w[4 * kSBlock] += z * gx - x * gz; w[5 * kSBlock] += x * gy - y * gx;
-            }
+            if (WANT_GRAD) flush();
         }
         // ---------------- outputs ----------------
         {

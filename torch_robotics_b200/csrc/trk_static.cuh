@@ -1559,7 +1559,7 @@ cudaError_t launch_objective_ext_t(int n_sms, const float* host_words, const flo
     hp.ee_enabled = h->ee_enabled;
     constexpr int kEE = R::L - 1;
     const size_t table_words = (size_t)hp.n_pairs2 * 8 + (size_t)hp.n_sph * 4 + ((sizeof(HotParams) + 15) / 16) * 4 + ((ext_nwords + 3) & ~3);
-    const size_t smem = (table_words + (size_t)(6 * n_ps + 6 * R::D + 3) * kSBlock) * sizeof(float);
+    const size_t smem = (table_words + (size_t)(3 * n_ps + 6 * R::D + 3) * kSBlock) * sizeof(float);
     auto launch = [&](auto k) {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
