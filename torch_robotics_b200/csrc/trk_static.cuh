@@ -1087,6 +1087,8 @@ __global__ void __launch_bounds__(kSBlock) k_ik_adam_static(IKParams P, const fl
 
 // The same with the end-effector body (topo index EE) at compile time and the folded tree of trk_hot.cuh: only the movable
 // ancestors of the EE body are composed, fixed chains cost three FMAs, the joints off the EE chain never enter the loop body.
+// (A 7-blocks-per-SM variant, 72 registers with a few spills, that holds BASELINE config 4's 125,000 seeds per GPU in one wave
+// was measured slower than 1.3 waves at 96 registers: 2.71 vs 2.43 ms.  The kernel is issue-bound, not wave-bound.)
 template <class R, int EE>
 __global__ void __launch_bounds__(kSBlock) k_ik_adam_hot(IKParams P, const float* __restrict__ step_size, const float* __restrict__ bc2_sqrt,
                                                          const float* __restrict__ target_seed, long long n_seeds,

@@ -84,8 +84,7 @@ def gather_best_solutions(q_local: torch.Tensor, err_local: torch.Tensor, valid_
     rank, w = world()
     S, D = q_local.shape
     kk = min(k, S)
-    key = torch.where(valid_local, err_local, torch.full_like(err_local, float("inf")))
-    order = torch.argsort(key, stable=True)[:kk]
+    order = _smallest_k(torch.where(valid_local, err_local, torch.full_like(err_local, float("inf"))), kk)
     block = torch.full((k, D + 2), float("inf"), dtype=q_local.dtype, device=q_local.device)
     block[:kk, :D] = q_local[order]
     block[:kk, D] = err_local[order]
@@ -97,10 +96,23 @@ def gather_best_solutions(q_local: torch.Tensor, err_local: torch.Tensor, valid_
         allb = torch.cat(blocks, 0)
     else:
         allb = block
-    gkey = torch.where(allb[:, D + 1] > 0, allb[:, D], torch.full_like(allb[:, D], float("inf")))
-    top = torch.argsort(gkey, stable=True)[:k]
+    top = _smallest_k(torch.where(allb[:, D + 1] > 0, allb[:, D], torch.full_like(allb[:, D], float("inf"))), k)
     sel = allb[top]
     return sel[:, :D], sel[:, D], sel[:, D + 1] > 0
+
+
+def _smallest_k(key: torch.Tensor, k: int) -> torch.Tensor:
+    """Indices of the k smallest entries of a non-negative fp32 key, ascending, ties by index (what a stable argsort gives) -
+    as one top-k over 64-bit integers (key bits << 32 | index: for non-negative floats the bit pattern orders like the value,
+    +inf last) instead of a full sort of the batch."""
+    n = key.shape[0]
+    if key.dtype != torch.float32 or n >= (1 << 31):
+        return torch.argsort(key, stable=True)[:k]
+    # (an SE(3) error can round to a tiny negative value: its bit pattern is a negative integer and still ranks first; no host
+    # synchronisation is spent on checking)
+    packed = (key.contiguous().view(torch.int32).to(torch.int64) << 32) | torch.arange(n, device=key.device, dtype=torch.int64)
+    vals = torch.topk(packed, k, largest=False, sorted=True).values
+    return vals & 0xFFFFFFFF
 
 
 def bind_to_gpu_numa_node(device_index: int) -> bool:
