@@ -121,7 +121,7 @@ class ClockSampler(threading.Thread):
             self.nv = None
 
     def run(self):
-        if self.nv is None:
+        if self.nv is None or os.environ.get("TRK_BENCH_NO_SAMPLER"):
             return
         nv = self.nv
         names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
@@ -314,7 +314,8 @@ def main():
     # weak scaling: rank r owns rows [r n, (r + 1) n) of one seeded global batch
     q_host = torch.from_numpy(sample_q(desc, n, GLOBAL_SEED, row0=rank * n)).pin_memory()
     q = q_host.to(dev)
-    tots = [torch.empty(n, device=dev), torch.empty(n, device=dev)]
+    RING = 4
+    tots = [torch.empty(n, device=dev) for _ in range(RING)]
     tot = tots[0]
     grad = torch.empty_like(q)
     main_stream = torch.cuda.current_stream(dev)
@@ -326,36 +327,42 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    REDUCE_ON_MAIN = os.environ.get("TRK_BENCH_REDUCE", "side") == "main"          # development A/B switches
+    NO_COLLECTIVE = os.environ.get("TRK_BENCH_REDUCE", "side") == "none"
+
     def run_steps(qd, tots, gradd, cost_obj, k):
         """k steps: fused kernel on the main stream; the cost reduction of step i (device sum + all-reduce) runs on the side
-        stream while step i + 1 computes (the cost output is double-buffered: `tots` holds two arrays).  Returns (per-launch
+        stream while the following steps compute (the cost output is a ring of len(tots) arrays, so the ranks may drift by that
+        many steps before a slow all-reduce holds anybody up).  Returns (per-launch
         kernel ms list, span ms first launch -> last reduction, the last reduced total, collective ms list)."""
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(k)]
         ends = [torch.cuda.Event(enable_timing=True) for _ in range(k)]
         c0 = [torch.cuda.Event(enable_timing=True) for _ in range(k)]
         c1 = [torch.cuda.Event(enable_timing=True) for _ in range(k)]
         last = torch.cuda.Event(enable_timing=True)
-        red_done = [None, None]
-        parts = [torch.empty(cost_obj.MAX_BLOCK_SUMS, device=dev), torch.empty(cost_obj.MAX_BLOCK_SUMS, device=dev)]
+        depth = len(tots)
+        red_done = [None] * depth
+        parts = [torch.empty(cost_obj.MAX_BLOCK_SUMS, device=dev) for _ in range(depth)]
         for i in range(k):
-            totd = tots[i & 1]
-            if red_done[i & 1] is not None:
-                main_stream.wait_event(red_done[i & 1])      # step i overwrites what step i - 2's reduction read
+            totd = tots[i % depth]
+            if red_done[i % depth] is not None:
+                main_stream.wait_event(red_done[i % depth])      # step i overwrites what step i - depth's reduction read
             starts[i].record(main_stream)
             # cost + gradient + the kernel's per-block partial sums of the cost (first stage of the reduction, fused)
-            cost_obj.objective_sum(qd, out_grad=gradd, out_total=totd, out_block_sums=parts[i & 1])
+            cost_obj.objective_sum(qd, out_grad=gradd, out_total=totd, out_block_sums=parts[i % depth])
             ends[i].record(main_stream)
-            side.wait_event(ends[i])
-            with torch.cuda.stream(side):
-                s = parts[i & 1].sum(dtype=torch.float64).reshape(1)
-                c0[i].record(side)
-                if world > 1:
+            red_stream = main_stream if REDUCE_ON_MAIN else side
+            red_stream.wait_event(ends[i])
+            with torch.cuda.stream(red_stream):
+                s = parts[i % depth].sum(dtype=torch.float64).reshape(1)
+                c0[i].record(red_stream)
+                if world > 1 and not NO_COLLECTIVE:
                     dist.all_reduce(s, op=dist.ReduceOp.SUM)
-                c1[i].record(side)
+                c1[i].record(red_stream)
                 sums.copy_(s)
                 ev = torch.cuda.Event()
-                ev.record(side)
-                red_done[i & 1] = ev
+                ev.record(red_stream)
+                red_done[i % depth] = ev
         main_stream.wait_stream(side)
         last.record(main_stream)
         torch.cuda.synchronize()
@@ -364,10 +371,15 @@ def main():
         return kernel_ms, starts[0].elapsed_time(last), float(sums.item()), coll_ms
 
     # ---------------- headline (weak scaling) ----------------
-    run_steps(q, tots, grad, dc, args.warmup)
-    barrier()
+    # Warm-up: the W steps asked for plus enough untimed steps to keep every GPU busy for ~15 ms right up to the barrier that opens
+    # the timed region.  (With 8 ranks the rendezvous around a short warm-up leaves some GPUs idle long enough to drop their clocks:
+    # the first ~10 timed launches then ran at 0.35 ms instead of 0.20 ms and a 20-step run reported 0.31-0.37 ms per step.)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    warm_extra = max(0, 64 - args.warmup)
+    run_steps(q, tots, grad, dc, args.warmup)
+    barrier()
+    run_steps(q, tots, grad, dc, warm_extra)
     barrier()
     t_wall0 = time.perf_counter()
     kernel_ms, span_ms, total_sum, coll_ms = run_steps(q, tots, grad, dc, args.steps)
@@ -375,7 +387,7 @@ def main():
     t_wall = time.perf_counter() - t_wall0
     clocks_headline = sampler.result()
     total_ms = float(sum(kernel_ms))
-    r_total = tots[(args.steps - 1) & 1].clone()
+    r_total = tots[(args.steps - 1) % RING].clone()
 
     # ---------------- shard identity + strong scaling (the headline batch split N ways) ----------------
     strong = None
@@ -385,12 +397,12 @@ def main():
         ns = (hi_r - lo_r) * HORIZON
         # every rank evaluates its shard of the GLOBAL batch of rank 0 (rows [0, n)); rank 0 also evaluates the whole batch
         qs = torch.from_numpy(sample_q(desc, ns, GLOBAL_SEED, row0=lo_r * HORIZON)).to(dev)
-        tss, gs = [torch.empty(ns, device=dev), torch.empty(ns, device=dev)], torch.empty_like(qs)
-        run_steps(qs, tss, gs, dc, 3)
+        tss, gs = [torch.empty(ns, device=dev) for _ in range(RING)], torch.empty_like(qs)
+        run_steps(qs, tss, gs, dc, 64)
         barrier()
         k_ms, s_ms, s_sum, s_coll = run_steps(qs, tss, gs, dc, args.steps)
         barrier()
-        ts = tss[(args.steps - 1) & 1]
+        ts = tss[(args.steps - 1) % RING]
         mine = torch.tensor([tensor_hash(ts, gs) - (1 << 63)], dtype=torch.int64, device=dev)
         hashes = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(hashes, mine)
@@ -478,7 +490,7 @@ def main():
         h2d, d2h = n * desc.n_dofs * 4, n * (desc.n_dofs + 1) * 4
         out = {
             "metric": METRIC, "value": value, "unit": "configs/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "warmup_extra_untimed_steps": warm_extra, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(world),
             "kernel_family": model.kernel_family, "headline_kernel": HEADLINE_KERNEL, "build_hash": build_hash(),
@@ -489,7 +501,7 @@ def main():
                          "peak_source": f"148 SMs x 128 lanes x 2 x sm_max_mhz ({peaks['source']} MEASURED_PEAKS.json)",
                          "hbm": {"achieved": kernel_rate * BYTES_PER_CFG / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                  "frac": kernel_rate * BYTES_PER_CFG / 1e9 / peaks["hbm_gbs"]}},
-            "collective": {"op": "fused per-block partial sums (trk_objective_sums) -> fp64 sum of <= 2048 values + NCCL all-reduce(SUM) of the scalar, once per step, side stream",
+            "collective": {"op": "fused per-block partial sums (trk_objective_sums) -> fp64 sum of <= 8192 values + NCCL all-reduce(SUM) of the scalar, once per step, side stream",
                            "collective_ms": float(np.median(coll_ms)) if (coll_ms and world > 1) else 0.0,
                            "total_cost_last_step": total_sum},
             "e2e": {"value": world * n / e2e_s, "unit": "configs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -498,7 +510,7 @@ def main():
                     "frac_of_copy_ceiling": copy_s / e2e_s,
                     "api": "C ABI trk_objective_host(pinned q) -> pinned cost, grad_q (8 chunks, H2D / kernel / D2H on three streams); "
                            "copy_only = the same bytes both ways at once without the kernel, all ranks concurrently (the box's ceiling)"},
-            "gpu_launches": args.steps,          # one launch of the fused objective kernel per step (+ a memset and a 2048-value sum of its partials)
+            "gpu_launches": args.steps,          # one launch of the fused objective kernel per step (+ a memset and an 8192-value sum of its partials)
             "numa_bound": numa_bound,
             "clocks": {**sampler.result(), "samples_during_headline": clocks_headline["samples"],
                        "note": "sampled at 1 kHz over every timed region of this run (headline, strong, e2e, configs 4 and 5)"},
@@ -609,11 +621,11 @@ def bench_cfg5(torch, dist, D, dev, rank, world, run_steps, n_total=1 << 24):
         s1 = min(ns, s0 + slab)
         g = torch.Generator(device=dev).manual_seed(5000 + (lo_r + s0) // slab)
         q5[s0:s1] = lo_t + torch.rand((s1 - s0, ds.n_dofs), generator=g, device=dev) * (hi_t - lo_t)
-    tots, grad = [torch.empty(ns, device=dev), torch.empty(ns, device=dev)], torch.empty_like(q5)
-    run_steps(q5, tots, grad, dcs, 2)
+    tots, grad = [torch.empty(ns, device=dev) for _ in range(4)], torch.empty_like(q5)
+    run_steps(q5, tots, grad, dcs, 3)
     if world > 1:
         dist.barrier()
-    k = 3
+    k = 4
     k_ms, span, s_sum, coll = run_steps(q5, tots, grad, dcs, k)
     t = torch.tensor([span / k, float(np.mean(k_ms))], dtype=torch.float64, device=dev)
     if world > 1:

@@ -199,7 +199,7 @@ int trk_objective(const trk_model* model, const trk_cost* cost, const float* q, 
  * deterministic for a given batch size.  Returns TRK_E_UNSUPPORTED when the model / cost table is not served by the
  * headline kernel (trk_hot.cuh); sum cost_total instead.
  */
-#define TRK_MAX_BLOCK_SUMS 2048
+#define TRK_MAX_BLOCK_SUMS 8192
 int trk_objective_sums(const trk_model* model, const trk_cost* cost, const float* q, int64_t n, const float* ee_target_cfg,
                        float margin_override, float* cost_total, float* grad_q, float* block_sums, void* stream);
 

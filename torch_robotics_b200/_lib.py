@@ -385,7 +385,7 @@ class DeviceCost:
                                   ptr(occ), ptr(amin), stream_ptr(dev)), "trk_objective")
         return dict(total=total, terms=terms, grad_q=grad, occupancy=occ, argmin=amin)
 
-    MAX_BLOCK_SUMS = 2048
+    MAX_BLOCK_SUMS = 8192
 
     def objective_sum(self, q: torch.Tensor, out_grad: torch.Tensor, out_total: Optional[torch.Tensor] = None,
                       out_block_sums: Optional[torch.Tensor] = None, margin_override: Optional[float] = None) -> torch.Tensor:
