@@ -565,9 +565,9 @@ def bench_cfg4(torch, dist, D, model, desc, dev, rank, world, S=1_000_000, iters
     def once():
         a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         a.record()
-        res = model.ik_adam(q0, Ht, ee, lo, hi, n_iters=iters, lr=0.2, se3_eps=0.05)
+        res = model.ik_adam(q0, Ht, ee, lo, hi, n_iters=iters, lr=0.2, se3_eps=0.05, best_k=k_best)
         b.record()
-        best = D.gather_best_solutions(res["q"], res["err"], res["valid"], k=k_best)
+        best = D.gather_best_solutions(res["q"], res["err"], res["valid"], k=k_best, local_keys=res["best_keys"])
         c.record()
         torch.cuda.synchronize()
         return a.elapsed_time(b), b.elapsed_time(c), res, best
@@ -589,7 +589,8 @@ def bench_cfg4(torch, dist, D, model, desc, dev, rank, world, S=1_000_000, iters
     return {"workload": "panda_adam_ik", "seeds_total": S, "seeds_per_rank": s_loc, "iters": iters, "ms_kernel": ms_k, "collective_ms": ms_c,
             "ms_total": ms_t, "seed_iters_per_s": S * iters / (ms_t * 1e-3), "fp32_frac_per_gpu": S * iters / (ms_k * 1e-3) * 1200 / fp32_peak / world,
             "flop_per_seed_iter": 1200, "valid_fraction": float(nv.item()) / S, "best_err": [float(v) for v in best[1].tolist()],
-            "collective": f"per-rank top-{k_best} + NCCL all-gather of [{k_best}, D+2] + local top-{k_best} (distributed.gather_best_solutions)"}
+            "collective": f"per-block top-{k_best} in the IK kernel (trk_ik_adam_best) -> per-rank top-{k_best} + NCCL all-gather of [{k_best}, D+2] + "
+                          f"top-{k_best} (distributed.gather_best_solutions)"}
 
 
 def bench_cfg5(torch, dist, D, dev, rank, world, run_steps, n_total=1 << 24):

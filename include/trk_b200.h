@@ -263,6 +263,20 @@ int trk_ik_adam(const trk_model* model, const trk_ik_params* params, const float
                 int32_t* valid_count, float* loss_sum, float* loss_sqsum, void* stream);
 
 /*
+ * trk_ik_adam with the first stage of the best-solution selection fused into the kernel (robot_tree.py:303-384 returns every
+ * seed; a caller that wants the k best valid ones - BASELINE config 4: per-rank top-k, all-gather, top-k - otherwise runs a
+ * select over all seeds).  Seeds are processed in blocks of TRK_IK_BLOCK_SEEDS; best_keys [ceil(n / TRK_IK_BLOCK_SEEDS) * best_k]
+ * int64 DEVICE memory receives, per block and ascending, the best_k smallest keys
+ *     (bits of the final SE(3) error, or of +inf for a seed that fails the termination test) << 32 | seed index,
+ * 0x7fffffffffffffff where a block has fewer seeds.  The k smallest keys overall are the k best seeds, ties by index.
+ * Compiled-in robots with the EE on their last body only; TRK_E_UNSUPPORTED otherwise.
+ */
+#define TRK_IK_BLOCK_SEEDS 128
+int trk_ik_adam_best(const trk_model* model, const trk_ik_params* params, const float* step_size, const float* bc2_sqrt,
+                     const float* target_seed, int64_t n, float* q_io, float* err_out, uint8_t* valid_out,
+                     int32_t* valid_count, int64_t* best_keys, int32_t best_k, void* stream);
+
+/*
  * Replaces DifferentiableTree.compute_analytical_jacobian_all_links (robot_tree.py:250-265), which differentiates
  * FK + rotation_matrix_to_q (geometrics/quaternion.py:135-166) with torch.autograd.functional.jacobian.
  * q [N, D] -> J [N, L, 7, D]: rows 0-2 d position / d q, rows 3-6 d quaternion (w, x, y, z) / d q, bodies in <link>

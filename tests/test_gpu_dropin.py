@@ -383,3 +383,31 @@ def test_inverse_kinematics_500_iterations_config4_settings():
     # same NUMBER of valid seeds within the binomial spread of 64 draws at p ~ 0.75 (sigma = 3.5)
     assert len(np.setxor1d(idx, g["idx_valid_500"])) <= 12
     assert abs(len(idx) - len(g["idx_valid_500"])) <= 6
+
+
+def test_fused_ik_best_k_equals_selection_over_all_seeds():
+    """trk_ik_adam_best: the per-block candidate keys give exactly the k best valid seeds a selection over every seed gives
+    (same seeds, same order, ties by index), through gather_best_solutions with and without the keys; ragged last block; a
+    robot the fused selection does not serve falls back silently."""
+    from conftest import get_desc
+    from torch_robotics_b200 import distributed as D
+    from torch_robotics_b200._lib import DeviceModel
+    g, d = load_golden("ik_panda"), get_desc("panda")
+    m = DeviceModel(d, DEV)
+    rng = np.random.default_rng(9)
+    for S in (5, 128, 1000, 4099):
+        q0 = (g["lower"] + rng.random((S, 7)) * (g["upper"] - g["lower"])).astype(np.float32)
+        r = m.ik_adam(t(q0), g["H_target"], 10, g["lower"], g["upper"], n_iters=60, lr=0.2, se3_eps=0.05, best_k=8)
+        assert r["best_keys"] is not None and r["best_keys"].shape[0] == ((S + 127) // 128) * 8
+        a = D.gather_best_solutions(r["q"], r["err"], r["valid"], k=8, local_keys=r["best_keys"])
+        b = D.gather_best_solutions(r["q"], r["err"], r["valid"], k=8)
+        nv = int(r["valid"].sum())
+        kk = min(8, S)
+        assert torch.equal(a[2][:kk], b[2][:kk]) and int(a[2].sum()) == min(nv, 8)
+        sel = a[2][:kk]
+        assert torch.equal(a[0][:kk][sel], b[0][:kk][sel]) and torch.equal(a[1][:kk][sel], b[1][:kk][sel])
+    dk = get_desc("kuka_iiwa")                      # its EE is not what the fused selection is compiled for? (last body is): use a mid link
+    mk = DeviceModel(dk, DEV)
+    qk = t(np.zeros((64, 7), np.float32))
+    rk = mk.ik_adam(qk, np.eye(4, dtype=np.float32), 3, dk.lo[dk.controlled], dk.hi[dk.controlled], n_iters=3, best_k=4)
+    assert rk["best_keys"] is None

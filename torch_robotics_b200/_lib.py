@@ -59,7 +59,7 @@ EXPORTS = [
     "trk_abi_version", "trk_last_error", "trk_model_create", "trk_model_destroy", "trk_model_kernel_family",
     "trk_fk_forward", "trk_fk_backward", "trk_cost_create", "trk_cost_destroy", "trk_cost_set_ee_target",
     "trk_cost_set_weights", "trk_objective", "trk_objective_host", "trk_cost_stage", "trk_selftest_sqrt", "trk_ik_adam",
-    "trk_link_jacobian", "trk_geometric_jacobian", "trk_objective_sums",
+    "trk_link_jacobian", "trk_geometric_jacobian", "trk_objective_sums", "trk_ik_adam_best",
 ]
 
 
@@ -99,6 +99,7 @@ def lib() -> C.CDLL:
         L.trk_geometric_jacobian.argtypes = [vp, vp, i64, i32, C.c_uint32, vp, vp, vp, vp]
         L.trk_objective_host.argtypes = [vp, vp, vp, i64, i32, vp, vp]
         L.trk_ik_adam.argtypes = [vp, C.POINTER(IKParamsC), vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
+        L.trk_ik_adam_best.argtypes = [vp, C.POINTER(IKParamsC), vp, vp, vp, i64, vp, vp, vp, vp, vp, i32, vp]
         for name in EXPORTS:
             fn = getattr(L, name)
             if fn.restype is C.c_int and name not in ("trk_abi_version",):
@@ -241,7 +242,8 @@ class DeviceModel:
 
 
     def ik_adam(self, q0: torch.Tensor, H_target, ee_link: int, lower, upper, n_iters: int, n_updates: Optional[int] = None,
-                lr=1e-2, betas=(0.9, 0.999), eps=1e-8, w_se3=1.0, w_joint_limits=300.0, se3_eps=1e-1, want_loss_stats=False):
+                lr=1e-2, betas=(0.9, 0.999), eps=1e-8, w_se3=1.0, w_joint_limits=300.0, se3_eps=1e-1, want_loss_stats=False,
+                best_k: int = 0):
         """Fused Adam IK (trk_ik_adam).  q0 [S, D] is not modified.  Returns dict(q, err, valid (bool), valid_count
         [n_iters] int32, loss_sum / loss_sqsum [n_iters] or None).  Compiled-in robots run the register-resident kernel,
         any other tree the runtime-tree one (state in shared-memory columns)."""
@@ -282,9 +284,21 @@ class DeviceModel:
         ls = torch.empty(n_iters, dtype=torch.float32, device=dev) if want_loss_stats else None
         lq = torch.empty(n_iters, dtype=torch.float32, device=dev) if want_loss_stats else None
         ptr = lambda x: None if x is None else x.data_ptr()
-        check(lib().trk_ik_adam(self.handle, C.byref(p), step_size.data_ptr(), bc2.data_ptr(), ptr(tgt_seed), S, q.data_ptr(),
-                                err.data_ptr(), valid.data_ptr(), count.data_ptr(), ptr(ls), ptr(lq), stream_ptr(dev)), "trk_ik_adam")
-        return dict(q=q, err=err, valid=valid.bool(), valid_count=count, loss_sum=ls, loss_sqsum=lq)
+        best = None
+        if best_k > 0 and not want_loss_stats:
+            # per-block candidates for distributed.gather_best_solutions (trk_ik_adam_best); robots the fused selection does
+            # not serve fall through to the plain call and the caller selects over all seeds
+            best = torch.empty(((S + 127) // 128) * int(best_k), dtype=torch.int64, device=dev)
+            rc = lib().trk_ik_adam_best(self.handle, C.byref(p), step_size.data_ptr(), bc2.data_ptr(), ptr(tgt_seed), S, q.data_ptr(),
+                                        err.data_ptr(), valid.data_ptr(), count.data_ptr(), best.data_ptr(), int(best_k), stream_ptr(dev))
+            if rc == -4:      # TRK_E_UNSUPPORTED
+                best = None
+            else:
+                check(rc, "trk_ik_adam_best")
+        if best is None:
+            check(lib().trk_ik_adam(self.handle, C.byref(p), step_size.data_ptr(), bc2.data_ptr(), ptr(tgt_seed), S, q.data_ptr(),
+                                    err.data_ptr(), valid.data_ptr(), count.data_ptr(), ptr(ls), ptr(lq), stream_ptr(dev)), "trk_ik_adam")
+        return dict(q=q, err=err, valid=valid.bool(), valid_count=count, loss_sum=ls, loss_sqsum=lq, best_keys=best)
 
 
 class DeviceCost:

@@ -1326,9 +1326,31 @@ static int objective_impl(const trk_model* m, const trk_cost* c, const float* q,
     return e == cudaSuccess ? TRK_OK : cuda_fail(e, "objective launch");
 }
 
+static int ik_impl(const trk_model* m, const trk_ik_params* p, const float* step_size, const float* bc2_sqrt,
+                   const float* target_seed, int64_t n, float* q_io, float* err_out, uint8_t* valid_out, int32_t* valid_count,
+                   float* loss_sum, float* loss_sqsum, int64_t* best_keys, int best_k, void* stream);
+
 int trk_ik_adam(const trk_model* m, const trk_ik_params* p, const float* step_size, const float* bc2_sqrt,
                 const float* target_seed, int64_t n, float* q_io, float* err_out, uint8_t* valid_out, int32_t* valid_count,
                 float* loss_sum, float* loss_sqsum, void* stream) {
+    return ik_impl(m, p, step_size, bc2_sqrt, target_seed, n, q_io, err_out, valid_out, valid_count, loss_sum, loss_sqsum, nullptr, 0, stream);
+}
+
+int trk_ik_adam_best(const trk_model* m, const trk_ik_params* p, const float* step_size, const float* bc2_sqrt,
+                     const float* target_seed, int64_t n, float* q_io, float* err_out, uint8_t* valid_out, int32_t* valid_count,
+                     int64_t* best_keys, int32_t best_k, void* stream) {
+    TRK_CHECK_PTR(m, "model"); TRK_CHECK_PTR(p, "params"); TRK_CHECK_PTR(best_keys, "best_keys");
+    if (best_k < 1 || best_k > TRK_IK_BLOCK_SEEDS) return fail(TRK_E_RANGE, "best_k=%d outside [1, %d]", best_k, TRK_IK_BLOCK_SEEDS);
+    if (n >= (1ll << 32)) return fail(TRK_E_RANGE, "n=%lld: seed indices must fit 32 bits", (long long)n);
+    static const bool no_hot = getenv("TRK_B200_NO_HOT") != nullptr;
+    if (!m->family || no_hot || p->ee_link != trk::static_family_last_body(m->family))
+        return fail(TRK_E_UNSUPPORTED, "the fused per-block top-k needs a compiled-in robot with the EE on its last body (use trk_ik_adam and select on the host side)");
+    return ik_impl(m, p, step_size, bc2_sqrt, target_seed, n, q_io, err_out, valid_out, valid_count, nullptr, nullptr, best_keys, best_k, stream);
+}
+
+static int ik_impl(const trk_model* m, const trk_ik_params* p, const float* step_size, const float* bc2_sqrt,
+                   const float* target_seed, int64_t n, float* q_io, float* err_out, uint8_t* valid_out, int32_t* valid_count,
+                   float* loss_sum, float* loss_sqsum, int64_t* best_keys, int best_k, void* stream) {
     TRK_CHECK_PTR(m, "model"); TRK_CHECK_PTR(p, "params");
 
     if (n < 0) return fail(TRK_E_RANGE, "n=%lld", (long long)n);
@@ -1346,6 +1368,7 @@ int trk_ik_adam(const trk_model* m, const trk_ik_params* p, const float* step_si
     P.w_se3 = p->w_se3; P.w_lim = p->w_joint_limits; P.se3_eps = p->se3_eps;
     for (int c = 0; c < m->D; ++c) { P.lower[c] = p->lower[c]; P.upper[c] = p->upper[c]; }
     if (p->H_target) memcpy(P.target, p->H_target, sizeof(P.target));
+    P.best_keys = reinterpret_cast<unsigned long long*>(best_keys); P.best_k = best_k;
     for (int b = p->ee_link; b >= 0; b = m->parent[b])   // q columns of the joints between the root and the EE body
         if (m->qidx[b] >= 0) P.anc_mask |= 1u << m->qidx[b];
     DeviceGuard guard(m->device);

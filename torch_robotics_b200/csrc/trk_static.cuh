@@ -967,6 +967,10 @@ struct IKParams {
     float lr, beta1, beta2, eps, w_se3, w_lim, se3_eps, pad;
     float lower[TRK_MAX_DOFS], upper[TRK_MAX_DOFS];
     float target[16];
+    // k_ik_adam_hot only: when set, every block also leaves its best_k best seeds as sortable 64-bit keys
+    // (bits of the final SE(3) error, +inf for invalid seeds, << 32 | seed index), ascending, at best_keys[block * best_k ...]
+    unsigned long long* best_keys;
+    int best_k, pad_k;
 };
 
 // EE: processing position of the end-effector body when it is the robot's last body (the usual choice), -1 = run time
@@ -1233,6 +1237,28 @@ __global__ void __launch_bounds__(kSBlock) k_ik_adam_hot(IKParams P, const float
         sfor<D>([&](auto c) { q_io[seed * D + c] = qv[c]; });
         if (err_out) err_out[seed] = err;
         if (valid_out) valid_out[seed] = valid ? 1 : 0;
+    }
+    if (P.best_keys) {
+        // first stage of gather_best_solutions fused here: the block's best_k smallest keys, by repeated block-wide minimum
+        // (keys are unique: the seed index is part of them).  The caller's top-k then runs over blocks * best_k candidates
+        // instead of every seed (a multi-pass radix select over 10^5-10^6 keys costs more than the whole solve of a small batch).
+        __shared__ unsigned long long s_min[kSBlock / 32];
+        const unsigned long long kEmpty = 0x7FFFFFFFFFFFFFFFull;
+        const unsigned e_bits = (valid && live) ? __float_as_uint(err) : 0x7f800000u;
+        unsigned long long key = live ? (((unsigned long long)e_bits << 32) | (unsigned long long)(unsigned)seed) : kEmpty;
+        for (int r = 0; r < P.best_k; ++r) {
+            unsigned long long m = key;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o); m = t < m ? t : m; }
+            __syncthreads();
+            if (lane == 0) s_min[threadIdx.x >> 5] = m;
+            __syncthreads();
+            m = s_min[0];
+#pragma unroll
+            for (int w = 1; w < kSBlock / 32; ++w) m = s_min[w] < m ? s_min[w] : m;
+            if (threadIdx.x == 0) P.best_keys[(long long)blockIdx.x * P.best_k + r] = m;
+            if (key == m) key = kEmpty;
+        }
     }
 }
 

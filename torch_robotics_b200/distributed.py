@@ -74,22 +74,26 @@ def all_valid(local_all_valid: bool, device) -> bool:
     return bool(flag.item())
 
 
-def gather_best_solutions(q_local: torch.Tensor, err_local: torch.Tensor, valid_local: torch.Tensor, k: int):
+def gather_best_solutions(q_local: torch.Tensor, err_local: torch.Tensor, valid_local: torch.Tensor, k: int, local_keys=None):
     """Global k best IK solutions.
 
     q_local [S, D], err_local [S] (SE(3) error), valid_local [S] bool on this rank.  Each rank selects its
     k best valid seeds (invalid ones are ranked last), the [k, D+2] blocks are all-gathered and every rank
     takes the global top-k.  Returns (q [k, D], err [k], valid [k] bool), identical on all ranks and equal
-    to a single-process top-k over the concatenated seeds (ties broken by global seed order)."""
+    to a single-process top-k over the concatenated seeds (ties broken by global seed order).
+    local_keys: the per-block candidate keys of DeviceModel.ik_adam(best_k >= k) (error bits << 32 | seed index, int64): the
+    local selection then runs over blocks * best_k candidates instead of all S seeds."""
     rank, w = world()
     S, D = q_local.shape
     kk = min(k, S)
-    flag = valid_local.to(q_local.dtype)
     inf = torch.full((), float("inf"), dtype=err_local.dtype, device=err_local.device)
-    order = _smallest_k(torch.where(valid_local, err_local, inf), kk)
-    # one gather of [q | err | valid] rows instead of three indexed reads and four slice writes (a dozen tiny launches matter
-    # when the whole solve takes 2 ms)
-    block = torch.cat([q_local, err_local[:, None], flag[:, None]], dim=1).index_select(0, order)
+    if local_keys is not None:
+        order = torch.topk(local_keys, kk, largest=False, sorted=True).values & 0xFFFFFFFF
+    else:
+        order = _smallest_k(torch.where(valid_local, err_local, inf), kk)
+    # [q | err | valid] rows of the selected seeds (a dozen tiny launches matter when the whole solve takes 2 ms)
+    block = torch.cat([q_local.index_select(0, order), err_local.index_select(0, order)[:, None],
+                       valid_local.index_select(0, order).to(q_local.dtype)[:, None]], dim=1)
     if kk < k:
         pad = torch.full((k - kk, D + 2), float("inf"), dtype=q_local.dtype, device=q_local.device)
         pad[:, D + 1] = 0
