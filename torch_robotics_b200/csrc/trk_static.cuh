@@ -1519,10 +1519,14 @@ inline cudaError_t launch_objective_hot(int n_sms, const float* host_words, cons
         // Eight blocks per resident slot, not one: a kernel that runs concurrently (e.g. the NCCL all-reduce of the previous
         // step's cost on another stream) can take a slot away, and with exactly one block per slot the displaced block would only
         // start after another had finished ALL its tiles (measured: 0.21 -> 0.36 ms per launch on 8 GPUs).  With eight the loss is
-        // one eighth of a block's share; the per-block prologue (sphere tables, ~1 us) is amortised over >= 7 tiles.
+        // one eighth of a block's share; the per-block prologue (sphere tables, ~1 us) is amortised over >= 4 tiles.
         int grid = persistent_grid(k, n_sms, smem, n);
         {
-            const long long tiles = (n + kSBlock - 1) / kSBlock, want = (long long)grid * 8;
+            // m blocks per slot, m = 1 .. 8, keeping >= 4 tiles per block so that a small batch does not pay a prologue per tile
+            const long long tiles = (n + kSBlock - 1) / kSBlock;
+            long long m = tiles / (4LL * grid);
+            m = m < 1 ? 1 : (m > 8 ? 8 : m);
+            const long long want = (long long)grid * m;
             grid = (int)(tiles < want ? tiles : want);
             if (grid > TRK_MAX_BLOCK_SUMS) grid = TRK_MAX_BLOCK_SUMS - (TRK_MAX_BLOCK_SUMS % (n_sms > 0 ? n_sms : 1));
         }
