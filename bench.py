@@ -573,20 +573,29 @@ def bench_cfg4(torch, dist, D, model, desc, dev, rank, world, S=1_000_000, iters
         return a.elapsed_time(b), b.elapsed_time(c), res, best
     once()
     runs = []
-    for _ in range(3):
+    res = best = None
+    for _ in range(5):
+        # only the timings are kept: holding every run's result tensors made the caching allocator go back to cudaMalloc on
+        # some runs, which showed up as 60 - 120 ms "kernel" times on all ranks at once
+        res = best = None
         if world > 1:
             dist.barrier()
-        runs.append(once())
+        tk, tc, res, best = once()
+        runs.append((tk, tc))
     ms_k = float(np.median([r[0] for r in runs]))
     ms_c = float(np.median([r[1] for r in runs]))
-    res, best = runs[-1][2], runs[-1][3]
+    print(f"[cfg4 rank {rank}] kernel ms per run {[round(r[0], 3) for r in runs]}, selection ms {[round(r[1], 3) for r in runs]}", file=sys.stderr)
     t = torch.tensor([ms_k, ms_c, ms_k + ms_c], dtype=torch.float64, device=dev)
     nv = res["valid"].sum().to(torch.float64).reshape(1)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(nv, op=dist.ReduceOp.SUM)
     ms_k, ms_c, ms_t = [float(v) for v in t.tolist()]
-    return {"workload": "panda_adam_ik", "seeds_total": S, "seeds_per_rank": s_loc, "iters": iters, "ms_kernel": ms_k, "collective_ms": ms_c,
+    best_k = torch.tensor([min(r[0] for r in runs)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(best_k, op=dist.ReduceOp.MAX)
+    return {"workload": "panda_adam_ik", "seeds_total": S, "seeds_per_rank": s_loc, "iters": iters, "ms_kernel": ms_k, "ms_kernel_best_of_5": float(best_k.item()),
+            "collective_ms": ms_c,
             "ms_total": ms_t, "seed_iters_per_s": S * iters / (ms_t * 1e-3), "fp32_frac_per_gpu": S * iters / (ms_k * 1e-3) * 1200 / fp32_peak / world,
             "flop_per_seed_iter": 1200, "valid_fraction": float(nv.item()) / S, "best_err": [float(v) for v in best[1].tolist()],
             "collective": f"per-block top-{k_best} in the IK kernel (trk_ik_adam_best) -> per-rank top-{k_best} + NCCL all-gather of [{k_best}, D+2] + "
