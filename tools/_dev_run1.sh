@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-python tools/time_objective.py 2>&1 | tail -1
-python -m pytest tests/test_gpu_baseline_configs.py -m gpu -q 2>&1 | tail -2
+python tools/sanitize_smoke.py 2>&1 | tail -2
+timeout 600 compute-sanitizer --tool memcheck python tools/sanitize_smoke.py > gpurun_out/r02_san_memcheck.log 2>&1; tail -4 gpurun_out/r02_san_memcheck.log
+timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_smoke.py > gpurun_out/r02_san_racecheck.log 2>&1; tail -4 gpurun_out/r02_san_racecheck.log

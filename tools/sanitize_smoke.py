@@ -68,6 +68,23 @@ for robot in (RobotPanda(tensor_args=TA), RobotPanda(sphere_config=True, tensor_
     task.compute_collision_cost(qt).sum().backward()
     task.compute_collision(qt.detach())
     robot.diff_panda.compute_analytical_jacobian_all_links(qt.detach().reshape(-1, 7))
+# round 2 kernels: attached-body objective (plain sphere scene), fused cost sums, IK with the per-block top-k, geometric Jacobian
+env2 = EnvSpheres3D(tensor_args=TA)
+for robot in (RobotPanda(sphere_config=True, tensor_args=TA), RobotPanda(grasped_object=GraspedObjectPandaBox(tensor_args=TA), tensor_args=TA)):
+    task = PlanningTask(env=env2, robot=robot, tensor_args=TA)
+    qt = (robot.q_min + torch.rand(5, 31, 7, device=dev) * (robot.q_max - robot.q_min))
+    task.compute_cost_and_grad(qt)
+    task.compute_collision(qt, margin=0.0)
+g3 = load_golden("planning_panda_spheres3d"); m3 = DeviceModel(get_desc("panda"), dev)
+dc3 = DeviceCost(m3, planning_cost_from_golden(g3))
+q3 = torch.as_tensor(rng.uniform(-2, 2, (777, 7)).astype(np.float32), device=dev)
+dc3.objective_sum(q3, out_grad=torch.empty_like(q3), out_total=torch.empty(777, device=dev))
+dc3.objective(q3, want_grad=False, want_terms=True, want_occupancy=True, want_argmin=True)
+gi = load_golden("ik_panda")
+m3.ik_adam(torch.as_tensor(rng.uniform(-1, 1, (333, 7)).astype(np.float32), device=dev), gi["H_target"], 10, gi["lower"], gi["upper"], n_iters=7, lr=0.2,
+           se3_eps=0.05, best_k=8)
+m3.geometric_jacobian(q3, 10, 0x7f)
+DeviceModel(get_desc("tiago_dual_holo"), dev).geometric_jacobian(torch.zeros(40, 14, device=dev), 12, 0x3fff)
 X = (torch.rand(300, 3, device=dev) * 2.4 - 1.2).requires_grad_(True)
 env.grid_map_sdf_obj_fixed(X).sum().backward()
 torch.cuda.synchronize()
