@@ -709,7 +709,8 @@ struct trk_cost {
     std::vector<float> h_words;  // host mirror, for the setters
     // attached-body models (trk_ext.cuh): every referenced body as (movable anchor, offset); built when the model is one
     float* d_ext = nullptr;
-    int ext_nwords = 0, ext_n_ps = 0;
+    int ext_nwords = 0;
+    std::vector<float> h_ext;    // host copy (the launcher reads the header)
     bool ext_ok = false;
     // host-buffer pipeline (trk_objective_host): staging buffers, streams and events, created on first use
     float* hp_q = nullptr; float* hp_cost = nullptr; float* hp_grad = nullptr;
@@ -821,14 +822,35 @@ static int build_ext_tables(const trk_model* m, const trk_cost_desc* d, trk_cost
     std::vector<int> new_slot(ps.size());
     for (size_t i = 0; i < order.size(); ++i) new_slot[order[i]] = (int)i;
     const int n_ps = (int)ps.size();
+    // runs: pairs that share a hub body and whose other bodies hang on one anchor.  The hub of a pair is its end with the larger
+    // number of pairs (the link a grasped object's points are all checked against), ties: the second body.
+    struct Item { int hub, other, col_o, p; };
+    std::vector<Item> its(P);
+    {
+        std::vector<int> degree(m->L, 0);
+        for (int p = 0; p < P; ++p) { ++degree[d->pair_i[p]]; ++degree[d->pair_j[p]]; }
+        for (int p = 0; p < P; ++p) {
+            const int bi = d->pair_i[p], bj = d->pair_j[p];
+            const bool hub_is_i = degree[bi] > degree[bj];
+            its[p].hub = new_slot[slot_of_body[hub_is_i ? bi : bj]];
+            its[p].other = new_slot[slot_of_body[hub_is_i ? bj : bi]];
+            its[p].col_o = ps[order[its[p].other]].col;
+            its[p].p = p;
+        }
+        std::stable_sort(its.begin(), its.end(), [](const Item& a, const Item& b) { return a.hub != b.hub ? a.hub < b.hub : a.col_o < b.col_o; });
+    }
+    int n_runs = 0;
+    for (int k = 0; k < P; ++k) if (k == 0 || its[k].hub != its[k - 1].hub || its[k].col_o != its[k - 1].col_o) ++n_runs;
     int off = (int)(sizeof(trk::ExtHeader) / 4);
     auto take = [&](int nw) { int o = off; off = align4(off + nw); return o; };
-    const int o_pts = take(NA + 1), o_pt = take(8 * S), o_pss = take(NA + 1), o_ps = take(4 * n_ps), o_psc = take(n_ps), o_pair = take(4 * P);
+    const int o_pts = take(NA + 1), o_pt = take(8 * S), o_pss = take(NA + 1), o_ps = take(4 * n_ps), o_run = take(4 * n_runs),
+              o_item = take(4 * P);
     std::vector<float> w(off, 0.f);
     int* iw = reinterpret_cast<int*>(w.data());
     trk::ExtHeader* h = reinterpret_cast<trk::ExtHeader*>(w.data());
     h->n_pts = S; h->n_ps = n_ps; h->n_pairs = P; h->n_anchor = NA;
-    h->off_pt_start = o_pts; h->off_pt = o_pt; h->off_ps_start = o_pss; h->off_ps = o_ps; h->off_ps_col = o_psc; h->off_pair = o_pair;
+    h->off_pt_start = o_pts; h->off_pt = o_pt; h->off_ps_start = o_pss; h->off_ps = o_ps; h->off_run = o_run; h->off_item = o_item;
+    h->n_runs = n_runs;
     h->total_words = off;
     {
         int k = 0;
@@ -836,12 +858,12 @@ static int build_ext_tables(const trk_model* m, const trk_cost_desc* d, trk_cost
             while (k < S && pts[k].anchor < a) ++k;
             iw[o_pts + a] = k;
         }
-        for (int k2 = 0; k2 < S; ++k2) {
-            float* r = w.data() + o_pt + 8 * k2;
-            r[0] = pts[k2].t[0]; r[1] = pts[k2].t[1]; r[2] = pts[k2].t[2];
-            r[3] = d->pt_margin_obj[pts[k2].s]; r[4] = d->pt_margin_ws[pts[k2].s];
-            reinterpret_cast<int*>(r)[5] = pts[k2].s;
-        }
+    }
+    for (int k2 = 0; k2 < S; ++k2) {
+        float* r = w.data() + o_pt + 8 * k2;
+        r[0] = pts[k2].t[0]; r[1] = pts[k2].t[1]; r[2] = pts[k2].t[2];
+        r[3] = d->pt_margin_obj[pts[k2].s]; r[4] = d->pt_margin_ws[pts[k2].s];       // [5], [6]: occupancy margins, written by the kernel
+        reinterpret_cast<int*>(r)[7] = pts[k2].s;
     }
     {
         int k = 0;
@@ -853,19 +875,21 @@ static int build_ext_tables(const trk_model* m, const trk_cost_desc* d, trk_cost
             const Ps& e = ps[order[k2]];
             float* r = w.data() + o_ps + 4 * k2;
             r[0] = e.t[0]; r[1] = e.t[1]; r[2] = e.t[2];
-            iw[o_psc + k2] = e.col;
         }
-        std::vector<int> porder(P);
-        for (int p = 0; p < P; ++p) porder[p] = p;
-        std::stable_sort(porder.begin(), porder.end(), [&](int a, int b) { return new_slot[slot_of_body[d->pair_i[a]]] < new_slot[slot_of_body[d->pair_i[b]]]; });
-        for (int k2 = 0; k2 < P; ++k2) {       // sorted by body i's slot (slots are grouped by anchor): runs share the i-side accumulator
-            const int p = porder[k2];
-            float* r = w.data() + o_pair + 4 * k2;
-            const int si = new_slot[slot_of_body[d->pair_i[p]]], sj = new_slot[slot_of_body[d->pair_j[p]]];
-            reinterpret_cast<int*>(r)[0] = si;
-            reinterpret_cast<int*>(r)[1] = sj;
-            r[2] = d->pair_margin[p];
-            reinterpret_cast<int*>(r)[3] = (iw[o_psc + si] & 0xff) | ((iw[o_psc + sj] & 0xff) << 8);
+        int run = -1;
+        for (int k2 = 0; k2 < P; ++k2) {
+            if (k2 == 0 || its[k2].hub != its[k2 - 1].hub || its[k2].col_o != its[k2 - 1].col_o) {
+                ++run;
+                int* rr = iw + o_run + 4 * run;
+                rr[0] = its[k2].hub; rr[1] = k2;
+                rr[3] = (ps[order[its[k2].hub]].col & 0xff) | ((its[k2].col_o & 0xff) << 8);
+                if (k2 == 0 || its[k2].hub != its[k2 - 1].hub) rr[3] |= 0x10000;
+            }
+            if (k2 + 1 == P || its[k2 + 1].hub != its[k2].hub) iw[o_run + 4 * run + 3] |= 0x20000;
+            iw[o_run + 4 * run + 2] = k2 + 1;
+            float* r = w.data() + o_item + 4 * k2;
+            reinterpret_cast<int*>(r)[0] = its[k2].other;
+            r[1] = d->pair_margin[its[k2].p];
         }
     }
     DeviceGuard guard(m->device);
@@ -873,7 +897,7 @@ static int build_ext_tables(const trk_model* m, const trk_cost_desc* d, trk_cost
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(ext tables)");
     e = cudaMemcpy(c->d_ext, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpy(ext tables)");
-    c->ext_nwords = (int)w.size(); c->ext_n_ps = n_ps; c->ext_ok = true;
+    c->ext_nwords = (int)w.size(); c->h_ext = w; c->ext_ok = true;
     return TRK_OK;
 }
 
@@ -1301,7 +1325,7 @@ static int objective_impl(const trk_model* m, const trk_cost* c, const float* q,
                            gh->ws_enabled &&
                            (!gh->ee_enabled || (gh->ee_w_pos > 0.f && gh->ee_w_rot > 0.f && gh->ee_link == trk::static_family_last_body(m->ext_family)));
         if (scene && !no_hot) {
-            cudaError_t e = trk::launch_static_objective_ext(m->ext_family, m->n_sms, c->h_words.data(), c->d_words, c->d_ext, c->ext_nwords, c->ext_n_ps,
+            cudaError_t e = trk::launch_static_objective_ext(m->ext_family, m->n_sms, c->h_words.data(), c->d_words, c->d_ext, c->ext_nwords, c->h_ext.data(),
                                                              gh->S, q, n, margin_override, use_override, cost_total, cost_terms, grad_q, occupancy, argmin, st);
             if (e == cudaSuccess) return TRK_OK;
             if (e != cudaErrorInvalidValue) return cuda_fail(e, "objective(ext)");

@@ -1579,35 +1579,42 @@ inline int static_family_last_body(int family) {
 }
 
 template <class R>
-cudaError_t launch_objective_ext_t(int n_sms, const float* host_words, const float* cost_words, const float* ext_words, int ext_nwords, int n_ps,
-                                   int n_points, const float* q, long long n, float margin_override, int use_override, float* cost_total,
-                                   float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin, cudaStream_t st) {
-    HotParams hp;
+cudaError_t launch_objective_ext_t(int n_sms, const float* host_words, const float* cost_words, const float* ext_words, int ext_nwords,
+                                   const float* ext_host, int n_points, const float* q, long long n, float margin_override, int use_override,
+                                   float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin, cudaStream_t st) {
+    ExtParams ep;
     const CostHeader* h = reinterpret_cast<const CostHeader*>(host_words);
+    const ExtHeader* eh = reinterpret_cast<const ExtHeader*>(ext_host);
     const int* iw = reinterpret_cast<const int*>(host_words);
-    std::memset(&hp, 0, sizeof(hp));
-    for (int i = 0; i < 4; ++i) hp.w[i] = h->w[i];
-    for (int i = 0; i < 3; ++i) { hp.ws_min[i] = h->ws_min[i]; hp.ws_max[i] = h->ws_max[i]; hp.ee_t[i] = h->ee_t[i]; }
-    for (int i = 0; i < 9; ++i) hp.ee_R[i] = h->ee_R[i];
-    hp.ee_w_pos = h->ee_w_pos; hp.ee_w_rot = h->ee_w_rot; hp.ee_square = h->ee_square;
-    hp.tol = host_words[h->off_obj_tol]; hp.c2max = host_words[h->off_obj_c2max];
-    hp.lowmask = (1u << (iw[h->off_obj_ident] >> OBJ_BITS_SHIFT)) - 1u;
-    hp.n_pairs2 = (iw[h->off_obj_qstart + 1] - iw[h->off_obj_qstart]) / 2;
-    hp.n_sph = iw[h->off_obj_start + 1] - iw[h->off_obj_start];
-    hp.off_sphq = h->off_sphq + 4 * iw[h->off_obj_qstart];
-    hp.off_sph = h->off_sph + 4 * iw[h->off_obj_start];
-    hp.use_override = use_override; hp.margin_override = margin_override;
-    hp.ee_enabled = h->ee_enabled;
+    std::memset(&ep, 0, sizeof(ep));
+    ep.w0 = h->w[0]; ep.w1 = h->w[1]; ep.w2 = h->w[2]; ep.w3 = h->w[3];
+    for (int i = 0; i < 3; ++i) { ep.ws_min[i] = h->ws_min[i]; ep.ws_max[i] = h->ws_max[i]; ep.ee_t[i] = h->ee_t[i]; }
+    for (int i = 0; i < 9; ++i) ep.ee_R[i] = h->ee_R[i];
+    ep.ee_w_pos = h->ee_w_pos; ep.ee_w_rot = h->ee_w_rot; ep.ee_square = h->ee_square;
+    ep.tol = host_words[h->off_obj_tol]; ep.c2max = host_words[h->off_obj_c2max];
+    ep.lowmask = (1u << (iw[h->off_obj_ident] >> OBJ_BITS_SHIFT)) - 1u;
+    ep.n_pairs2 = (iw[h->off_obj_qstart + 1] - iw[h->off_obj_qstart]) / 2;
+    ep.n_sph = iw[h->off_obj_start + 1] - iw[h->off_obj_start];
+    ep.off_sphq = h->off_sphq + 4 * iw[h->off_obj_qstart];
+    ep.off_sph = h->off_sph + 4 * iw[h->off_obj_start];
+    ep.use_override = use_override; ep.margin_override = margin_override;
+    ep.ee_enabled = h->ee_enabled;
+    ep.D = R::D; ep.n_ps = eh->n_ps; ep.n_runs = eh->n_runs; ep.n_points = n_points; ep.ext_nwords = ext_nwords;
+    // shared memory: ExtParams | ext words | scan table | sphere table | per-thread scratch
+    ep.o_ew = (kExtParamWords + 3) & ~3;
+    ep.o_pt_start = ep.o_ew + eh->off_pt_start; ep.o_pt = ep.o_ew + eh->off_pt; ep.o_ps_start = ep.o_ew + eh->off_ps_start;
+    ep.o_ps = ep.o_ew + eh->off_ps; ep.o_run = ep.o_ew + eh->off_run; ep.o_item = ep.o_ew + eh->off_item;
+    ep.o_tq = ep.o_ew + ((ext_nwords + 3) & ~3);
+    ep.o_tsph = ep.o_tq + ep.n_pairs2 * 8;
+    ep.o_scratch = ep.o_tsph + ep.n_sph * 4;
     constexpr int kEE = R::L - 1;
-    const size_t table_words = (size_t)hp.n_pairs2 * 8 + (size_t)hp.n_sph * 4 + ((sizeof(HotParams) + 15) / 16) * 4 + ((ext_nwords + 3) & ~3);
-    const size_t smem = (table_words + (size_t)(3 * n_ps + 6 * R::D + 3) * kSBlock) * sizeof(float);
+    const size_t smem = ((size_t)ep.o_scratch + (size_t)(3 * ep.n_ps + 6 * R::D + 3) * kSBlock) * sizeof(float);
     auto launch = [&](auto k) {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
-        k<<<persistent_grid(k, n_sms, smem, n), kSBlock, smem, st>>>(hp, cost_words, ext_words, ext_nwords, n_ps, q, n, cost_total, cost_terms, grad_q,
-                                                                     occupancy, argmin, n_points);
+        k<<<persistent_grid(k, n_sms, smem, n), kSBlock, smem, st>>>(ep, cost_words, ext_words, q, n, cost_total, cost_terms, grad_q, occupancy, argmin);
         return cudaGetLastError();
     };
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
@@ -1678,7 +1685,7 @@ cudaError_t launch_objective_t(int n_sms, const float* host_words, const float* 
     KW template cudaError_t launch_ik_t<Rb>(const IKParams&, const float*, const float*, const float*, long long, float*, float*,        \
                                             uint8_t*, int*, float*, float*, cudaStream_t);                                                \
     KW template cudaError_t launch_link_jacobian_t<Rb>(int, const float*, long long, float*, cudaStream_t, bool*);                       \
-    KW template cudaError_t launch_objective_ext_t<Rb>(int, const float*, const float*, const float*, int, int, int, const float*, long long, float, \
+    KW template cudaError_t launch_objective_ext_t<Rb>(int, const float*, const float*, const float*, int, const float*, int, const float*, long long, float, \
                                                        int, float*, float*, float*, uint8_t*, int*, cudaStream_t);
 #ifndef TRK_INST_ROBOT   // family dispatch: main translation unit only
 #define TRK_DECLARE_EXTERN(Rb) TRK_LAUNCHER_SIGNATURES(extern, Rb)
@@ -1698,14 +1705,14 @@ inline cudaError_t launch_static_ik(int family, const IKParams& P, const float* 
 }
 
 inline cudaError_t launch_static_objective_ext(int family, int n_sms, const float* host_words, const float* cost_words, const float* ext_words,
-                                               int ext_nwords, int n_ps, int n_points, const float* q, long long n, float margin_override,
+                                               int ext_nwords, const float* ext_host, int n_points, const float* q, long long n, float margin_override,
                                                int use_override, float* cost_total, float* cost_terms, float* grad_q, uint8_t* occupancy,
                                                int* argmin, cudaStream_t st) {
     int id = 0;
 #define X(Rb) \
     ++id;     \
     if (family == id)  \
-        return launch_objective_ext_t<Rb>(n_sms, host_words, cost_words, ext_words, ext_nwords, n_ps, n_points, q, n, margin_override, use_override, \
+        return launch_objective_ext_t<Rb>(n_sms, host_words, cost_words, ext_words, ext_nwords, ext_host, n_points, q, n, margin_override, use_override, \
                                           cost_total, cost_terms, grad_q, occupancy, argmin, st);
     TRK_FOR_EACH_STATIC_ROBOT(X)
 #undef X
