@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q 2>&1 | tail -4 | tee gpurun_out/r2_gpu_tests_b.log
-python tools/bench_sphere_model.py 2>&1 | tail -2 | tee gpurun_out/r2_ext_v4_full.jsonl
-timeout 600 compute-sanitizer --tool memcheck python tools/sanitize_smoke.py > gpurun_out/r02_san_memcheck.log 2>&1; tail -2 gpurun_out/r02_san_memcheck.log
+for i in 1 2; do for v in nobar bar; do
+  TRK_B200_LIB=build_variants/libtrk_$v.so python tools/time_objective.py 2>&1 | tail -1 | tee -a gpurun_out/r2_variants_c.txt
+done; done
+TRK_B200_LIB=build_variants/libtrk_nobar.so python -m pytest tests/test_gpu_baseline_configs.py tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -3
