@@ -33,8 +33,8 @@ def timed(fn, inner=10):
     return float(np.median(ts))
 
 
-def fk_lines(name, d, n):
-    m = DeviceModel(d, "cuda:0")
+def fk_lines(name, d, n, library=None):
+    m = DeviceModel(d, "cuda:0", library=library)
     q = torch.as_tensor(np.random.default_rng(0).uniform(-1, 1, (n, d.n_dofs)).astype(np.float32), device="cuda:0")
     H = m.fk_forward(q)
     G = torch.randn_like(H)
@@ -47,9 +47,33 @@ def fk_lines(name, d, n):
     return m
 
 
+def specialised_lines(d_iiwa):
+    """The same robot through a library specialised at run time (specialize.py), and the UR10 with an ad-hoc collision model:
+    default library (table-driven kernel) against the specialised one (headline kernel)."""
+    import specialized_cases as sc
+    from torch_robotics_b200 import specialize as sp
+    from torch_robotics_b200.descriptor import build_cost_descriptor
+    fk_lines("iiwa7_allegro (specialised)", d_iiwa, 1 << 19, library=sp.build_specialized_library(d_iiwa))
+    d, cm = sc.ur10_collision()
+    rng = np.random.default_rng(11)
+    centers = rng.uniform(-0.7, 0.7, (10, 3)).astype(np.float32)
+    cost = build_cost_descriptor(pt_link=cm["pt_link"], pt_radius=np.full(len(cm["pt_link"]), 0.08, np.float32), cutoff_obj=0.02,
+                                 objects=[(centers, np.full(10, 0.12, np.float32), None, None)], ws_min=[-1.2, -1.2, -0.4], ws_max=[1.2, 1.2, 1.4],
+                                 self_pairs=cm["pairs"], self_margin=[0.05], ee_link=cm["ee_body"], ee_target=np.eye(4, dtype=np.float32))
+    n = 1 << 21
+    q = torch.as_tensor(rng.uniform(-np.pi, np.pi, (n, d.n_dofs)).astype(np.float32), device="cuda:0")
+    tot, grad = torch.empty(n, device="cuda:0"), torch.empty(n, d.n_dofs, device="cuda:0")
+    for name, lib in (("default library", None), ("specialised", sp.build_specialized_library(d, cm))):
+        dc = DeviceCost(DeviceModel(d, "cuda:0", library=lib), cost)
+        ms = timed(lambda: dc.objective(q, want_terms=False, out_total=tot, out_grad=grad))
+        print(json.dumps({"robot": f"ur10 + ad-hoc collision model ({name})", "n": n, "ms": ms, "configs_per_s": n / ms * 1e3}))
+
+
 def main():
     urdf = os.path.join(ROOT, "torch_robotics_b200", "data", "urdf", "robots")
-    fk_lines("iiwa7_allegro", compile_urdf(os.path.join(urdf, "kuka_iiwa", "urdf", "iiwa7_allegro.urdf"), "iiwa7_allegro"), 1 << 19)
+    d_iiwa = compile_urdf(os.path.join(urdf, "kuka_iiwa", "urdf", "iiwa7_allegro.urdf"), "iiwa7_allegro")
+    fk_lines("iiwa7_allegro", d_iiwa, 1 << 19)
+    specialised_lines(d_iiwa)
     os.environ["TRK_B200_FORCE_GENERIC"] = "1"
     from conftest import get_desc, load_golden, planning_cost_from_golden
     d = get_desc("panda")

@@ -53,6 +53,7 @@ class IKParamsC(C.Structure):
 
 
 _lib = None
+_libs = {}                      # path -> configured CDLL (the default library and run-time specialised ones: specialize.py)
 _lib_lock = threading.Lock()
 
 EXPORTS = [
@@ -63,19 +64,22 @@ EXPORTS = [
 ]
 
 
-def lib() -> C.CDLL:
-    global _lib
-    if _lib is not None:
-        return _lib
+def load_library(path: str) -> C.CDLL:
+    """dlopen a build of the C ABI (include/trk_b200.h) and declare its signatures; one handle per path."""
+    path = os.path.abspath(path)
+    L = _libs.get(path)
+    if L is not None:
+        return L
     with _lib_lock:
-        if _lib is not None:
-            return _lib
-        if not os.path.exists(LIB_PATH):
+        L = _libs.get(path)
+        if L is not None:
+            return L
+        if not os.path.exists(path):
             raise ImportError(
-                f"{LIB_PATH} not found: the sm_100a CUDA library has not been built. "
+                f"{path} not found: the sm_100a CUDA library has not been built. "
                 "Run `python -c \"import __graft_entry__ as g; g.build()\"` in the repository root. "
                 "There is no CPU or PyTorch fallback for this path.")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
         L.trk_abi_version.restype = C.c_int
         L.trk_last_error.restype = C.c_char_p
@@ -101,18 +105,24 @@ def lib() -> C.CDLL:
         L.trk_ik_adam.argtypes = [vp, C.POINTER(IKParamsC), vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
         L.trk_ik_adam_best.argtypes = [vp, C.POINTER(IKParamsC), vp, vp, vp, i64, vp, vp, vp, vp, vp, i32, vp]
         for name in EXPORTS:
-            fn = getattr(L, name)
-            if fn.restype is C.c_int and name not in ("trk_abi_version",):
-                pass
+            getattr(L, name)              # every declared entry point must be exported
         if L.trk_abi_version() != 1:
-            raise ImportError("libtrk_b200.so ABI version mismatch")
-        _lib = L
-        return _lib
+            raise ImportError(f"{path}: ABI version mismatch")
+        _libs[path] = L
+        return L
 
 
-def check(rc: int, what: str) -> None:
+def lib() -> C.CDLL:
+    """The default library (all shipped robots compiled in)."""
+    global _lib
+    if _lib is None:
+        _lib = load_library(LIB_PATH)
+    return _lib
+
+
+def check(rc: int, what: str, L: Optional[C.CDLL] = None) -> None:
     if rc != 0:
-        msg = lib().trk_last_error().decode("utf-8", "replace")
+        msg = (L or lib()).trk_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"{what} failed (status {rc}): {msg}")
 
 
@@ -146,8 +156,11 @@ def stream_ptr(device: torch.device) -> int:
 class DeviceModel:
     """Device-resident kinematic tree (trk_model) for one (descriptor, device)."""
 
-    def __init__(self, desc, device):
+    def __init__(self, desc, device, library: Optional[str] = None):
+        """library: path of a specialised build of the C ABI for this robot (specialize.build_specialized_library);
+        default: the package's library with the shipped robots compiled in."""
         self.desc = desc
+        self._L = load_library(library) if library else lib()
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError(f"cannot create a device model on '{device}': CUDA only")
@@ -165,20 +178,20 @@ class DeviceModel:
                        _fp(k["axis"]), _ip(k["q_index"]), _fp(k["R_fixed"]), _fp(k["trans"]), _fp(k["lo"]), _fp(k["hi"]),
                        _ip(k["has_lim"]), _ip(k["topo"]), _fp(k["base"]))
         h = C.c_void_p()
-        check(lib().trk_model_create(C.byref(md), idx, C.byref(h)), "trk_model_create")
+        check(self._L.trk_model_create(C.byref(md), idx, C.byref(h)), "trk_model_create", self._L)
         self.handle = h
         self.n_links, self.n_dofs = desc.n_links, desc.n_dofs
         self._ik_schedules = {}
 
     @property
     def kernel_family(self) -> str:
-        return lib().trk_model_kernel_family(self.handle).decode()
+        return self._L.trk_model_kernel_family(self.handle).decode()
 
     def __del__(self):
         h = getattr(self, "handle", None)
-        if h and _lib is not None:
+        if h and getattr(self, "_L", None) is not None:
             try:
-                _lib.trk_model_destroy(h)
+                self._L.trk_model_destroy(h)
             except Exception:
                 pass
             self.handle = None
@@ -198,8 +211,8 @@ class DeviceModel:
             raise RuntimeError(f"q is on {q.device} but the model lives on {self.device}")
         p, n_sel, keep = self._sel(link_sel)
         H = torch.empty((q.shape[0], n_sel, 4, 4), dtype=torch.float32, device=q.device)
-        check(lib().trk_fk_forward(self.handle, q.data_ptr(), q.shape[0], p, n_sel, H.data_ptr(), stream_ptr(q.device)),
-              "trk_fk_forward")
+        check(self._L.trk_fk_forward(self.handle, q.data_ptr(), q.shape[0], p, n_sel, H.data_ptr(), stream_ptr(q.device)),
+              "trk_fk_forward", self._L)
         return H
 
     def link_jacobian(self, q: torch.Tensor) -> torch.Tensor:
@@ -210,7 +223,7 @@ class DeviceModel:
         if q.device != self.device:
             raise RuntimeError(f"q is on {q.device} but the model lives on {self.device}")
         J = torch.empty((q.shape[0], self.n_links, 7, self.n_dofs), dtype=torch.float32, device=q.device)
-        check(lib().trk_link_jacobian(self.handle, q.data_ptr(), q.shape[0], J.data_ptr(), stream_ptr(q.device)), "trk_link_jacobian")
+        check(self._L.trk_link_jacobian(self.handle, q.data_ptr(), q.shape[0], J.data_ptr(), stream_ptr(q.device)), "trk_link_jacobian", self._L)
         return J
 
     def geometric_jacobian(self, q: torch.Tensor, link: int, col_mask: int):
@@ -225,8 +238,8 @@ class DeviceModel:
         pose = torch.empty((n, 12), dtype=torch.float32, device=q.device)
         lin = torch.empty((n, 3, self.n_dofs), dtype=torch.float32, device=q.device)
         ang = torch.empty_like(lin)
-        check(lib().trk_geometric_jacobian(self.handle, q.data_ptr(), n, int(link), int(col_mask) & 0xFFFFFFFF, pose.data_ptr(), lin.data_ptr(),
-                                           ang.data_ptr(), stream_ptr(q.device)), "trk_geometric_jacobian")
+        check(self._L.trk_geometric_jacobian(self.handle, q.data_ptr(), n, int(link), int(col_mask) & 0xFFFFFFFF, pose.data_ptr(), lin.data_ptr(),
+                                           ang.data_ptr(), stream_ptr(q.device)), "trk_geometric_jacobian", self._L)
         return pose, lin, ang
 
     def fk_backward(self, q: torch.Tensor, G: torch.Tensor, link_sel=None) -> torch.Tensor:
@@ -236,8 +249,8 @@ class DeviceModel:
         if tuple(G.shape) != (q.shape[0], n_sel, 4, 4):
             raise RuntimeError(f"grad_H must be [{q.shape[0]}, {n_sel}, 4, 4], got {tuple(G.shape)}")
         grad = torch.empty_like(q)
-        check(lib().trk_fk_backward(self.handle, q.data_ptr(), q.shape[0], p, n_sel, G.data_ptr(), grad.data_ptr(),
-                                    stream_ptr(q.device)), "trk_fk_backward")
+        check(self._L.trk_fk_backward(self.handle, q.data_ptr(), q.shape[0], p, n_sel, G.data_ptr(), grad.data_ptr(),
+                                    stream_ptr(q.device)), "trk_fk_backward", self._L)
         return grad
 
 
@@ -289,15 +302,15 @@ class DeviceModel:
             # per-block candidates for distributed.gather_best_solutions (trk_ik_adam_best); robots the fused selection does
             # not serve fall through to the plain call and the caller selects over all seeds
             best = torch.empty(((S + 127) // 128) * int(best_k), dtype=torch.int64, device=dev)
-            rc = lib().trk_ik_adam_best(self.handle, C.byref(p), step_size.data_ptr(), bc2.data_ptr(), ptr(tgt_seed), S, q.data_ptr(),
+            rc = self._L.trk_ik_adam_best(self.handle, C.byref(p), step_size.data_ptr(), bc2.data_ptr(), ptr(tgt_seed), S, q.data_ptr(),
                                         err.data_ptr(), valid.data_ptr(), count.data_ptr(), best.data_ptr(), int(best_k), stream_ptr(dev))
             if rc == -4:      # TRK_E_UNSUPPORTED
                 best = None
             else:
-                check(rc, "trk_ik_adam_best")
+                check(rc, "trk_ik_adam_best", self._L)
         if best is None:
-            check(lib().trk_ik_adam(self.handle, C.byref(p), step_size.data_ptr(), bc2.data_ptr(), ptr(tgt_seed), S, q.data_ptr(),
-                                    err.data_ptr(), valid.data_ptr(), count.data_ptr(), ptr(ls), ptr(lq), stream_ptr(dev)), "trk_ik_adam")
+            check(self._L.trk_ik_adam(self.handle, C.byref(p), step_size.data_ptr(), bc2.data_ptr(), ptr(tgt_seed), S, q.data_ptr(),
+                                    err.data_ptr(), valid.data_ptr(), count.data_ptr(), ptr(ls), ptr(lq), stream_ptr(dev)), "trk_ik_adam", self._L)
         return dict(q=q, err=err, valid=valid.bool(), valid_count=count, loss_sum=ls, loss_sqsum=lq, best_keys=best)
 
 
@@ -344,26 +357,26 @@ class DeviceCost:
         cd.clamp_self, cd.clamp_obj, cd.clamp_ws = int(cost.clamp_self), int(cost.clamp_obj), int(cost.clamp_ws)
         cd.weights = (C.c_float * 4)(*[float(v) for v in cost.weights])
         h = C.c_void_p()
-        check(lib().trk_cost_create(model.handle, C.byref(cd), C.byref(h)), "trk_cost_create")
+        check(model._L.trk_cost_create(model.handle, C.byref(cd), C.byref(h)), "trk_cost_create", self.model._L)
         self.handle = h
 
     def __del__(self):
         h = getattr(self, "handle", None)
-        if h and _lib is not None:
+        if h and getattr(getattr(self, "model", None), "_L", None) is not None:
             try:
-                _lib.trk_cost_destroy(h)
+                self.model._L.trk_cost_destroy(h)
             except Exception:
                 pass
             self.handle = None
 
     def set_ee_target(self, H) -> None:
         H = np.ascontiguousarray(np.asarray(H.detach().cpu().numpy() if torch.is_tensor(H) else H, np.float32).reshape(16))
-        check(lib().trk_cost_set_ee_target(self.handle, _fp(H), stream_ptr(self.model.device)), "trk_cost_set_ee_target")
+        check(self.model._L.trk_cost_set_ee_target(self.handle, _fp(H), stream_ptr(self.model.device)), "trk_cost_set_ee_target", self.model._L)
         self.cost.ee_target = H.reshape(4, 4).copy()
 
     def set_weights(self, w) -> None:
         w = np.ascontiguousarray(np.asarray(w, np.float32).reshape(4))
-        check(lib().trk_cost_set_weights(self.handle, _fp(w), stream_ptr(self.model.device)), "trk_cost_set_weights")
+        check(self.model._L.trk_cost_set_weights(self.handle, _fp(w), stream_ptr(self.model.device)), "trk_cost_set_weights", self.model._L)
         self.cost.weights = w.copy()
 
     def objective(self, q: torch.Tensor, want_grad=True, want_terms=True, want_occupancy=False, want_argmin=False,
@@ -395,8 +408,8 @@ class DeviceCost:
                 raise RuntimeError(f"ee_target_cfg must be [{n}, 4, 4]")
         mo = float("nan") if margin_override is None else float(margin_override)
         ptr = lambda t: None if t is None else t.data_ptr()
-        check(lib().trk_objective(m.handle, self.handle, q.data_ptr(), n, ptr(tgt), mo, ptr(total), ptr(terms), ptr(grad),
-                                  ptr(occ), ptr(amin), stream_ptr(dev)), "trk_objective")
+        check(self.model._L.trk_objective(m.handle, self.handle, q.data_ptr(), n, ptr(tgt), mo, ptr(total), ptr(terms), ptr(grad),
+                                  ptr(occ), ptr(amin), stream_ptr(dev)), "trk_objective", self.model._L)
         return dict(total=total, terms=terms, grad_q=grad, occupancy=occ, argmin=amin)
 
     MAX_BLOCK_SUMS = 8192
@@ -416,8 +429,8 @@ class DeviceCost:
             if buf is not None and (tuple(buf.shape) != shape or buf.dtype != torch.float32 or buf.device != dev or not buf.is_contiguous()):
                 raise RuntimeError(f"{name} must be a contiguous float32 tensor of shape {shape} on {dev}")
         mo = float("nan") if margin_override is None else float(margin_override)
-        check(lib().trk_objective_sums(m.handle, self.handle, q.data_ptr(), n, None, mo, None if out_total is None else out_total.data_ptr(),
-                                       out_grad.data_ptr(), bs.data_ptr(), stream_ptr(dev)), "trk_objective_sums")
+        check(self.model._L.trk_objective_sums(m.handle, self.handle, q.data_ptr(), n, None, mo, None if out_total is None else out_total.data_ptr(),
+                                       out_grad.data_ptr(), bs.data_ptr(), stream_ptr(dev)), "trk_objective_sums", self.model._L)
         return bs
 
     def objective_host(self, q_host: torch.Tensor, cost_host: torch.Tensor, grad_host: Optional[torch.Tensor] = None,
@@ -431,8 +444,8 @@ class DeviceCost:
         if q_host.ndim != 2 or q_host.shape[1] != self.model.n_dofs or cost_host.shape != (n,) or \
                 (grad_host is not None and tuple(grad_host.shape) != (n, self.model.n_dofs)):
             raise RuntimeError("objective_host: shape mismatch")
-        check(lib().trk_objective_host(self.model.handle, self.handle, q_host.data_ptr(), n, int(n_chunks), cost_host.data_ptr(),
-                                       None if grad_host is None else grad_host.data_ptr()), "trk_objective_host")
+        check(self.model._L.trk_objective_host(self.model.handle, self.handle, q_host.data_ptr(), n, int(n_chunks), cost_host.data_ptr(),
+                                       None if grad_host is None else grad_host.data_ptr()), "trk_objective_host", self.model._L)
 
     def cost_stage(self, link_pos: torch.Tensor, ee_pose: Optional[torch.Tensor] = None, want_grad=True,
                    want_occupancy=False, want_argmin=False, ee_target_cfg=None, margin_override: Optional[float] = None):
@@ -458,6 +471,6 @@ class DeviceCost:
             raise RuntimeError(f"ee_target_cfg must be [{n}, 4, 4] on {dev}, got {tuple(tgt.shape)} on {tgt.device}")
         mo = float("nan") if margin_override is None else float(margin_override)
         ptr = lambda t: None if t is None else t.data_ptr()
-        check(lib().trk_cost_stage(m.handle, self.handle, link_pos.data_ptr(), ptr(ee_pose), n, ptr(tgt), mo, ptr(total),
-                                   ptr(terms), ptr(gpos), ptr(gee), ptr(occ), ptr(amin), stream_ptr(dev)), "trk_cost_stage")
+        check(self.model._L.trk_cost_stage(m.handle, self.handle, link_pos.data_ptr(), ptr(ee_pose), n, ptr(tgt), mo, ptr(total),
+                                   ptr(terms), ptr(gpos), ptr(gee), ptr(occ), ptr(amin), stream_ptr(dev)), "trk_cost_stage", self.model._L)
         return dict(total=total, terms=terms, grad_pos=gpos, grad_ee=gee, occupancy=occ, argmin=amin)

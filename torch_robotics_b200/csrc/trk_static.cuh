@@ -21,7 +21,14 @@
 #include <type_traits>
 #include <utility>
 
+// The robots of the compiled-in family: the shipped set, or - for a library specialised at run time for ONE user robot
+// (torch_robotics_b200/specialize.py builds a private libtrk with -DTRK_ROBOTS_HEADER="<generated header>") - that robot
+// (`robots::Jit`, optionally with its collision model `robots::JitCollision` and TRK_JIT_HAS_COLLISION defined).
+#ifdef TRK_ROBOTS_HEADER
+#include TRK_ROBOTS_HEADER
+#else
 #include "robots_generated.cuh"
+#endif
 #include "trk_device.cuh"
 
 #ifdef TRK_ONLY_PANDA   // development builds: instantiate the compiled-in family for one robot only
@@ -1304,8 +1311,15 @@ cudaError_t launch_ik_t(const IKParams& P, const float* step_size, const float* 
 // in_registers: body positions / gradients of the model fit in registers (k_objective_cm); otherwise the model only
 // fixes the shared-memory slot numbering of k_objective_static at compile time
 template <class R> struct CollisionModelOf { using type = void; static constexpr bool in_registers = false; };
+#ifndef TRK_ROBOTS_HEADER
 template <> struct CollisionModelOf<robots::Panda> { using type = robots::PandaCollision; static constexpr bool in_registers = true; };
 template <> struct CollisionModelOf<robots::Stretch> { using type = robots::StretchCollision; static constexpr bool in_registers = false; };
+#elif defined(TRK_JIT_HAS_COLLISION)
+template <> struct CollisionModelOf<robots::Jit> {
+    using type = robots::JitCollision;
+    static constexpr bool in_registers = robots::JitCollision::S <= 8 && robots::JitCollision::P <= 16;
+};
+#endif
 
 // does a runtime cost table list exactly CM's points and pairs?
 template <class CM>

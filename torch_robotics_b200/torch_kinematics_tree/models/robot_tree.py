@@ -78,8 +78,37 @@ class DifferentiableTree(torch.nn.Module):
                                "CUDA (sm_100a) only and has no CPU fallback")
         idx = device.index if device.index is not None else torch.cuda.current_device()
         if idx not in self._device_models:
-            self._device_models[idx] = DeviceModel(self._desc, torch.device("cuda", idx))
+            self._device_models[idx] = DeviceModel(self._desc, torch.device("cuda", idx), library=self._library_for_current_tree())
         return self._device_models[idx]
+
+    def specialize(self, collision_points=None, self_collision_pairs=None, ee_link=None, cache_dir=None, verbose=False):
+        """Compile this robot into the unrolled kernel family (specialize.py): afterwards FK, its reverse mode, the link
+        Jacobians, the fused IK and - when a collision model is given - the fused planning objective run on kernels
+        generated for exactly this tree, as the ten shipped robots do, instead of the table-driven runtime-tree kernels.
+        No counterpart in the reference; results follow the same parity bars (tests/test_specialize.py).
+
+        collision_points / self_collision_pairs / ee_link: link names or body indices of the planning objective's
+        collision model (RobotBase's link_idxs_for_object_collision_checking, its self-collision pairs and link_name_ee);
+        omit all three to specialise the kinematics only.  Takes about a minute of nvcc the first time; the library is
+        cached by content (TRK_B200_JIT_DIR, default torch_robotics_b200/csrc/jit).  Attaching links / points or moving
+        the base afterwards returns the tree to the default library.  Returns the library's path."""
+        from ... import specialize as sp
+        to_idx = lambda v: self._name_to_idx_map[v] if isinstance(v, str) else int(v)
+        collision = None
+        if collision_points is not None or self_collision_pairs is not None or ee_link is not None:
+            if ee_link is None:
+                raise ValueError("a compile-time collision model needs the end-effector link (ee_link)")
+            collision = dict(pt_link=[to_idx(v) for v in (collision_points or [])],
+                             pairs=[(to_idx(a), to_idx(b)) for a, b in (self_collision_pairs or [])], ee_body=to_idx(ee_link))
+        path = sp.build_specialized_library(self._desc, collision, cache_dir=cache_dir, verbose=verbose)
+        self._model_generation += 1          # dependants (PlanningTask's fused cost, the fields' device costs) rebuild on the new library
+        self._library = (path, self._model_generation)
+        self._device_models.clear()
+        return path
+
+    def _library_for_current_tree(self):
+        lib_gen = getattr(self, "_library", None)
+        return lib_gen[0] if lib_gen is not None and lib_gen[1] == self._model_generation else None
 
     def _refresh_after_attach(self):
         self._bodies = [BodyView(self._desc, i) for i in range(self._desc.n_links)]
