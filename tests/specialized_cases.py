@@ -27,8 +27,8 @@ def ur10_collision():
 
 
 def build_all(verbose=False):
+    from concurrent.futures import ThreadPoolExecutor
     from torch_robotics_b200 import specialize as sp
-    paths = [sp.build_specialized_library(iiwa7_allegro_desc(), None, verbose=verbose)]
     d, cm = ur10_collision()
-    paths.append(sp.build_specialized_library(d, cm, verbose=verbose))
-    return paths
+    with ThreadPoolExecutor(max_workers=2) as ex:
+        return list(ex.map(lambda a: sp.build_specialized_library(a[0], a[1], verbose=verbose), [(iiwa7_allegro_desc(), None), (d, cm)]))

@@ -72,3 +72,38 @@ def test_gpu_planning_task_matches_reference(tag):
     task_grid = PlanningTask(env=env_grid, robot=task.robot, tensor_args=TA)
     cg = task_grid.compute_collision_cost(q.detach())
     assert torch.isfinite(cg).all() and (cg - c.detach()).abs().max().item() < 5 * 2.5 * 0.02 * 3 ** 0.5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["table_shelf", "maze_boxes"])
+@pytest.mark.parametrize("with_ee", [True, False])
+def test_gpu_box_scene_headline_kernel_vs_oracle(tag, with_ee):
+    """A scene made of boxes only (posed objects of rounded boxes) runs on k_objective_hot<..., SCENE = 1>, with or without an
+    EE term: terms, gradients, occupancy (default margins and margin = 0) and the per-object arg-min against the C oracle on
+    random configurations; the fused block sums exist (only the headline kernel has them)."""
+    from torch_robotics_b200._lib import DeviceCost, DeviceModel
+    g, d = load_golden(f"planning_panda_{tag}"), get_desc("panda")
+    cost = planning_cost_from_golden(g, with_ee=with_ee)
+    m = DeviceModel(d, "cuda:0")
+    dc = DeviceCost(m, cost)
+    rng = np.random.default_rng(3)
+    lo, hi = d.lo[d.controlled], d.hi[d.controlled]
+    q = (lo + rng.random((40_009, 7), dtype=np.float32) * (hi - lo)).astype(np.float32)
+    q[:64] = g["q"].reshape(-1, 7)[:64]
+    qt = torch.as_tensor(q, device="cuda:0")
+    r = dc.objective(qt, want_terms=True, want_occupancy=True, want_argmin=True)
+    o = co.objective(co.Tree(d), co.Cost(cost), q)
+    assert rel_err(r["terms"].cpu().numpy(), o["terms"]) < 1e-5
+    same = np.all((r["argmin"].cpu().numpy() == o["argmin"]).reshape(len(q), -1), axis=1)
+    assert np.mean(same) > 0.999
+    gd = np.abs(r["grad_q"].cpu().numpy() - o["grad_q"]).max(axis=1) / np.abs(o["grad_q"]).max()
+    assert np.all(gd[same] < 1e-4) and np.mean(gd < 1e-4) > 0.999
+    assert np.mean(r["occupancy"].cpu().numpy() == o["occ"]) > 0.9995
+    r0 = dc.objective(qt, want_grad=False, want_terms=False, want_occupancy=True, margin_override=0.0)
+    o0 = co.objective(co.Tree(d), co.Cost(cost), q, margin_override=0.0)
+    assert np.mean(r0["occupancy"].cpu().numpy() == o0["occ"]) > 0.9995
+    assert torch.equal(r0["total"], r["total"])
+    total, grad = torch.empty(len(q), device="cuda:0"), torch.empty(len(q), 7, device="cuda:0")
+    parts = dc.objective_sum(qt, out_grad=grad, out_total=total)
+    assert torch.equal(total, r["total"]) and torch.equal(grad, r["grad_q"])
+    assert abs(float(parts.sum(dtype=torch.float64)) - float(total.sum(dtype=torch.float64))) < 1e-3 * abs(float(total.sum(dtype=torch.float64)))

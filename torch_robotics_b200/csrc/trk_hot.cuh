@@ -32,6 +32,11 @@ namespace trk {
 #define TRK_HOT_QSTAGE 1
 #endif
 
+#ifndef TRK_HOT_SCAN_UNROLL   // sphere pairs per trip of the scan loop
+#define TRK_HOT_SCAN_UNROLL 2
+#endif
+constexpr int kHotScanUnroll = TRK_HOT_SCAN_UNROLL;
+
 constexpr int kHotMaxPairs = 16, kHotMaxPoints = 16;
 
 struct HotParams {
@@ -56,8 +61,13 @@ struct HotParams {
     // k_objective_ext only (its margins live in device tables): the occupancy tests use this margin instead when set
     int   use_override;
     float margin_override;
-    int   ee_enabled;          // k_objective_ext: 0 = no EE term (the headline kernel is only selected with one)
+    int   ee_enabled;          // 0 = the cost table has no EE term (PlanningTask.compute_collision_cost): c_ee = 0, no EE wrench
+    // box scenes (SCENE == 1: up to kHotMaxObjects posed objects made of boxes / rounded boxes only, e.g. EnvTableShelf,
+    // EnvMazeBoxes3D): offsets of the general tables in the cost buffer; arg-min of the constant points per object
+    int   n_obj, n_box, off_box, off_obj_box_start, off_obj_ident, off_obj_R, off_obj_pos;
+    int   widx_const_obj[4][kHotMaxPoints];
 };
+constexpr int kHotMaxObjects = 4;
 
 __device__ __forceinline__ float fmax_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ float fmin_nan(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
@@ -402,7 +412,9 @@ struct HotPlan {
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
-template <class R, class CM, int EE, bool PER_CFG_TARGET, bool WANT_GRAD>
+// SCENE_EE: bit 0 = the scene is made of boxes (else: one equal-radius identity-pose sphere object), bit 1 = the cost table has
+// no EE term (PlanningTask.compute_collision_cost)
+template <class R, class CM, int EE, bool PER_CFG_TARGET, bool WANT_GRAD, int SCENE_EE = 0>
 __global__ void __launch_bounds__(kSBlock, TRK_HOT_MINBLOCKS)
 k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ cost_words, const float* __restrict__ q, long long n,
                 const float* __restrict__ ee_target_cfg, float* __restrict__ cost_total, float* __restrict__ cost_terms,
@@ -410,13 +422,31 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
     using T = HTree<R>;
     using Plan = HotPlan<R, CM, EE>;
     constexpr int L = R::L, D = R::D, S = CM::S, P = CM::P;
+    constexpr int SCENE = SCENE_EE & 1;
+    constexpr bool HAS_EE = (SCENE_EE & 2) == 0;
     static_assert(S <= kHotMaxPoints && P <= kHotMaxPairs, "collision model too large for HotParams");
     extern __shared__ __align__(16) float hsm[];
     // [n_pairs2 * 8] scan table, two spheres interleaved: (ax, bx, ay, by) (az, bz, aw, bw) | [n_sph * 4] (c, r) | q tiles
     float4* tq = reinterpret_cast<float4*>(hsm);
     float4* tsph = tq + 2 * hp.n_pairs2;
     const int tid = threadIdx.x;
-    {
+    if constexpr (SCENE == 1) {
+        // box scene: [2 n_box] boxes (c.xyz, radius | half.xyz, rounded flag) | [4 n_obj] objects (pos.xyz, identity flag |
+        // R rows with the object's box range in the .w of rows 0 and 1)
+        const float4* box = reinterpret_cast<const float4*>(cost_words + hp.off_box);
+        for (int i = tid; i < 2 * hp.n_box; i += kSBlock) tq[i] = __ldg(box + i);
+        float4* tobj = tq + 2 * hp.n_box;
+        const int* iw = reinterpret_cast<const int*>(cost_words);
+        for (int o = tid; o < hp.n_obj; o += kSBlock) {
+            const float* Ro = cost_words + hp.off_obj_R + 9 * o;
+            const float* po = cost_words + hp.off_obj_pos + 3 * o;
+            const bool ident = (iw[hp.off_obj_ident + o] & OBJ_IDENTITY) != 0;
+            tobj[4 * o + 0] = make_float4(po[0], po[1], po[2], ident ? 1.f : 0.f);
+            tobj[4 * o + 1] = make_float4(Ro[0], Ro[1], Ro[2], __int_as_float(iw[hp.off_obj_box_start + o]));
+            tobj[4 * o + 2] = make_float4(Ro[3], Ro[4], Ro[5], __int_as_float(iw[hp.off_obj_box_start + o + 1]));
+            tobj[4 * o + 3] = make_float4(Ro[6], Ro[7], Ro[8], 0.f);
+        }
+    } else {
         const float* sphq = cost_words + hp.off_sphq;
         for (int i = tid; i < hp.n_pairs2 * 8; i += kSBlock) {
             const int k = i >> 2, comp = i & 3;
@@ -526,22 +556,22 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
             }
         });
         // ---------------- EE SE(3) term (geometrics/utils.py:130-154; distance_fields.py:347-356) ----------------
-        float Rt[9], pt[3];
-        if constexpr (PER_CFG_TARGET) {
-            const float* Ht = ee_target_cfg + (live ? cfg : 0) * 16;
+        float c_ee = 0.f, eF[3] = {0.f, 0.f, 0.f}, eT[3] = {0.f, 0.f, 0.f};
+        if constexpr (HAS_EE) {
+            float Rt[9], pt[3];
+            if constexpr (PER_CFG_TARGET) {
+                const float* Ht = ee_target_cfg + (live ? cfg : 0) * 16;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const float4 row = __ldg(reinterpret_cast<const float4*>(Ht) + i);
-                Rt[i * 3 + 0] = row.x; Rt[i * 3 + 1] = row.y; Rt[i * 3 + 2] = row.z; pt[i] = row.w;
+                for (int i = 0; i < 3; ++i) {
+                    const float4 row = __ldg(reinterpret_cast<const float4*>(Ht) + i);
+                    Rt[i * 3 + 0] = row.x; Rt[i * 3 + 1] = row.y; Rt[i * 3 + 2] = row.z; pt[i] = row.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) Rt[i] = hp.ee_R[i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) pt[i] = hp.ee_t[i];
             }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 9; ++i) Rt[i] = hp.ee_R[i];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) pt[i] = hp.ee_t[i];
-        }
-        float c_ee, eF[3], eT[3];
-        {
             float dg[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i)
@@ -595,9 +625,108 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
                 if constexpr (Plan::has_force(bj)) add_force(IC<bj>{}, vx * inv, vy * inv, vz * inv);
             }
         });
+        constexpr int ND = Plan::n_dyn_points();
+        // workspace box of one moving point (distance_fields.py:319-332): the six half-space distances in the reference's order
+        // [x - min (3), max - x (3)]; value = margin - smallest distance (= the reference's max of margin - d_i: rounding is
+        // monotone); the gradient goes to the first index that attains the smallest distance.  (gx, gy, gz): the object term's
+        // force on the point, completed here and handed to the point's body.
+        float c_obj = hp.c_obj_const, c_ws = hp.c_ws_const;
+        auto ws_and_force = [&](auto kc, float x, float y, float z, float gx, float gy, float gz) {
+            constexpr int k = decltype(kc)::value, s = Plan::dyn_point(k), b = T::tix(CM::pt_link[s]);
+            const float e0 = __fsub_rn(x, hp.ws_min[0]), e1 = __fsub_rn(y, hp.ws_min[1]), e2 = __fsub_rn(z, hp.ws_min[2]);
+            const float f0 = __fsub_rn(hp.ws_max[0], x), f1 = __fsub_rn(hp.ws_max[1], y), f2 = __fsub_rn(hp.ws_max[2], z);
+            const float emin = fmin3(e0, e1, e2), fmn = fmin3(f0, f1, f2);
+            const float dmin = fminf(emin, fmn);
+            occ_ws = occ_ws || (dmin < hp.mo_ws[s]);
+            c_ws = __fadd_rn(c_ws, -__fsub_rn(dmin, hp.m_ws[s]));
+            if constexpr (WANT_GRAD) {
+                const bool upper = fmn < emin;                       // ties go to the lower index: the x - min side
+                float g = upper ? hp.w[2] : -hp.w[2];
+                g = (dmin != 0.f) ? g : 0.f;                         // sign(d) |d| has zero gradient at d == 0
+                const float a0 = upper ? f0 : e0, a1 = upper ? f1 : e1;
+                const bool p0 = a0 == dmin, p1 = a1 == dmin;
+                gx += p0 ? g : 0.f;
+                gy += (!p0 && p1) ? g : 0.f;
+                gz += (!p0 && !p1) ? g : 0.f;
+                if constexpr (Plan::has_force(b)) add_force(IC<b>{}, gx, gy, gz);
+            }
+        };
+        // ---------------- box scene: every object's boxes against all moving points (primitives.py:219-223, :326-334, :397-398;
+        // distance_fields.py: margin - sdf, max over objects) ----------------
+        [[maybe_unused]] int widx[ND > 0 ? ND : 1];       // sphere scene: index of each moving point's nearest sphere
+        if constexpr (SCENE == 1) {
+            const float kInf = __int_as_float(0x7f800000);
+            const float4* tobj = tq + 2 * hp.n_box;
+            float vmax[ND > 0 ? ND : 1];
+            int wobj[ND > 0 ? ND : 1], wbox[ND > 0 ? ND : 1];
+            auto to_object = [&](const float4 o0, const float4 r0, const float4 r1, const float4 r2, float x, float y, float z, float& xo,
+                                 float& yo, float& zo) {      // x' = (x - pos) @ R for a posed object
+                xo = x; yo = y; zo = z;
+                if (o0.w == 0.f) {
+                    const float d0 = __fsub_rn(x, o0.x), d1 = __fsub_rn(y, o0.y), d2 = __fsub_rn(z, o0.z);
+                    xo = __fmaf_rn(d2, r2.x, __fmaf_rn(d1, r1.x, __fmul_rn(d0, r0.x)));
+                    yo = __fmaf_rn(d2, r2.y, __fmaf_rn(d1, r1.y, __fmul_rn(d0, r0.y)));
+                    zo = __fmaf_rn(d2, r2.z, __fmaf_rn(d1, r1.z, __fmul_rn(d0, r0.z)));
+                }
+            };
+#pragma unroll 1
+            for (int o = 0; o < hp.n_obj; ++o) {
+                const float4 o0 = tobj[4 * o], r0 = tobj[4 * o + 1], r1 = tobj[4 * o + 2], r2 = tobj[4 * o + 3];
+                const int kb0 = __float_as_int(r0.w), kb1 = __float_as_int(r1.w);
+                float Xo[ND > 0 ? ND : 1][3], best[ND > 0 ? ND : 1];
+                int bb[ND > 0 ? ND : 1];
+                sfor<ND>([&](auto kc) {
+                    constexpr int b = T::tix(CM::pt_link[Plan::dyn_point(decltype(kc)::value)]);
+                    to_object(o0, r0, r1, r2, Pb[b][0], Pb[b][1], Pb[b][2], Xo[kc][0], Xo[kc][1], Xo[kc][2]);
+                    best[kc] = kInf; bb[kc] = -1;
+                });
+                float4 bc = tq[2 * kb0], bh = tq[2 * kb0 + 1];
+#pragma unroll 1
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const float4 c = bc, hh = bh;
+                    const int kn = (kb + 1 < kb1) ? kb + 1 : kb;        // the next box is in flight during this one
+                    bc = tq[2 * kn]; bh = tq[2 * kn + 1];
+#pragma unroll
+                    for (int k = 0; k < ND; ++k) {
+                        const float sd = box_sdf(c, hh, Xo[k][0], Xo[k][1], Xo[k][2]);
+                        const bool better = sd < best[k];                // strict: the earlier primitive wins ties
+                        best[k] = better ? sd : best[k];
+                        bb[k] = better ? kb : bb[k];
+                    }
+                }
+                sfor<ND>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value, s = Plan::dyn_point(k);
+                    occ_obj = occ_obj || (best[k] < hp.mo_obj[s]);
+                    const float val = -__fsub_rn(best[k], hp.m_obj[s]);
+                    if (argmin && live) argmin[cfg * (long long)(hp.n_obj * S) + o * S + s] = bb[k] >= 0 ? bb[k] - kb0 : 0;
+                    if (o == 0 || val > vmax[k]) { vmax[k] = val; wobj[k] = o; wbox[k] = bb[k]; }   // the first maximal object keeps the gradient
+                });
+            }
+            sfor<ND>([&](auto kc) {
+                constexpr int k = decltype(kc)::value, s = Plan::dyn_point(k), b = T::tix(CM::pt_link[s]);
+                const float x = Pb[b][0], y = Pb[b][1], z = Pb[b][2];
+                c_obj = __fadd_rn(c_obj, vmax[k]);
+                float gx = 0.f, gy = 0.f, gz = 0.f;
+                if constexpr (WANT_GRAD) {
+                    if (wbox[k] >= 0) {
+                        const int o = wobj[k];
+                        const float4 o0 = tobj[4 * o], r0 = tobj[4 * o + 1], r1 = tobj[4 * o + 2], r2 = tobj[4 * o + 3];
+                        float xo, yo, zo, ux, uy, uz;
+                        to_object(o0, r0, r1, r2, x, y, z, xo, yo, zo);
+                        box_sdf_grad(tq[2 * wbox[k]], tq[2 * wbox[k] + 1], xo, yo, zo, ux, uy, uz);
+                        if (o0.w == 0.f) {         // back to the world frame: g = R g'
+                            const float wx = r0.x * ux + r0.y * uy + r0.z * uz, wy = r1.x * ux + r1.y * uy + r1.z * uz,
+                                        wz = r2.x * ux + r2.y * uy + r2.z * uz;
+                            ux = wx; uy = wy; uz = wz;
+                        }
+                        gx = -(hp.w[1] * ux); gy = -(hp.w[1] * uy); gz = -(hp.w[1] * uz);
+                    }
+                }
+                ws_and_force(kc, x, y, z, gx, gy, gz);
+            });
+        } else {
         // ---------------- sphere object: joint scan of the moving collision points, two spheres per FFMA2 ----------------
         // (points whose position is a compile-time constant were evaluated on the host: HotParams::*_const)
-        constexpr int ND = Plan::n_dyn_points();
         float m1[ND > 0 ? ND : 1], m2[ND > 0 ? ND : 1];
         {
             float2 X2[ND > 0 ? ND : 1][3];
@@ -611,7 +740,7 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
             const unsigned keep = ~hp.lowmask;
             unsigned idx = 0u;
             float4 t0 = tq[0], t1 = tq[1];
-#pragma unroll 1
+#pragma unroll kHotScanUnroll
             for (int j = 0; j < hp.n_pairs2; ++j, idx += 2u) {
                 const float2 cx = make_float2(t0.x, t0.y), cy = make_float2(t0.z, t0.w), cz = make_float2(t1.x, t1.y), cw = make_float2(t1.z, t1.w);
                 const int jn = (j + 1 < hp.n_pairs2) ? j + 1 : j;      // next pair's table entry is in flight during this one
@@ -627,7 +756,6 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
                 }
             }
         }
-        int widx[ND > 0 ? ND : 1];
         bool all_certain = true;
         sfor<ND>([&](auto kc) {
             constexpr int k = decltype(kc)::value, b = T::tix(CM::pt_link[Plan::dyn_point(k)]);
@@ -653,7 +781,6 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
             });
         }
         // ---------------- moving collision points: exact evaluation of the winner + workspace box ----------------
-        float c_obj = hp.c_obj_const, c_ws = hp.c_ws_const;
         sfor<ND>([&](auto kc) {
             constexpr int k = decltype(kc)::value, s = Plan::dyn_point(k), b = T::tix(CM::pt_link[s]);
             const float x = Pb[b][0], y = Pb[b][1], z = Pb[b][2];
@@ -663,29 +790,10 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
             const float best = __fsub_rn(norm3_clamped(vx, vy, vz, rs), c.w);
             occ_obj = occ_obj || (best < hp.mo_obj[s]);
             c_obj = __fadd_rn(c_obj, -__fsub_rn(best, hp.m_obj[s]));
-            // workspace box (distance_fields.py:319-332): the six half-space distances in the reference's order
-            // [x - min (3), max - x (3)]; value = margin - smallest distance (= the reference's max of margin - d_i: rounding
-            // is monotone); the gradient goes to the first index that attains the smallest distance
-            const float e0 = __fsub_rn(x, hp.ws_min[0]), e1 = __fsub_rn(y, hp.ws_min[1]), e2 = __fsub_rn(z, hp.ws_min[2]);
-            const float f0 = __fsub_rn(hp.ws_max[0], x), f1 = __fsub_rn(hp.ws_max[1], y), f2 = __fsub_rn(hp.ws_max[2], z);
-            const float emin = fmin3(e0, e1, e2), fmn = fmin3(f0, f1, f2);
-            const float dmin = fminf(emin, fmn);
-            occ_ws = occ_ws || (dmin < hp.mo_ws[s]);
-            c_ws = __fadd_rn(c_ws, -__fsub_rn(dmin, hp.m_ws[s]));
-            if constexpr (WANT_GRAD) {
-                const float w1 = hp.w[1] * rs;
-                float gx = -(w1 * vx), gy = -(w1 * vy), gz = -(w1 * vz);
-                const bool upper = fmn < emin;                       // ties go to the lower index: the x - min side
-                float g = upper ? hp.w[2] : -hp.w[2];
-                g = (dmin != 0.f) ? g : 0.f;                         // sign(d) |d| has zero gradient at d == 0
-                const float a0 = upper ? f0 : e0, a1 = upper ? f1 : e1;
-                const bool p0 = a0 == dmin, p1 = a1 == dmin;
-                gx += p0 ? g : 0.f;
-                gy += (!p0 && p1) ? g : 0.f;
-                gz += (!p0 && !p1) ? g : 0.f;
-                if constexpr (Plan::has_force(b)) add_force(IC<b>{}, gx, gy, gz);
-            }
+            const float w1 = hp.w[1] * rs;
+            ws_and_force(kc, x, y, z, -(w1 * vx), -(w1 * vy), -(w1 * vz));
         });
+        }
         // ---------------- outputs ----------------
         if (live) {
             const float total = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(hp.w[0], c_self), __fmul_rn(hp.w[1], c_obj)), __fmul_rn(hp.w[2], c_ws)),
@@ -695,12 +803,22 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
             if (cost_terms) reinterpret_cast<float4*>(cost_terms)[cfg] = make_float4(c_self, c_obj, c_ws, c_ee);
             if (occupancy) occupancy[cfg] = (uint8_t)(hp.occ_const | (occ_self ? TRK_OCC_SELF : 0u) | (occ_obj ? TRK_OCC_OBJECT : 0u) | (occ_ws ? TRK_OCC_WS : 0u));
             if (argmin) {
-                int* row = argmin + cfg * S;
-                sfor<S>([&](auto sc) {
-                    constexpr int s = decltype(sc)::value, rk = Plan::dyn_rank(s);
-                    if constexpr (rk >= 0) row[s] = widx[rk];
-                    else row[s] = hp.widx_const[s];
-                });
+                if constexpr (SCENE == 1) {      // the moving points' entries were written object by object; the constant points' here
+                    for (int o = 0; o < hp.n_obj; ++o) {
+                        int* row = argmin + cfg * (long long)(hp.n_obj * S) + o * S;
+                        sfor<S>([&](auto sc) {
+                            constexpr int s = decltype(sc)::value;
+                            if constexpr (Plan::dyn_rank(s) < 0) row[s] = hp.widx_const_obj[o][s];
+                        });
+                    }
+                } else {
+                    int* row = argmin + cfg * S;
+                    sfor<S>([&](auto sc) {
+                        constexpr int s = decltype(sc)::value, rk = Plan::dyn_rank(s);
+                        if constexpr (rk >= 0) row[s] = widx[rk];
+                        else row[s] = hp.widx_const[s];
+                    });
+                }
             }
         }
         // ---------------- reverse mode: leaf -> root over the movable bodies ----------------

@@ -1310,14 +1310,16 @@ cudaError_t launch_ik_t(const IKParams& P, const float* step_size, const float* 
 // which compile-time collision model (if any) belongs to a compiled-in robot
 // in_registers: body positions / gradients of the model fit in registers (k_objective_cm); otherwise the model only
 // fixes the shared-memory slot numbering of k_objective_static at compile time
-template <class R> struct CollisionModelOf { using type = void; static constexpr bool in_registers = false; };
+// hot_scenes: k_objective_hot is also instantiated for box scenes and for cost tables without an EE term (compile time: the
+// config-5 Stretch model only exists with its sphere scene and EE term)
+template <class R> struct CollisionModelOf { using type = void; static constexpr bool in_registers = false, hot_scenes = false; };
 #ifndef TRK_ROBOTS_HEADER
-template <> struct CollisionModelOf<robots::Panda> { using type = robots::PandaCollision; static constexpr bool in_registers = true; };
-template <> struct CollisionModelOf<robots::Stretch> { using type = robots::StretchCollision; static constexpr bool in_registers = false; };
+template <> struct CollisionModelOf<robots::Panda> { using type = robots::PandaCollision; static constexpr bool in_registers = true, hot_scenes = true; };
+template <> struct CollisionModelOf<robots::Stretch> { using type = robots::StretchCollision; static constexpr bool in_registers = false, hot_scenes = false; };
 #elif defined(TRK_JIT_HAS_COLLISION)
 template <> struct CollisionModelOf<robots::Jit> {
     using type = robots::JitCollision;
-    static constexpr bool in_registers = robots::JitCollision::S <= 8 && robots::JitCollision::P <= 16;
+    static constexpr bool in_registers = robots::JitCollision::S <= 8 && robots::JitCollision::P <= 16, hot_scenes = true;
 };
 #endif
 
@@ -1470,7 +1472,7 @@ inline cudaError_t launch_objective_cm_k(int n_sms, const float* cost_words, int
 // Host side of k_objective_hot: the uniform scalars of the cost table become kernel parameters (margins already resolved
 // against `margin_override`), the sphere tables stay in the device cost buffer.
 template <class R, class CM, int EE>
-inline void hot_params_from_cost(const float* hw, float margin_override, int use_override, HotParams& hp) {
+inline void hot_params_from_cost(const float* hw, float margin_override, int use_override, HotParams& hp, bool box_scene = false) {
     const CostHeader* h = reinterpret_cast<const CostHeader*>(hw);
     const int* iw = reinterpret_cast<const int*>(hw);
     std::memset(&hp, 0, sizeof(hp));
@@ -1485,7 +1487,8 @@ inline void hot_params_from_cost(const float* hw, float margin_override, int use
     for (int i = 0; i < 4; ++i) hp.w[i] = h->w[i];
     for (int i = 0; i < 3; ++i) { hp.ws_min[i] = h->ws_min[i]; hp.ws_max[i] = h->ws_max[i]; hp.ee_t[i] = h->ee_t[i]; }
     for (int i = 0; i < 9; ++i) hp.ee_R[i] = h->ee_R[i];
-    hp.ee_w_pos = h->ee_w_pos; hp.ee_w_rot = h->ee_w_rot; hp.ee_square = h->ee_square;
+    hp.ee_w_pos = h->ee_w_pos; hp.ee_w_rot = h->ee_w_rot; hp.ee_square = h->ee_square; hp.ee_enabled = h->ee_enabled;
+    if (box_scene) return;      // the object tables and the constant points of a box scene: hot_params_box_scene
     hp.tol = hw[h->off_obj_tol]; hp.c2max = hw[h->off_obj_c2max];
     hp.lowmask = (1u << (iw[h->off_obj_ident] >> OBJ_BITS_SHIFT)) - 1u;
     hp.n_pairs2 = (iw[h->off_obj_qstart + 1] - iw[h->off_obj_qstart]) / 2;
@@ -1517,14 +1520,78 @@ inline void hot_params_from_cost(const float* hw, float margin_override, int use
     }
 }
 
+// Box scene (SCENE == 1 of k_objective_hot): offsets of the general tables, and the collision points at constant positions
+// evaluated once on the host with the device arithmetic of object_point_term / box_sdf (trk_device.cuh) restated in correctly
+// rounded host operations: per object the nearest box (strict <: the earlier one wins ties), occupancy against the
+// occupancy margin, value = margin - sdf, the first maximal object keeps it; then the workspace term as in the sphere scene.
+template <class R, class CM, int EE>
+inline void hot_params_box_scene(const float* hw, HotParams& hp) {
+    const CostHeader* h = reinterpret_cast<const CostHeader*>(hw);
+    const int* iw = reinterpret_cast<const int*>(hw);
+    hp.n_obj = h->nObj; hp.n_box = h->KB; hp.off_box = h->off_box; hp.off_obj_box_start = h->off_obj_box_start;
+    hp.off_obj_ident = h->off_obj_ident; hp.off_obj_R = h->off_obj_R; hp.off_obj_pos = h->off_obj_pos;
+    hp.n_pairs2 = 0; hp.n_sph = 0;
+    hp.c_obj_const = 0.f; hp.c_ws_const = 0.f; hp.occ_const = 0u;
+    constexpr auto cp = HotPlan<R, CM, EE>::kConstPoints;
+    const float* box = hw + h->off_box;
+    auto host_box_sdf = [&](int kb, float x, float y, float z) {
+        const float* c = box + 8 * kb;
+        const float* hh = c + 4;
+        const float ax = fabsf(x - c[0]), ay = fabsf(y - c[1]), az = fabsf(z - c[2]);
+        float qx = ax - hh[0], qy = ay - hh[1], qz = az - hh[2];
+        if (hh[3] == 0.f) return fmaxf(fmaxf(qx, qy), qz);
+        const float r = c[3];
+        qx = qx + r; qy = qy + r; qz = qz + r;
+        const float mq = fmaxf(fmaxf(qx, qy), qz);
+        const float px = fmaxf(qx, 0.f), py = fmaxf(qy, 0.f), pz = fmaxf(qz, 0.f);
+        const float nrm = sqrtf(fmaf(pz, pz, fmaf(py, py, px * px)));
+        return (fminf(mq, 0.f) + nrm) - r;
+    };
+    for (int s2 = 0; s2 < CM::S; ++s2) {
+        if (!cp.is_const[s2]) continue;
+        const float x = cp.pos[s2][0], y = cp.pos[s2][1], z = cp.pos[s2][2];
+        float vmax = 0.f;
+        for (int o = 0; o < h->nObj; ++o) {
+            float xo = x, yo = y, zo = z;
+            if (!(iw[h->off_obj_ident + o] & OBJ_IDENTITY)) {
+                const float* Ro = hw + h->off_obj_R + 9 * o;
+                const float* po = hw + h->off_obj_pos + 3 * o;
+                const float d0 = x - po[0], d1 = y - po[1], d2 = z - po[2];
+                xo = fmaf(d2, Ro[6], fmaf(d1, Ro[3], d0 * Ro[0]));
+                yo = fmaf(d2, Ro[7], fmaf(d1, Ro[4], d0 * Ro[1]));
+                zo = fmaf(d2, Ro[8], fmaf(d1, Ro[5], d0 * Ro[2]));
+            }
+            const int kb0 = iw[h->off_obj_box_start + o], kb1 = iw[h->off_obj_box_start + o + 1];
+            float best = INFINITY;
+            int bb = -1;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const float sd = host_box_sdf(kb, xo, yo, zo);
+                if (sd < best) { best = sd; bb = kb; }
+            }
+            if (o < kHotMaxObjects) hp.widx_const_obj[o][s2] = bb >= 0 ? bb - kb0 : 0;
+            if (best < hp.mo_obj[s2]) hp.occ_const |= TRK_OCC_OBJECT;
+            const float val = -(best - hp.m_obj[s2]);
+            if (o == 0 || val > vmax) vmax = val;
+        }
+        hp.c_obj_const = hp.c_obj_const + vmax;
+        const float d[6] = {x - hp.ws_min[0], y - hp.ws_min[1], z - hp.ws_min[2], hp.ws_max[0] - x, hp.ws_max[1] - y, hp.ws_max[2] - z};
+        float dmin = d[0];
+        for (int i = 1; i < 6; ++i) dmin = fminf(dmin, d[i]);
+        if (dmin < hp.mo_ws[s2]) hp.occ_const |= TRK_OCC_WS;
+        hp.c_ws_const = hp.c_ws_const + -(dmin - hp.m_ws[s2]);
+    }
+}
+
 template <class R, class CM, int EE>
 inline cudaError_t launch_objective_hot(int n_sms, const float* host_words, const float* cost_words, const float* q, long long n,
                                         const float* ee_target_cfg, float margin_override, int use_override, float* cost_total,
                                         float* cost_terms, float* grad_q, uint8_t* occupancy, int* argmin, float* block_sums, int* n_block_sums,
-                                        cudaStream_t st) {
+                                        cudaStream_t st, bool box_scene = false) {
     HotParams hp;
-    hot_params_from_cost<R, CM, EE>(host_words, margin_override, use_override, hp);
-    const size_t smem = ((size_t)hp.n_pairs2 * 8 + (size_t)hp.n_sph * 4 + (TRK_HOT_QSTAGE >= 2 ? 2 * kSBlock * R::D : 0)) * sizeof(float);
+    hot_params_from_cost<R, CM, EE>(host_words, margin_override, use_override, hp, box_scene);
+    if (box_scene) hot_params_box_scene<R, CM, EE>(host_words, hp);
+    const size_t smem = box_scene ? ((size_t)hp.n_box * 8 + (size_t)hp.n_obj * 16) * sizeof(float)
+                                  : ((size_t)hp.n_pairs2 * 8 + (size_t)hp.n_sph * 4 + (TRK_HOT_QSTAGE >= 2 ? 2 * kSBlock * R::D : 0)) * sizeof(float);
     auto launch = [&](auto k) {
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1548,6 +1615,22 @@ inline cudaError_t launch_objective_hot(int n_sms, const float* host_words, cons
         k<<<grid, kSBlock, smem, st>>>(hp, cost_words, q, n, ee_target_cfg, cost_total, cost_terms, grad_q, occupancy, argmin, block_sums);
         return cudaGetLastError();
     };
+    if constexpr (CollisionModelOf<R>::hot_scenes) {
+        if (!hp.ee_enabled) {          // no EE term in the cost table (PlanningTask.compute_collision_cost): SCENE_EE bit 1
+            if (box_scene) return grad_q ? launch(k_objective_hot<R, CM, EE, false, true, 3>) : launch(k_objective_hot<R, CM, EE, false, false, 3>);
+            return grad_q ? launch(k_objective_hot<R, CM, EE, false, true, 2>) : launch(k_objective_hot<R, CM, EE, false, false, 2>);
+        }
+        if (box_scene) {
+            if (grad_q) {
+                if (ee_target_cfg) return launch(k_objective_hot<R, CM, EE, true, true, 1>);
+                return launch(k_objective_hot<R, CM, EE, false, true, 1>);
+            }
+            if (ee_target_cfg) return launch(k_objective_hot<R, CM, EE, true, false, 1>);
+            return launch(k_objective_hot<R, CM, EE, false, false, 1>);
+        }
+    } else {
+        if (!hp.ee_enabled || box_scene) return cudaErrorInvalidValue;      // not instantiated for this robot: the caller's condition excludes it
+    }
     if (grad_q) {
         if (ee_target_cfg) return launch(k_objective_hot<R, CM, EE, true, true>);
         return launch(k_objective_hot<R, CM, EE, false, true>);
@@ -1653,11 +1736,22 @@ cudaError_t launch_objective_t(int n_sms, const float* host_words, const float* 
                 // model's own EE body + joint-scan scene + workspace box and both EE weights on + no relu + 16-byte aligned q:
                 // the headline kernel (trk_hot.cuh)
                 static const bool no_hot = std::getenv("TRK_B200_NO_HOT") != nullptr;   // A/B switch
-                if ((cm_match & 14) == 14 && !clamp_any && !no_hot && (reinterpret_cast<uintptr_t>(q) & 15u) == 0 &&
+                // the EE term sits on the model's own EE body - or, for robots with every scene instantiated, there is none
+                const bool ee_ok = (cm_match & 2) != 0 || (CollisionModelOf<R>::hot_scenes && (cm_match & 32) != 0);
+                // (q needs 16-byte alignment only for the cp.async staging variants; the default prefetches it with scalar loads)
+                const bool q_ok = TRK_HOT_QSTAGE < 2 || (reinterpret_cast<uintptr_t>(q) & 15u) == 0;
+                if ((cm_match & 12) == 12 && ee_ok && !clamp_any && !no_hot && q_ok &&
                     (!ee_target_cfg || (reinterpret_cast<uintptr_t>(ee_target_cfg) & 15u) == 0)) {
                     constexpr int kEE = STree<R>::topo_index_of(CM::ee_body);
                     return launch_objective_hot<R, CM, kEE>(n_sms, host_words, cost_words, q, n, ee_target_cfg, margin_override, use_override,
                                                             cost_total, cost_terms, grad_q, occupancy, argmin, block_sums, n_block_sums, st);
+                }
+                // the same kernel on a scene of boxes (EnvTableShelf, EnvMazeBoxes3D, ...): bit 4 already says "no relu"
+                if (CollisionModelOf<R>::hot_scenes && (cm_match & 24) == 24 && ee_ok && !no_hot && q_ok &&
+                    (!ee_target_cfg || (reinterpret_cast<uintptr_t>(ee_target_cfg) & 15u) == 0)) {
+                    constexpr int kEE = STree<R>::topo_index_of(CM::ee_body);
+                    return launch_objective_hot<R, CM, kEE>(n_sms, host_words, cost_words, q, n, ee_target_cfg, margin_override, use_override,
+                                                            cost_total, cost_terms, grad_q, occupancy, argmin, block_sums, n_block_sums, st, true);
                 }
             }
             if constexpr (CollisionModelOf<R>::in_registers) {
@@ -1777,15 +1871,21 @@ inline int cm_match_value(const float* host_cost_words) {
         const int need = OBJ_IDENTITY | OBJ_UNIFORM_RADIUS;
         const bool joint_scene = hh->nObj == 1 && hh->KB == 0 && (iw[hh->off_obj_ident] & (need | OBJ_GRID)) == need &&
                                  iw[hh->off_obj_start + 1] > iw[hh->off_obj_start];
-        const bool hot_terms = hh->ws_enabled && hh->ee_w_pos > 0.f && hh->ee_w_rot > 0.f;
-        return 1 | ((hh->ee_enabled && hh->ee_link == CM::ee_body) ? 2 : 0) | (joint_scene ? 4 : 0) | (hot_terms ? 8 : 0);
+        const bool hot_terms = hh->ws_enabled && (!hh->ee_enabled || (hh->ee_w_pos > 0.f && hh->ee_w_rot > 0.f));
+        // box scene: 1 .. kHotMaxObjects objects, each made of boxes only (no spheres, no voxel grid), nothing relu-clamped
+        bool box_scene = hh->nObj >= 1 && hh->nObj <= kHotMaxObjects && hh->KB > 0 && !hh->clamp_self && !hh->clamp_obj && !hh->clamp_ws;
+        for (int o = 0; box_scene && o < hh->nObj; ++o)
+            box_scene = iw[hh->off_obj_start + o + 1] == iw[hh->off_obj_start + o] && !(iw[hh->off_obj_ident + o] & OBJ_GRID) &&
+                        iw[hh->off_obj_box_start + o + 1] > iw[hh->off_obj_box_start + o];
+        return 1 | ((hh->ee_enabled && hh->ee_link == CM::ee_body) ? 2 : 0) | (joint_scene ? 4 : 0) | (hot_terms ? 8 : 0) | (box_scene ? 16 : 0) |
+               (hh->ee_enabled ? 0 : 32);
     }
 }
 
 // > 0 when `family` has a compile-time collision model and the (host copy of the) cost table matches it;
 // bit 1: the end-effector term is enabled on the model's own EE body (CM::ee_body); bit 2: the scene is one equal-radius
-// identity-pose sphere object (the joint-scan scene); bit 3: workspace box on and both EE weights positive (what
-// k_objective_hot assumes on top of bits 1 and 2)
+// identity-pose sphere object (the joint-scan scene); bit 3: workspace box on and, with an EE term, both EE weights positive
+// (what k_objective_hot assumes); bit 4: a scene of boxes only, nothing relu-clamped; bit 5: no EE term at all
 inline int static_cm_match(int family, const float* host_cost_words) {
     int id = 0;
 #define X(Rb)                                                                          \
