@@ -75,12 +75,13 @@ def test_gpu_planning_task_matches_reference(tag):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tag", ["table_shelf", "maze_boxes"])
+@pytest.mark.parametrize("tag", ["table_shelf", "maze_boxes", "spheres3d_extra", "boxes", "two_objects"])
 @pytest.mark.parametrize("with_ee", [True, False])
-def test_gpu_box_scene_headline_kernel_vs_oracle(tag, with_ee):
-    """A scene made of boxes only (posed objects of rounded boxes) runs on k_objective_hot<..., SCENE = 1>, with or without an
-    EE term: terms, gradients, occupancy (default margins and margin = 0) and the per-object arg-min against the C oracle on
-    random configurations; the fused block sums exist (only the headline kernel has them)."""
+def test_gpu_general_scene_headline_kernel_vs_oracle(tag, with_ee):
+    """Scenes beyond the single sphere object - posed objects of rounded boxes, several sphere objects, spheres and boxes mixed,
+    unequal radii - run on k_objective_hot<..., SCENE = 1>, with or without an EE term: terms, gradients, occupancy (default
+    margins and margin = 0) and the per-object arg-min against the C oracle on random configurations; the fused block sums exist
+    (only the headline kernel has them)."""
     from torch_robotics_b200._lib import DeviceCost, DeviceModel
     g, d = load_golden(f"planning_panda_{tag}"), get_desc("panda")
     cost = planning_cost_from_golden(g, with_ee=with_ee)
@@ -89,7 +90,8 @@ def test_gpu_box_scene_headline_kernel_vs_oracle(tag, with_ee):
     rng = np.random.default_rng(3)
     lo, hi = d.lo[d.controlled], d.hi[d.controlled]
     q = (lo + rng.random((40_009, 7), dtype=np.float32) * (hi - lo)).astype(np.float32)
-    q[:64] = g["q"].reshape(-1, 7)[:64]
+    gq = g["q"].reshape(-1, 7)[:64]
+    q[:len(gq)] = gq
     qt = torch.as_tensor(q, device="cuda:0")
     r = dc.objective(qt, want_terms=True, want_occupancy=True, want_argmin=True)
     o = co.objective(co.Tree(d), co.Cost(cost), q)

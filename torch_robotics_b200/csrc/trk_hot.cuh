@@ -62,9 +62,11 @@ struct HotParams {
     int   use_override;
     float margin_override;
     int   ee_enabled;          // 0 = the cost table has no EE term (PlanningTask.compute_collision_cost): c_ee = 0, no EE wrench
-    // box scenes (SCENE == 1: up to kHotMaxObjects posed objects made of boxes / rounded boxes only, e.g. EnvTableShelf,
-    // EnvMazeBoxes3D): offsets of the general tables in the cost buffer; arg-min of the constant points per object
+    // general scenes (SCENE == 1: up to kHotMaxObjects posed objects of spheres and / or boxes and rounded boxes, e.g.
+    // EnvTableShelf, EnvMazeBoxes3D, EnvSpheres3DExtraObjects): offsets of the general tables in the cost buffer; arg-min of the
+    // constant points per object
     int   n_obj, n_box, off_box, off_obj_box_start, off_obj_ident, off_obj_R, off_obj_pos;
+    int   n_sph_all, n_sphq_all, off_sph_all, off_sphq_all, off_obj_start, off_obj_qstart, off_obj_tol, off_obj_c2max;
     int   widx_const_obj[4][kHotMaxPoints];
 };
 constexpr int kHotMaxObjects = 4;
@@ -431,20 +433,35 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
     float4* tsph = tq + 2 * hp.n_pairs2;
     const int tid = threadIdx.x;
     if constexpr (SCENE == 1) {
-        // box scene: [2 n_box] boxes (c.xyz, radius | half.xyz, rounded flag) | [4 n_obj] objects (pos.xyz, identity flag |
-        // R rows with the object's box range in the .w of rows 0 and 1)
+        // general scene: [2 n_box] boxes (c.xyz, radius | half.xyz, rounded flag) | [n_sph_all] spheres (c, r) | [2 n_sphq_all]
+        // scan table, two spheres interleaved | [6 n_obj] objects: (pos.xyz, identity flag) (R rows; .w: box range, first sphere)
+        // (sphere count, first scan pair, scan pairs, index mask) (tol, c2max, uniform-radius flag, -)
         const float4* box = reinterpret_cast<const float4*>(cost_words + hp.off_box);
         for (int i = tid; i < 2 * hp.n_box; i += kSBlock) tq[i] = __ldg(box + i);
-        float4* tobj = tq + 2 * hp.n_box;
+        float4* gsph = tq + 2 * hp.n_box;
+        const float4* sph = reinterpret_cast<const float4*>(cost_words + hp.off_sph_all);
+        for (int i = tid; i < hp.n_sph_all; i += kSBlock) gsph[i] = __ldg(sph + i);
+        float* gq = reinterpret_cast<float*>(gsph + hp.n_sph_all);
+        const float* sphq = cost_words + hp.off_sphq_all;
+        for (int i = tid; i < hp.n_sphq_all * 4; i += kSBlock) {
+            const int k = i >> 2, comp = i & 3;
+            gq[(k >> 1) * 8 + comp * 2 + (k & 1)] = __ldg(sphq + i);
+        }
+        float4* tobj = reinterpret_cast<float4*>(gq) + hp.n_sphq_all;
         const int* iw = reinterpret_cast<const int*>(cost_words);
         for (int o = tid; o < hp.n_obj; o += kSBlock) {
             const float* Ro = cost_words + hp.off_obj_R + 9 * o;
             const float* po = cost_words + hp.off_obj_pos + 3 * o;
-            const bool ident = (iw[hp.off_obj_ident + o] & OBJ_IDENTITY) != 0;
-            tobj[4 * o + 0] = make_float4(po[0], po[1], po[2], ident ? 1.f : 0.f);
-            tobj[4 * o + 1] = make_float4(Ro[0], Ro[1], Ro[2], __int_as_float(iw[hp.off_obj_box_start + o]));
-            tobj[4 * o + 2] = make_float4(Ro[3], Ro[4], Ro[5], __int_as_float(iw[hp.off_obj_box_start + o + 1]));
-            tobj[4 * o + 3] = make_float4(Ro[6], Ro[7], Ro[8], 0.f);
+            const int flags = iw[hp.off_obj_ident + o];
+            const int k0 = iw[hp.off_obj_start + o], k1 = iw[hp.off_obj_start + o + 1];
+            const int q0 = iw[hp.off_obj_qstart + o], q1 = iw[hp.off_obj_qstart + o + 1];
+            tobj[6 * o + 0] = make_float4(po[0], po[1], po[2], (flags & OBJ_IDENTITY) ? 1.f : 0.f);
+            tobj[6 * o + 1] = make_float4(Ro[0], Ro[1], Ro[2], __int_as_float(iw[hp.off_obj_box_start + o]));
+            tobj[6 * o + 2] = make_float4(Ro[3], Ro[4], Ro[5], __int_as_float(iw[hp.off_obj_box_start + o + 1]));
+            tobj[6 * o + 3] = make_float4(Ro[6], Ro[7], Ro[8], __int_as_float(k0));
+            tobj[6 * o + 4] = make_float4(__int_as_float(k1 - k0), __int_as_float(q0 / 2), __int_as_float((q1 - q0) / 2),
+                                          __int_as_float((1 << (flags >> OBJ_BITS_SHIFT)) - 1));
+            tobj[6 * o + 5] = make_float4(cost_words[hp.off_obj_tol + o], cost_words[hp.off_obj_c2max + o], (flags & OBJ_UNIFORM_RADIUS) ? 1.f : 0.f, 0.f);
         }
     } else {
         const float* sphq = cost_words + hp.off_sphq;
@@ -651,14 +668,16 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
                 if constexpr (Plan::has_force(b)) add_force(IC<b>{}, gx, gy, gz);
             }
         };
-        // ---------------- box scene: every object's boxes against all moving points (primitives.py:219-223, :326-334, :397-398;
-        // distance_fields.py: margin - sdf, max over objects) ----------------
+        // ---------------- general scene: every object's spheres and boxes against all moving points (primitives.py:135-139 spheres,
+        // :219-223 / :326-334 boxes, :397-398 object pose; distance_fields.py: margin - sdf, max over objects) ----------------
         [[maybe_unused]] int widx[ND > 0 ? ND : 1];       // sphere scene: index of each moving point's nearest sphere
         if constexpr (SCENE == 1) {
             const float kInf = __int_as_float(0x7f800000);
-            const float4* tobj = tq + 2 * hp.n_box;
+            const float4* gsph = tq + 2 * hp.n_box;
+            const float4* gq = gsph + hp.n_sph_all;
+            const float4* tobj = gq + hp.n_sphq_all;
             float vmax[ND > 0 ? ND : 1];
-            int wobj[ND > 0 ? ND : 1], wbox[ND > 0 ? ND : 1];
+            int wobj[ND > 0 ? ND : 1], wsel[ND > 0 ? ND : 1];      // winner: object, primitive (spheres of the object first, then its boxes)
             auto to_object = [&](const float4 o0, const float4 r0, const float4 r1, const float4 r2, float x, float y, float z, float& xo,
                                  float& yo, float& zo) {      // x' = (x - pos) @ R for a posed object
                 xo = x; yo = y; zo = z;
@@ -671,35 +690,98 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
             };
 #pragma unroll 1
             for (int o = 0; o < hp.n_obj; ++o) {
-                const float4 o0 = tobj[4 * o], r0 = tobj[4 * o + 1], r1 = tobj[4 * o + 2], r2 = tobj[4 * o + 3];
-                const int kb0 = __float_as_int(r0.w), kb1 = __float_as_int(r1.w);
+                const float4 o0 = tobj[6 * o], r0 = tobj[6 * o + 1], r1 = tobj[6 * o + 2], r2 = tobj[6 * o + 3], o4 = tobj[6 * o + 4];
+                const int kb0 = __float_as_int(r0.w), kb1 = __float_as_int(r1.w), k0 = __float_as_int(r2.w), ns = __float_as_int(o4.x);
                 float Xo[ND > 0 ? ND : 1][3], best[ND > 0 ? ND : 1];
-                int bb[ND > 0 ? ND : 1];
+                int bsel[ND > 0 ? ND : 1];
                 sfor<ND>([&](auto kc) {
                     constexpr int b = T::tix(CM::pt_link[Plan::dyn_point(decltype(kc)::value)]);
                     to_object(o0, r0, r1, r2, Pb[b][0], Pb[b][1], Pb[b][2], Xo[kc][0], Xo[kc][1], Xo[kc][2]);
-                    best[kc] = kInf; bb[kc] = -1;
+                    best[kc] = kInf; bsel[kc] = -1;
                 });
-                float4 bc = tq[2 * kb0], bh = tq[2 * kb0 + 1];
-#pragma unroll 1
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    const float4 c = bc, hh = bh;
-                    const int kn = (kb + 1 < kb1) ? kb + 1 : kb;        // the next box is in flight during this one
-                    bc = tq[2 * kn]; bh = tq[2 * kn + 1];
+                if (ns > 0) {
+                    const float4 o5 = tobj[6 * o + 5];
+                    const float4* sphs = gsph + k0;
+                    bool exact = o5.z == 0.f;                     // unequal radii: every sphere exactly (rare: the shipped scenes are uniform)
+                    if (!exact) {
+                        // joint scan of the object's equal-radius spheres: keys |c|^2 - 2 x.c, two spheres per FFMA2, the two smallest
+                        // per point; a near tie (or NaN) on any point sends the object to the exact loop
+                        const float4* pq = gq + 2 * __float_as_int(o4.y);
+                        const int np2 = __float_as_int(o4.z);
+                        const unsigned lowmask = (unsigned)__float_as_int(o4.w), keep = ~lowmask;
+                        float m1[ND > 0 ? ND : 1], m2[ND > 0 ? ND : 1];
 #pragma unroll
-                    for (int k = 0; k < ND; ++k) {
-                        const float sd = box_sdf(c, hh, Xo[k][0], Xo[k][1], Xo[k][2]);
-                        const bool better = sd < best[k];                // strict: the earlier primitive wins ties
-                        best[k] = better ? sd : best[k];
-                        bb[k] = better ? kb : bb[k];
+                        for (int k = 0; k < ND; ++k) { m1[k] = kInf; m2[k] = kInf; }
+                        unsigned idx = 0u;
+                        float4 t0 = pq[0], t1 = pq[1];
+#pragma unroll 1
+                        for (int j = 0; j < np2; ++j, idx += 2u) {
+                            const float2 cx = make_float2(t0.x, t0.y), cy = make_float2(t0.z, t0.w), cz = make_float2(t1.x, t1.y), cw = make_float2(t1.z, t1.w);
+                            const int jn = (j + 1 < np2) ? j + 1 : j;
+                            t0 = pq[2 * jn]; t1 = pq[2 * jn + 1];
+#pragma unroll
+                            for (int k = 0; k < ND; ++k) {
+                                const float2 k2 = __ffma2_rn(make_float2(Xo[k][0], Xo[k][0]), cx,
+                                                             __ffma2_rn(make_float2(Xo[k][1], Xo[k][1]), cy, __ffma2_rn(make_float2(Xo[k][2], Xo[k][2]), cz, cw)));
+                                const float pa = __uint_as_float((__float_as_uint(k2.x) & keep) | idx);
+                                const float pb = __uint_as_float((__float_as_uint(k2.y) & keep) | (idx + 1u));
+                                const float lo = fminf(pa, pb), hi = fmaxf(pa, pb);
+                                m2[k] = fmin3(fmaxf(m1[k], lo), m2[k], hi);
+                                m1[k] = fminf(m1[k], lo);
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < ND; ++k) {
+                            const float xx = __fmaf_rn(Xo[k][2], Xo[k][2], __fmaf_rn(Xo[k][1], Xo[k][1], __fmul_rn(Xo[k][0], Xo[k][0])));
+                            exact = exact || !((m2[k] - m1[k]) > o5.x * (xx + o5.y));
+                            bsel[k] = (int)(__float_as_uint(m1[k]) & lowmask);
+                        }
+                        if (!exact) {
+#pragma unroll
+                            for (int k = 0; k < ND; ++k) {
+                                const float4 c = sphs[bsel[k]];
+                                best[k] = __fsub_rn(norm3_rn(__fsub_rn(Xo[k][0], c.x), __fsub_rn(Xo[k][1], c.y), __fsub_rn(Xo[k][2], c.z)), c.w);
+                            }
+                        }
+                    }
+                    if (exact) {                                   // first index wins ties (strict <)
+#pragma unroll
+                        for (int k = 0; k < ND; ++k) { best[k] = kInf; bsel[k] = 0; }
+#pragma unroll 1
+                        for (int kk = 0; kk < ns; ++kk) {
+                            const float4 c = sphs[kk];
+#pragma unroll
+                            for (int k = 0; k < ND; ++k) {
+                                const float sd = __fsub_rn(norm3_rn(__fsub_rn(Xo[k][0], c.x), __fsub_rn(Xo[k][1], c.y), __fsub_rn(Xo[k][2], c.z)), c.w);
+                                const bool better = sd < best[k];
+                                best[k] = better ? sd : best[k];
+                                bsel[k] = better ? kk : bsel[k];
+                            }
+                        }
+                    }
+                }
+                if (kb0 < kb1) {
+                    float4 bc = tq[2 * kb0], bh = tq[2 * kb0 + 1];
+#pragma unroll 1
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        const float4 c = bc, hh = bh;
+                        const int kn = (kb + 1 < kb1) ? kb + 1 : kb;        // the next box is in flight during this one
+                        bc = tq[2 * kn]; bh = tq[2 * kn + 1];
+#pragma unroll
+                        for (int k = 0; k < ND; ++k) {
+                            const float sd = box_sdf(c, hh, Xo[k][0], Xo[k][1], Xo[k][2]);
+                            const bool better = sd < best[k];                // strict: the earlier primitive wins ties
+                            best[k] = better ? sd : best[k];
+                            bsel[k] = better ? ns + (kb - kb0) : bsel[k];
+                        }
                     }
                 }
                 sfor<ND>([&](auto kc) {
                     constexpr int k = decltype(kc)::value, s = Plan::dyn_point(k);
                     occ_obj = occ_obj || (best[k] < hp.mo_obj[s]);
                     const float val = -__fsub_rn(best[k], hp.m_obj[s]);
-                    if (argmin && live) argmin[cfg * (long long)(hp.n_obj * S) + o * S + s] = bb[k] >= 0 ? bb[k] - kb0 : 0;
-                    if (o == 0 || val > vmax[k]) { vmax[k] = val; wobj[k] = o; wbox[k] = bb[k]; }   // the first maximal object keeps the gradient
+                    if (argmin && live) argmin[cfg * (long long)(hp.n_obj * S) + o * S + s] = bsel[k] >= 0 ? bsel[k] : 0;
+                    if (o == 0 || val > vmax[k]) { vmax[k] = val; wobj[k] = o; wsel[k] = bsel[k]; }   // the first maximal object keeps the gradient
                 });
             }
             sfor<ND>([&](auto kc) {
@@ -708,12 +790,22 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
                 c_obj = __fadd_rn(c_obj, vmax[k]);
                 float gx = 0.f, gy = 0.f, gz = 0.f;
                 if constexpr (WANT_GRAD) {
-                    if (wbox[k] >= 0) {
+                    if (wsel[k] >= 0) {
                         const int o = wobj[k];
-                        const float4 o0 = tobj[4 * o], r0 = tobj[4 * o + 1], r1 = tobj[4 * o + 2], r2 = tobj[4 * o + 3];
+                        const float4 o0 = tobj[6 * o], r0 = tobj[6 * o + 1], r1 = tobj[6 * o + 2], r2 = tobj[6 * o + 3];
+                        const int ns = __float_as_int(tobj[6 * o + 4].x);
                         float xo, yo, zo, ux, uy, uz;
                         to_object(o0, r0, r1, r2, x, y, z, xo, yo, zo);
-                        box_sdf_grad(tq[2 * wbox[k]], tq[2 * wbox[k] + 1], xo, yo, zo, ux, uy, uz);
+                        if (wsel[k] < ns) {          // unit vector from the sphere centre to the point (zero when they coincide)
+                            const float4 c = gsph[__float_as_int(r2.w) + wsel[k]];
+                            const float vx = __fsub_rn(xo, c.x), vy = __fsub_rn(yo, c.y), vz = __fsub_rn(zo, c.z);
+                            float rs;
+                            norm3_clamped(vx, vy, vz, rs);
+                            ux = vx * rs; uy = vy * rs; uz = vz * rs;
+                        } else {
+                            const int kb = __float_as_int(r0.w) + (wsel[k] - ns);
+                            box_sdf_grad(tq[2 * kb], tq[2 * kb + 1], xo, yo, zo, ux, uy, uz);
+                        }
                         if (o0.w == 0.f) {         // back to the world frame: g = R g'
                             const float wx = r0.x * ux + r0.y * uy + r0.z * uz, wy = r1.x * ux + r1.y * uy + r1.z * uz,
                                         wz = r2.x * ux + r2.y * uy + r2.z * uz;

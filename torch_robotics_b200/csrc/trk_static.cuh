@@ -1520,20 +1520,23 @@ inline void hot_params_from_cost(const float* hw, float margin_override, int use
     }
 }
 
-// Box scene (SCENE == 1 of k_objective_hot): offsets of the general tables, and the collision points at constant positions
+// General scene (SCENE == 1 of k_objective_hot): offsets of the general tables, and the collision points at constant positions
 // evaluated once on the host with the device arithmetic of object_point_term / box_sdf (trk_device.cuh) restated in correctly
-// rounded host operations: per object the nearest box (strict <: the earlier one wins ties), occupancy against the
-// occupancy margin, value = margin - sdf, the first maximal object keeps it; then the workspace term as in the sphere scene.
+// rounded host operations: per object the nearest primitive (spheres first, then boxes; strict <: the earlier one wins ties),
+// occupancy against the occupancy margin, value = margin - sdf, the first maximal object keeps it; then the workspace term.
 template <class R, class CM, int EE>
 inline void hot_params_box_scene(const float* hw, HotParams& hp) {
     const CostHeader* h = reinterpret_cast<const CostHeader*>(hw);
     const int* iw = reinterpret_cast<const int*>(hw);
     hp.n_obj = h->nObj; hp.n_box = h->KB; hp.off_box = h->off_box; hp.off_obj_box_start = h->off_obj_box_start;
     hp.off_obj_ident = h->off_obj_ident; hp.off_obj_R = h->off_obj_R; hp.off_obj_pos = h->off_obj_pos;
+    hp.n_sph_all = h->K; hp.n_sphq_all = iw[h->off_obj_qstart + h->nObj]; hp.off_sph_all = h->off_sph; hp.off_sphq_all = h->off_sphq;
+    hp.off_obj_start = h->off_obj_start; hp.off_obj_qstart = h->off_obj_qstart; hp.off_obj_tol = h->off_obj_tol; hp.off_obj_c2max = h->off_obj_c2max;
     hp.n_pairs2 = 0; hp.n_sph = 0;
     hp.c_obj_const = 0.f; hp.c_ws_const = 0.f; hp.occ_const = 0u;
     constexpr auto cp = HotPlan<R, CM, EE>::kConstPoints;
     const float* box = hw + h->off_box;
+    const float* sph = hw + h->off_sph;
     auto host_box_sdf = [&](int kb, float x, float y, float z) {
         const float* c = box + 8 * kb;
         const float* hh = c + 4;
@@ -1561,14 +1564,21 @@ inline void hot_params_box_scene(const float* hw, HotParams& hp) {
                 yo = fmaf(d2, Ro[7], fmaf(d1, Ro[4], d0 * Ro[1]));
                 zo = fmaf(d2, Ro[8], fmaf(d1, Ro[5], d0 * Ro[2]));
             }
+            const int k0 = iw[h->off_obj_start + o], k1 = iw[h->off_obj_start + o + 1];
             const int kb0 = iw[h->off_obj_box_start + o], kb1 = iw[h->off_obj_box_start + o + 1];
             float best = INFINITY;
-            int bb = -1;
+            int sel = -1;
+            for (int k = k0; k < k1; ++k) {
+                const float vx = xo - sph[4 * k], vy = yo - sph[4 * k + 1], vz = zo - sph[4 * k + 2];
+                const float sd = sqrtf(fmaf(vz, vz, fmaf(vy, vy, vx * vx))) - sph[4 * k + 3];
+                if (sd < best) { best = sd; sel = k - k0; }         // strict: the first index wins ties
+            }
+            if (k1 > k0 && sel < 0) sel = 0;                         // NaN position: the exact scan leaves index 0 (best stays inf)
             for (int kb = kb0; kb < kb1; ++kb) {
                 const float sd = host_box_sdf(kb, xo, yo, zo);
-                if (sd < best) { best = sd; bb = kb; }
+                if (sd < best) { best = sd; sel = (k1 - k0) + (kb - kb0); }
             }
-            if (o < kHotMaxObjects) hp.widx_const_obj[o][s2] = bb >= 0 ? bb - kb0 : 0;
+            if (o < kHotMaxObjects) hp.widx_const_obj[o][s2] = sel >= 0 ? sel : 0;
             if (best < hp.mo_obj[s2]) hp.occ_const |= TRK_OCC_OBJECT;
             const float val = -(best - hp.m_obj[s2]);
             if (o == 0 || val > vmax) vmax = val;
@@ -1590,7 +1600,7 @@ inline cudaError_t launch_objective_hot(int n_sms, const float* host_words, cons
     HotParams hp;
     hot_params_from_cost<R, CM, EE>(host_words, margin_override, use_override, hp, box_scene);
     if (box_scene) hot_params_box_scene<R, CM, EE>(host_words, hp);
-    const size_t smem = box_scene ? ((size_t)hp.n_box * 8 + (size_t)hp.n_obj * 16) * sizeof(float)
+    const size_t smem = box_scene ? ((size_t)hp.n_box * 8 + (size_t)hp.n_sph_all * 4 + (size_t)hp.n_sphq_all * 4 + (size_t)hp.n_obj * 24) * sizeof(float)
                                   : ((size_t)hp.n_pairs2 * 8 + (size_t)hp.n_sph * 4 + (TRK_HOT_QSTAGE >= 2 ? 2 * kSBlock * R::D : 0)) * sizeof(float);
     auto launch = [&](auto k) {
         if (smem > 48 * 1024) {
@@ -1746,7 +1756,7 @@ cudaError_t launch_objective_t(int n_sms, const float* host_words, const float* 
                     return launch_objective_hot<R, CM, kEE>(n_sms, host_words, cost_words, q, n, ee_target_cfg, margin_override, use_override,
                                                             cost_total, cost_terms, grad_q, occupancy, argmin, block_sums, n_block_sums, st);
                 }
-                // the same kernel on a scene of boxes (EnvTableShelf, EnvMazeBoxes3D, ...): bit 4 already says "no relu"
+                // the same kernel on a general scene (EnvTableShelf, EnvMazeBoxes3D, EnvSpheres3DExtraObjects, ...): bit 4 already says "no relu"
                 if (CollisionModelOf<R>::hot_scenes && (cm_match & 24) == 24 && ee_ok && !no_hot && q_ok &&
                     (!ee_target_cfg || (reinterpret_cast<uintptr_t>(ee_target_cfg) & 15u) == 0)) {
                     constexpr int kEE = STree<R>::topo_index_of(CM::ee_body);
@@ -1872,11 +1882,11 @@ inline int cm_match_value(const float* host_cost_words) {
         const bool joint_scene = hh->nObj == 1 && hh->KB == 0 && (iw[hh->off_obj_ident] & (need | OBJ_GRID)) == need &&
                                  iw[hh->off_obj_start + 1] > iw[hh->off_obj_start];
         const bool hot_terms = hh->ws_enabled && (!hh->ee_enabled || (hh->ee_w_pos > 0.f && hh->ee_w_rot > 0.f));
-        // box scene: 1 .. kHotMaxObjects objects, each made of boxes only (no spheres, no voxel grid), nothing relu-clamped
-        bool box_scene = hh->nObj >= 1 && hh->nObj <= kHotMaxObjects && hh->KB > 0 && !hh->clamp_self && !hh->clamp_obj && !hh->clamp_ws;
+        // general scene: 1 .. kHotMaxObjects posed objects of spheres and / or boxes (no voxel grid), nothing relu-clamped
+        bool box_scene = hh->nObj >= 1 && hh->nObj <= kHotMaxObjects && !hh->clamp_self && !hh->clamp_obj && !hh->clamp_ws;
         for (int o = 0; box_scene && o < hh->nObj; ++o)
-            box_scene = iw[hh->off_obj_start + o + 1] == iw[hh->off_obj_start + o] && !(iw[hh->off_obj_ident + o] & OBJ_GRID) &&
-                        iw[hh->off_obj_box_start + o + 1] > iw[hh->off_obj_box_start + o];
+            box_scene = !(iw[hh->off_obj_ident + o] & OBJ_GRID) &&
+                        (iw[hh->off_obj_start + o + 1] > iw[hh->off_obj_start + o] || iw[hh->off_obj_box_start + o + 1] > iw[hh->off_obj_box_start + o]);
         return 1 | ((hh->ee_enabled && hh->ee_link == CM::ee_body) ? 2 : 0) | (joint_scene ? 4 : 0) | (hot_terms ? 8 : 0) | (box_scene ? 16 : 0) |
                (hh->ee_enabled ? 0 : 32);
     }
@@ -1885,7 +1895,7 @@ inline int cm_match_value(const float* host_cost_words) {
 // > 0 when `family` has a compile-time collision model and the (host copy of the) cost table matches it;
 // bit 1: the end-effector term is enabled on the model's own EE body (CM::ee_body); bit 2: the scene is one equal-radius
 // identity-pose sphere object (the joint-scan scene); bit 3: workspace box on and, with an EE term, both EE weights positive
-// (what k_objective_hot assumes); bit 4: a scene of boxes only, nothing relu-clamped; bit 5: no EE term at all
+// (what k_objective_hot assumes); bit 4: a general scene (<= 4 posed objects of spheres / boxes, no grid), nothing relu-clamped; bit 5: no EE term at all
 inline int static_cm_match(int family, const float* host_cost_words) {
     int id = 0;
 #define X(Rb)                                                                          \
