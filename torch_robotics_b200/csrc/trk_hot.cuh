@@ -68,6 +68,13 @@ struct HotParams {
     int   n_obj, n_box, off_box, off_obj_box_start, off_obj_ident, off_obj_R, off_obj_pos;
     int   n_sph_all, n_sphq_all, off_sph_all, off_sphq_all, off_obj_start, off_obj_qstart, off_obj_tol, off_obj_c2max;
     int   widx_const_obj[4][kHotMaxPoints];
+    // voxel-SDF object of a general scene (grid_map_sdf.py; identity pose, owns no primitives): cell = clamp(floor((x - lo) /
+    // extent * nf)), one float4 (sdf, gradient) per cell in HBM.  The host cannot read the grid, so the constant points are
+    // evaluated by the kernel there: vconst[s] = their value over the other objects (-inf when there are none)
+    int   grid_obj, grid_n[3];           // grid_obj < 0: no voxel grid
+    float grid_lo[3], grid_extent[3], grid_nf[3];
+    const float4* grid_data;
+    float vconst[kHotMaxPoints];
 };
 constexpr int kHotMaxObjects = 4;
 
@@ -435,7 +442,7 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
     if constexpr (SCENE == 1) {
         // general scene: [2 n_box] boxes (c.xyz, radius | half.xyz, rounded flag) | [n_sph_all] spheres (c, r) | [2 n_sphq_all]
         // scan table, two spheres interleaved | [6 n_obj] objects: (pos.xyz, identity flag) (R rows; .w: box range, first sphere)
-        // (sphere count, first scan pair, scan pairs, index mask) (tol, c2max, uniform-radius flag, -)
+        // (sphere count, first scan pair, scan pairs, index mask) (tol, c2max, uniform-radius flag, voxel-grid flag)
         const float4* box = reinterpret_cast<const float4*>(cost_words + hp.off_box);
         for (int i = tid; i < 2 * hp.n_box; i += kSBlock) tq[i] = __ldg(box + i);
         float4* gsph = tq + 2 * hp.n_box;
@@ -461,7 +468,8 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
             tobj[6 * o + 3] = make_float4(Ro[6], Ro[7], Ro[8], __int_as_float(k0));
             tobj[6 * o + 4] = make_float4(__int_as_float(k1 - k0), __int_as_float(q0 / 2), __int_as_float((q1 - q0) / 2),
                                           __int_as_float((1 << (flags >> OBJ_BITS_SHIFT)) - 1));
-            tobj[6 * o + 5] = make_float4(cost_words[hp.off_obj_tol + o], cost_words[hp.off_obj_c2max + o], (flags & OBJ_UNIFORM_RADIUS) ? 1.f : 0.f, 0.f);
+            tobj[6 * o + 5] = make_float4(cost_words[hp.off_obj_tol + o], cost_words[hp.off_obj_c2max + o], (flags & OBJ_UNIFORM_RADIUS) ? 1.f : 0.f,
+                                          (flags & OBJ_GRID) ? 1.f : 0.f);
         }
     } else {
         const float* sphq = cost_words + hp.off_sphq;
@@ -699,8 +707,33 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
                     to_object(o0, r0, r1, r2, Pb[b][0], Pb[b][1], Pb[b][2], Xo[kc][0], Xo[kc][1], Xo[kc][2]);
                     best[kc] = kInf; bsel[kc] = -1;
                 });
+                const float4 o5 = tobj[6 * o + 5];
+                if (o5.w != 0.f) {           // voxel SDF lookup (grid_map_sdf.py:96-112): one 16-byte gather per point
+                    auto lookup = [&](float x, float y, float z, float& sd) {
+                        const int i0 = grid_cell(x, hp.grid_lo[0], hp.grid_extent[0], hp.grid_nf[0], hp.grid_n[0]);
+                        const int i1 = grid_cell(y, hp.grid_lo[1], hp.grid_extent[1], hp.grid_nf[1], hp.grid_n[1]);
+                        const int i2 = grid_cell(z, hp.grid_lo[2], hp.grid_extent[2], hp.grid_nf[2], hp.grid_n[2]);
+                        const int idx = (i0 * hp.grid_n[1] + i1) * hp.grid_n[2] + i2;
+                        sd = __ldg(&hp.grid_data[idx].x);
+                        return idx;
+                    };
+#pragma unroll
+                    for (int k = 0; k < ND; ++k) bsel[k] = lookup(Xo[k][0], Xo[k][1], Xo[k][2], best[k]);
+                    // the constant points: the same cell for every configuration (an L1 hit), combined with the host's value
+                    // over the other objects
+                    sfor<S>([&](auto sc) {
+                        constexpr int s = decltype(sc)::value;
+                        if constexpr (Plan::dyn_rank(s) < 0) {
+                            constexpr auto cp = Plan::kConstPoints;
+                            float sd;
+                            const int idx = lookup(cp.pos[s][0], cp.pos[s][1], cp.pos[s][2], sd);
+                            occ_obj = occ_obj || (sd < hp.mo_obj[s]);
+                            c_obj = __fadd_rn(c_obj, fmaxf(hp.vconst[s], -__fsub_rn(sd, hp.m_obj[s])));
+                            if (argmin && live) argmin[cfg * (long long)(hp.n_obj * S) + o * S + s] = idx;
+                        }
+                    });
+                }
                 if (ns > 0) {
-                    const float4 o5 = tobj[6 * o + 5];
                     const float4* sphs = gsph + k0;
                     bool exact = o5.z == 0.f;                     // unequal radii: every sphere exactly (rare: the shipped scenes are uniform)
                     if (!exact) {
@@ -796,7 +829,10 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
                         const int ns = __float_as_int(tobj[6 * o + 4].x);
                         float xo, yo, zo, ux, uy, uz;
                         to_object(o0, r0, r1, r2, x, y, z, xo, yo, zo);
-                        if (wsel[k] < ns) {          // unit vector from the sphere centre to the point (zero when they coincide)
+                        if (tobj[6 * o + 5].w != 0.f) {      // voxel grid: the cell carries the gradient
+                            const float4 cell = __ldg(hp.grid_data + wsel[k]);
+                            ux = cell.y; uy = cell.z; uz = cell.w;
+                        } else if (wsel[k] < ns) {   // unit vector from the sphere centre to the point (zero when they coincide)
                             const float4 c = gsph[__float_as_int(r2.w) + wsel[k]];
                             const float vx = __fsub_rn(xo, c.x), vy = __fsub_rn(yo, c.y), vz = __fsub_rn(zo, c.z);
                             float rs;
@@ -897,6 +933,7 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
             if (argmin) {
                 if constexpr (SCENE == 1) {      // the moving points' entries were written object by object; the constant points' here
                     for (int o = 0; o < hp.n_obj; ++o) {
+                        if (o == hp.grid_obj) continue;       // written with the lookup
                         int* row = argmin + cfg * (long long)(hp.n_obj * S) + o * S;
                         sfor<S>([&](auto sc) {
                             constexpr int s = decltype(sc)::value;

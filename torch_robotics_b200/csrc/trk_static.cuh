@@ -1534,6 +1534,8 @@ inline void hot_params_box_scene(const float* hw, HotParams& hp) {
     hp.off_obj_start = h->off_obj_start; hp.off_obj_qstart = h->off_obj_qstart; hp.off_obj_tol = h->off_obj_tol; hp.off_obj_c2max = h->off_obj_c2max;
     hp.n_pairs2 = 0; hp.n_sph = 0;
     hp.c_obj_const = 0.f; hp.c_ws_const = 0.f; hp.occ_const = 0u;
+    hp.grid_obj = h->grid_obj; hp.grid_data = h->grid_data;
+    for (int i = 0; i < 3; ++i) { hp.grid_n[i] = h->grid_n[i]; hp.grid_lo[i] = h->grid_lo[i]; hp.grid_extent[i] = h->grid_extent[i]; hp.grid_nf[i] = h->grid_nf[i]; }
     constexpr auto cp = HotPlan<R, CM, EE>::kConstPoints;
     const float* box = hw + h->off_box;
     const float* sph = hw + h->off_sph;
@@ -1553,8 +1555,10 @@ inline void hot_params_box_scene(const float* hw, HotParams& hp) {
     for (int s2 = 0; s2 < CM::S; ++s2) {
         if (!cp.is_const[s2]) continue;
         const float x = cp.pos[s2][0], y = cp.pos[s2][1], z = cp.pos[s2][2];
-        float vmax = 0.f;
+        float vmax = -INFINITY;           // over the objects the host can evaluate (not the voxel grid: the kernel looks it up)
+        bool first = true;
         for (int o = 0; o < h->nObj; ++o) {
+            if (o == h->grid_obj) continue;
             float xo = x, yo = y, zo = z;
             if (!(iw[h->off_obj_ident + o] & OBJ_IDENTITY)) {
                 const float* Ro = hw + h->off_obj_R + 9 * o;
@@ -1581,9 +1585,11 @@ inline void hot_params_box_scene(const float* hw, HotParams& hp) {
             if (o < kHotMaxObjects) hp.widx_const_obj[o][s2] = sel >= 0 ? sel : 0;
             if (best < hp.mo_obj[s2]) hp.occ_const |= TRK_OCC_OBJECT;
             const float val = -(best - hp.m_obj[s2]);
-            if (o == 0 || val > vmax) vmax = val;
+            if (first || val > vmax) vmax = val;
+            first = false;
         }
-        hp.c_obj_const = hp.c_obj_const + vmax;
+        hp.vconst[s2] = vmax;
+        if (h->grid_obj < 0) hp.c_obj_const = hp.c_obj_const + vmax;      // with a grid the kernel adds max(vconst, grid value)
         const float d[6] = {x - hp.ws_min[0], y - hp.ws_min[1], z - hp.ws_min[2], hp.ws_max[0] - x, hp.ws_max[1] - y, hp.ws_max[2] - z};
         float dmin = d[0];
         for (int i = 1; i < 6; ++i) dmin = fminf(dmin, d[i]);
@@ -1882,11 +1888,11 @@ inline int cm_match_value(const float* host_cost_words) {
         const bool joint_scene = hh->nObj == 1 && hh->KB == 0 && (iw[hh->off_obj_ident] & (need | OBJ_GRID)) == need &&
                                  iw[hh->off_obj_start + 1] > iw[hh->off_obj_start];
         const bool hot_terms = hh->ws_enabled && (!hh->ee_enabled || (hh->ee_w_pos > 0.f && hh->ee_w_rot > 0.f));
-        // general scene: 1 .. kHotMaxObjects posed objects of spheres and / or boxes (no voxel grid), nothing relu-clamped
+        // general scene: 1 .. kHotMaxObjects objects - posed sets of spheres and / or boxes, the voxel-SDF object -, nothing relu-clamped
         bool box_scene = hh->nObj >= 1 && hh->nObj <= kHotMaxObjects && !hh->clamp_self && !hh->clamp_obj && !hh->clamp_ws;
         for (int o = 0; box_scene && o < hh->nObj; ++o)
-            box_scene = !(iw[hh->off_obj_ident + o] & OBJ_GRID) &&
-                        (iw[hh->off_obj_start + o + 1] > iw[hh->off_obj_start + o] || iw[hh->off_obj_box_start + o + 1] > iw[hh->off_obj_box_start + o]);
+            box_scene = (iw[hh->off_obj_ident + o] & OBJ_GRID) || iw[hh->off_obj_start + o + 1] > iw[hh->off_obj_start + o] ||
+                        iw[hh->off_obj_box_start + o + 1] > iw[hh->off_obj_box_start + o];
         return 1 | ((hh->ee_enabled && hh->ee_link == CM::ee_body) ? 2 : 0) | (joint_scene ? 4 : 0) | (hot_terms ? 8 : 0) | (box_scene ? 16 : 0) |
                (hh->ee_enabled ? 0 : 32);
     }
