@@ -471,6 +471,10 @@ def main():
     extra = {}
     if rank == 0 and world == 1 and not args.skip_extra:
         extra = secondary_kernels(torch, model, desc, q, dev)
+        try:
+            extra["scenes"] = scene_lines(torch, dev)
+        except Exception as e:      # informative block: never lose the headline line over it
+            extra["scenes"] = {"unavailable": f"{type(e).__name__}: {e}"}
 
     sampler.stop_flag = True
     times = torch.tensor([span_ms, total_ms, e2e_s, copy_s], dtype=torch.float64, device=dev)
@@ -646,6 +650,42 @@ def bench_cfg5(torch, dist, D, dev, rank, world, run_steps, n_total=1 << 24):
             "configs_total": n_total, "configs_per_rank": ns, "ms_per_step": ms, "ms_kernel": ms_k, "configs_per_s": n_total / (ms * 1e-3),
             "fp32_frac_per_gpu": ns / (ms_k * 1e-3) * 5880 / fp32_peak, "flop_per_config": 5880, "kernel_family": mdl.kernel_family,
             "collective_ms": float(np.median(coll)) if (coll and world > 1) else 0.0, "total_cost": s_sum, "scaling": "strong"}
+
+
+def scene_lines(torch, dev):
+    """PlanningTask.compute_cost_and_grad (the three collision fields, no EE term) on the shipped 3-D environments, 1,048,576
+    configurations: the callers' usual entry point, served by the headline kernel's scene variants."""
+    from torch_robotics_b200.environments.env_maze_boxes_3d import EnvMazeBoxes3D
+    from torch_robotics_b200.environments.env_spheres_3d import EnvSpheres3D
+    from torch_robotics_b200.environments.env_spheres_3d_extra_objects import EnvSpheres3DExtraObjects
+    from torch_robotics_b200.environments.env_table_shelf import EnvTableShelf
+    from torch_robotics_b200.robots.robot_panda import RobotPanda
+    from torch_robotics_b200.tasks.tasks import PlanningTask
+    TA = dict(device=str(dev), dtype=torch.float32)
+    robot = RobotPanda(tensor_args=TA)
+    b, h = 16384, 64
+    q = robot.q_min + torch.rand(b, h, 7, device=dev) * (robot.q_max - robot.q_min)
+    out = {}
+    for name, mk in (("EnvSpheres3D", lambda: EnvSpheres3D(tensor_args=TA)),
+                     ("EnvSpheres3DExtraObjects", lambda: EnvSpheres3DExtraObjects(tensor_args=TA)),
+                     ("EnvTableShelf", lambda: EnvTableShelf(tensor_args=TA)),
+                     ("EnvMazeBoxes3D", lambda: EnvMazeBoxes3D(tensor_args=TA)),
+                     ("EnvTableShelf_voxel_sdf_1cm", lambda: EnvTableShelf(precompute_sdf_obj_fixed=True, sdf_cell_size=0.01, tensor_args=TA))):
+        task = PlanningTask(env=mk(), robot=robot, tensor_args=TA)
+        for _ in range(3):
+            task.compute_cost_and_grad(q)
+        torch.cuda.synchronize()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            task.compute_cost_and_grad(q)
+        e.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(e) / 10
+        out[name] = {"ms": ms, "configs_per_s": b * h / ms * 1e3}
+        del task
+    out["note"] = "PlanningTask.compute_cost_and_grad (self + objects + workspace, no EE term), 16384 x 64 configurations, 10 calls"
+    return out
 
 
 def secondary_kernels(torch, model, desc, q, dev):

@@ -85,6 +85,30 @@ m3.ik_adam(torch.as_tensor(rng.uniform(-1, 1, (333, 7)).astype(np.float32), devi
            se3_eps=0.05, best_k=8)
 m3.geometric_jacobian(q3, 10, 0x7f)
 DeviceModel(get_desc("tiago_dual_holo"), dev).geometric_jacobian(torch.zeros(40, 14, device=dev), 12, 0x3fff)
+# later in round 2: the headline kernel's scene variants (no EE term; boxes, two sphere objects, voxel grid + extra object),
+# and a library specialised at run time
+from torch_robotics_b200.environments.env_maze_boxes_3d import EnvMazeBoxes3D
+from torch_robotics_b200.environments.env_spheres_3d_extra_objects import EnvSpheres3DExtraObjects
+from torch_robotics_b200.environments.env_table_shelf import EnvTableShelf
+robot_p = RobotPanda(tensor_args=TA)
+for mk in (lambda: EnvSpheres3D(tensor_args=TA), lambda: EnvTableShelf(tensor_args=TA), lambda: EnvMazeBoxes3D(tensor_args=TA),
+           lambda: EnvSpheres3DExtraObjects(tensor_args=TA),
+           lambda: EnvSpheres3DExtraObjects(precompute_sdf_obj_fixed=True, sdf_cell_size=0.05, tensor_args=TA)):
+    task = PlanningTask(env=mk(), robot=robot_p, tensor_args=TA)
+    qt = (robot_p.q_min + torch.rand(3, 43, 7, device=dev) * (robot_p.q_max - robot_p.q_min))
+    task.compute_cost_and_grad(qt)
+    task.compute_collision(qt, margin=0.0)
+    dcs = task._fused_cost(qt.device)
+    dcs.objective(qt.reshape(-1, 7), want_grad=True, want_terms=True, want_occupancy=True, want_argmin=True)
+
+import specialized_cases as sc
+from torch_robotics_b200 import specialize as sp
+d_i = sc.iiwa7_allegro_desc()
+m_i = DeviceModel(d_i, dev, library=sp.build_specialized_library(d_i))
+q_i = torch.rand(77, d_i.n_dofs, device=dev) - 0.5
+H_i = m_i.fk_forward(q_i)
+m_i.fk_backward(q_i, torch.randn_like(H_i))
+m_i.link_jacobian(q_i)
 X = (torch.rand(300, 3, device=dev) * 2.4 - 1.2).requires_grad_(True)
 env.grid_map_sdf_obj_fixed(X).sum().backward()
 torch.cuda.synchronize()
