@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q -x 2>&1 | tail -8 | tee gpurun_out/r2_gpu_tests_c.log
-python tools/time_objective.py 2>&1 | tail -1 | tee gpurun_out/r2_time_hot_c.json
-python tools/bench_envs.py 2>&1 | tail -6 | tee gpurun_out/r2_bench_envs.jsonl
+ncu --set full --clock-control none --import-source on -k regex:k_ik_adam_hot -s 1 -c 1 -f -o gpurun_out/r2_ik_hot python tools/bench_ik.py > gpurun_out/r2_ik_ncu.log 2>&1
+tail -2 gpurun_out/r2_ik_ncu.log
