@@ -154,6 +154,44 @@ def test_gpu_bit_exact_masks_vs_oracle(case):
     assert (gd >= 1e-4).sum() <= 30 and gd[gd < 1e-4].max() < 1e-4
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["grasped_box", "sphere_model"])
+@pytest.mark.parametrize("scene", ["table_shelf", "spheres3d_extra_voxel"])
+def test_gpu_attached_models_on_general_scenes_vs_oracle(case, scene):
+    """Attached-body Panda models on scenes beyond the single sphere object - posed rounded boxes; a voxel SDF plus an extra
+    sphere object - run on k_objective_ext<..., SCENE = 1> (general_scene_eval).  Terms, gradients, occupancy and per-object
+    arg-min against the C oracle; and against the runtime-tree kernels of the same library (TRK_B200_NO_HOT=1 in a fresh
+    process is not needed: the oracle is the reference of both)."""
+    from torch_robotics_b200._lib import DeviceCost, DeviceModel
+    from torch_robotics_b200.environments.env_spheres_3d_extra_objects import EnvSpheres3DExtraObjects
+    from torch_robotics_b200.environments.env_table_shelf import EnvTableShelf
+    from torch_robotics_b200.tasks.tasks import PlanningTask
+    TA = dict(device="cuda:0", dtype=torch.float32)
+    r = grasped_robot(TA) if case == "grasped_box" else sphere_robot(TA)
+    env = EnvTableShelf(tensor_args=TA) if scene == "table_shelf" else \
+        EnvSpheres3DExtraObjects(precompute_sdf_obj_fixed=True, sdf_cell_size=0.04, tensor_args=TA)
+    task = PlanningTask(env=env, robot=r, tensor_args=TA)
+    cost = task.cost_descriptor()
+    d = r.diff_panda._desc
+    rng = np.random.default_rng(19)
+    lo, hi = r.q_min.cpu().numpy(), r.q_max.cpu().numpy()
+    q = (lo + rng.random((20_011, 7), dtype=np.float32) * (hi - lo)).astype(np.float32)
+    dc = DeviceCost(DeviceModel(d, "cuda:0"), cost)
+    out = dc.objective(torch.as_tensor(q, device="cuda:0"), want_grad=True, want_terms=True, want_occupancy=True, want_argmin=True)
+    if getattr(cost, "grid_obj", -1) >= 0:      # the oracle reads the same grid
+        cost.grid_data = cost.grid_data.detach().cpu().numpy() if torch.is_tensor(cost.grid_data) else cost.grid_data
+    o = co.objective(co.Tree(d), co.Cost(cost), q)
+    assert rel_err(out["terms"].cpu().numpy(), o["terms"]) < 1e-5
+    same = np.all((out["argmin"].cpu().numpy() == o["argmin"]).reshape(len(q), -1), axis=1)
+    assert np.mean(same) > 0.998
+    gd = np.abs(out["grad_q"].cpu().numpy() - o["grad_q"]).max(axis=1) / np.abs(o["grad_q"]).max()
+    assert np.all(gd[same] < 1e-4)
+    assert np.mean(out["occupancy"].cpu().numpy() == o["occ"]) > 0.9995
+    occ0 = dc.objective(torch.as_tensor(q, device="cuda:0"), want_grad=False, want_terms=False, want_occupancy=True, margin_override=0.0)
+    o0 = co.objective(co.Tree(d), co.Cost(cost), q, margin_override=0.0)
+    assert np.mean(occ0["occupancy"].cpu().numpy() == o0["occ"]) > 0.9995
+
+
 # ---------------------------------------------------------------------------------------------- Tiago sphere model
 def tiago_with_spheres():
     """tiago_dual_holo (19 links, two arms) + the 14 spheres of data/configs/tiago, attached as points."""

@@ -1320,8 +1320,9 @@ static int objective_impl(const trk_model* m, const trk_cost* c, const float* q,
         // a compiled-in robot with attached bodies in the common scene: unrolled FK + points evaluated at their anchors (trk_ext.cuh)
         static const bool no_hot = getenv("TRK_B200_NO_HOT") != nullptr;   // A/B switch
         const int need = OBJ_IDENTITY | OBJ_UNIFORM_RADIUS;
-        const bool scene = gh->nObj == 1 && gh->KB == 0 && (giw[gh->off_obj_ident] & (need | OBJ_GRID)) == need &&
-                           giw[gh->off_obj_start + 1] > giw[gh->off_obj_start] && !gh->clamp_self && !gh->clamp_obj && !gh->clamp_ws &&
+        const bool sphere_scene = gh->nObj == 1 && gh->KB == 0 && (giw[gh->off_obj_ident] & (need | OBJ_GRID)) == need &&
+                                  giw[gh->off_obj_start + 1] > giw[gh->off_obj_start];
+        const bool scene = (sphere_scene || trk::general_scene_ok(c->h_words.data())) && !gh->clamp_self && !gh->clamp_obj && !gh->clamp_ws &&
                            gh->ws_enabled &&
                            (!gh->ee_enabled || (gh->ee_w_pos > 0.f && gh->ee_w_rot > 0.f && gh->ee_link == trk::static_family_last_body(m->ext_family)));
         if (scene && !no_hot) {

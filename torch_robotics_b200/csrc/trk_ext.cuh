@@ -54,6 +54,14 @@ struct alignas(16) ExtParams {     // kernel parameter; the block's shared memor
     int ee_square, ee_enabled, use_override; float margin_override;
     int off_sphq, off_sph, ext_nwords, o_ew;
     int o_run, o_item, n_runs, n_points;
+    // general scene (scene == 1: the tables of general_scene_eval, trk_hot.cuh) instead of the single sphere object
+    int scene, n_obj, n_box, n_sph_all;
+    int n_sphq_all, off_box, off_sph_all, off_sphq_all;
+    int off_obj_box_start, off_obj_ident, off_obj_R, off_obj_pos;
+    int off_obj_start, off_obj_qstart, off_obj_tol, off_obj_c2max;
+    int o_gbox, grid_n[3];
+    float grid_lo[3], grid_extent[3], grid_nf[3], pad2[3];
+    const float4* grid_data; long long pad3;
 };
 constexpr int kExtParamWords = (int)(sizeof(ExtParams) / 4);
 
@@ -64,12 +72,60 @@ struct ExtConsts {
     float4 wmin, wmax;                 // workspace box; .w = weight of the object term / of the workspace term
     float tol, tol_c2; unsigned lowmask; int n_pairs2;
     const float4* tq; const float4* tsph;
+    GeneralScene GS;                   // scene == 1 only
 };
-template <int W, bool GRAD, bool ARGMIN>
+template <int W, bool GRAD, bool ARGMIN, int SCENE>
 static __device__ __forceinline__ void ext_group(float r0, float r1, float r2, float r3, float r4, float r5, float r6, float r7, float r8,
                                                  float px, float py, float pz, const float4* __restrict__ rec, const ExtConsts& K,
                                                  const ExtParams* __restrict__ ep, int* __restrict__ argmin_row, ExtAcc& A) {
     const float kInf = __int_as_float(0x7f800000);
+    // workspace box of one point (distance_fields.py:319-332) + the point's force (gx, gy, gz: the object term's share) into the wrench
+    auto ws_and_wrench = [&](const float4 mr, float x, float y, float z, float gx, float gy, float gz) {
+        const float e0 = __fsub_rn(x, K.wmin.x), e1 = __fsub_rn(y, K.wmin.y), e2 = __fsub_rn(z, K.wmin.z);
+        const float f0 = __fsub_rn(K.wmax.x, x), f1 = __fsub_rn(K.wmax.y, y), f2 = __fsub_rn(K.wmax.z, z);
+        const float emin = fmin3(e0, e1, e2), fmn = fmin3(f0, f1, f2);
+        const float dmin = fminf(emin, fmn);
+        A.occ_ws = A.occ_ws || (dmin < mr.z);
+        A.c_ws = __fadd_rn(A.c_ws, -__fsub_rn(dmin, mr.x));
+        if constexpr (GRAD) {
+            const bool upper = fmn < emin;                       // ties go to the lower index: the x - min side
+            float gg = upper ? K.wmax.w : -K.wmax.w;
+            gg = (dmin != 0.f) ? gg : 0.f;                       // sign(d) |d| has zero gradient at d == 0
+            const float a0 = upper ? f0 : e0, a1 = upper ? f1 : e1;
+            const bool p0 = a0 == dmin, p1 = a1 == dmin;
+            gx += p0 ? gg : 0.f;
+            gy += (!p0 && p1) ? gg : 0.f;
+            gz += (!p0 && !p1) ? gg : 0.f;
+            A.Fx += gx; A.Fy += gy; A.Fz += gz;
+            A.Tx = fmaf(y, gz, fmaf(-z, gy, A.Tx));
+            A.Ty = fmaf(z, gx, fmaf(-x, gz, A.Ty));
+            A.Tz = fmaf(x, gy, fmaf(-y, gx, A.Tz));
+        }
+    };
+    if constexpr (SCENE == 1) {
+        float X[W][3], mg[W], mog[W], vmax[W], ug[W][3];
+        int pidx[W];
+#pragma unroll
+        for (int p = 0; p < W; ++p) {
+            const float4 t = rec[2 * p], mr = rec[2 * p + 1];
+            X[p][0] = fmaf(r2, t.z, fmaf(r1, t.y, fmaf(r0, t.x, px)));
+            X[p][1] = fmaf(r5, t.z, fmaf(r4, t.y, fmaf(r3, t.x, py)));
+            X[p][2] = fmaf(r8, t.z, fmaf(r7, t.y, fmaf(r6, t.x, pz)));
+            mg[p] = t.w; mog[p] = mr.y; pidx[p] = __float_as_int(mr.w);
+        }
+        const int n_points = ep->n_points;
+        general_scene_eval<W, GRAD>(K.GS, X, mg, mog, vmax, A.occ_obj, ug, [&](int o, int p, int idx) {
+            if constexpr (ARGMIN) argmin_row[o * n_points + pidx[p]] = idx;
+        });
+#pragma unroll
+        for (int p = 0; p < W; ++p) {
+            A.c_obj = __fadd_rn(A.c_obj, vmax[p]);
+            float gx = 0.f, gy = 0.f, gz = 0.f;
+            if constexpr (GRAD) { gx = -(K.wmin.w * ug[p][0]); gy = -(K.wmin.w * ug[p][1]); gz = -(K.wmin.w * ug[p][2]); }
+            ws_and_wrench(rec[2 * p + 1], X[p][0], X[p][1], X[p][2], gx, gy, gz);
+        }
+        return;
+    }
     const unsigned keep = ~K.lowmask;
     float X[W][3], m1[W], m2[W];
 #pragma unroll
@@ -139,33 +195,13 @@ static __device__ __forceinline__ void ext_group(float r0, float r1, float r2, f
         if constexpr (ARGMIN) argmin_row[__float_as_int(mr.w)] = widx[p];
         A.occ_obj = A.occ_obj || (best < mr.y);
         A.c_obj = __fadd_rn(A.c_obj, -__fsub_rn(best, m_obj));
-        const float e0 = __fsub_rn(x, K.wmin.x), e1 = __fsub_rn(y, K.wmin.y), e2 = __fsub_rn(z, K.wmin.z);
-        const float f0 = __fsub_rn(K.wmax.x, x), f1 = __fsub_rn(K.wmax.y, y), f2 = __fsub_rn(K.wmax.z, z);
-        const float emin = fmin3(e0, e1, e2), fmn = fmin3(f0, f1, f2);
-        const float dmin = fminf(emin, fmn);
-        A.occ_ws = A.occ_ws || (dmin < mr.z);
-        A.c_ws = __fadd_rn(A.c_ws, -__fsub_rn(dmin, mr.x));
-        if constexpr (GRAD) {
-            const float w1 = K.wmin.w * rs;
-            float gx = -(w1 * vx), gy = -(w1 * vy), gz = -(w1 * vz);
-            const bool upper = fmn < emin;                       // ties go to the lower index: the x - min side
-            float gg = upper ? K.wmax.w : -K.wmax.w;
-            gg = (dmin != 0.f) ? gg : 0.f;                       // sign(d) |d| has zero gradient at d == 0
-            const float a0 = upper ? f0 : e0, a1 = upper ? f1 : e1;
-            const bool p0 = a0 == dmin, p1 = a1 == dmin;
-            gx += p0 ? gg : 0.f;
-            gy += (!p0 && p1) ? gg : 0.f;
-            gz += (!p0 && !p1) ? gg : 0.f;
-            A.Fx += gx; A.Fy += gy; A.Fz += gz;
-            A.Tx = fmaf(y, gz, fmaf(-z, gy, A.Tx));
-            A.Ty = fmaf(z, gx, fmaf(-x, gz, A.Ty));
-            A.Tz = fmaf(x, gy, fmaf(-y, gx, A.Tz));
-        }
+        const float w1 = K.wmin.w * rs;
+        ws_and_wrench(mr, x, y, z, -(w1 * vx), -(w1 * vy), -(w1 * vz));
     }
 }
 
 // points [l, l1) of one anchor: quads, then at most one pair and one single point - no padding lanes
-template <bool GRAD, bool ARGMIN>
+template <bool GRAD, bool ARGMIN, int SCENE>
 static __device__ __forceinline__ void ext_points(float r0, float r1, float r2, float r3, float r4, float r5, float r6, float r7, float r8,
                                                   float px, float py, float pz, int l, int l1, const ExtParams* __restrict__ ep,
                                                   int* __restrict__ argmin_row, ExtAcc& A) {
@@ -176,17 +212,27 @@ static __device__ __forceinline__ void ext_points(float r0, float r1, float r2, 
     K.lowmask = ep->lowmask; K.n_pairs2 = ep->n_pairs2;
     K.tq = reinterpret_cast<const float4*>(esm + ep->o_tq);
     K.tsph = reinterpret_cast<const float4*>(esm + ep->o_tsph);
+    if constexpr (SCENE == 1) {
+        K.GS.box = reinterpret_cast<const float4*>(esm + ep->o_gbox);
+        K.GS.sph = K.GS.box + 2 * ep->n_box; K.GS.sphq = K.GS.sph + ep->n_sph_all; K.GS.obj = K.GS.sphq + ep->n_sphq_all;
+        K.GS.n_obj = ep->n_obj; K.GS.grid_data = ep->grid_data;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { K.GS.grid_n[i] = ep->grid_n[i]; K.GS.grid_lo[i] = ep->grid_lo[i]; K.GS.grid_extent[i] = ep->grid_extent[i]; K.GS.grid_nf[i] = ep->grid_nf[i]; }
+    }
     const float4* pt = reinterpret_cast<const float4*>(esm + ep->o_pt);
+    if constexpr (SCENE == 0)          // (the general evaluation holds more per point: pairs there)
 #pragma unroll 1
-    for (; l + 4 <= l1; l += 4) ext_group<4, GRAD, ARGMIN>(r0, r1, r2, r3, r4, r5, r6, r7, r8, px, py, pz, pt + 2 * l, K, ep, argmin_row, A);
-    if (l + 2 <= l1) { ext_group<2, GRAD, ARGMIN>(r0, r1, r2, r3, r4, r5, r6, r7, r8, px, py, pz, pt + 2 * l, K, ep, argmin_row, A); l += 2; }
-    if (l < l1) ext_group<1, GRAD, ARGMIN>(r0, r1, r2, r3, r4, r5, r6, r7, r8, px, py, pz, pt + 2 * l, K, ep, argmin_row, A);
+    for (; l + 4 <= l1; l += 4) ext_group<4, GRAD, ARGMIN, SCENE>(r0, r1, r2, r3, r4, r5, r6, r7, r8, px, py, pz, pt + 2 * l, K, ep, argmin_row, A);
+#pragma unroll 1
+    for (; l + 2 <= l1; l += 2) ext_group<2, GRAD, ARGMIN, SCENE>(r0, r1, r2, r3, r4, r5, r6, r7, r8, px, py, pz, pt + 2 * l, K, ep, argmin_row, A);
+    if (l < l1) ext_group<1, GRAD, ARGMIN, SCENE>(r0, r1, r2, r3, r4, r5, r6, r7, r8, px, py, pz, pt + 2 * l, K, ep, argmin_row, A);
 }
 
 // Everything anchored at one movable body (or the root, col = -1) whose world pose is (Rw, pw).  Per-thread scratch in shared
 // memory, [slot][thread] layout (stride kSBlock): PS [3 n_ps] positions of the pair bodies | WS [6 D] wrench (F, T about the world
 // origin) of the bodies anchored at each movable body | ACC [3] c_obj, c_ws, occupancy bits.  One non-inlined function: the unrolled
 // FK calls it once per movable body (inlined it would be 70 KB of straight-line code).
+template <int SCENE>
 static __device__ __noinline__ void ext_at_anchor(float r0, float r1, float r2, float r3, float r4, float r5, float r6, float r7, float r8,
                                                   float px, float py, float pz, int anchor, int col, int* __restrict__ argmin_row, bool want_grad) {
     extern __shared__ __align__(16) float esm[];
@@ -209,13 +255,10 @@ static __device__ __noinline__ void ext_at_anchor(float r0, float r1, float r2, 
     const int g0 = ism[ep->o_pt_start + anchor], g1 = ism[ep->o_pt_start + anchor + 1];
     ExtAcc A{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, false, false};
     if (g0 < g1) {
-        if (want_grad) {
-            if (argmin_row) ext_points<true, true>(r0, r1, r2, r3, r4, r5, r6, r7, r8, px, py, pz, g0, g1, ep, argmin_row, A);
-            else ext_points<true, false>(r0, r1, r2, r3, r4, r5, r6, r7, r8, px, py, pz, g0, g1, ep, argmin_row, A);
-        } else {
-            if (argmin_row) ext_points<false, true>(r0, r1, r2, r3, r4, r5, r6, r7, r8, px, py, pz, g0, g1, ep, argmin_row, A);
-            else ext_points<false, false>(r0, r1, r2, r3, r4, r5, r6, r7, r8, px, py, pz, g0, g1, ep, argmin_row, A);
-        }
+#define TRK_EXT_POINTS(G_, A_, S_) ext_points<G_, A_, S_>(r0, r1, r2, r3, r4, r5, r6, r7, r8, px, py, pz, g0, g1, ep, argmin_row, A)
+        if (want_grad) { if (argmin_row) TRK_EXT_POINTS(true, true, SCENE); else TRK_EXT_POINTS(true, false, SCENE); }
+        else           { if (argmin_row) TRK_EXT_POINTS(false, true, SCENE); else TRK_EXT_POINTS(false, false, SCENE); }
+#undef TRK_EXT_POINTS
     }
     float* WS = PS + 3 * ep->n_ps * kSBlock;
     if (col >= 0) {
@@ -231,7 +274,9 @@ static __device__ __noinline__ void ext_at_anchor(float r0, float r1, float r2, 
     }
 }
 
-template <class R, int EE, bool WANT_GRAD>
+// SCENE: 0 = one equal-radius identity-pose sphere object (lean scan), 1 = general scene (general_scene_eval of trk_hot.cuh); separate
+// kernels and separate anchor functions, so that the general evaluation's register needs do not reach the sphere scene
+template <class R, int EE, bool WANT_GRAD, int SCENE = 0>
 __global__ void __launch_bounds__(kSBlock, TRK_EXT_MINBLOCKS) k_objective_ext(const __grid_constant__ ExtParams ep, const float* __restrict__ cost_words,
                                                            const float* __restrict__ ext_words_g, const float* __restrict__ q, long long n,
                                                            float* __restrict__ cost_total, float* __restrict__ cost_terms,
@@ -246,15 +291,34 @@ __global__ void __launch_bounds__(kSBlock, TRK_EXT_MINBLOCKS) k_objective_ext(co
         for (int i = tid; i < kExtParamWords; i += kSBlock) esm[i] = psrc[i];
         float* ew = esm + ep.o_ew;
         for (int i = tid; i < ep.ext_nwords; i += kSBlock) ew[i] = __ldg(ext_words_g + i);
-        const float* sphq = cost_words + ep.off_sphq;
-        float* tqw = esm + ep.o_tq;
-        for (int i = tid; i < ep.n_pairs2 * 8; i += kSBlock) {      // two spheres interleaved: (ax, bx, ay, by) (az, bz, aw, bw)
-            const int k = i >> 2, comp = i & 3;
-            tqw[(k >> 1) * 8 + comp * 2 + (k & 1)] = __ldg(sphq + i);
+        if constexpr (SCENE == 1) {          // the tables of general_scene_eval
+            float4* gbox = reinterpret_cast<float4*>(esm + ep.o_gbox);
+            const float4* box = reinterpret_cast<const float4*>(cost_words + ep.off_box);
+            for (int i = tid; i < 2 * ep.n_box; i += kSBlock) gbox[i] = __ldg(box + i);
+            float4* gsph = gbox + 2 * ep.n_box;
+            const float4* sph = reinterpret_cast<const float4*>(cost_words + ep.off_sph_all);
+            for (int i = tid; i < ep.n_sph_all; i += kSBlock) gsph[i] = __ldg(sph + i);
+            float* gq = reinterpret_cast<float*>(gsph + ep.n_sph_all);
+            const float* sphq = cost_words + ep.off_sphq_all;
+            for (int i = tid; i < ep.n_sphq_all * 4; i += kSBlock) {
+                const int k = i >> 2, comp = i & 3;
+                gq[(k >> 1) * 8 + comp * 2 + (k & 1)] = __ldg(sphq + i);
+            }
+            float4* tobj = reinterpret_cast<float4*>(gq) + ep.n_sphq_all;
+            for (int o = tid; o < ep.n_obj; o += kSBlock)
+                general_scene_object_record(tobj + 6 * o, cost_words, o, ep.off_obj_R, ep.off_obj_pos, ep.off_obj_ident, ep.off_obj_start,
+                                            ep.off_obj_qstart, ep.off_obj_box_start, ep.off_obj_tol, ep.off_obj_c2max);
+        } else {
+            const float* sphq = cost_words + ep.off_sphq;
+            float* tqw = esm + ep.o_tq;
+            for (int i = tid; i < ep.n_pairs2 * 8; i += kSBlock) {      // two spheres interleaved: (ax, bx, ay, by) (az, bz, aw, bw)
+                const int k = i >> 2, comp = i & 3;
+                tqw[(k >> 1) * 8 + comp * 2 + (k & 1)] = __ldg(sphq + i);
+            }
+            const float4* sph = reinterpret_cast<const float4*>(cost_words + ep.off_sph);
+            float4* tsph = reinterpret_cast<float4*>(esm + ep.o_tsph);
+            for (int i = tid; i < ep.n_sph; i += kSBlock) tsph[i] = __ldg(sph + i);
         }
-        const float4* sph = reinterpret_cast<const float4*>(cost_words + ep.off_sph);
-        float4* tsph = reinterpret_cast<float4*>(esm + ep.o_tsph);
-        for (int i = tid; i < ep.n_sph; i += kSBlock) tsph[i] = __ldg(sph + i);
     }
     __syncthreads();
     const int4* runs = reinterpret_cast<const int4*>(esm + ep.o_run);
@@ -277,11 +341,11 @@ __global__ void __launch_bounds__(kSBlock, TRK_EXT_MINBLOCKS) k_objective_ext(co
         float qv[D];
         sfor<D>([&](auto c) { qv[c] = __ldg(qrow + c); });
         ACC[0] = 0.f; ACC[kSBlock] = 0.f; ACC[2 * kSBlock] = 0.f;
-        int* amrow = argmin ? argmin + cfg * ep.n_points : nullptr;
+        int* amrow = argmin ? argmin + cfg * (long long)(ep.n_points * (SCENE == 1 ? ep.n_obj : 1)) : nullptr;
         // ---------------- forward: unrolled FK; everything anchored at a body is evaluated while its pose is in registers ----------------
         float W[L][12], JA[D > 0 ? D : 1][3], PJ[D > 0 ? D : 1][3], Ree[9], pee[3];
         unsigned pass = 0u;
-        ext_at_anchor(1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0, -1, amrow, false);     // root-anchored bodies
+        ext_at_anchor<SCENE>(1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0, -1, amrow, false);     // root-anchored bodies
         sfor<L>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
             if constexpr (T::pix(i) >= 0 && T::movable(i)) {
@@ -299,7 +363,7 @@ __global__ void __launch_bounds__(kSBlock, TRK_EXT_MINBLOCKS) k_objective_ext(co
                 T::template compose<i, T::small_angle(i)>(W[a], theta, W[i]);
                 T::template joint_axis<i>(W[a], W[i], JA[qi]);
                 sfor<3>([&](auto rc) { PJ[qi][rc] = W[i][9 + rc]; });
-                ext_at_anchor(W[i][0], W[i][1], W[i][2], W[i][3], W[i][4], W[i][5], W[i][6], W[i][7], W[i][8], W[i][9], W[i][10], W[i][11],
+                ext_at_anchor<SCENE>(W[i][0], W[i][1], W[i][2], W[i][3], W[i][4], W[i][5], W[i][6], W[i][7], W[i][8], W[i][9], W[i][10], W[i][11],
                               1 + qi, qi, amrow, WANT_GRAD);
             }
         });

@@ -143,6 +143,203 @@ __device__ __forceinline__ float hdot3(float w0, float w1, float w2, float c0, f
 }
 
 // ------------------------------------------------------------------------------------------
+// General scene, shared by k_objective_hot (SCENE 1) and k_objective_ext: up to kHotMaxObjects objects - posed sets of
+// spheres and / or boxes and rounded boxes, and the voxel-SDF object - against NP points at once (primitives.py:135-139
+// spheres, :219-223 / :326-334 boxes, :397-398 object pose, grid_map_sdf.py:96-112 voxel lookup; distance_fields.py:
+// value = margin - sdf, max over objects, the first maximal object keeps the gradient).  Tables in shared memory:
+//   box [2 n_box] (c.xyz, radius | half.xyz, rounded flag) | sph [n_sph] (c, r) | sphq [2 pairs] scan table, two spheres
+//   interleaved | obj [6 n_obj]: (pos.xyz, identity flag) (R rows; .w: box range, first sphere) (sphere count, first scan pair,
+//   scan pairs, index mask) (tol, c2max, uniform-radius flag, voxel-grid flag)
+// Per object the points are taken to the object frame once; an equal-radius sphere set goes through the FFMA2 key scan (a near
+// tie or NaN on any point sends the object to the exact loop), unequal radii are evaluated exactly; every box exactly, all
+// points per step of a rolled loop (the next box in flight); strict <: the earlier primitive wins ties.
+// ------------------------------------------------------------------------------------------
+struct GeneralScene {
+    const float4* box; const float4* sph; const float4* sphq; const float4* obj;
+    int n_obj;
+    const float4* grid_data;
+    int grid_n[3];
+    float grid_lo[3], grid_extent[3], grid_nf[3];
+};
+
+__device__ __forceinline__ int general_grid_lookup(const GeneralScene& G, float x, float y, float z, float& sd) {
+    const int i0 = grid_cell(x, G.grid_lo[0], G.grid_extent[0], G.grid_nf[0], G.grid_n[0]);
+    const int i1 = grid_cell(y, G.grid_lo[1], G.grid_extent[1], G.grid_nf[1], G.grid_n[1]);
+    const int i2 = grid_cell(z, G.grid_lo[2], G.grid_extent[2], G.grid_nf[2], G.grid_n[2]);
+    const int idx = (i0 * G.grid_n[1] + i1) * G.grid_n[2] + i2;
+    sd = __ldg(&G.grid_data[idx].x);
+    return idx;
+}
+
+// the object tables of a general scene, written by one thread per object (prologue of both kernels)
+__device__ __forceinline__ void general_scene_object_record(float4* rec, const float* __restrict__ cost_words, int o, int off_obj_R, int off_obj_pos,
+                                                            int off_obj_ident, int off_obj_start, int off_obj_qstart, int off_obj_box_start,
+                                                            int off_obj_tol, int off_obj_c2max) {
+    const int* iw = reinterpret_cast<const int*>(cost_words);
+    const float* Ro = cost_words + off_obj_R + 9 * o;
+    const float* po = cost_words + off_obj_pos + 3 * o;
+    const int flags = iw[off_obj_ident + o];
+    const int k0 = iw[off_obj_start + o], k1 = iw[off_obj_start + o + 1];
+    const int q0 = iw[off_obj_qstart + o], q1 = iw[off_obj_qstart + o + 1];
+    rec[0] = make_float4(po[0], po[1], po[2], (flags & OBJ_IDENTITY) ? 1.f : 0.f);
+    rec[1] = make_float4(Ro[0], Ro[1], Ro[2], __int_as_float(iw[off_obj_box_start + o]));
+    rec[2] = make_float4(Ro[3], Ro[4], Ro[5], __int_as_float(iw[off_obj_box_start + o + 1]));
+    rec[3] = make_float4(Ro[6], Ro[7], Ro[8], __int_as_float(k0));
+    rec[4] = make_float4(__int_as_float(k1 - k0), __int_as_float(q0 / 2), __int_as_float((q1 - q0) / 2), __int_as_float((1 << (flags >> OBJ_BITS_SHIFT)) - 1));
+    rec[5] = make_float4(cost_words[off_obj_tol + o], cost_words[off_obj_c2max + o], (flags & OBJ_UNIFORM_RADIUS) ? 1.f : 0.f, (flags & OBJ_GRID) ? 1.f : 0.f);
+}
+
+// X: world positions; m / mo: cost and occupancy margins; vmax: value of each point (max over objects of margin - sdf);
+// u: world-frame d sdf / d x of the winner (zero when there is none); amin(o, p, index): arg-min of point p in object o
+template <int NP, bool GRAD, class ArgminFn>
+__device__ __forceinline__ void general_scene_eval(const GeneralScene& G, const float (&X)[NP > 0 ? NP : 1][3], const float (&m)[NP > 0 ? NP : 1],
+                                                   const float (&mo)[NP > 0 ? NP : 1], float (&vmax)[NP > 0 ? NP : 1], bool& occ,
+                                                   float (&u)[NP > 0 ? NP : 1][3], ArgminFn&& amin) {
+    constexpr int N1 = NP > 0 ? NP : 1;
+    const float kInf = __int_as_float(0x7f800000);
+    int wobj[N1], wsel[N1];      // winner: object, primitive (spheres of the object first, then its boxes; the cell of a voxel grid)
+    auto to_object = [&](const float4 o0, const float4 r0, const float4 r1, const float4 r2, float x, float y, float z, float& xo, float& yo,
+                         float& zo) {      // x' = (x - pos) @ R for a posed object
+        xo = x; yo = y; zo = z;
+        if (o0.w == 0.f) {
+            const float d0 = __fsub_rn(x, o0.x), d1 = __fsub_rn(y, o0.y), d2 = __fsub_rn(z, o0.z);
+            xo = __fmaf_rn(d2, r2.x, __fmaf_rn(d1, r1.x, __fmul_rn(d0, r0.x)));
+            yo = __fmaf_rn(d2, r2.y, __fmaf_rn(d1, r1.y, __fmul_rn(d0, r0.y)));
+            zo = __fmaf_rn(d2, r2.z, __fmaf_rn(d1, r1.z, __fmul_rn(d0, r0.z)));
+        }
+    };
+#pragma unroll 1
+    for (int o = 0; o < G.n_obj; ++o) {
+        const float4 o0 = G.obj[6 * o], r0 = G.obj[6 * o + 1], r1 = G.obj[6 * o + 2], r2 = G.obj[6 * o + 3], o4 = G.obj[6 * o + 4];
+        const int kb0 = __float_as_int(r0.w), kb1 = __float_as_int(r1.w), k0 = __float_as_int(r2.w), ns = __float_as_int(o4.x);
+        float Xo[N1][3], best[N1];
+        int bsel[N1];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            to_object(o0, r0, r1, r2, X[k][0], X[k][1], X[k][2], Xo[k][0], Xo[k][1], Xo[k][2]);
+            best[k] = kInf; bsel[k] = -1;
+        }
+        const float4 o5 = G.obj[6 * o + 5];
+        if (o5.w != 0.f) {           // voxel SDF lookup: one 4-byte gather per point (the winner's gradient is gathered at the end)
+#pragma unroll
+            for (int k = 0; k < NP; ++k) bsel[k] = general_grid_lookup(G, Xo[k][0], Xo[k][1], Xo[k][2], best[k]);
+        }
+        if (ns > 0) {
+            const float4* sphs = G.sph + k0;
+            bool exact = o5.z == 0.f;                     // unequal radii: every sphere exactly (rare: the shipped scenes are uniform)
+            if (!exact) {
+                const float4* pq = G.sphq + 2 * __float_as_int(o4.y);
+                const int np2 = __float_as_int(o4.z);
+                const unsigned lowmask = (unsigned)__float_as_int(o4.w), keep = ~lowmask;
+                float m1[N1], m2[N1];
+#pragma unroll
+                for (int k = 0; k < NP; ++k) { m1[k] = kInf; m2[k] = kInf; }
+                unsigned idx = 0u;
+                float4 t0 = pq[0], t1 = pq[1];
+#pragma unroll 1
+                for (int j = 0; j < np2; ++j, idx += 2u) {
+                    const float2 cx = make_float2(t0.x, t0.y), cy = make_float2(t0.z, t0.w), cz = make_float2(t1.x, t1.y), cw = make_float2(t1.z, t1.w);
+                    const int jn = (j + 1 < np2) ? j + 1 : j;
+                    t0 = pq[2 * jn]; t1 = pq[2 * jn + 1];
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        const float2 k2 = __ffma2_rn(make_float2(Xo[k][0], Xo[k][0]), cx,
+                                                     __ffma2_rn(make_float2(Xo[k][1], Xo[k][1]), cy, __ffma2_rn(make_float2(Xo[k][2], Xo[k][2]), cz, cw)));
+                        const float pa = __uint_as_float((__float_as_uint(k2.x) & keep) | idx);
+                        const float pb = __uint_as_float((__float_as_uint(k2.y) & keep) | (idx + 1u));
+                        const float lo = fminf(pa, pb), hi = fmaxf(pa, pb);
+                        m2[k] = fmin3(fmaxf(m1[k], lo), m2[k], hi);
+                        m1[k] = fminf(m1[k], lo);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NP; ++k) {
+                    const float xx = __fmaf_rn(Xo[k][2], Xo[k][2], __fmaf_rn(Xo[k][1], Xo[k][1], __fmul_rn(Xo[k][0], Xo[k][0])));
+                    exact = exact || !((m2[k] - m1[k]) > o5.x * (xx + o5.y));
+                    bsel[k] = (int)(__float_as_uint(m1[k]) & lowmask);
+                }
+                if (!exact) {
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        const float4 c = sphs[bsel[k]];
+                        best[k] = __fsub_rn(norm3_rn(__fsub_rn(Xo[k][0], c.x), __fsub_rn(Xo[k][1], c.y), __fsub_rn(Xo[k][2], c.z)), c.w);
+                    }
+                }
+            }
+            if (exact) {                                   // first index wins ties (strict <)
+#pragma unroll
+                for (int k = 0; k < NP; ++k) { best[k] = kInf; bsel[k] = 0; }
+#pragma unroll 1
+                for (int kk = 0; kk < ns; ++kk) {
+                    const float4 c = sphs[kk];
+#pragma unroll
+                    for (int k = 0; k < NP; ++k) {
+                        const float sd = __fsub_rn(norm3_rn(__fsub_rn(Xo[k][0], c.x), __fsub_rn(Xo[k][1], c.y), __fsub_rn(Xo[k][2], c.z)), c.w);
+                        const bool better = sd < best[k];
+                        best[k] = better ? sd : best[k];
+                        bsel[k] = better ? kk : bsel[k];
+                    }
+                }
+            }
+        }
+        if (kb0 < kb1) {
+            float4 bc = G.box[2 * kb0], bh = G.box[2 * kb0 + 1];
+#pragma unroll 1
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const float4 c = bc, hh = bh;
+                const int kn = (kb + 1 < kb1) ? kb + 1 : kb;        // the next box is in flight during this one
+                bc = G.box[2 * kn]; bh = G.box[2 * kn + 1];
+#pragma unroll
+                for (int k = 0; k < NP; ++k) {
+                    const float sd = box_sdf(c, hh, Xo[k][0], Xo[k][1], Xo[k][2]);
+                    const bool better = sd < best[k];                // strict: the earlier primitive wins ties
+                    best[k] = better ? sd : best[k];
+                    bsel[k] = better ? ns + (kb - kb0) : bsel[k];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            occ = occ || (best[k] < mo[k]);
+            const float val = -__fsub_rn(best[k], m[k]);
+            amin(o, k, bsel[k] >= 0 ? bsel[k] : 0);
+            if (o == 0 || val > vmax[k]) { vmax[k] = val; wobj[k] = o; wsel[k] = bsel[k]; }   // the first maximal object keeps the gradient
+        }
+    }
+    if constexpr (GRAD) {
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+            float ux = 0.f, uy = 0.f, uz = 0.f;
+            if (wsel[k] >= 0) {
+                const int o = wobj[k];
+                const float4 o0 = G.obj[6 * o], r0 = G.obj[6 * o + 1], r1 = G.obj[6 * o + 2], r2 = G.obj[6 * o + 3];
+                const int ns = __float_as_int(G.obj[6 * o + 4].x);
+                float xo, yo, zo;
+                to_object(o0, r0, r1, r2, X[k][0], X[k][1], X[k][2], xo, yo, zo);
+                if (G.obj[6 * o + 5].w != 0.f) {      // voxel grid: the cell carries the gradient
+                    const float4 cell = __ldg(G.grid_data + wsel[k]);
+                    ux = cell.y; uy = cell.z; uz = cell.w;
+                } else if (wsel[k] < ns) {             // unit vector from the sphere centre to the point (zero when they coincide)
+                    const float4 c = G.sph[__float_as_int(r2.w) + wsel[k]];
+                    const float vx = __fsub_rn(xo, c.x), vy = __fsub_rn(yo, c.y), vz = __fsub_rn(zo, c.z);
+                    float rs;
+                    norm3_clamped(vx, vy, vz, rs);
+                    ux = vx * rs; uy = vy * rs; uz = vz * rs;
+                } else {
+                    const int kb = __float_as_int(r0.w) + (wsel[k] - ns);
+                    box_sdf_grad(G.box[2 * kb], G.box[2 * kb + 1], xo, yo, zo, ux, uy, uz);
+                }
+                if (o0.w == 0.f) {                     // back to the world frame: g = R g'
+                    const float wx = r0.x * ux + r0.y * uy + r0.z * uz, wy = r1.x * ux + r1.y * uy + r1.z * uz, wz = r2.x * ux + r2.y * uy + r2.z * uz;
+                    ux = wx; uy = wy; uz = wz;
+                }
+            }
+            u[k][0] = ux; u[k][1] = uy; u[k][2] = uz;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // compile-time view of a robot's tables with the fixed chains folded away
 // ------------------------------------------------------------------------------------------
 struct HXf { float R[9]; float t[3]; };
@@ -455,22 +652,9 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
             gq[(k >> 1) * 8 + comp * 2 + (k & 1)] = __ldg(sphq + i);
         }
         float4* tobj = reinterpret_cast<float4*>(gq) + hp.n_sphq_all;
-        const int* iw = reinterpret_cast<const int*>(cost_words);
-        for (int o = tid; o < hp.n_obj; o += kSBlock) {
-            const float* Ro = cost_words + hp.off_obj_R + 9 * o;
-            const float* po = cost_words + hp.off_obj_pos + 3 * o;
-            const int flags = iw[hp.off_obj_ident + o];
-            const int k0 = iw[hp.off_obj_start + o], k1 = iw[hp.off_obj_start + o + 1];
-            const int q0 = iw[hp.off_obj_qstart + o], q1 = iw[hp.off_obj_qstart + o + 1];
-            tobj[6 * o + 0] = make_float4(po[0], po[1], po[2], (flags & OBJ_IDENTITY) ? 1.f : 0.f);
-            tobj[6 * o + 1] = make_float4(Ro[0], Ro[1], Ro[2], __int_as_float(iw[hp.off_obj_box_start + o]));
-            tobj[6 * o + 2] = make_float4(Ro[3], Ro[4], Ro[5], __int_as_float(iw[hp.off_obj_box_start + o + 1]));
-            tobj[6 * o + 3] = make_float4(Ro[6], Ro[7], Ro[8], __int_as_float(k0));
-            tobj[6 * o + 4] = make_float4(__int_as_float(k1 - k0), __int_as_float(q0 / 2), __int_as_float((q1 - q0) / 2),
-                                          __int_as_float((1 << (flags >> OBJ_BITS_SHIFT)) - 1));
-            tobj[6 * o + 5] = make_float4(cost_words[hp.off_obj_tol + o], cost_words[hp.off_obj_c2max + o], (flags & OBJ_UNIFORM_RADIUS) ? 1.f : 0.f,
-                                          (flags & OBJ_GRID) ? 1.f : 0.f);
-        }
+        for (int o = tid; o < hp.n_obj; o += kSBlock)
+            general_scene_object_record(tobj + 6 * o, cost_words, o, hp.off_obj_R, hp.off_obj_pos, hp.off_obj_ident, hp.off_obj_start,
+                                        hp.off_obj_qstart, hp.off_obj_box_start, hp.off_obj_tol, hp.off_obj_c2max);
     } else {
         const float* sphq = cost_words + hp.off_sphq;
         for (int i = tid; i < hp.n_pairs2 * 8; i += kSBlock) {
@@ -676,181 +860,45 @@ k_objective_hot(const __grid_constant__ HotParams hp, const float* __restrict__ 
                 if constexpr (Plan::has_force(b)) add_force(IC<b>{}, gx, gy, gz);
             }
         };
-        // ---------------- general scene: every object's spheres and boxes against all moving points (primitives.py:135-139 spheres,
-        // :219-223 / :326-334 boxes, :397-398 object pose; distance_fields.py: margin - sdf, max over objects) ----------------
+        // ---------------- general scene: every object's spheres, boxes and voxel grid against all moving points ----------------
         [[maybe_unused]] int widx[ND > 0 ? ND : 1];       // sphere scene: index of each moving point's nearest sphere
         if constexpr (SCENE == 1) {
-            const float kInf = __int_as_float(0x7f800000);
-            const float4* gsph = tq + 2 * hp.n_box;
-            const float4* gq = gsph + hp.n_sph_all;
-            const float4* tobj = gq + hp.n_sphq_all;
-            float vmax[ND > 0 ? ND : 1];
-            int wobj[ND > 0 ? ND : 1], wsel[ND > 0 ? ND : 1];      // winner: object, primitive (spheres of the object first, then its boxes)
-            auto to_object = [&](const float4 o0, const float4 r0, const float4 r1, const float4 r2, float x, float y, float z, float& xo,
-                                 float& yo, float& zo) {      // x' = (x - pos) @ R for a posed object
-                xo = x; yo = y; zo = z;
-                if (o0.w == 0.f) {
-                    const float d0 = __fsub_rn(x, o0.x), d1 = __fsub_rn(y, o0.y), d2 = __fsub_rn(z, o0.z);
-                    xo = __fmaf_rn(d2, r2.x, __fmaf_rn(d1, r1.x, __fmul_rn(d0, r0.x)));
-                    yo = __fmaf_rn(d2, r2.y, __fmaf_rn(d1, r1.y, __fmul_rn(d0, r0.y)));
-                    zo = __fmaf_rn(d2, r2.z, __fmaf_rn(d1, r1.z, __fmul_rn(d0, r0.z)));
-                }
-            };
-#pragma unroll 1
-            for (int o = 0; o < hp.n_obj; ++o) {
-                const float4 o0 = tobj[6 * o], r0 = tobj[6 * o + 1], r1 = tobj[6 * o + 2], r2 = tobj[6 * o + 3], o4 = tobj[6 * o + 4];
-                const int kb0 = __float_as_int(r0.w), kb1 = __float_as_int(r1.w), k0 = __float_as_int(r2.w), ns = __float_as_int(o4.x);
-                float Xo[ND > 0 ? ND : 1][3], best[ND > 0 ? ND : 1];
-                int bsel[ND > 0 ? ND : 1];
-                sfor<ND>([&](auto kc) {
-                    constexpr int b = T::tix(CM::pt_link[Plan::dyn_point(decltype(kc)::value)]);
-                    to_object(o0, r0, r1, r2, Pb[b][0], Pb[b][1], Pb[b][2], Xo[kc][0], Xo[kc][1], Xo[kc][2]);
-                    best[kc] = kInf; bsel[kc] = -1;
-                });
-                const float4 o5 = tobj[6 * o + 5];
-                if (o5.w != 0.f) {           // voxel SDF lookup (grid_map_sdf.py:96-112): one 16-byte gather per point
-                    auto lookup = [&](float x, float y, float z, float& sd) {
-                        const int i0 = grid_cell(x, hp.grid_lo[0], hp.grid_extent[0], hp.grid_nf[0], hp.grid_n[0]);
-                        const int i1 = grid_cell(y, hp.grid_lo[1], hp.grid_extent[1], hp.grid_nf[1], hp.grid_n[1]);
-                        const int i2 = grid_cell(z, hp.grid_lo[2], hp.grid_extent[2], hp.grid_nf[2], hp.grid_n[2]);
-                        const int idx = (i0 * hp.grid_n[1] + i1) * hp.grid_n[2] + i2;
-                        sd = __ldg(&hp.grid_data[idx].x);
-                        return idx;
-                    };
-#pragma unroll
-                    for (int k = 0; k < ND; ++k) bsel[k] = lookup(Xo[k][0], Xo[k][1], Xo[k][2], best[k]);
-                    // the constant points: the same cell for every configuration (an L1 hit), combined with the host's value
-                    // over the other objects
-                    sfor<S>([&](auto sc) {
-                        constexpr int s = decltype(sc)::value;
-                        if constexpr (Plan::dyn_rank(s) < 0) {
-                            constexpr auto cp = Plan::kConstPoints;
-                            float sd;
-                            const int idx = lookup(cp.pos[s][0], cp.pos[s][1], cp.pos[s][2], sd);
-                            occ_obj = occ_obj || (sd < hp.mo_obj[s]);
-                            c_obj = __fadd_rn(c_obj, fmaxf(hp.vconst[s], -__fsub_rn(sd, hp.m_obj[s])));
-                            if (argmin && live) argmin[cfg * (long long)(hp.n_obj * S) + o * S + s] = idx;
-                        }
-                    });
-                }
-                if (ns > 0) {
-                    const float4* sphs = gsph + k0;
-                    bool exact = o5.z == 0.f;                     // unequal radii: every sphere exactly (rare: the shipped scenes are uniform)
-                    if (!exact) {
-                        // joint scan of the object's equal-radius spheres: keys |c|^2 - 2 x.c, two spheres per FFMA2, the two smallest
-                        // per point; a near tie (or NaN) on any point sends the object to the exact loop
-                        const float4* pq = gq + 2 * __float_as_int(o4.y);
-                        const int np2 = __float_as_int(o4.z);
-                        const unsigned lowmask = (unsigned)__float_as_int(o4.w), keep = ~lowmask;
-                        float m1[ND > 0 ? ND : 1], m2[ND > 0 ? ND : 1];
-#pragma unroll
-                        for (int k = 0; k < ND; ++k) { m1[k] = kInf; m2[k] = kInf; }
-                        unsigned idx = 0u;
-                        float4 t0 = pq[0], t1 = pq[1];
-#pragma unroll 1
-                        for (int j = 0; j < np2; ++j, idx += 2u) {
-                            const float2 cx = make_float2(t0.x, t0.y), cy = make_float2(t0.z, t0.w), cz = make_float2(t1.x, t1.y), cw = make_float2(t1.z, t1.w);
-                            const int jn = (j + 1 < np2) ? j + 1 : j;
-                            t0 = pq[2 * jn]; t1 = pq[2 * jn + 1];
-#pragma unroll
-                            for (int k = 0; k < ND; ++k) {
-                                const float2 k2 = __ffma2_rn(make_float2(Xo[k][0], Xo[k][0]), cx,
-                                                             __ffma2_rn(make_float2(Xo[k][1], Xo[k][1]), cy, __ffma2_rn(make_float2(Xo[k][2], Xo[k][2]), cz, cw)));
-                                const float pa = __uint_as_float((__float_as_uint(k2.x) & keep) | idx);
-                                const float pb = __uint_as_float((__float_as_uint(k2.y) & keep) | (idx + 1u));
-                                const float lo = fminf(pa, pb), hi = fmaxf(pa, pb);
-                                m2[k] = fmin3(fmaxf(m1[k], lo), m2[k], hi);
-                                m1[k] = fminf(m1[k], lo);
-                            }
-                        }
-#pragma unroll
-                        for (int k = 0; k < ND; ++k) {
-                            const float xx = __fmaf_rn(Xo[k][2], Xo[k][2], __fmaf_rn(Xo[k][1], Xo[k][1], __fmul_rn(Xo[k][0], Xo[k][0])));
-                            exact = exact || !((m2[k] - m1[k]) > o5.x * (xx + o5.y));
-                            bsel[k] = (int)(__float_as_uint(m1[k]) & lowmask);
-                        }
-                        if (!exact) {
-#pragma unroll
-                            for (int k = 0; k < ND; ++k) {
-                                const float4 c = sphs[bsel[k]];
-                                best[k] = __fsub_rn(norm3_rn(__fsub_rn(Xo[k][0], c.x), __fsub_rn(Xo[k][1], c.y), __fsub_rn(Xo[k][2], c.z)), c.w);
-                            }
-                        }
+            GeneralScene GS;
+            GS.box = tq; GS.sph = tq + 2 * hp.n_box; GS.sphq = GS.sph + hp.n_sph_all; GS.obj = GS.sphq + hp.n_sphq_all; GS.n_obj = hp.n_obj;
+            GS.grid_data = hp.grid_data;
+            sfor<3>([&](auto i) { GS.grid_n[i] = hp.grid_n[i]; GS.grid_lo[i] = hp.grid_lo[i]; GS.grid_extent[i] = hp.grid_extent[i]; GS.grid_nf[i] = hp.grid_nf[i]; });
+            float X[ND > 0 ? ND : 1][3], mg[ND > 0 ? ND : 1], mog[ND > 0 ? ND : 1], vmax[ND > 0 ? ND : 1], ug[ND > 0 ? ND : 1][3];
+            sfor<ND>([&](auto kc) {
+                constexpr int s = Plan::dyn_point(decltype(kc)::value), b = T::tix(CM::pt_link[s]);
+                sfor<3>([&](auto rc) { X[kc][rc] = Pb[b][rc]; });
+                mg[kc] = hp.m_obj[s]; mog[kc] = hp.mo_obj[s];
+            });
+            int dyn_s[ND > 0 ? ND : 1];          // moving point -> point index (compile-time values; indexed by the unrolled loops)
+            sfor<ND>([&](auto kc) { dyn_s[kc] = Plan::dyn_point(decltype(kc)::value); });
+            general_scene_eval<ND, WANT_GRAD>(GS, X, mg, mog, vmax, occ_obj, ug, [&](int o, int k, int idx) {
+                if (argmin && live) argmin[cfg * (long long)(hp.n_obj * S) + o * S + dyn_s[k]] = idx;
+            });
+            if (hp.grid_obj >= 0) {
+                // the constant points against the voxel grid: the host cannot read it; the same cell for every configuration (an
+                // L1 hit), combined with the host's value over the other objects
+                sfor<S>([&](auto sc) {
+                    constexpr int s = decltype(sc)::value;
+                    if constexpr (Plan::dyn_rank(s) < 0) {
+                        constexpr auto cp = Plan::kConstPoints;
+                        float sd;
+                        const int idx = general_grid_lookup(GS, cp.pos[s][0], cp.pos[s][1], cp.pos[s][2], sd);
+                        occ_obj = occ_obj || (sd < hp.mo_obj[s]);
+                        c_obj = __fadd_rn(c_obj, fmaxf(hp.vconst[s], -__fsub_rn(sd, hp.m_obj[s])));
+                        if (argmin && live) argmin[cfg * (long long)(hp.n_obj * S) + hp.grid_obj * S + s] = idx;
                     }
-                    if (exact) {                                   // first index wins ties (strict <)
-#pragma unroll
-                        for (int k = 0; k < ND; ++k) { best[k] = kInf; bsel[k] = 0; }
-#pragma unroll 1
-                        for (int kk = 0; kk < ns; ++kk) {
-                            const float4 c = sphs[kk];
-#pragma unroll
-                            for (int k = 0; k < ND; ++k) {
-                                const float sd = __fsub_rn(norm3_rn(__fsub_rn(Xo[k][0], c.x), __fsub_rn(Xo[k][1], c.y), __fsub_rn(Xo[k][2], c.z)), c.w);
-                                const bool better = sd < best[k];
-                                best[k] = better ? sd : best[k];
-                                bsel[k] = better ? kk : bsel[k];
-                            }
-                        }
-                    }
-                }
-                if (kb0 < kb1) {
-                    float4 bc = tq[2 * kb0], bh = tq[2 * kb0 + 1];
-#pragma unroll 1
-                    for (int kb = kb0; kb < kb1; ++kb) {
-                        const float4 c = bc, hh = bh;
-                        const int kn = (kb + 1 < kb1) ? kb + 1 : kb;        // the next box is in flight during this one
-                        bc = tq[2 * kn]; bh = tq[2 * kn + 1];
-#pragma unroll
-                        for (int k = 0; k < ND; ++k) {
-                            const float sd = box_sdf(c, hh, Xo[k][0], Xo[k][1], Xo[k][2]);
-                            const bool better = sd < best[k];                // strict: the earlier primitive wins ties
-                            best[k] = better ? sd : best[k];
-                            bsel[k] = better ? ns + (kb - kb0) : bsel[k];
-                        }
-                    }
-                }
-                sfor<ND>([&](auto kc) {
-                    constexpr int k = decltype(kc)::value, s = Plan::dyn_point(k);
-                    occ_obj = occ_obj || (best[k] < hp.mo_obj[s]);
-                    const float val = -__fsub_rn(best[k], hp.m_obj[s]);
-                    if (argmin && live) argmin[cfg * (long long)(hp.n_obj * S) + o * S + s] = bsel[k] >= 0 ? bsel[k] : 0;
-                    if (o == 0 || val > vmax[k]) { vmax[k] = val; wobj[k] = o; wsel[k] = bsel[k]; }   // the first maximal object keeps the gradient
                 });
             }
             sfor<ND>([&](auto kc) {
                 constexpr int k = decltype(kc)::value, s = Plan::dyn_point(k), b = T::tix(CM::pt_link[s]);
-                const float x = Pb[b][0], y = Pb[b][1], z = Pb[b][2];
                 c_obj = __fadd_rn(c_obj, vmax[k]);
                 float gx = 0.f, gy = 0.f, gz = 0.f;
-                if constexpr (WANT_GRAD) {
-                    if (wsel[k] >= 0) {
-                        const int o = wobj[k];
-                        const float4 o0 = tobj[6 * o], r0 = tobj[6 * o + 1], r1 = tobj[6 * o + 2], r2 = tobj[6 * o + 3];
-                        const int ns = __float_as_int(tobj[6 * o + 4].x);
-                        float xo, yo, zo, ux, uy, uz;
-                        to_object(o0, r0, r1, r2, x, y, z, xo, yo, zo);
-                        if (tobj[6 * o + 5].w != 0.f) {      // voxel grid: the cell carries the gradient
-                            const float4 cell = __ldg(hp.grid_data + wsel[k]);
-                            ux = cell.y; uy = cell.z; uz = cell.w;
-                        } else if (wsel[k] < ns) {   // unit vector from the sphere centre to the point (zero when they coincide)
-                            const float4 c = gsph[__float_as_int(r2.w) + wsel[k]];
-                            const float vx = __fsub_rn(xo, c.x), vy = __fsub_rn(yo, c.y), vz = __fsub_rn(zo, c.z);
-                            float rs;
-                            norm3_clamped(vx, vy, vz, rs);
-                            ux = vx * rs; uy = vy * rs; uz = vz * rs;
-                        } else {
-                            const int kb = __float_as_int(r0.w) + (wsel[k] - ns);
-                            box_sdf_grad(tq[2 * kb], tq[2 * kb + 1], xo, yo, zo, ux, uy, uz);
-                        }
-                        if (o0.w == 0.f) {         // back to the world frame: g = R g'
-                            const float wx = r0.x * ux + r0.y * uy + r0.z * uz, wy = r1.x * ux + r1.y * uy + r1.z * uz,
-                                        wz = r2.x * ux + r2.y * uy + r2.z * uz;
-                            ux = wx; uy = wy; uz = wz;
-                        }
-                        gx = -(hp.w[1] * ux); gy = -(hp.w[1] * uy); gz = -(hp.w[1] * uz);
-                    }
-                }
-                ws_and_force(kc, x, y, z, gx, gy, gz);
+                if constexpr (WANT_GRAD) { gx = -(hp.w[1] * ug[k][0]); gy = -(hp.w[1] * ug[k][1]); gz = -(hp.w[1] * ug[k][2]); }
+                ws_and_force(kc, Pb[b][0], Pb[b][1], Pb[b][2], gx, gy, gz);
             });
         } else {
         // ---------------- sphere object: joint scan of the moving collision points, two spheres per FFMA2 ----------------

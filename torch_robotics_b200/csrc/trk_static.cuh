@@ -1691,6 +1691,18 @@ inline int static_family_last_body(int family) {
     return -1;
 }
 
+// general scene of general_scene_eval (trk_hot.cuh): 1 .. kHotMaxObjects objects - posed sets of spheres and / or boxes, the
+// voxel-SDF object -, nothing relu-clamped
+inline bool general_scene_ok(const float* host_cost_words) {
+    const CostHeader* hh = reinterpret_cast<const CostHeader*>(host_cost_words);
+    const int* iw = reinterpret_cast<const int*>(host_cost_words);
+    bool ok = hh->nObj >= 1 && hh->nObj <= kHotMaxObjects && !hh->clamp_self && !hh->clamp_obj && !hh->clamp_ws;
+    for (int o = 0; ok && o < hh->nObj; ++o)
+        ok = (iw[hh->off_obj_ident + o] & OBJ_GRID) || iw[hh->off_obj_start + o + 1] > iw[hh->off_obj_start + o] ||
+             iw[hh->off_obj_box_start + o + 1] > iw[hh->off_obj_box_start + o];
+    return ok;
+}
+
 template <class R>
 cudaError_t launch_objective_ext_t(int n_sms, const float* host_words, const float* cost_words, const float* ext_words, int ext_nwords,
                                    const float* ext_host, int n_points, const float* q, long long n, float margin_override, int use_override,
@@ -1712,6 +1724,21 @@ cudaError_t launch_objective_ext_t(int n_sms, const float* host_words, const flo
     ep.off_sph = h->off_sph + 4 * iw[h->off_obj_start];
     ep.use_override = use_override; ep.margin_override = margin_override;
     ep.ee_enabled = h->ee_enabled;
+    {   // the single equal-radius identity-pose sphere object keeps its lean path; anything else general_scene_ok accepts is scene 1
+        const int need = OBJ_IDENTITY | OBJ_UNIFORM_RADIUS;
+        const bool joint = h->nObj == 1 && h->KB == 0 && (iw[h->off_obj_ident] & (need | OBJ_GRID)) == need && iw[h->off_obj_start + 1] > iw[h->off_obj_start];
+        ep.scene = joint ? 0 : 1;
+        if (!joint && !general_scene_ok(host_words)) return cudaErrorInvalidValue;
+    }
+    if (ep.scene == 1) {
+        ep.n_pairs2 = 0; ep.n_sph = 0;
+        ep.n_obj = h->nObj; ep.n_box = h->KB; ep.n_sph_all = h->K; ep.n_sphq_all = iw[h->off_obj_qstart + h->nObj];
+        ep.off_box = h->off_box; ep.off_sph_all = h->off_sph; ep.off_sphq_all = h->off_sphq;
+        ep.off_obj_box_start = h->off_obj_box_start; ep.off_obj_ident = h->off_obj_ident; ep.off_obj_R = h->off_obj_R; ep.off_obj_pos = h->off_obj_pos;
+        ep.off_obj_start = h->off_obj_start; ep.off_obj_qstart = h->off_obj_qstart; ep.off_obj_tol = h->off_obj_tol; ep.off_obj_c2max = h->off_obj_c2max;
+        ep.grid_data = h->grid_data;
+        for (int i = 0; i < 3; ++i) { ep.grid_n[i] = h->grid_n[i]; ep.grid_lo[i] = h->grid_lo[i]; ep.grid_extent[i] = h->grid_extent[i]; ep.grid_nf[i] = h->grid_nf[i]; }
+    }
     ep.D = R::D; ep.n_ps = eh->n_ps; ep.n_runs = eh->n_runs; ep.n_points = n_points; ep.ext_nwords = ext_nwords;
     // shared memory: ExtParams | ext words | scan table | sphere table | per-thread scratch
     ep.o_ew = (kExtParamWords + 3) & ~3;
@@ -1719,7 +1746,8 @@ cudaError_t launch_objective_ext_t(int n_sms, const float* host_words, const flo
     ep.o_ps = ep.o_ew + eh->off_ps; ep.o_run = ep.o_ew + eh->off_run; ep.o_item = ep.o_ew + eh->off_item;
     ep.o_tq = ep.o_ew + ((ext_nwords + 3) & ~3);
     ep.o_tsph = ep.o_tq + ep.n_pairs2 * 8;
-    ep.o_scratch = ep.o_tsph + ep.n_sph * 4;
+    ep.o_gbox = ep.o_tsph + ep.n_sph * 4;
+    ep.o_scratch = ep.o_gbox + (ep.scene == 1 ? (2 * ep.n_box + ep.n_sph_all + ep.n_sphq_all + 6 * ep.n_obj) * 4 : 0);
     constexpr int kEE = R::L - 1;
     const size_t smem = ((size_t)ep.o_scratch + (size_t)(3 * ep.n_ps + 6 * R::D + 3) * kSBlock) * sizeof(float);
     auto launch = [&](auto k) {
@@ -1731,6 +1759,7 @@ cudaError_t launch_objective_ext_t(int n_sms, const float* host_words, const flo
         return cudaGetLastError();
     };
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    if (ep.scene == 1) return grad_q ? launch(k_objective_ext<R, kEE, true, 1>) : launch(k_objective_ext<R, kEE, false, 1>);
     if (grad_q) return launch(k_objective_ext<R, kEE, true>);
     return launch(k_objective_ext<R, kEE, false>);
 }
@@ -1888,11 +1917,7 @@ inline int cm_match_value(const float* host_cost_words) {
         const bool joint_scene = hh->nObj == 1 && hh->KB == 0 && (iw[hh->off_obj_ident] & (need | OBJ_GRID)) == need &&
                                  iw[hh->off_obj_start + 1] > iw[hh->off_obj_start];
         const bool hot_terms = hh->ws_enabled && (!hh->ee_enabled || (hh->ee_w_pos > 0.f && hh->ee_w_rot > 0.f));
-        // general scene: 1 .. kHotMaxObjects objects - posed sets of spheres and / or boxes, the voxel-SDF object -, nothing relu-clamped
-        bool box_scene = hh->nObj >= 1 && hh->nObj <= kHotMaxObjects && !hh->clamp_self && !hh->clamp_obj && !hh->clamp_ws;
-        for (int o = 0; box_scene && o < hh->nObj; ++o)
-            box_scene = (iw[hh->off_obj_ident + o] & OBJ_GRID) || iw[hh->off_obj_start + o + 1] > iw[hh->off_obj_start + o] ||
-                        iw[hh->off_obj_box_start + o + 1] > iw[hh->off_obj_box_start + o];
+        const bool box_scene = general_scene_ok(host_cost_words);
         return 1 | ((hh->ee_enabled && hh->ee_link == CM::ee_body) ? 2 : 0) | (joint_scene ? 4 : 0) | (hot_terms ? 8 : 0) | (box_scene ? 16 : 0) |
                (hh->ee_enabled ? 0 : 32);
     }
