@@ -101,6 +101,12 @@ for mk in (lambda: EnvSpheres3D(tensor_args=TA), lambda: EnvTableShelf(tensor_ar
     dcs = task._fused_cost(qt.device)
     dcs.objective(qt.reshape(-1, 7), want_grad=True, want_terms=True, want_occupancy=True, want_argmin=True)
 
+for robot_a in (RobotPanda(sphere_config=True, tensor_args=TA), RobotPanda(grasped_object=GraspedObjectPandaBox(tensor_args=TA), tensor_args=TA)):
+    for mk in (lambda: EnvTableShelf(tensor_args=TA), lambda: EnvSpheres3DExtraObjects(precompute_sdf_obj_fixed=True, sdf_cell_size=0.05, tensor_args=TA)):
+        task = PlanningTask(env=mk(), robot=robot_a, tensor_args=TA)
+        qt = (robot_a.q_min + torch.rand(2, 37, 7, device=dev) * (robot_a.q_max - robot_a.q_min))
+        task.compute_cost_and_grad(qt)
+        task._fused_cost(qt.device).objective(qt.reshape(-1, 7), want_grad=False, want_terms=True, want_occupancy=True, want_argmin=True, margin_override=0.0)
 import specialized_cases as sc
 from torch_robotics_b200 import specialize as sp
 d_i = sc.iiwa7_allegro_desc()
