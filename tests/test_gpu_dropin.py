@@ -173,6 +173,31 @@ def test_inverse_kinematics_matches_reference_iterates():
             assert len(diff) <= 2
 
 
+def test_inverse_kinematics_small_batch_stops_when_every_seed_is_valid():
+    """The reference breaks out of the loop at the first iteration at which all seeds are valid (robot_tree.py:356).  A small batch
+    started near a solution gets there within tens of iterations: the fused path (probing runs of 64 / 256 iterations before
+    max_iters) must return the iterate of that very iteration, as the torch-Adam loop over the FK op (debug=True) does."""
+    from torch_robotics_b200.torch_kinematics_tree.models.robots import DifferentiableFrankaPanda
+    panda = DifferentiableFrankaPanda(gripper=False, device=DEV)
+    q_star = torch.tensor([[0.3, -0.4, 0.2, -1.8, 0.1, 1.5, 0.6]], device=DEV)
+    Ht = panda.compute_forward_kinematics_all_links(q_star, link_list=["ee_link"]).squeeze(1)[0]
+    gen = torch.Generator(device="cpu").manual_seed(7)
+    q0 = (q_star.cpu() + 0.15 * torch.randn(16, 7, generator=gen)).to(DEV)
+    kw = dict(link_name="ee_link", batch_size=16, max_iters=500, lr=5e-2, se3_eps=5e-2, q0_noise=0.0, eps_joint_lim=torch.pi / 64, print_freq=-1)
+    q_fused, idx_fused = panda.inverse_kinematics(Ht, q0=q0.clone(), **kw)
+    q_loop, idx_loop = panda.inverse_kinematics(Ht, q0=q0.clone(), debug=True, **kw)
+    assert idx_fused.numel() == 16 and idx_loop.numel() == 16                      # both stopped because every seed was valid
+    # same stopping iteration (1e-3), or - when a seed sits on the termination boundary there - the neighbouring one: an Adam step
+    # moves a coordinate by at most ~lr
+    dq = float((q_fused.detach() - q_loop.detach()).abs().max())
+    assert dq < 1.5 * kw["lr"], dq
+    print(f"early IK stop: max |q_fused - q_loop| = {dq:.2e} (lr = {kw['lr']})")
+    # the stop is early: the iterate is not the 500-iteration one (which has converged much further)
+    H = panda.compute_forward_kinematics_all_links(q_fused.detach(), link_list=["ee_link"]).squeeze(1)
+    from torch_robotics_b200.torch_kinematics_tree.geometrics.utils import SE3_distance
+    assert float(SE3_distance(H, Ht).max()) > 5e-3
+
+
 def test_fused_ik_kernel_vs_oracle_and_torch_loop():
     """trk_ik_adam (one kernel, state in registers) against the numpy restatement of the reference loop and
     against the same loop run with torch.optim.Adam over the FK autograd.Function."""

@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-python tools/sanitize_smoke.py 2>&1 | tail -2
-timeout 600 compute-sanitizer --tool memcheck python tools/sanitize_smoke.py > gpurun_out/r02_san_memcheck.log 2>&1; tail -3 gpurun_out/r02_san_memcheck.log
-timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_smoke.py > gpurun_out/r02_san_racecheck.log 2>&1; tail -3 gpurun_out/r02_san_racecheck.log
+python -m pytest tests/test_gpu_dropin.py tests/test_reference_examples.py -m gpu -q -x -s -k "inverse or ik" 2>&1 | grep -v "^$" | tail -12

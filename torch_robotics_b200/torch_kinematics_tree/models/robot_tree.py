@@ -263,9 +263,17 @@ class DifferentiableTree(torch.nn.Module):
         ee = self._name_to_idx_map[link_name]
         kw = dict(lr=lr, se3_eps=se3_eps, w_se3=1.0, w_joint_limits=300.0)
         want_stats = print_freq != -1
-        r = model.ik_adam(q0, H_target, ee, lower, upper, n_iters=max_iters, want_loss_stats=want_stats, **kw)
-        count = r["valid_count"].cpu()
-        hit = torch.nonzero(count == batch_size)
+        # The reference stops at the first iteration at which EVERY seed is valid (robot_tree.py:356).  A large batch practically
+        # never gets there, so it runs max_iters once; a small batch often converges within tens of iterations, so it is probed
+        # with short runs first (the kernel is deterministic: a run of n iterations is the prefix of a longer one) instead of
+        # paying max_iters + k iterations for a stop at k.
+        probes = [n for n in (64, 256) if n < max_iters] if (batch_size <= 4096 and not want_stats) else []
+        for n in probes + [max_iters]:
+            r = model.ik_adam(q0, H_target, ee, lower, upper, n_iters=n, want_loss_stats=want_stats, **kw)
+            count = r["valid_count"].cpu()
+            hit = torch.nonzero(count == batch_size)
+            if hit.numel() > 0:
+                break
         n_done = max_iters
         if hit.numel() > 0:          # every seed was valid at iteration `it`: the reference stops before updating
             n_done = int(hit[0])
