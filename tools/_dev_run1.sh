@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_dropin.py tests/test_reference_examples.py -m gpu -q -x -s -k "inverse or ik" 2>&1 | grep -v "^$" | tail -12
+python -m pytest tests -m gpu -q 2>&1 | tail -4 | tee gpurun_out/final_gpu_tests.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
