@@ -202,7 +202,9 @@ def build_specialized_library(desc, collision: Optional[dict] = None, cache_dir:
                             jobs[1][jobs[1].index("-o") + 1]], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed while linking the specialised library:\n" + r.stderr[-4000:])
-        os.replace(tmp_out, out) if os.path.dirname(tmp_out) == os.path.dirname(out) else shutil.move(tmp_out, out)
+        staged = out + f".tmp{os.getpid()}"        # same directory as the target: the final rename is atomic, a concurrent builder
+        shutil.move(tmp_out, staged)               # of the same robot (another rank) never sees a half-written library
+        os.replace(staged, out)
     finally:
         shutil.rmtree(work, ignore_errors=True)
     return out
