@@ -57,6 +57,25 @@ def test_private_library_builds_loads_and_exports_the_abi():
         assert L is _lib.load_library(path)             # one handle per path
 
 
+def test_tree_specialize_bookkeeping_without_a_gpu():
+    """DifferentiableTree.specialize builds (here: finds) the library, bumps the model generation so that dependants rebuild
+    their device costs, and is dropped again when the tree changes; a collision model needs the EE link."""
+    from torch_robotics_b200 import _lib
+    from torch_robotics_b200.torch_kinematics_tree.models.robot_tree import DifferentiableTree
+    tree = DifferentiableTree(os.path.join(sc.DATA, "kuka_iiwa", "urdf", "iiwa7_allegro.urdf"), "iiwa7_allegro", device="cuda:0")
+    assert tree._library_for_current_tree() is None
+    gen = tree._model_generation
+    path = tree.specialize()
+    assert os.path.exists(path) and tree._library_for_current_tree() == path and tree._model_generation == gen + 1
+    assert path == sc.build_all()[0]                                   # the content-addressed cache: the same robot, the same file
+    tree.attach_points([("palm_link", (0.0, 0.0, 0.05))])              # another tree: the default library serves it again
+    assert tree._library_for_current_tree() is None
+    with pytest.raises(ValueError, match="ee_link"):
+        tree.specialize(collision_points=["palm_link"])
+    with pytest.raises(ImportError, match="not found"):
+        _lib.load_library(os.path.join(os.path.dirname(path), "libtrk_jit_does_not_exist.so"))
+
+
 # --------------------------------------------------------------------------------------------- GPU
 torch = pytest.importorskip("torch")
 DEV = "cuda:0"
