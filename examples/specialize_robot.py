@@ -4,15 +4,17 @@ content), then FK / its reverse mode / the fused planning objective of this tree
     python examples/specialize_robot.py            (needs a B200 and nvcc)
 """
 import os
+import sys
 import time
 
 import torch
 
-from torch_robotics_b200.torch_kinematics_tree.models.robot_tree import DifferentiableTree
-from torch_robotics_b200.torch_kinematics_tree.utils.files import get_robot_path
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from torch_robotics_b200.torch_kinematics_tree.models.robot_tree import DifferentiableTree  # noqa: E402
+from torch_robotics_b200.torch_kinematics_tree.utils.files import get_robot_path  # noqa: E402
 
 device = "cuda:0"
-urdf = os.path.join(get_robot_path(), "kuka_iiwa", "urdf", "iiwa7_allegro.urdf")      # iiwa7 arm + Allegro hand: 29 links, 23 DoF
+urdf = os.path.join(str(get_robot_path()), "kuka_iiwa", "urdf", "iiwa7_allegro.urdf")      # iiwa7 arm + Allegro hand: 29 links, 23 DoF
 tree = DifferentiableTree(urdf, "iiwa7_allegro", device=device)
 q = torch.rand(1 << 18, tree._n_dofs, device=device) - 0.5
 

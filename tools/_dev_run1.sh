@@ -1,3 +1,1 @@
-mkdir -p gpurun_out
-python -m pytest tests -m gpu -q 2>&1 | tail -4 | tee gpurun_out/final_gpu_tests.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+python examples/specialize_robot.py 2>&1 | tail -5
