@@ -1,3 +1,3 @@
-# scratch script of the development loop: `gpurun -- bash tools/_dev_run1.sh`
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q 2>&1 | tail -4
+ncu --set full --clock-control none --import-source on -k regex:k_objective_hot -s 28 -c 1 -f -o gpurun_out/r2_hot_tableshelf python tools/bench_envs.py > /dev/null 2>&1
+ls -la gpurun_out/r2_hot_tableshelf.ncu-rep
