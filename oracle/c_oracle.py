@@ -66,8 +66,13 @@ class Tree:
                              R_fixed=_a(d.R_fixed, np.float32), trans=_a(d.trans, np.float32), lo=_a(d.lo, np.float32),
                              hi=_a(d.hi, np.float32), has_lim=_a(d.has_lim, np.int32), topo=_a(d.topo, np.int32))
         P = lambda n: k[n].ctypes.data_as(ip if k[n].dtype == np.int32 else fp)
+        base = None
+        bR, bt = np.asarray(getattr(d, "base_R", np.eye(3)), np.float32), np.asarray(getattr(d, "base_t", np.zeros(3)), np.float32)
+        if not np.array_equal(bR, np.eye(3, dtype=np.float32)) or np.any(bt != 0):      # root pose = base pose (robot_tree.py:133)
+            k["base"] = _a(np.concatenate([bR.reshape(9), bt.reshape(3)]), np.float32)
+            base = k["base"].ctypes.data_as(fp)
         self.s = OrcTree(d.n_links, d.n_dofs, P("parent"), P("kind"), P("axis_k"), P("axis_s"), P("axis"), P("q_index"),
-                         P("R_fixed"), P("trans"), P("lo"), P("hi"), P("has_lim"), P("topo"), None)
+                         P("R_fixed"), P("trans"), P("lo"), P("hi"), P("has_lim"), P("topo"), base)
         self.L, self.D = d.n_links, d.n_dofs
 
 

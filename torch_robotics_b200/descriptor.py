@@ -445,6 +445,35 @@ def grid_cell_index(x, lo, extent, n):
     return idx.clamp(torch.zeros_like(hi), hi)
 
 
+def cost_in_translated_frame(cost: "CostDescriptor", t) -> "CostDescriptor":
+    """The same objective seen from a frame translated by `t` (frame origin at world point t, axes parallel to the world's):
+    every world-fixed quantity is shifted by -t.  Distances, hence costs, gradients w.r.t. q, occupancy and arg-min, are those
+    of the world-frame evaluation up to one fp32 rounding of the shifted constants.  Used for a robot whose base pose is a pure
+    translation (DifferentiableTree.update_base_pose, reference robot_tree.py:133): the tree keeps its own base frame - and with
+    it the unrolled kernels of the compiled-in family - while the scene is pulled back (tasks/tasks.py:_fused_cost).
+    A rotated base cannot be served this way: the workspace box would no longer be axis-aligned."""
+    import copy
+    t = np.asarray(t, np.float32).reshape(3)
+    c = copy.copy(cost)
+    n_obj = len(c.obj_identity)
+    c.sph_center, c.box_center, c.obj_pos = c.sph_center.copy(), c.box_center.copy(), c.obj_pos.copy()
+    for o in range(n_obj):
+        if c.obj_identity[o]:      # world-frame primitives: shift them (the object keeps the identity pose and its fast paths)
+            c.sph_center[c.obj_start[o]:c.obj_start[o + 1]] -= t
+            c.box_center[c.obj_box_start[o]:c.obj_box_start[o + 1]] -= t
+            if o == c.grid_obj:
+                c.grid_lo = (np.asarray(c.grid_lo, np.float32) - t).astype(np.float32)
+        else:                      # posed object: x' = (x - pos) @ R, so only its position moves
+            c.obj_pos[o] -= t
+    if c.ws_enabled:
+        c.ws_min, c.ws_max = (np.asarray(c.ws_min, np.float32) - t).astype(np.float32), (np.asarray(c.ws_max, np.float32) - t).astype(np.float32)
+    if getattr(c, "ee_enabled", 0):
+        tgt = np.asarray(c.ee_target, np.float32).reshape(4, 4).copy()
+        tgt[:3, 3] -= t
+        c.ee_target = tgt
+    return c
+
+
 def build_cost_descriptor(
         pt_link=(), pt_radius=(), cutoff_obj=0.0, cutoff_ws=None,
         objects=(), ws_min=None, ws_max=None,

@@ -17,6 +17,7 @@ import sys
 
 from .. import ops
 from .._lib import DeviceCost
+from ..descriptor import cost_in_translated_frame
 from ..descriptor import build_cost_descriptor
 from ..torch_planning_objectives.fields.distance_fields import (
     CollisionObjectDistanceField, CollisionWorkspaceBoundariesDistanceField, _tree_of)
@@ -103,15 +104,26 @@ class PlanningTask(Task):
         # keyed on content identity AND on the tree's model generation (update_base_pose / attach_* rebuild the device
         # model); the entry keeps every object whose id is part of the key alive, so ids cannot be recycled under it
         key = (torch.device(device).index, getattr(tree, "_model_generation", 0), sig, tuple(settings), id(ee_field), ee_link_name)
+        # A base pose that is a pure translation (update_base_pose): the objective is evaluated in the robot's base frame - the
+        # tree without the base pose keeps the unrolled kernels - on the scene shifted by -t (cost_in_translated_frame); costs,
+        # gradients, occupancy and arg-min are frame-independent.  A rotated base stays on the runtime-tree kernels.
+        shift = tree.base_translation() if hasattr(tree, "base_translation") else None
         entry = self._fused.get(key)
         if entry is None:
             if len(self._fused) > 8:
                 self._fused.clear()
-            entry = (DeviceCost(tree.device_model(device), self.cost_descriptor(ee_field, ee_link_name)), refs, tuple(srefs), ee_field)
+            desc = self.cost_descriptor(ee_field, ee_link_name)
+            if shift is not None:
+                model, desc = tree.device_model_in_base_frame(device), cost_in_translated_frame(desc, shift)
+            else:
+                model = tree.device_model(device)
+            entry = (DeviceCost(model, desc), refs, tuple(srefs), ee_field)
             self._fused[key] = entry
         dc = entry[0]
         if ee_field is not None:
-            tgt = torch.as_tensor(ee_field.target_H).reshape(4, 4).detach().float().cpu().numpy()
+            tgt = torch.as_tensor(ee_field.target_H).reshape(4, 4).detach().float().cpu().numpy().copy()
+            if shift is not None:
+                tgt[:3, 3] -= shift
             if (tgt != dc.cost.ee_target).any():
                 dc.set_ee_target(tgt)
         return dc

@@ -81,6 +81,24 @@ class DifferentiableTree(torch.nn.Module):
             self._device_models[idx] = DeviceModel(self._desc, torch.device("cuda", idx), library=self._library_for_current_tree())
         return self._device_models[idx]
 
+    def base_translation(self):
+        """The base pose as a pure translation [3] (fp32) - or None when it is the identity or has a rotation."""
+        R, t = np.asarray(self._desc.base_R, np.float32), np.asarray(self._desc.base_t, np.float32).reshape(3)
+        return t.copy() if np.array_equal(R, np.eye(3, dtype=np.float32)) and np.any(t != 0) else None
+
+    def device_model_in_base_frame(self, device) -> DeviceModel:
+        """The tree WITHOUT its base pose (the compiled-in kernels serve it when the robot is a shipped one); callers pull the
+        scene back into the base frame instead (descriptor.cost_in_translated_frame)."""
+        import copy
+        device = torch.device(device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        key = ("base_frame", idx)
+        if key not in self._device_models:
+            d = copy.copy(self._desc)
+            d.base_R, d.base_t = np.eye(3, dtype=np.float32), np.zeros(3, np.float32)
+            self._device_models[key] = DeviceModel(d, torch.device("cuda", idx))
+        return self._device_models[key]
+
     def specialize(self, collision_points=None, self_collision_pairs=None, ee_link=None, cache_dir=None, verbose=False):
         """Compile this robot into the unrolled kernel family (specialize.py): afterwards FK, its reverse mode, the link
         Jacobians, the fused IK and - when a collision model is given - the fused planning objective run on kernels
