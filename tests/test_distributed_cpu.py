@@ -34,10 +34,15 @@ def _worker(rank, world_size, port, ret):
         valid = torch.rand(101, generator=g) > 0.4
         l2, h2 = D.shard_bounds(101, rank, world_size)
         bq, berr, bvalid = D.gather_best_solutions(q[l2:h2], err[l2:h2], valid[l2:h2], k=5)
+        # per-iteration valid counts of a 20-iteration solve: rank 0 (51 seeds) is all-valid from iteration 7, rank 1 (50) from 11
+        cnt = torch.full((20,), 3, dtype=torch.int32)
+        cnt[(7 if rank == 0 else 11):] = h2 - l2
+        first = D.first_all_valid_iteration(cnt, h2 - l2)
+        never = D.first_all_valid_iteration(torch.zeros(20, dtype=torch.int32), h2 - l2)
         flag_all = D.all_valid(True, "cpu")
         flag_one = D.all_valid(rank != 1, "cpu")
         ret[rank] = dict(tot=float(tot), terms=tterms, bq=bq, berr=berr, bvalid=bvalid, ref_tot=float(cost.double().sum()),
-                         ref_terms=terms.double().sum(0), q=q, err=err, valid=valid, flag_all=flag_all, flag_one=flag_one)
+                         ref_terms=terms.double().sum(0), q=q, err=err, valid=valid, flag_all=flag_all, flag_one=flag_one, first=first, never=never)
     finally:
         dist.destroy_process_group()
 
@@ -62,6 +67,7 @@ def test_world_size_2_gloo():
             assert abs(r["tot"] - r["ref_tot"]) < 1e-9
             assert torch.allclose(r["terms"], r["ref_terms"], atol=1e-9)
             assert r["flag_all"] is True and r["flag_one"] is False
+            assert r["first"] == 11 and r["never"] == -1
         assert torch.equal(r0["bq"], r1["bq"]) and torch.equal(r0["berr"], r1["berr"])
         key = torch.where(r0["valid"], r0["err"], torch.full_like(r0["err"], float("inf")))
         top = torch.argsort(key, stable=True)[:5]
@@ -70,6 +76,7 @@ def test_world_size_2_gloo():
 
 
 def test_single_process_is_identity():
+    assert D.first_all_valid_iteration(torch.tensor([0, 2, 5, 5]), 5) == 2
     c = torch.arange(12.0).reshape(3, 4)
     assert float(D.total_cost(c)) == float(c.sum())
     q = torch.randn(9, 3)

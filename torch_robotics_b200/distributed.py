@@ -74,6 +74,18 @@ def all_valid(local_all_valid: bool, device) -> bool:
     return bool(flag.item())
 
 
+def first_all_valid_iteration(valid_count: torch.Tensor, local_batch: int) -> int:
+    """The iteration at which the reference's IK loop would stop on the WHOLE (sharded) batch - the first one at which every
+    seed of every rank is valid (robot_tree.py:356) - or -1.  valid_count [n_iters]: this rank's per-iteration count of valid
+    seeds (DeviceModel.ik_adam(...)["valid_count"]); one all-reduce(SUM) of the count vector and of the batch sizes replaces a
+    flag exchange per iteration."""
+    v = torch.cat([valid_count.to(torch.int64).reshape(-1), torch.tensor([int(local_batch)], dtype=torch.int64, device=valid_count.device)])
+    if world()[1] > 1:
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+    hit = torch.nonzero(v[:-1] == v[-1])
+    return int(hit[0]) if hit.numel() else -1
+
+
 def gather_best_solutions(q_local: torch.Tensor, err_local: torch.Tensor, valid_local: torch.Tensor, k: int, local_keys=None):
     """Global k best IK solutions.
 
